@@ -1,0 +1,60 @@
+"""In-tree build of libctxb200.so (nvcc, sm_100a).  Used by __graft_entry__.build()."""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libctxb200.so"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _embed(header: Path, out: Path, symbol: str) -> None:
+    """Turn the integrator template into a C string the library hands to NVRTC."""
+    data = header.read_bytes()
+    lines = [f"// generated from {header.name} by catalax_b200/_build.py -- do not edit",
+             f"extern const char {symbol}[];", f"const char {symbol}[] = {{"]
+    for i in range(0, len(data), 20):
+        lines.append("  " + ",".join(str(b) for b in data[i:i + 20]) + ",")
+    lines.append("  0};")
+    out.write_text("\n".join(lines) + "\n")
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "ctx_b200.h"]
+
+
+def _stamp() -> str:
+    h = hashlib.sha256()
+    for p in sources():
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    stamp_file = HERE / "csrc" / ".build_stamp"
+    stamp = _stamp()
+    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return LIB
+    gen = CSRC / "_gen"
+    gen.mkdir(exist_ok=True)
+    _embed(CSRC / "ctx_integrator.cuh", gen / "ctx_integrator_embed.cpp", "ctx_integrator_src")
+    cu = [str(p) for p in sorted(CSRC.glob("*.cu"))]
+    cmd = [NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+           *cu, str(gen / "ctx_integrator_embed.cpp"), "-o", str(LIB), "-lnvrtc",
+           "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True, cwd=str(CSRC))
+    stamp_file.write_text(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,425 @@
+// ctx_api.cu -- C ABI of libctxb200.so: NVRTC compilation of per-model kernels + launches.
+//
+// Boundary being replaced: the Python callable of catalax/tools/simulation.py:160-196
+// (`Simulation._prepare_func`) -- see include/ctx_b200.h for the per-function citations.
+// No torch types, no CPU fallback: without a CUDA device every compute entry point fails with
+// CTX_E_NOGPU.
+#include "../../include/ctx_b200.h"
+
+#include <cuda_runtime_api.h>
+#include <nvrtc.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <sys/stat.h>
+#include <unistd.h>
+
+extern const char ctx_integrator_src[];  // generated from ctx_integrator.cuh (embed step)
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CTX_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver              \
+                      ? CTX_E_NOGPU : CTX_E_CUDA,                                           \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+  } while (0)
+
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+
+std::string cache_dir() {
+  const char* e = getenv("CTX_B200_CACHE");
+  std::string d;
+  if (e && *e) d = e;
+  else {
+    const char* home = getenv("HOME");
+    d = std::string(home && *home ? home : "/tmp") + "/.cache/catalax_b200";
+  }
+  return d;
+}
+
+void mkdirs(const std::string& d) {
+  std::string cur;
+  for (size_t i = 0; i <= d.size(); ++i) {
+    if (i == d.size() || d[i] == '/') {
+      if (!cur.empty()) mkdir(cur.c_str(), 0755);
+    }
+    if (i < d.size()) cur += d[i];
+  }
+}
+
+struct Variant {
+  std::vector<char> cubin;
+  cudaLibrary_t lib = nullptr;
+  std::map<std::string, cudaKernel_t> kernels;
+  int loaded_device = -1;
+};
+
+}  // namespace
+
+struct ctx_model {
+  std::string field_src;
+  ctx_model_desc desc;
+  std::mutex mu;
+  std::map<int, Variant> variants;  // key = solver*2 + tan
+  // host-call staging (ctx_solve_host)
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+};
+
+namespace {
+
+// Kernel-argument block; layout must match `struct ctx_solve_args` in ctx_integrator.cuh.
+template <typename real>
+struct SolveArgs {
+  const real* y0;
+  const real* theta;
+  const real* consts;
+  const real* ts;
+  real* ys;
+  real* sens;
+  int* status;
+  int* n_accepted;
+  int* n_rejected;
+  unsigned long long* work_counter;
+  long long B;
+  int T;
+  int max_steps;
+  int stride_y0, stride_theta, stride_consts, stride_ts;
+  real rtol, atol, dt0;
+};
+
+int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
+  if (!v.cubin.empty()) return CTX_OK;
+  std::string src;
+  src += m->desc.dtype == CTX_F64 ? "typedef double real;\n#define R(x) x\n"
+                                  : "typedef float real;\n#define R(x) x##f\n";
+  src += "__device__ __forceinline__ real ctx_sign(real x) { return x > R(0.0) ? R(1.0) : "
+         "(x < R(0.0) ? R(-1.0) : x); }\n";
+  src += m->field_src;
+  src += "\n#include \"ctx_integrator.cuh\"\n";
+  std::vector<std::string> opts = {
+      "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+      std::string("-DCTX_F64=") + (m->desc.dtype == CTX_F64 ? "1" : "0"),
+      "-DCTX_SOLVER=" + std::to_string(solver), "-DCTX_TAN=" + std::to_string(tan)};
+  const char* extra = getenv("CTX_B200_NVRTC_FLAGS");
+  if (extra && *extra) {
+    std::string e(extra), cur;
+    for (char ch : e + " ") {
+      if (ch == ' ') { if (!cur.empty()) opts.push_back(cur); cur.clear(); }
+      else cur += ch;
+    }
+  }
+  std::string keysrc = src + "\x01" + ctx_integrator_src;
+  for (auto& o : opts) keysrc += "\x02" + o;
+  int nv_major = 0, nv_minor = 0;
+  nvrtcVersion(&nv_major, &nv_minor);
+  keysrc += "\x03" + std::to_string(nv_major) + "." + std::to_string(nv_minor);
+  char name[64];
+  snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)fnv1a(keysrc),
+           (unsigned long long)fnv1a(keysrc, 0x9e3779b97f4a7c15ull));
+  const std::string dir = cache_dir();
+  const std::string path = dir + "/" + name;
+  const bool use_disk = !(getenv("CTX_B200_NO_DISK_CACHE"));
+  if (use_disk) {
+    if (FILE* f = fopen(path.c_str(), "rb")) {
+      fseek(f, 0, SEEK_END);
+      long n = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      if (n > 0) {
+        v.cubin.resize(n);
+        if (fread(v.cubin.data(), 1, n, f) != (size_t)n) v.cubin.clear();
+      }
+      fclose(f);
+      if (!v.cubin.empty()) return CTX_OK;
+    }
+  }
+  nvrtcProgram prog;
+  const char* hdr_src[] = {ctx_integrator_src};
+  const char* hdr_name[] = {"ctx_integrator.cuh"};
+  nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "ctx_model.cu", 1, hdr_src, hdr_name);
+  if (r != NVRTC_SUCCESS) return fail(CTX_E_NVRTC, nvrtcGetErrorString(r));
+  std::vector<const char*> copts;
+  for (auto& o : opts) copts.push_back(o.c_str());
+  r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+  if (r != NVRTC_SUCCESS) {
+    size_t ln = 0;
+    nvrtcGetProgramLogSize(prog, &ln);
+    std::string log(ln, '\0');
+    nvrtcGetProgramLog(prog, log.data());
+    nvrtcDestroyProgram(&prog);
+    return fail(CTX_E_NVRTC, std::string("nvrtc: ") + nvrtcGetErrorString(r) + "\n" + log);
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  v.cubin.resize(n);
+  nvrtcGetCUBIN(prog, v.cubin.data());
+  nvrtcDestroyProgram(&prog);
+  if (use_disk) {
+    mkdirs(dir);
+    std::string tmp = path + "." + std::to_string((long)getpid()) + ".tmp";
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      fwrite(v.cubin.data(), 1, v.cubin.size(), f);
+      fclose(f);
+      rename(tmp.c_str(), path.c_str());
+    }
+  }
+  return CTX_OK;
+}
+
+int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_t* out) {
+  if (solver < 0 || solver > 3) return fail(CTX_E_INVALID, "unknown solver id");
+  if (tan && m->desc.n_dirs <= 0)
+    return fail(CTX_E_INVALID, "model was generated without sensitivity directions");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Variant& v = m->variants[solver * 2 + tan];
+  int rc = compile_variant(m, solver, tan, v);
+  if (rc) return rc;
+  int dev = 0;
+  CTX_CUDA(cudaGetDevice(&dev));
+  if (!v.lib || v.loaded_device != dev) {
+    CTX_CUDA(cudaLibraryLoadData(&v.lib, v.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    v.loaded_device = dev;
+    v.kernels.clear();
+  }
+  auto it = v.kernels.find(kname);
+  if (it == v.kernels.end()) {
+    cudaKernel_t k;
+    CTX_CUDA(cudaLibraryGetKernel(&k, v.lib, kname));
+    it = v.kernels.emplace(kname, k).first;
+  }
+  *out = it->second;
+  return CTX_OK;
+}
+
+template <typename real>
+int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0,
+                 const void* theta, const void* consts, const void* ts, void* ys, void* sens,
+                 int32_t* status, int32_t* nacc, int32_t* nrej, void* ws, size_t ws_bytes,
+                 cudaStream_t stream) {
+  const ctx_model_desc& d = m->desc;
+  if (cfg->batch <= 0) return CTX_OK;
+  if (cfg->n_times <= 0) return fail(CTX_E_INVALID, "n_times must be >= 1");
+  const size_t need = ctx_workspace_bytes(m, cfg);
+  if (ws_bytes < need || (need && !ws)) return fail(CTX_E_WORKSPACE, "workspace too small");
+  int* scratch = (int*)ws;  // [3*B] dummies when the caller passes NULL outputs
+  SolveArgs<real> a;
+  a.y0 = (const real*)y0;
+  a.theta = (const real*)theta;
+  a.consts = (const real*)consts;
+  a.ts = (const real*)ts;
+  a.ys = (real*)ys;
+  a.sens = (real*)sens;
+  unsigned long long* counter = (unsigned long long*)ws;
+  char* p = (char*)ws + 256;
+  a.status = status ? status : (int*)p;
+  p += status ? 0 : sizeof(int) * cfg->batch;
+  a.n_accepted = nacc ? nacc : (int*)p;
+  p += nacc ? 0 : sizeof(int) * cfg->batch;
+  a.n_rejected = nrej ? nrej : (int*)p;
+  (void)scratch;
+  a.work_counter = counter;
+  a.B = cfg->batch;
+  a.T = cfg->n_times;
+  a.max_steps = cfg->max_steps;
+  a.stride_y0 = cfg->in_axes[0] == 0 ? d.n_states : 0;
+  a.stride_theta = cfg->in_axes[1] == 0 ? d.n_params : 0;
+  a.stride_consts = cfg->in_axes[2] == 0 ? d.n_consts : 0;
+  a.stride_ts = cfg->in_axes[3] == 0 ? cfg->n_times : 0;
+  a.rtol = (real)cfg->rtol;
+  a.atol = (real)cfg->atol;
+  a.dt0 = (real)cfg->dt0;
+
+  const int kernel = cfg->kernel == 0 ? 1 : cfg->kernel;
+  cudaKernel_t k;
+  void* params[] = {&a};
+  if (kernel == 1) {
+    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v0", &k);
+    if (rc) return rc;
+    const unsigned block = 128;
+    const unsigned long long grid = (cfg->batch + block - 1) / block;
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
+    g_launches++;
+  } else {
+    return fail(CTX_E_INVALID, "unknown kernel id");
+  }
+  return CTX_OK;
+}
+
+int dispatch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0,
+                   const void* theta, const void* consts, const void* ts, void* ys, void* sens,
+                   int32_t* status, int32_t* nacc, int32_t* nrej, void* ws, size_t ws_bytes,
+                   void* stream) {
+  if (!m || !cfg) return fail(CTX_E_INVALID, "null model or config");
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  if (m->desc.dtype == CTX_F64)
+    return launch_solve<double>(m, cfg, tan, y0, theta, consts, ts, ys, sens, status, nacc, nrej,
+                                ws, ws_bytes, (cudaStream_t)stream);
+  return launch_solve<float>(m, cfg, tan, y0, theta, consts, ts, ys, sens, status, nacc, nrej, ws,
+                             ws_bytes, (cudaStream_t)stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctx_abi_version(void) { return CTX_ABI_VERSION; }
+
+int ctx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+size_t ctx_last_error(char* buf, size_t n) {
+  if (buf && n) {
+    size_t k = g_err.size() < n - 1 ? g_err.size() : n - 1;
+    memcpy(buf, g_err.data(), k);
+    buf[k] = '\0';
+  }
+  return g_err.size();
+}
+
+int64_t ctx_launch_count(void) { return g_launches.load(); }
+
+int ctx_model_compile(const char* field_src, const ctx_model_desc* desc, ctx_model** out) {
+  if (!field_src || !desc || !out) return fail(CTX_E_INVALID, "null argument");
+  if (desc->n_states <= 0 || desc->n_params < 0 || desc->n_consts < 0 || desc->n_dirs < 0 ||
+      (desc->dtype != CTX_F32 && desc->dtype != CTX_F64))
+    return fail(CTX_E_INVALID, "bad model descriptor");
+  // the generated text carries its own sizes; refuse a mismatching descriptor
+  auto has = [&](const char* macro, int v) {
+    std::string needle = std::string("#define ") + macro + " " + std::to_string(v) + "\n";
+    return strstr(field_src, needle.c_str()) != nullptr;
+  };
+  if (!has("CTX_S", desc->n_states) || !has("CTX_P", desc->n_params) ||
+      !has("CTX_C", desc->n_consts) || !has("CTX_D", desc->n_dirs))
+    return fail(CTX_E_INVALID, "descriptor does not match the CTX_S/P/C/D macros of field_src");
+  ctx_model* m = new ctx_model;
+  m->field_src = field_src;
+  m->desc = *desc;
+  *out = m;
+  return CTX_OK;
+}
+
+void ctx_model_free(ctx_model* m) {
+  if (!m) return;
+  for (auto& kv : m->variants)
+    if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+  if (m->stage) cudaFree(m->stage);
+  delete m;
+}
+
+int ctx_model_cubin(ctx_model* m, int32_t solver, int32_t with_tangents, const void** cubin,
+                    size_t* nbytes) {
+  if (!m || !cubin || !nbytes) return fail(CTX_E_INVALID, "null argument");
+  if (solver < 0 || solver > 3) return fail(CTX_E_INVALID, "unknown solver id");
+  if (with_tangents && m->desc.n_dirs <= 0)
+    return fail(CTX_E_INVALID, "model was generated without sensitivity directions");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Variant& v = m->variants[solver * 2 + (with_tangents ? 1 : 0)];
+  int rc = compile_variant(m, solver, with_tangents ? 1 : 0, v);
+  if (rc) return rc;
+  *cubin = v.cubin.data();
+  *nbytes = v.cubin.size();
+  return CTX_OK;
+}
+
+size_t ctx_workspace_bytes(const ctx_model* m, const ctx_solve_cfg* cfg) {
+  (void)m;
+  if (!cfg || cfg->batch <= 0) return 0;
+  return 256 + 3 * sizeof(int32_t) * (size_t)cfg->batch;
+}
+
+int ctx_solve(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
+              const void* consts, const void* ts, void* ys, int32_t* status, int32_t* nacc,
+              int32_t* nrej, void* ws, size_t ws_bytes, void* stream) {
+  return dispatch_solve(m, cfg, 0, y0, theta, consts, ts, ys, nullptr, status, nacc, nrej, ws,
+                        ws_bytes, stream);
+}
+
+int ctx_solve_sens(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
+                   const void* consts, const void* ts, void* ys, void* sens, int32_t* status,
+                   int32_t* nacc, int32_t* nrej, void* ws, size_t ws_bytes, void* stream) {
+  if (!sens) return fail(CTX_E_INVALID, "sens output is null");
+  return dispatch_solve(m, cfg, 1, y0, theta, consts, ts, ys, sens, status, nacc, nrej, ws,
+                        ws_bytes, stream);
+}
+
+int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
+                   const void* consts, const void* ts, void* ys, int32_t* status, int32_t* nacc,
+                   int32_t* nrej) {
+  if (!m || !cfg) return fail(CTX_E_INVALID, "null model or config");
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  const ctx_model_desc& d = m->desc;
+  const size_t w = d.dtype == CTX_F64 ? 8 : 4;
+  const size_t B = (size_t)cfg->batch, T = (size_t)cfg->n_times;
+  auto rows = [&](int ax) { return cfg->in_axes[ax] == 0 ? B : (size_t)1; };
+  auto al = [](size_t n) { return (n + 255) / 256 * 256; };
+  const size_t n_y0 = al(rows(0) * d.n_states * w), n_th = al(rows(1) * d.n_params * w),
+               n_c = al(rows(2) * d.n_consts * w), n_ts = al(rows(3) * T * w),
+               n_ys = al(B * T * d.n_states * w), n_i = al(B * 4);
+  const size_t n_ws = al(ctx_workspace_bytes(m, cfg));
+  const size_t total = n_y0 + n_th + n_c + n_ts + n_ys + 3 * n_i + n_ws;
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (m->stage_bytes < total) {
+      if (m->stage) cudaFree(m->stage);
+      m->stage = nullptr;
+      m->stage_bytes = 0;
+      CTX_CUDA(cudaMalloc(&m->stage, total));
+      m->stage_bytes = total;
+    }
+  }
+  char* p = (char*)m->stage;
+  char* dy0 = p; p += n_y0;
+  char* dth = p; p += n_th;
+  char* dc = p; p += n_c;
+  char* dts = p; p += n_ts;
+  char* dys = p; p += n_ys;
+  int32_t* dst = (int32_t*)p; p += n_i;
+  int32_t* dna = (int32_t*)p; p += n_i;
+  int32_t* dnr = (int32_t*)p; p += n_i;
+  char* dws = p;
+  cudaStream_t s = 0;
+  CTX_CUDA(cudaMemcpyAsync(dy0, y0, rows(0) * d.n_states * w, cudaMemcpyHostToDevice, s));
+  if (d.n_params)
+    CTX_CUDA(cudaMemcpyAsync(dth, theta, rows(1) * d.n_params * w, cudaMemcpyHostToDevice, s));
+  if (d.n_consts)
+    CTX_CUDA(cudaMemcpyAsync(dc, consts, rows(2) * d.n_consts * w, cudaMemcpyHostToDevice, s));
+  CTX_CUDA(cudaMemcpyAsync(dts, ts, rows(3) * T * w, cudaMemcpyHostToDevice, s));
+  int rc = ctx_solve(m, cfg, dy0, dth, dc, dts, dys, dst, dna, dnr, dws, n_ws, s);
+  if (rc) return rc;
+  CTX_CUDA(cudaMemcpyAsync(ys, dys, B * T * d.n_states * w, cudaMemcpyDeviceToHost, s));
+  if (status) CTX_CUDA(cudaMemcpyAsync(status, dst, B * 4, cudaMemcpyDeviceToHost, s));
+  if (nacc) CTX_CUDA(cudaMemcpyAsync(nacc, dna, B * 4, cudaMemcpyDeviceToHost, s));
+  if (nrej) CTX_CUDA(cudaMemcpyAsync(nrej, dnr, B * 4, cudaMemcpyDeviceToHost, s));
+  CTX_CUDA(cudaStreamSynchronize(s));
+  return CTX_OK;
+}
+
+}  // extern "C"

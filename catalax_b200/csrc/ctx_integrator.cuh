@@ -1,0 +1,370 @@
+// ctx_integrator.cuh -- batched adaptive-step ODE integrator template for sm_100a.
+//
+// Compiled at run time by NVRTC (see ctx_api.cu) AFTER the code-generated vector field of
+// one model, which defines CTX_S/CTX_P/CTX_C/CTX_D and ctx_rhs()/ctx_rhs_tan().
+//
+// Replaces the XLA computation the reference triggers at
+//   catalax/tools/simulation.py:259-273  diffeqsolve(ODETerm(stack), solver(), t0=0, t1=time[-1],
+//                                         dt0, y0, args=(theta, consts, y0), SaveAt(ts=time),
+//                                         PIDController(rtol, atol) | ConstantStepSize(),
+//                                         max_steps, throw)
+//   catalax/tools/simulation.py:346-355  jax.vmap(..., in_axes)
+// Algorithm (diffrax 0.7, restated in oracle/diffrax_oracle.py): FSAL explicit RK step with
+// increments k_i = f_i*dt, error = sum b_err_i k_i, I-controller
+//   factor = clip(0.9 * scaled^(-1/5), keep ? 1 : 0.2, 10),  keep = scaled < 1,
+// end-of-interval clipping (tol 1e-6 f32 / 1e-10 f64), dense output at ts on accepted steps,
+// inf in every slot that was never reached.
+//
+// Compile-time switches (passed as -D by ctx_api.cu):
+//   CTX_F64      0|1   arithmetic type (reference default is f32; enable_x64 -> f64)
+//   CTX_SOLVER   0 tsit5 | 1 dopri5 | 2 euler | 3 heun      (simulation.py:23-26, simconfig.py:16)
+//   CTX_TAN      0|1   carry the D forward tangents of ctx_rhs_tan through the same steps
+#pragma once
+
+#if CTX_F64
+#define CTX_INF __longlong_as_double(0x7ff0000000000000LL)
+#define CTX_TOL_END 1e-10
+#else
+#define CTX_INF __int_as_float(0x7f800000)
+#define CTX_TOL_END 1e-6f
+#endif
+
+#if CTX_TAN
+#define CTX_N (CTX_S * (1 + CTX_D))
+#else
+#define CTX_N (CTX_S)
+#endif
+
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#define CTX_NST 7
+#define CTX_ADAPTIVE 1
+#elif CTX_SOLVER == 2
+#define CTX_NST 1
+#define CTX_ADAPTIVE 0
+#else
+#define CTX_NST 2
+#define CTX_ADAPTIVE 0
+#endif
+
+struct ctx_solve_args {
+  const real* y0;      // [B,S] or [S]
+  const real* theta;   // [B,P] or [P]
+  const real* consts;  // [B,C] or [C]
+  const real* ts;      // [B,T] or [T]
+  real* ys;            // [B,T,S]
+  real* sens;          // [B,T,S,D] or null        (jax.jacobian layout, simulation.py:315)
+  int* status;         // [B]   0 ok | 1 max_steps reached | 2 non-finite step size
+  int* n_accepted;     // [B]
+  int* n_rejected;     // [B]
+  unsigned long long* work_counter;  // persistent kernels: next unclaimed trajectory
+  long long B;
+  int T;
+  int max_steps;
+  int stride_y0, stride_theta, stride_consts, stride_ts;  // elements per row, 0 = shared
+  real rtol, atol, dt0;
+};
+
+// ------------------------------------------------------------------ vector field
+__device__ __forceinline__ void ctx_field(const real t, const real* Y, const real* th,
+                                          const real* c, const real* y0, real* dY) {
+#if CTX_TAN
+  ctx_rhs_tan(t, Y, Y + CTX_S, th, c, y0, dY, dY + CTX_S);
+#else
+  ctx_rhs(t, Y, th, c, y0, dY);
+#endif
+}
+
+// ------------------------------------------------------------------ tableaus
+#if CTX_SOLVER == 0
+// Tsitouras 2011 (diffrax Tsit5); b_err = b_sol - b_hat.
+#define A21 R(0.161)
+#define A31 R(-0.008480655492356988544426874250230774675121177393430391537369234245294192976164141156943)
+#define A32 R(0.3354806554923569885444268742502307746751211773934303915373692342452941929761641411569)
+#define A41 R(2.897153057105493432130432594192938764924887287701866490314866693455023795137503079289)
+#define A42 R(-6.359448489975074843148159912383825625952700647415626703305928850207288721235210244366)
+#define A43 R(4.362295432869581411017727318190886861027813359713760212991062156752264926097707165077)
+#define A51 R(5.325864828439256604428877920840511317836476253097040101202360397727981648835607691791)
+#define A52 R(-11.74888356406282787774717033978577296188744178259862899288666928009020615663593781589)
+#define A53 R(7.495539342889836208304604784564358155658679161518186721010132816213648793440552049753)
+#define A54 R(-0.09249506636175524925650207933207191611349983406029535244034750452930469056411389539635)
+#define A61 R(5.861455442946420028659251486982647890394337666164814434818157239052507339770711679748)
+#define A62 R(-12.92096931784710929170611868178335939541780751955743459166312250439928519268343184452)
+#define A63 R(8.159367898576158643180400794539253485181918321135053305748355423955009222648673734986)
+#define A64 R(-0.07158497328140099722453054252582973869127213147363544882721139659546372402303777878835)
+#define A65 R(-0.02826905039406838290900305721271224146717633626879770007617876201276764571291579142206)
+#define A71 R(0.09646076681806522951816731316512876333711995238157997181903319145764851595234062815396)
+#define A72 R(0.01)
+#define A73 R(0.4798896504144995747752495322905965199130404621990332488332634944254542060153074523509)
+#define A74 R(1.379008574103741893192274821856872770756462643091360525934940067397245698027561293331)
+#define A75 R(-3.290069515436080679901047585711363850115683290894936158531296799594813811049925401677)
+#define A76 R(2.324710524099773982415355918398765796109060233222962411944060046314465391054716027841)
+#define C2 R(0.161)
+#define C3 R(0.327)
+#define C4 R(0.9)
+#define C5 R(0.9800255409045096857298102862870245954942137979563024768854764293221195950761080302604)
+#define E1 R(0.0017800110522257773)
+#define E2 R(0.0008164344596567463)
+#define E3 R(-0.007880878010261994)
+#define E4 R(0.1447110071732629)
+#define E5 R(-0.5823571654525552)
+#define E6 R(0.45808210592918686)
+#define E7 R(-0.015151515151515152)
+#elif CTX_SOLVER == 1
+// Dormand-Prince 5(4) (diffrax Dopri5) + Shampine's mid-point weights.
+#define A21 R(0.2)
+#define A31 R(0.075)
+#define A32 R(0.225)
+#define A41 R(0.9777777777777777)
+#define A42 R(-3.7333333333333334)
+#define A43 R(3.5555555555555554)
+#define A51 R(2.9525986892242035)
+#define A52 R(-11.595793324188385)
+#define A53 R(9.822892851699436)
+#define A54 R(-0.2908093278463649)
+#define A61 R(2.8462752525252526)
+#define A62 R(-10.757575757575758)
+#define A63 R(8.906422717743473)
+#define A64 R(0.2784090909090909)
+#define A65 R(-0.2735313036020583)
+#define A71 R(0.09114583333333333)
+#define A72 R(0.0)
+#define A73 R(0.44923629829290207)
+#define A74 R(0.6510416666666666)
+#define A75 R(-0.322376179245283)
+#define A76 R(0.13095238095238096)
+#define C2 R(0.2)
+#define C3 R(0.3)
+#define C4 R(0.8)
+#define C5 R(0.8888888888888888)
+#define E1 R(0.0012326388888888873)
+#define E2 R(0.0)
+#define E3 R(-0.004252770290506136)
+#define E4 R(0.036979166666666674)
+#define E5 R(-0.05086379716981132)
+#define E6 R(0.04190476190476192)
+#define E7 R(-0.025)
+#define M1 R(0.10013431883002395)
+#define M2 R(0.0)
+#define M3 R(0.3918321794184259)
+#define M4 R(-0.02982460176594817)
+#define M5 R(0.05893268337240795)
+#define M6 R(-0.04497888809104361)
+#define M7 R(0.023904308236133973)
+#endif
+
+// ------------------------------------------------------------------ one RK step
+// K[i] holds f_i (not f_i*dt); the dt factor is applied once per stage sum.
+// On entry K[0] = f(tprev, y).  On exit K[1..] are the stage slopes and ynew = y1.
+__device__ __forceinline__ void ctx_rk_stages(const real tp, const real dt, const real* y,
+                                              real (*K)[CTX_N], const real* th, const real* c,
+                                              const real* y0, real* ynew) {
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+  real yt[CTX_N];
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) yt[i] = y[i] + dt * (A21 * K[0][i]);
+  ctx_field(tp + C2 * dt, yt, th, c, y0, K[1]);
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) yt[i] = y[i] + dt * (A31 * K[0][i] + A32 * K[1][i]);
+  ctx_field(tp + C3 * dt, yt, th, c, y0, K[2]);
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i)
+    yt[i] = y[i] + dt * (A41 * K[0][i] + A42 * K[1][i] + A43 * K[2][i]);
+  ctx_field(tp + C4 * dt, yt, th, c, y0, K[3]);
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i)
+    yt[i] = y[i] + dt * (A51 * K[0][i] + A52 * K[1][i] + A53 * K[2][i] + A54 * K[3][i]);
+  ctx_field(tp + C5 * dt, yt, th, c, y0, K[4]);
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i)
+    yt[i] = y[i] + dt * (A61 * K[0][i] + A62 * K[1][i] + A63 * K[2][i] + A64 * K[3][i] +
+                         A65 * K[4][i]);
+  ctx_field(tp + dt, yt, th, c, y0, K[5]);
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i)
+    ynew[i] = y[i] + dt * (A71 * K[0][i] + A72 * K[1][i] + A73 * K[2][i] + A74 * K[3][i] +
+                           A75 * K[4][i] + A76 * K[5][i]);
+  ctx_field(tp + dt, ynew, th, c, y0, K[6]);
+#elif CTX_SOLVER == 2
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) ynew[i] = y[i] + dt * K[0][i];
+#else
+  real yt[CTX_N];
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) yt[i] = y[i] + dt * K[0][i];
+  ctx_field(tp + dt, yt, th, c, y0, K[1]);
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) ynew[i] = y[i] + dt * (R(0.5) * K[0][i] + R(0.5) * K[1][i]);
+#endif
+}
+
+#if CTX_ADAPTIVE
+// scaled error norm of PIDController: rms(y_err / (atol + rtol*max(|y0|,|y1|))) over the S
+// model states only (tangents never enter the norm: the factor is under stop_gradient).
+__device__ __forceinline__ real ctx_scaled_error(const real dt, const real* y, const real* ynew,
+                                                 const real (*K)[CTX_N], const real rtol,
+                                                 const real atol) {
+  bool has_nan = false;
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) has_nan |= (ynew[i] != ynew[i]);
+  real ssq = R(0.0);
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) {
+    real e = dt * (E1 * K[0][i] + E2 * K[1][i] + E3 * K[2][i] + E4 * K[3][i] + E5 * K[4][i] +
+                   E6 * K[5][i] + E7 * K[6][i]);
+    if (e != e) e = CTX_INF;
+    const real y1 = has_nan ? y[i] : ynew[i];
+    const real sc = atol + fmax(fabs(y[i]), fabs(y1)) * rtol;
+    const real r = e / sc;
+    ssq += r * r;
+  }
+  return sqrt(ssq / (real)CTX_S);
+}
+#endif
+
+// ------------------------------------------------------------------ dense output
+// Evaluate the solver's interpolant of the accepted step [tp, tp+dt] at time tq.
+__device__ __forceinline__ void ctx_dense(const real tq, const real tp, const real tn,
+                                          const real* y, const real* ynew,
+                                          const real (*K)[CTX_N], real* out) {
+  const real den = tn - tp;
+  const real dt = den;
+  const real th = (den == R(0.0)) ? R(0.0) : (tq - tp) / den;
+#if CTX_SOLVER == 0
+  const real t2 = th * th;
+  const real b1 = R(-1.0530884977290216) * th * (th - R(1.3299890189751412)) *
+                  (t2 - R(1.4364028541716351) * th + R(0.7139816917074209));
+  const real b2 = R(0.1017) * t2 * (t2 - R(2.1966568338249754) * th + R(1.2949852507374631));
+  const real b3 = R(2.490627285651252793) * t2 *
+                  (t2 - R(2.38535645472061657) * th + R(1.57803468208092486));
+  const real b4 = R(-16.54810288924490272) * (th - R(1.21712927295533244)) *
+                  (th - R(0.61620406037800089)) * t2;
+  const real b5 = R(47.37952196281928122) * (th - R(1.203071208372362603)) *
+                  (th - R(0.658047292653547382)) * t2;
+  const real b6 = R(-34.87065786149660974) * (th - R(1.2)) * (th - R(0.666666666666666667)) * t2;
+  const real b7 = R(2.5) * (th - R(1.0)) * (th - R(0.6)) * t2;
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i)
+    out[i] = y[i] + dt * (b1 * K[0][i] + b2 * K[1][i] + b3 * K[2][i] + b4 * K[3][i] +
+                          b5 * K[4][i] + b6 * K[5][i] + b7 * K[6][i]);
+#elif CTX_SOLVER == 1
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) {
+    const real ymid = y[i] + dt * (M1 * K[0][i] + M2 * K[1][i] + M3 * K[2][i] + M4 * K[3][i] +
+                                   M5 * K[4][i] + M6 * K[5][i] + M7 * K[6][i]);
+    const real f0 = dt * K[0][i], f1 = dt * K[6][i];
+    const real y0_ = y[i], y1_ = ynew[i];
+    const real a = R(2.0) * (f1 - f0) - R(8.0) * (y1_ + y0_) + R(16.0) * ymid;
+    const real b = R(5.0) * f0 - R(3.0) * f1 + R(18.0) * y0_ + R(14.0) * y1_ - R(32.0) * ymid;
+    const real c = f1 - R(4.0) * f0 - R(11.0) * y0_ - R(5.0) * y1_ + R(16.0) * ymid;
+    out[i] = (((a * th + b) * th + c) * th + f0) * th + y0_;
+  }
+#else
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) out[i] = y[i] + th * (ynew[i] - y[i]);
+#endif
+}
+
+__device__ __forceinline__ void ctx_store_point(const ctx_solve_args& a, const long long b,
+                                                const int idx, const real* v) {
+  real* o = a.ys + ((size_t)b * a.T + idx) * CTX_S;
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) o[i] = v[i];
+#if CTX_TAN
+  if (a.sens) {
+    real* s = a.sens + ((size_t)b * a.T + idx) * (CTX_S * CTX_D);
+#pragma unroll
+    for (int d = 0; d < CTX_D; ++d)
+#pragma unroll
+      for (int i = 0; i < CTX_S; ++i) s[i * CTX_D + d] = v[CTX_S + d * CTX_S + i];
+  }
+#endif
+}
+
+// ------------------------------------------------------------------ kernel v0
+// One thread per trajectory, static assignment, direct stores.
+extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_args a) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+
+  real y[CTX_N], ynew[CTX_N], y0[CTX_S];
+  real th[CTX_P > 0 ? CTX_P : 1], c[CTX_C > 0 ? CTX_C : 1];
+  real K[CTX_NST][CTX_N];
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)b * a.stride_y0 + i];
+#pragma unroll
+  for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)b * a.stride_theta + i];
+#pragma unroll
+  for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)b * a.stride_consts + i];
+#if CTX_TAN
+#pragma unroll
+  for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
+#pragma unroll
+  for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
+#endif
+  const real* ts = a.ts + (size_t)b * a.stride_ts;
+  const int T = a.T;
+  const real t_end = ts[T - 1];
+  real tprev = R(0.0);
+  real tnext = fmin(tprev + a.dt0, t_end);
+  int idx = 0, nacc = 0, nrej = 0, status = 0;
+
+  if (!(tprev < t_end)) {  // t0 == t1: every requested time is t0
+    for (; idx < T; ++idx) ctx_store_point(a, b, idx, y);
+  }
+  ctx_field(tprev, y, th, c, y0, K[0]);
+
+  for (int n = 0; tprev < t_end; ++n) {
+    if (n >= a.max_steps) { status = 1; break; }
+    const real dt = tnext - tprev;
+    ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
+    bool keep = true;
+    real dt_next = a.dt0;
+#if CTX_ADAPTIVE
+    const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
+    keep = scaled < R(1.0);
+    const real inv = R(1.0) / scaled;
+    real factor = R(0.9) * pow(inv, R(0.2));
+    factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
+    if (factor != factor) factor = inv;  // clip(NaN) stays NaN in the reference
+    dt_next = dt * factor;
+#endif
+    if (keep) {
+      real out[CTX_N];
+      while (idx < T) {
+        const real tq = ts[idx];
+        if (!(tq <= tnext)) break;
+        ctx_dense(tq, tprev, tnext, y, ynew, K, out);
+        ctx_store_point(a, b, idx, out);
+        ++idx;
+      }
+#pragma unroll
+      for (int i = 0; i < CTX_N; ++i) y[i] = ynew[i];
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#pragma unroll
+      for (int i = 0; i < CTX_N; ++i) K[0][i] = K[6][i];
+#endif
+      tprev = tnext;
+      ++nacc;
+    } else {
+      ++nrej;
+    }
+#if !(CTX_SOLVER == 0 || CTX_SOLVER == 1)
+    if (keep) ctx_field(tprev, y, th, c, y0, K[0]);
+#endif
+    tprev = fmin(tprev, t_end);
+    real tn = tprev + dt_next;
+    if (tn > t_end - CTX_TOL_END) tn = keep ? t_end : tprev + R(0.5) * (t_end - tprev);
+    tnext = tn;
+    if (!(fabs(tnext) < CTX_INF)) { status = 2; break; }
+  }
+  if (tprev < t_end && status == 0) status = 1;
+  {
+    real inf[CTX_N];
+#pragma unroll
+    for (int i = 0; i < CTX_N; ++i) inf[i] = CTX_INF;
+    for (; idx < T; ++idx) ctx_store_point(a, b, idx, inf);
+  }
+  a.status[b] = status;
+  a.n_accepted[b] = nacc;
+  a.n_rejected[b] = nrej;
+}

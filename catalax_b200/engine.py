@@ -1,0 +1,218 @@
+"""ctypes binding of libctxb200.so (the C ABI in include/ctx_b200.h).
+
+This is the host side of the drop-in seam: the reference builds a jitted JAX closure in
+``catalax/tools/simulation.py:160-196`` and calls it at ``catalax/model/model.py:699`` and
+``catalax/mcmc/mcmc.py:448``; here the same call lands in CUDA kernels through plain C entry
+points.  PyTorch is used only for device memory and the current stream.
+
+There is deliberately NO CPU fallback: if the shared library is missing or no GPU is visible,
+every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / "libctxb200.so"
+_lib = None
+
+F32, F64 = 0, 1
+SOLVER_IDS = {"tsit5": 0, "dopri5": 1, "euler": 2, "heun": 3}
+LIKELIHOOD_IDS = {"normal": 0, "softlaplace": 1}
+
+
+class EngineError(RuntimeError):
+    """Raised for every failure of the native engine (carries the library's message)."""
+
+
+class ctx_model_desc(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("n_params", C.c_int32), ("n_consts", C.c_int32),
+                ("n_dirs", C.c_int32), ("n_theta_dirs", C.c_int32), ("dtype", C.c_int32)]
+
+
+class ctx_solve_cfg(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("in_axes", C.c_int32 * 4), ("batch", C.c_int64),
+                ("n_times", C.c_int32), ("max_steps", C.c_int32), ("rtol", C.c_double),
+                ("atol", C.c_double), ("dt0", C.c_double), ("kernel", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def lib() -> C.CDLL:
+    """Load libctxb200.so (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise EngineError(
+            f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "-- catalax_b200 has no CPU fallback")
+    L = C.CDLL(str(_LIB_PATH))
+    vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
+    L.ctx_abi_version.restype = C.c_int
+    L.ctx_device_count.restype = C.c_int
+    L.ctx_last_error.restype = C.c_size_t
+    L.ctx_last_error.argtypes = [C.c_char_p, C.c_size_t]
+    L.ctx_launch_count.restype = C.c_int64
+    L.ctx_model_compile.restype = C.c_int
+    L.ctx_model_compile.argtypes = [C.c_char_p, C.POINTER(ctx_model_desc), C.POINTER(vp)]
+    L.ctx_model_free.restype = None
+    L.ctx_model_free.argtypes = [vp]
+    L.ctx_model_cubin.restype = C.c_int
+    L.ctx_model_cubin.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.ctx_workspace_bytes.restype = C.c_size_t
+    L.ctx_workspace_bytes.argtypes = [vp, C.POINTER(ctx_solve_cfg)]
+    L.ctx_solve.restype = C.c_int
+    L.ctx_solve.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                            C.c_size_t, vp]
+    L.ctx_solve_sens.restype = C.c_int
+    L.ctx_solve_sens.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                 vp, C.c_size_t, vp]
+    L.ctx_solve_host.restype = C.c_int
+    L.ctx_solve_host.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(1 << 16)
+    lib().ctx_last_error(buf, len(buf))
+    return buf.value.decode(errors="replace")
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise EngineError(f"ctx error {rc}: {last_error()}")
+
+
+def device_count() -> int:
+    return int(lib().ctx_device_count())
+
+
+def launch_count() -> int:
+    return int(lib().ctx_launch_count())
+
+
+@dataclass
+class SolveOutput:
+    ys: "object"            # torch.Tensor [B,T,S]
+    status: "object"        # torch.int32 [B]
+    n_accepted: "object"
+    n_rejected: "object"
+    sens: Optional["object"] = None  # [B,T,S,D]
+
+
+class CompiledModel:
+    """One code-generated vector field bound to the native engine."""
+
+    def __init__(self, field, dtype: str = "float32"):
+        """field: catalax_b200.tools.codegen.GeneratedField."""
+        self.field = field
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype("float32"), np.dtype("float64")):
+            raise ValueError("dtype must be float32 or float64")
+        self.desc = ctx_model_desc(field.S, field.P, field.C, field.D, field.n_theta_dirs,
+                                   F64 if self.dtype == np.float64 else F32)
+        self._h = C.c_void_p()
+        _check(lib().ctx_model_compile(field.source.encode(), C.byref(self.desc), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().ctx_model_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ build-time helpers
+    def cubin(self, solver: str = "tsit5", tangents: bool = False) -> bytes:
+        """NVRTC-compile one kernel variant (works without a GPU) and return the cubin."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _check(lib().ctx_model_cubin(self._h, SOLVER_IDS[solver], int(tangents), C.byref(ptr),
+                                     C.byref(n)))
+        return C.string_at(ptr, n.value)
+
+    # ------------------------------------------------------------------ compute
+    def make_cfg(self, *, solver, in_axes, batch, n_times, max_steps, rtol, atol, dt0, kernel=0):
+        cfg = ctx_solve_cfg()
+        cfg.solver = SOLVER_IDS[solver]
+        for i, a in enumerate(in_axes):
+            cfg.in_axes[i] = 0 if a == 0 else -1
+        cfg.batch, cfg.n_times, cfg.max_steps = int(batch), int(n_times), int(max_steps)
+        cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
+        cfg.kernel = int(kernel)
+        return cfg
+
+    def solve(self, y0, theta, consts, ts, *, solver="tsit5", in_axes=(0, None, 0, None),
+              rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096, tangents=False, kernel=0,
+              out=None):
+        """Device-resident solve.  All inputs are torch CUDA tensors of this model's dtype."""
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = y0.device
+        if dev.type != "cuda":
+            raise EngineError("solve() needs CUDA tensors: catalax_b200 has no CPU fallback")
+        S, P, Cn, D = self.field.S, self.field.P, self.field.C, self.field.D
+
+        def prep(x, width, ax):
+            x = x.to(device=dev, dtype=tdt).contiguous()
+            want = 2 if ax == 0 else 1
+            if x.dim() != want or x.shape[-1] != width:
+                raise ValueError(f"expected a {want}-D array with last dim {width}, got {tuple(x.shape)}")
+            return x
+
+        Bs = [a.shape[0] for a, ax in ((y0, in_axes[0]), (theta, in_axes[1]),
+                                       (consts, in_axes[2]), (ts, in_axes[3])) if ax == 0]
+        B = Bs[0] if Bs else 1
+        if any(b != B for b in Bs):
+            raise ValueError(f"inconsistent batch sizes {Bs}")
+        T = ts.shape[-1]
+        y0 = prep(y0, S, in_axes[0]); theta = prep(theta, P, in_axes[1])
+        consts = prep(consts, Cn, in_axes[2]); ts = prep(ts, T, in_axes[3])
+        cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
+                            max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel)
+        with torch.cuda.device(dev):
+            ys = out if out is not None else torch.empty((B, T, S), dtype=tdt, device=dev)
+            status = torch.empty(B, dtype=torch.int32, device=dev)
+            nacc = torch.empty(B, dtype=torch.int32, device=dev)
+            nrej = torch.empty(B, dtype=torch.int32, device=dev)
+            wsb = int(lib().ctx_workspace_bytes(self._h, C.byref(cfg)))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            p = lambda t: C.c_void_p(t.data_ptr()) if t.numel() else C.c_void_p(0)
+            if tangents:
+                sens = torch.empty((B, T, S, D), dtype=tdt, device=dev)
+                _check(lib().ctx_solve_sens(self._h, C.byref(cfg), p(y0), p(theta), p(consts), p(ts),
+                                            p(ys), p(sens), p(status), p(nacc), p(nrej), p(ws), wsb,
+                                            C.c_void_p(stream)))
+            else:
+                sens = None
+                _check(lib().ctx_solve(self._h, C.byref(cfg), p(y0), p(theta), p(consts), p(ts), p(ys),
+                                       p(status), p(nacc), p(nrej), p(ws), wsb, C.c_void_p(stream)))
+        return SolveOutput(ys, status, nacc, nrej, sens)
+
+    def solve_host(self, y0, theta, consts, ts, *, solver="tsit5", in_axes=(0, None, 0, None),
+                   rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096, kernel=0, out=None):
+        """Host-buffer solve through ctx_solve_host: numpy in, numpy out, copies inside."""
+        dt = self.dtype
+        S, P, Cn = self.field.S, self.field.P, self.field.C
+        y0 = np.ascontiguousarray(y0, dtype=dt); theta = np.ascontiguousarray(theta, dtype=dt)
+        consts = np.ascontiguousarray(consts, dtype=dt); ts = np.ascontiguousarray(ts, dtype=dt)
+        Bs = [a.shape[0] for a, ax in ((y0, in_axes[0]), (theta, in_axes[1]),
+                                       (consts, in_axes[2]), (ts, in_axes[3])) if ax == 0]
+        B = Bs[0] if Bs else 1
+        T = ts.shape[-1]
+        cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
+                            max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel)
+        ys = out if out is not None else np.empty((B, T, S), dtype=dt)
+        status = np.empty(B, dtype=np.int32); nacc = np.empty(B, dtype=np.int32)
+        nrej = np.empty(B, dtype=np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        _check(lib().ctx_solve_host(self._h, C.byref(cfg), vp(y0), vp(theta), vp(consts), vp(ts),
+                                    vp(ys), vp(status), vp(nacc), vp(nrej)))
+        return SolveOutput(ys, status, nacc, nrej)

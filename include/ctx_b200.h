@@ -1,0 +1,125 @@
+/* ctx_b200.h -- C ABI of the B200-native Catalax solve engine (libctxb200.so).
+ *
+ * The reference (JR-1991/Catalax) has NO native/FFI interface: its seam for this path is the
+ * Python callable built by catalax/tools/simulation.py:160-196 (`Simulation._prepare_func`),
+ *     f(y0, parameters, constants, time) -> ys            [B,T,S]
+ * stored as Model._sim_func (catalax/model/model.py:786) and called from
+ * model.py:699 (simulate), mcmc/mcmc.py:448 (NUTS log-density), mcmc/loo.py:181,
+ * mcmc/predictive.py:151.  Every entry point below names the reference interface it replaces;
+ * INTEGRATION.md shows the reference-side binding (ctypes / jax.ffi) a maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; all array arguments of the *device* entry points are DEVICE pointers
+ *    owned by the caller; outputs are caller-allocated; nothing is aliased or retained;
+ *  - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and never
+ *    synchronise the device (the *_host variants synchronise the stream they are given);
+ *  - dtype (f32 | f64) is fixed per compiled model, like jax's x64 switch
+ *    (catalax/__init__.py:61-70); `real` below means that type;
+ *  - every function returns 0 on success, a negative CTX_E* code otherwise, and
+ *    ctx_last_error() returns the message of the last failure on the calling thread.
+ */
+#ifndef CTX_B200_H_
+#define CTX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTX_ABI_VERSION 1
+
+enum { CTX_F32 = 0, CTX_F64 = 1 };
+/* solver ids: simconfig.py:16 (`solver: Any = Tsit5`), simulation.py:23-26 (non-adaptive list) */
+enum { CTX_TSIT5 = 0, CTX_DOPRI5 = 1, CTX_EULER = 2, CTX_HEUN = 3 };
+/* per-trajectory status written by the solve kernels (diffrax RESULTS, throw=False path,
+ * simulation.py:255-257,271-272) */
+enum { CTX_TRAJ_OK = 0, CTX_TRAJ_MAX_STEPS = 1, CTX_TRAJ_BAD_STEP = 2 };
+/* likelihood ids: mcmc.py:59 (SoftLaplace default), Normal used by tests/docs */
+enum { CTX_LIK_NORMAL = 0, CTX_LIK_SOFTLAPLACE = 1 };
+
+enum {
+  CTX_OK = 0,
+  CTX_E_INVALID = -1,  /* bad argument */
+  CTX_E_NVRTC = -2,    /* run-time compilation failed (log in ctx_last_error) */
+  CTX_E_CUDA = -3,     /* CUDA runtime error */
+  CTX_E_NOGPU = -4,    /* no CUDA device: there is NO CPU fallback */
+  CTX_E_WORKSPACE = -5 /* workspace too small */
+};
+
+typedef struct ctx_model ctx_model;
+
+/* Sizes baked into the generated vector-field source; checked against its CTX_* macros. */
+typedef struct ctx_model_desc {
+  int32_t n_states;     /* S: Model.get_state_order() (model.py:906-926) */
+  int32_t n_params;     /* P: Model.get_parameter_order() (model.py:882-884) */
+  int32_t n_consts;     /* C: Model.get_constants_order() (model.py:984-994) */
+  int32_t n_dirs;       /* D: sensitivity directions generated (0 = none) */
+  int32_t n_theta_dirs; /* leading D_theta directions are parameters, the rest initial values */
+  int32_t dtype;        /* CTX_F32 | CTX_F64 */
+} ctx_model_desc;
+
+/* Frozen attributes of one solve = SimulationConfig (simconfig.py:8-20) + in_axes
+ * (inaxes.py:5-9; simulation.py:346-355). */
+typedef struct ctx_solve_cfg {
+  int32_t solver;      /* CTX_TSIT5 ... */
+  int32_t in_axes[4];  /* (y0, parameters, constants, time): 0 = batched on axis 0, -1 = None */
+  int64_t batch;       /* B */
+  int32_t n_times;     /* T = len(time) */
+  int32_t max_steps;   /* simconfig.py:19 */
+  double rtol, atol, dt0;
+  int32_t kernel;      /* 0 = auto, 1 = static one-thread-per-trajectory, 2 = persistent refill */
+  int32_t reserved;
+} ctx_solve_cfg;
+
+/* ---- model lifetime -------------------------------------------------------------------
+ * Replaces building the jitted closure: Simulation._prepare_func (simulation.py:160-196) and
+ * the sympy->JAX tracing of symbolicmodule.py:320-383.  `field_src` is the CUDA text emitted
+ * by catalax_b200/tools/codegen.py.  Kernels are NVRTC-compiled for sm_100a lazily per
+ * (solver, tangent) variant and cached (in process + on disk, CTX_B200_CACHE). */
+int ctx_model_compile(const char* field_src, const ctx_model_desc* desc, ctx_model** out);
+void ctx_model_free(ctx_model* m);
+/* Compile one kernel variant WITHOUT a GPU and return its cubin (for build checks, cuobjdump).
+ * The pointer stays valid until ctx_model_free. */
+int ctx_model_cubin(ctx_model* m, int32_t solver, int32_t with_tangents, const void** cubin,
+                    size_t* nbytes);
+
+/* ---- K1: batched solve ------------------------------------------------------------------
+ * Replaces `self._sim_func(y0, parameters, constants, saveat)` (model.py:699) =
+ * vmap(diffeqsolve(...)) (simulation.py:259-273,348).
+ * y0 [B,S]|[S], theta [B,P]|[P], consts [B,C]|[C], ts [B,T]|[T]  ->  ys [B,T,S];
+ * status / n_accepted / n_rejected [B] (int32, may be NULL). */
+size_t ctx_workspace_bytes(const ctx_model* m, const ctx_solve_cfg* cfg);
+int ctx_solve(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
+              const void* consts, const void* ts, void* ys, int32_t* status,
+              int32_t* n_accepted, int32_t* n_rejected, void* workspace, size_t ws_bytes,
+              void* stream);
+
+/* ---- K1 + tangents --------------------------------------------------------------------
+ * Replaces vmap(jax.jacobian(solve, argnums=k)) (simulation.py:279-323): additionally writes
+ * sens [B,T,S,D] = d ys / d(direction), directions = parameters (D_theta) then initial
+ * values (D_y0), in the layout jax.jacobian produces ([T,S,arg], simulation.py:315). */
+int ctx_solve_sens(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
+                   const void* consts, const void* ts, void* ys, void* sens, int32_t* status,
+                   int32_t* n_accepted, int32_t* n_rejected, void* workspace, size_t ws_bytes,
+                   void* stream);
+
+/* ---- host-buffer convenience (the call a reference-side ctypes binding would make) --------
+ * Same as ctx_solve but every array is a HOST pointer; device staging, the H2D / D2H copies
+ * and one stream synchronisation happen inside. */
+int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
+                   const void* consts, const void* ts, void* ys, int32_t* status,
+                   int32_t* n_accepted, int32_t* n_rejected);
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+int ctx_abi_version(void);
+int ctx_device_count(void); /* 0 when no GPU is visible; never throws */
+size_t ctx_last_error(char* buf, size_t n);
+/* number of kernel launches this library has issued in this process (bench "gpu_launches") */
+int64_t ctx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTX_B200_H_ */

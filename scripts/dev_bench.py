@@ -1,0 +1,41 @@
+"""Developer micro-benchmark of the solve kernels (not the judged bench.py)."""
+import argparse, json, sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np, torch
+from catalax_b200 import engine
+from catalax_b200.tools import codegen as cg
+from tests import cases
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--B", type=int, default=1 << 20)
+ap.add_argument("--T", type=int, nargs="+", default=[16, 1000])
+ap.add_argument("--dtype", nargs="+", default=["float32", "float64"])
+ap.add_argument("--kernel", type=int, nargs="+", default=[1])
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--rtol", type=float, default=1e-6)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+field = cg.generate_field(cases.field_spec(cases.michaelis_menten()))
+for dtype in a.dtype:
+    m = engine.CompiledModel(field, dtype)
+    y0, th, c = cases.mm_inputs(a.B, 0, np.dtype(dtype))
+    y0, th, c = (torch.as_tensor(x, device=dev) for x in (y0, th, c))
+    for T in a.T:
+        ts = torch.linspace(0, 100, T, dtype=y0.dtype, device=dev)
+        out_buf = torch.empty((a.B, T, 3), dtype=y0.dtype, device=dev)
+        for kernel in a.kernel:
+            times = []
+            for it in range(a.iters + 1):
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record()
+                o = m.solve(y0, th, c, ts, in_axes=(0, 0, 0, None), rtol=a.rtol, atol=a.rtol, kernel=kernel, out=out_buf)
+                e1.record(); torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            steps = int((o.n_accepted.sum() + o.n_rejected.sum()).item())
+            ms = min(times[1:])
+            byt = a.B * T * 3 * y0.element_size()
+            print(json.dumps(dict(dtype=dtype, T=T, kernel=kernel, ms=round(ms, 3), first_ms=round(times[0], 1),
+                                  steps=steps, steps_per_traj=round(steps / a.B, 1), rej_frac=round(float(o.n_rejected.sum().item()) / steps, 3),
+                                  gsteps_s=round(steps / ms / 1e6, 2), out_GBs=round(byt / ms / 1e6, 1),
+                                  fails=int((o.status != 0).sum().item()))), flush=True)

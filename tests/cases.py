@@ -1,0 +1,69 @@
+"""Shared model definitions + seeded inputs for oracle-vs-CUDA parity tests."""
+from __future__ import annotations
+
+import numpy as np
+import sympy as sp
+
+from catalax_b200.tools import codegen as cg
+
+
+def michaelis_menten():
+    """README model in ODE form (reference README.md:99-116)."""
+    S, E, P, Km, kc = sp.symbols("S E P K_m k_cat")
+    r = kc * E * S / (Km + S)
+    states, params, consts = ["E", "P", "S"], ["K_m", "k_cat"], []
+    odes = {"E": sp.Integer(0), "P": r, "S": -r}
+    return states, params, consts, odes, []
+
+
+def menten_fixture():
+    """tests/conftest.py:8-19 of the reference: 1 state, constant e."""
+    s1, e, kcat, km = sp.symbols("s1 e kcat k_m")
+    return ["s1"], ["k_m", "kcat"], ["e"], {"s1": kcat * e * s1 / (km + s1)}, []
+
+
+def nonautonomous():
+    """4-state field that exercises t, exp, pow, sqrt, *_init, constants."""
+    a, b, c, d, k1, k2, k3, q, t = sp.symbols("a b c d k1 k2 k3 q t")
+    a_init = sp.Symbol("a_init")
+    odes = {
+        "a": -k1 * a * sp.exp(-k3 * t) + q * sp.sqrt(b + 1),
+        "b": k1 * a - k2 * b ** 2 / (1 + b),
+        "c": k2 * b * b / (1 + b) - k3 * c * sp.sin(t),
+        "d": k3 * (a_init - d) + sp.tanh(c),
+    }
+    return ["a", "b", "c", "d"], ["k1", "k2", "k3"], ["q"], odes, []
+
+
+def mass_action_network(n_states=32):
+    """ring of first-order steps + second-order couplings."""
+    S = n_states
+    states = [f"x{i:02d}" for i in range(S)]
+    params = [f"k{j:02d}" for j in range(2 * S)]
+    reactions = []
+    for i in range(S):
+        xi = sp.Symbol(states[i])
+        reactions.append((f"r{i:02d}", [(1.0, states[i])], [(1.0, states[(i + 1) % S])],
+                          sp.Symbol(params[i]) * xi))
+    for i in range(S):
+        xi, xj = sp.Symbol(states[i]), sp.Symbol(states[(i + 5) % S])
+        reactions.append((f"r{S + i:02d}", [(1.0, states[i]), (1.0, states[(i + 5) % S])],
+                          [(1.0, states[(i + 11) % S])], sp.Symbol(params[S + i]) * xi * xj))
+    return states, params, [], {}, reactions
+
+
+def field_spec(model):
+    states, params, consts, odes, reactions = model
+    return cg.FieldSpec(list(states), list(params), list(consts), dict(odes), list(reactions))
+
+
+def mm_inputs(B, seed=0, dtype=np.float64):
+    """SURVEY §8d config 2 distributions (states ordered [E, P, S])."""
+    rng = np.random.default_rng(seed)
+    S0 = rng.uniform(50, 300, B)
+    E0 = rng.uniform(5, 20, B)
+    y0 = np.stack([E0, np.zeros(B), S0], axis=1).astype(dtype)
+    Km = np.exp(rng.uniform(np.log(0.01), np.log(1.0), B))
+    kc = np.exp(rng.uniform(np.log(0.02), np.log(0.5), B))
+    theta = np.stack([Km, kc], axis=1).astype(dtype)
+    return y0, theta, np.zeros((B, 0), dtype=dtype)
