@@ -9,6 +9,7 @@
 #include <cuda_runtime_api.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -108,6 +109,20 @@ struct SolveArgs {
   real rtol, atol, dt0;
 };
 
+// Warps per CTA of the persistent kernel so that its static shared memory
+// (ctx_warp_smem in ctx_integrator.cuh) stays below 48 KB; 0 = record too large.
+int v1_warps(const ctx_model_desc& d, int solver, int tan) {
+  const size_t w = d.dtype == CTX_F64 ? 8 : 4;
+  const size_t N = (size_t)d.n_states * (1 + (tan ? d.n_dirs : 0));
+  const size_t deg = solver <= 1 ? 4 : 1;
+  const size_t S = (size_t)d.n_states;
+  const size_t rec = 2 + (deg + 1) * N;
+  const size_t per_warp = 32 * rec * w + 512 + 32 * S * w + (tan ? 32 * (N - S) * w : 0) + 256;
+  size_t warps = (48 * 1024) / per_warp;
+  if (warps > 4) warps = 4;
+  return (int)warps;
+}
+
 int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
   if (!v.cubin.empty()) return CTX_OK;
   std::string src;
@@ -120,7 +135,8 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
   std::vector<std::string> opts = {
       "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
       std::string("-DCTX_F64=") + (m->desc.dtype == CTX_F64 ? "1" : "0"),
-      "-DCTX_SOLVER=" + std::to_string(solver), "-DCTX_TAN=" + std::to_string(tan)};
+      "-DCTX_SOLVER=" + std::to_string(solver), "-DCTX_TAN=" + std::to_string(tan),
+      "-DCTX_WARPS=" + std::to_string(std::max(1, v1_warps(m->desc, solver, tan)))};
   const char* extra = getenv("CTX_B200_NVRTC_FLAGS");
   if (extra && *extra) {
     std::string e(extra), cur;
@@ -249,10 +265,29 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.atol = (real)cfg->atol;
   a.dt0 = (real)cfg->dt0;
 
-  const int kernel = cfg->kernel == 0 ? 1 : cfg->kernel;
+  int kernel = cfg->kernel;
+  const int warps = v1_warps(m->desc, cfg->solver, tan);
+  if (kernel == 0) kernel = warps > 0 ? 2 : 1;
   cudaKernel_t k;
   void* params[] = {&a};
-  if (kernel == 1) {
+  if (kernel == 2) {
+    if (warps <= 0)
+      return fail(CTX_E_INVALID, "persistent kernel: step record does not fit shared memory");
+    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k);
+    if (rc) return rc;
+    const unsigned block = 32u * warps;
+    int dev = 0, sms = 0, per_sm = 0;
+    CTX_CUDA(cudaGetDevice(&dev));
+    CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, 0));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long grid = (unsigned long long)sms * per_sm;
+    const unsigned long long want = (cfg->batch + block - 1) / block;
+    if (grid > want) grid = want;
+    CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
+    g_launches++;
+  } else if (kernel == 1) {
     int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v0", &k);
     if (rc) return rc;
     const unsigned block = 128;

@@ -28,6 +28,9 @@
 #define CTX_INF __int_as_float(0x7f800000)
 #define CTX_TOL_END 1e-6f
 #endif
+#define CTX_ST_OK 0
+#define CTX_ST_MAX 1
+#define CTX_ST_BAD 2
 
 #if CTX_TAN
 #define CTX_N (CTX_S * (1 + CTX_D))
@@ -355,7 +358,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
     real tn = tprev + dt_next;
     if (tn > t_end - CTX_TOL_END) tn = keep ? t_end : tprev + R(0.5) * (t_end - tprev);
     tnext = tn;
-    if (!(fabs(tnext) < CTX_INF)) { status = 2; break; }
+    if (tprev < t_end && !(fabs(tnext) < CTX_INF)) { status = 2; break; }
   }
   if (tprev < t_end && status == 0) status = 1;
   {
@@ -367,4 +370,359 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
   a.status[b] = status;
   a.n_accepted[b] = nacc;
   a.n_rejected[b] = nrej;
+}
+
+// =====================================================================================
+// kernel v1: persistent warps, lane refill, warp-cooperative dense output
+// =====================================================================================
+// * Every lane integrates one trajectory.  When it finishes it claims the next unclaimed
+//   trajectory from a global counter (one warp-aggregated atomicAdd per refill), so all 32
+//   lanes of a warp execute a step attempt in every iteration regardless of how many
+//   accepted / rejected steps their trajectories need ("step-count compaction").
+// * Dense output is not evaluated by the lane that owns the step.  Each lane with an accepted
+//   step that covers requested times publishes the step's interpolant as polynomial
+//   coefficients in theta = (t - tprev)/dt in shared memory; the warp then spreads ALL pending
+//   save points of ALL its lanes evenly over its 32 lanes (consecutive lanes = consecutive
+//   save points of one trajectory), evaluates the polynomial (Horner), stages the results in
+//   shared memory and copies them out as contiguous runs: fully coalesced stores into
+//   ys[B,T,S] although neighbouring lanes integrate unrelated trajectories.
+// * inf-fill of failed trajectories and the t0 == t1 case reuse the same path (a constant
+//   polynomial inf / y0).
+//
+// Interpolant as a polynomial.  Tsit5: sum_i b_i(theta) = theta, b_1'(0) = 1 and b_2..b_7 carry
+// a factor theta^2, hence
+//   y(theta) = y0 + dt*[theta*k_1 + sum_{i>=2} b_i(theta) (k_i - k_1)]
+//            = y0 + theta*(a1 + theta*(a2 + theta*(a3 + theta*a4))),
+//   a1 = dt*k_1,  a_m = dt * sum_{i=2..7} TB_im (k_i - k_1)   (TB_im: theta^m coefficient of b_i).
+// Algebraically identical to diffrax's factored form; working on the differences k_i - k_1
+// removes the cancellation between the O(10) weights, so it is at least as accurate in f32.
+// Dopri5: diffrax's own quartic (a, b, c, f0, y0).  Euler/Heun: linear.
+#ifndef CTX_WARPS
+#define CTX_WARPS 4
+#endif
+#ifndef CTX_MIN_BLOCKS
+#define CTX_MIN_BLOCKS 1
+#endif
+#define CTX_FULL 0xffffffffu
+
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#define CTX_DEG 4
+#else
+#define CTX_DEG 1
+#endif
+#define CTX_NCOEF ((CTX_DEG + 1) * CTX_N)
+
+#if CTX_SOLVER == 0
+#define TB22 R(0.13169999999999999727)
+#define TB23 R(-0.22339999999999999818)
+#define TB24 R(0.1017)
+#define TB32 R(3.9302962368947515285)
+#define TB33 R(-5.9410338721315047347)
+#define TB34 R(2.490627285651252793)
+#define TB42 R(-12.411077166933676984)
+#define TB43 R(30.338188630282321598)
+#define TB44 R(-16.54810288924490272)
+#define TB52 R(37.509313416511039195)
+#define TB53 R(-88.178904894766401101)
+#define TB54 R(47.37952196281928122)
+#define TB62 R(-27.896526289197287806)
+#define TB63 R(65.091894674793671526)
+#define TB64 R(-34.87065786149660974)
+#define TB72 R(1.5)
+#define TB73 R(-4.0)
+#define TB74 R(2.5)
+#endif
+
+// coef[m*CTX_N + i] = theta^m coefficient of component i on the accepted step [tp, tp+dt]
+__device__ __forceinline__ void ctx_dense_coefs(const real dt, const real* y, const real* ynew,
+                                                const real (*K)[CTX_N], real* coef) {
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) {
+#if CTX_SOLVER == 0
+    const real d2 = K[1][i] - K[0][i], d3 = K[2][i] - K[0][i], d4 = K[3][i] - K[0][i],
+               d5 = K[4][i] - K[0][i], d6 = K[5][i] - K[0][i], d7 = K[6][i] - K[0][i];
+    coef[0 * CTX_N + i] = y[i];
+    coef[1 * CTX_N + i] = dt * K[0][i];
+    coef[2 * CTX_N + i] = dt * (TB22 * d2 + TB32 * d3 + TB42 * d4 + TB52 * d5 + TB62 * d6 + TB72 * d7);
+    coef[3 * CTX_N + i] = dt * (TB23 * d2 + TB33 * d3 + TB43 * d4 + TB53 * d5 + TB63 * d6 + TB73 * d7);
+    coef[4 * CTX_N + i] = dt * (TB24 * d2 + TB34 * d3 + TB44 * d4 + TB54 * d5 + TB64 * d6 + TB74 * d7);
+#elif CTX_SOLVER == 1
+    const real ymid = y[i] + dt * (M1 * K[0][i] + M2 * K[1][i] + M3 * K[2][i] + M4 * K[3][i] +
+                                   M5 * K[4][i] + M6 * K[5][i] + M7 * K[6][i]);
+    const real f0 = dt * K[0][i], f1 = dt * K[6][i];
+    const real y0_ = y[i], y1_ = ynew[i];
+    coef[0 * CTX_N + i] = y0_;
+    coef[1 * CTX_N + i] = f0;
+    coef[2 * CTX_N + i] = f1 - R(4.0) * f0 - R(11.0) * y0_ - R(5.0) * y1_ + R(16.0) * ymid;
+    coef[3 * CTX_N + i] = R(5.0) * f0 - R(3.0) * f1 + R(18.0) * y0_ + R(14.0) * y1_ - R(32.0) * ymid;
+    coef[4 * CTX_N + i] = R(2.0) * (f1 - f0) - R(8.0) * (y1_ + y0_) + R(16.0) * ymid;
+#else
+    coef[0 * CTX_N + i] = y[i];
+    coef[1 * CTX_N + i] = ynew[i] - y[i];
+#endif
+  }
+}
+
+struct ctx_warp_smem {
+  real rec[2 + CTX_NCOEF][32];   // tp, 1/dt, coefficients; one column per publishing lane
+  long long ts_off[32];          // element offset into ts of the segment's save j = 0
+  long long g_off[32];           // point index (b*T + idx) of the segment's save j = 0
+  real stage_y[32 * CTX_S];      // interpolated states of one round, [point][state]
+#if CTX_TAN
+  real stage_s[32 * CTX_S * CTX_D];  // tangents of one round, [point][state][direction]
+#endif
+  long long gpt[32];             // element index (point*S) of each staged point (mixed rounds)
+};
+
+extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
+ctx_solve_v1(const ctx_solve_args a) {
+  __shared__ ctx_warp_smem smem[CTX_WARPS];
+  ctx_warp_smem& w = smem[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned le_mask = CTX_FULL >> (31 - lane);
+  const int T = a.T;
+
+  // per-lane trajectory state
+  long long b = -1;           // trajectory index, -1 = lane is free
+  int phase = 0;              // 0 integrating | 1 emit a fill segment then retire
+  real y[CTX_N], ynew[CTX_N], y0[CTX_S];
+  real th[CTX_P > 0 ? CTX_P : 1], c[CTX_C > 0 ? CTX_C : 1];
+  real K[CTX_NST][CTX_N];
+  real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
+  int idx = 0, nacc = 0, nrej = 0, status = 0;
+  bool exhausted = false;
+  const real* tsr = a.ts;
+
+  while (true) {
+    // ------------------------------------------------------------- refill free lanes
+    const unsigned need = __ballot_sync(CTX_FULL, b < 0);
+    if (need && !exhausted) {
+      const int cnt = __popc(need);
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)cnt);
+      base = __shfl_sync(CTX_FULL, base, 0);
+      if (base + cnt >= (unsigned long long)a.B) exhausted = true;
+      if (b < 0) {
+        const unsigned long long nb = base + __popc(need & lt_mask);
+        if (nb < (unsigned long long)a.B) {
+          b = (long long)nb;
+#pragma unroll
+          for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)b * a.stride_y0 + i];
+#pragma unroll
+          for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)b * a.stride_theta + i];
+#pragma unroll
+          for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)b * a.stride_consts + i];
+#if CTX_TAN
+#pragma unroll
+          for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
+#pragma unroll
+          for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
+#endif
+          tsr = a.ts + (size_t)b * a.stride_ts;
+          t_end = tsr[T - 1];
+          tprev = R(0.0);
+          tnext = fmin(tprev + a.dt0, t_end);
+          idx = 0; nacc = 0; nrej = 0; status = 0;
+          phase = (tprev < t_end) ? 0 : 1;  // t0 == t1: emit y0 for every requested time
+          ctx_field(tprev, y, th, c, y0, K[0]);
+        }
+      }
+    }
+    if (__ballot_sync(CTX_FULL, b >= 0) == 0u) break;
+
+    // ------------------------------------------------------------- one step attempt
+    const bool stepping = (b >= 0) && phase == 0;
+    int nsave = 0;
+    bool accepted = false, retire = false;
+    real rec_tp = R(0.0), rec_dt = R(0.0);
+    if (stepping) {
+      const real dt = tnext - tprev;
+      ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
+      bool keep = true;
+      real dt_next = a.dt0;
+#if CTX_ADAPTIVE
+      const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
+      keep = scaled < R(1.0);
+      const real inv = R(1.0) / scaled;
+      real factor = R(0.9) * pow(inv, R(0.2));
+      factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
+      dt_next = dt * factor;
+      if (scaled != scaled) dt_next = scaled;  // NaN error norm poisons the step size
+#endif
+      rec_tp = tprev; rec_dt = dt;
+      real tp_new = tprev;
+      if (keep) {
+        // number of requested times in (.., tnext]: first index in [idx, T) with ts > tnext
+        if (!(tnext < t_end)) {
+          nsave = T - idx;
+        } else {
+          int lo = idx, hi = T;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (tsr[mid] <= tnext) lo = mid + 1; else hi = mid;
+          }
+          nsave = lo - idx;
+        }
+        tp_new = tnext;
+        accepted = true;
+        ++nacc;
+      } else {
+        ++nrej;
+      }
+      tp_new = fmin(tp_new, t_end);
+      real tn = tp_new + dt_next;
+      if (tn > t_end - CTX_TOL_END) tn = keep ? t_end : tp_new + R(0.5) * (t_end - tp_new);
+      const bool done = !(tp_new < t_end);
+      if (!done) {
+        if (!(fabs(tn) < CTX_INF)) status = CTX_ST_BAD;
+        else if (nacc + nrej >= a.max_steps) status = CTX_ST_MAX;
+      }
+      retire = done;
+      tprev = tp_new; tnext = tn;
+      phase = (status != 0) ? 1 : 0;  // failed: emit the inf fill in the next iteration
+    }
+    // a lane in phase 1 that did not step emits its fill segment now and retires
+    const bool filling = (b >= 0) && !stepping;
+    if (filling) { nsave = T - idx; retire = true; }
+
+    // ------------------------------------------------------------- cooperative saves
+    const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
+    if (nz) {
+      int incl = nsave;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(CTX_FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int off = incl - nsave;
+      const int total = __shfl_sync(CTX_FULL, incl, 31);
+      if (nsave > 0) {
+        const int s = __popc(nz & lt_mask);
+        real coef[CTX_NCOEF];
+        if (filling) {
+          const bool fill_inf = status != 0;
+#pragma unroll
+          for (int i = 0; i < CTX_N; ++i) coef[i] = fill_inf ? CTX_INF : y[i];
+#pragma unroll
+          for (int i = CTX_N; i < CTX_NCOEF; ++i) coef[i] = R(0.0);
+          w.rec[0][s] = R(0.0);
+          w.rec[1][s] = R(0.0);
+        } else {
+          ctx_dense_coefs(rec_dt, y, ynew, K, coef);
+          w.rec[0][s] = rec_tp;
+          w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+        }
+#pragma unroll
+        for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
+        w.ts_off[s] = (long long)((size_t)b * a.stride_ts) + idx - off;
+        w.g_off[s] = b * (long long)T + idx - off;
+      }
+      __syncwarp();
+      // myoff: where this lane's segment starts in the flattened list (none: never matches)
+      const unsigned myoff = nsave > 0 ? (unsigned)off : 0xffffffffu;
+      int seg_base = 0, s_have = -1;
+      real r_tp = R(0.0), r_inv = R(0.0), r_coef[CTX_NCOEF];
+      const real* tq_ptr = a.ts;       // &ts[segment offset + j] of this lane's point
+      long long r_ebase = 0;           // (g_off[s]) * S: element index of the segment's j = 0
+      for (int r0 = 0; r0 < total; r0 += 32) {
+        const unsigned dpos = myoff - (unsigned)r0;
+        const unsigned bits = __reduce_or_sync(CTX_FULL, dpos < 32u ? (1u << dpos) : 0u);
+        const int s = seg_base + __popc(bits & le_mask) - 1;
+        seg_base += __popc(bits);
+        const int j = r0 + lane;
+        const int cnt = min(32, total - r0);
+        const bool uniform = (bits & ~1u) == 0u;  // every point of this round: same segment
+        if (s != s_have) {  // (lanes past `total` follow the last segment: harmless)
+          s_have = s;
+          r_tp = w.rec[0][s]; r_inv = w.rec[1][s];
+#pragma unroll
+          for (int i = 0; i < CTX_NCOEF; ++i) r_coef[i] = w.rec[2 + i][s];
+          tq_ptr = a.ts + (w.ts_off[s] + j);
+          r_ebase = w.g_off[s] * CTX_S;
+        }
+        if (j < total) {
+          const real tq = *tq_ptr;
+          const real th_ = (tq - r_tp) * r_inv;
+#pragma unroll
+          for (int i = 0; i < CTX_N; ++i) {
+            real v = r_coef[CTX_DEG * CTX_N + i];
+#pragma unroll
+            for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + r_coef[mm * CTX_N + i];
+            if (i < CTX_S) w.stage_y[lane * CTX_S + i] = v;
+#if CTX_TAN
+            else {
+              const int dd = (i - CTX_S) / CTX_S, ii = (i - CTX_S) - dd * CTX_S;
+              w.stage_s[lane * (CTX_S * CTX_D) + ii * CTX_D + dd] = v;
+            }
+#endif
+          }
+          if (!uniform) w.gpt[lane] = r_ebase + (long long)j * CTX_S;
+        }
+        tq_ptr += 32;
+        __syncwarp();
+        if (uniform) {
+          // one contiguous run of a single trajectory: elements ebase + r0*S ...
+          real* dst = a.ys + (r_ebase + (long long)r0 * CTX_S);
+#pragma unroll
+          for (int mm = 0; mm < CTX_S; ++mm) {
+            const int e = lane + 32 * mm;
+            if (e < cnt * CTX_S) dst[e] = w.stage_y[e];
+          }
+#if CTX_TAN
+          if (a.sens) {
+            real* ds = a.sens + (r_ebase + (long long)r0 * CTX_S) * CTX_D;
+#pragma unroll
+            for (int mm = 0; mm < CTX_S * CTX_D; ++mm) {
+              const int e = lane + 32 * mm;
+              if (e < cnt * (CTX_S * CTX_D)) ds[e] = w.stage_s[e];
+            }
+          }
+#endif
+        } else {
+#pragma unroll
+          for (int mm = 0; mm < CTX_S; ++mm) {
+            const int e = lane + 32 * mm;
+            if (e < cnt * CTX_S) {
+              const int p = e / CTX_S, i = e - p * CTX_S;
+              a.ys[w.gpt[p] + i] = w.stage_y[e];
+            }
+          }
+#if CTX_TAN
+          if (a.sens) {
+#pragma unroll
+            for (int mm = 0; mm < CTX_S * CTX_D; ++mm) {
+              const int e = lane + 32 * mm;
+              if (e < cnt * (CTX_S * CTX_D)) {
+                const int p = e / (CTX_S * CTX_D), r = e - p * (CTX_S * CTX_D);
+                a.sens[w.gpt[p] * CTX_D + r] = w.stage_s[e];
+              }
+            }
+          }
+#endif
+        }
+        __syncwarp();
+      }
+    }
+
+    // ------------------------------------------------------------- advance / retire
+    if (accepted) {
+      idx += nsave;
+#pragma unroll
+      for (int i = 0; i < CTX_N; ++i) y[i] = ynew[i];
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#pragma unroll
+      for (int i = 0; i < CTX_N; ++i) K[0][i] = K[6][i];
+#else
+      ctx_field(tprev, y, th, c, y0, K[0]);
+#endif
+    }
+    if ((retire && phase == 0) || filling) {
+      a.status[b] = status;
+      a.n_accepted[b] = nacc;
+      a.n_rejected[b] = nrej;
+      b = -1;
+      phase = 0;
+    }
+  }
 }

@@ -1,0 +1,99 @@
+"""Dataset: list of measurements + dense-array export (reference: dataset/dataset.py).
+
+Only the members the simulate / log-density path touches are provided:
+``from_model`` :672-692, ``add_initial`` :188-206, ``add_measurement`` :208-231,
+``add_from_jax_array`` :233-254, ``from_jax_arrays`` :767-821, ``to_jax_arrays`` :390-434,
+``to_y0_matrix`` :436-451, ``to_config`` :1363-1392, ``pad`` :256-330.
+File formats (Croissant, EnzymeML, pandas) and plotting are out of scope.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from ..config import default_dtype
+from .measurement import Measurement
+
+
+class Dataset:
+    def __init__(self, states: List[str], id: Optional[str] = None, name: Optional[str] = None,
+                 description: Optional[str] = None, measurements: Optional[List[Measurement]] = None):
+        self.states = list(states)
+        self.id = id
+        self.name = name
+        self.description = description
+        self.measurements: List[Measurement] = list(measurements or [])
+
+    def __len__(self):
+        return len(self.measurements)
+
+    @classmethod
+    def from_model(cls, model) -> "Dataset":
+        states = model.get_state_order(modeled=False)
+        return cls(id=model.name, name=model.name, states=states)
+
+    def add_initial(self, time=None, **kwargs) -> None:
+        self.measurements.append(Measurement(time=time, initial_conditions=kwargs))
+
+    def add_measurement(self, measurement: Measurement) -> None:
+        assert not any(m.id == measurement.id for m in self.measurements), \
+            f"Measurement with ID={measurement.id} already exists."
+        unused = [s for s in measurement.data.keys() if s not in self.states]
+        if unused:
+            warnings.warn(f"States {unused} are not used in the dataset.")
+        self.measurements.append(measurement)
+
+    def add_from_jax_array(self, state_order: List[str], initial_condition: Dict[str, float],
+                           data, time) -> None:
+        data = np.asarray(data)
+        self.add_measurement(Measurement(
+            initial_conditions=initial_condition, time=time,
+            data={s: data[:, i] for i, s in enumerate(state_order)}))
+
+    @classmethod
+    def from_jax_arrays(cls, state_order: List[str], data, time, y0s) -> "Dataset":
+        data, time, y0s = np.asarray(data), np.asarray(time), np.asarray(y0s)
+        assert data.shape[0] == time.shape[0] == y0s.shape[0], \
+            "Data, time and initial conditions must have the same leading dimension"
+        ds = cls(states=list(state_order))
+        for i in range(data.shape[0]):
+            ds.add_from_jax_array(state_order=state_order, data=data[i], time=time[i],
+                                  initial_condition={s: float(y0s[i, j]) for j, s in enumerate(state_order)})
+        return ds
+
+    def to_jax_arrays(self, state_order: List[str], inits_to_array: bool = False):
+        data, time, inits = [], [], []
+        for meas in self.measurements:
+            d, t, i0 = meas.to_jax_arrays(state_order=state_order, inits_to_array=inits_to_array)
+            data.append(d); time.append(t); inits.append(i0)
+        if inits_to_array:
+            return np.stack(data, 0), np.stack(time, 0), np.stack(inits, 0)
+        return np.stack(data, 0), np.stack(time, 0), inits
+
+    def to_y0_matrix(self, state_order: List[str]) -> np.ndarray:
+        if len(self.measurements) == 0:
+            return np.zeros((0, len(state_order)), dtype=default_dtype())
+        return np.stack([m.to_y0_array(state_order=state_order) for m in self.measurements], 0) \
+            .reshape(len(self.measurements), len(state_order))
+
+    def to_config(self, nsteps: int = 100):
+        """SimulationConfig spanning each measurement's time range (dataset.py:1363-1392)."""
+        from ..model.simconfig import SimulationConfig
+
+        t0 = np.array([m.time[0] for m in self.measurements], dtype=default_dtype())
+        t1 = np.array([m.time[-1] for m in self.measurements], dtype=default_dtype())
+        return SimulationConfig(t0=t0, t1=t1, nsteps=nsteps)
+
+    def pad(self) -> "Dataset":
+        """Pad every measurement to the longest one: time continues last+1, last+2, ...,
+        data is NaN (dataset.py:256-330)."""
+        tmax = max(len(m.time) for m in self.measurements)
+        out = Dataset(states=self.states, id=self.id, name=self.name)
+        for m in self.measurements:
+            n = tmax - len(m.time)
+            time = np.concatenate([m.time, m.time[-1] + np.arange(1, n + 1, dtype=m.time.dtype)])
+            data = {s: np.concatenate([v, np.full(n, np.nan, dtype=v.dtype)]) for s, v in m.data.items()}
+            out.measurements.append(Measurement(m.initial_conditions, data, time, id=m.id))
+        return out

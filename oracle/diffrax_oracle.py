@@ -257,7 +257,7 @@ def solve(rhs, y0, theta, consts, ts, *, solver="tsit5", rtol=1e-5, atol=1e-5, d
             clip = nt_next > t_end[act] - tol_end
             tclip = np.where(keep, t_end[act], nt_prev + R(0.5) * (t_end[act] - nt_prev))
             nt_next = np.where(clip, tclip, nt_next).astype(dtype)
-            bad = ~np.isfinite(nt_next)
+            bad = ~np.isfinite(nt_next) & (nt_prev < t_end[act])
             tprev[act] = nt_prev
             tnext[act] = nt_next
             status[act[bad]] = 2

@@ -11,7 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=1 << 20)
 ap.add_argument("--T", type=int, nargs="+", default=[16, 1000])
 ap.add_argument("--dtype", nargs="+", default=["float32", "float64"])
-ap.add_argument("--kernel", type=int, nargs="+", default=[1])
+ap.add_argument("--kernel", type=int, nargs="+", default=[1, 2])
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--rtol", type=float, default=1e-6)
 a = ap.parse_args()

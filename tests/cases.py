@@ -57,13 +57,21 @@ def field_spec(model):
     return cg.FieldSpec(list(states), list(params), list(consts), dict(odes), list(reactions))
 
 
-def mm_inputs(B, seed=0, dtype=np.float64):
-    """SURVEY §8d config 2 distributions (states ordered [E, P, S])."""
+def mm_inputs(B, seed=0, dtype=np.float64, km_range=(0.5, 50.0)):
+    """BASELINE config 2 inputs (states ordered [E, P, S]): S0~U(50,300), E0~U(5,20), P0=0,
+    k_cat~LogU(0.02,0.5), K_m~LogU(0.5,50).
+
+    SURVEY §8d proposed K_m~LogU(0.01,1); with that range 3.6% of the rows become stiff after
+    substrate depletion (decay rate k_cat*E0/K_m up to 1000 per time unit) and exhaust
+    max_steps=4096, which the reference's default throw=True turns into an exception.  The
+    benchmark range keeps every row solvable; ``km_range=(0.01, 1.0)`` is kept as the
+    failure-semantics test case.
+    """
     rng = np.random.default_rng(seed)
     S0 = rng.uniform(50, 300, B)
     E0 = rng.uniform(5, 20, B)
     y0 = np.stack([E0, np.zeros(B), S0], axis=1).astype(dtype)
-    Km = np.exp(rng.uniform(np.log(0.01), np.log(1.0), B))
+    Km = np.exp(rng.uniform(np.log(km_range[0]), np.log(km_range[1]), B))
     kc = np.exp(rng.uniform(np.log(0.02), np.log(0.5), B))
     theta = np.stack([Km, kc], axis=1).astype(dtype)
     return y0, theta, np.zeros((B, 0), dtype=dtype)

@@ -33,48 +33,81 @@ def _run_pair(model, y0, theta, consts, ts, in_axes, dtype, solver="tsit5", rtol
     return ref, out
 
 
+KERNELS = [1, 2]  # 1 = static thread-per-trajectory, 2 = persistent refill + cooperative saves
+
+
+def _assert_close_f64(ys, ref_ys, rel=1e-6, atol=1e-6, abs_frac=1e-3):
+    """x64 bound: |diff| <= 1e-6*|ref| + 1e-3*atol.  The absolute term only matters for
+    components that have decayed below the solver's own atol, where both results are
+    stability-limited noise of size ~atol (observed: 1.4e-10 on values of +-1e-6)."""
+    np.testing.assert_array_equal(np.isinf(ys), np.isinf(ref_ys))
+    fin = np.isfinite(ref_ys)
+    bound = rel * np.abs(ref_ys[fin]) + abs_frac * atol
+    assert (np.abs(ys[fin] - ref_ys[fin]) <= bound).all(), \
+        float((np.abs(ys[fin] - ref_ys[fin]) / bound).max())
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("solver", ["tsit5", "dopri5"])
-def test_mm_config1_f64(solver):
+def test_mm_config1_f64(solver, kernel):
     """BASELINE config 1: README Michaelis-Menten, 2 rows, t1=100, nsteps=1000."""
     y0 = np.array([[10.0, 0.0, 100.0], [10.0, 0.0, 200.0]])
     theta = np.array([0.05, 0.1])
     ts = np.linspace(0, 100, 1000)
     ref, out = _run_pair(cases.michaelis_menten(), y0, theta, np.zeros((2, 0)), ts,
-                         (0, None, 0, None), np.float64, solver=solver, rtol=1e-5, atol=1e-5)
+                         (0, None, 0, None), np.float64, solver=solver, rtol=1e-5, atol=1e-5,
+                         kernel=kernel)
     ys = out.ys.cpu().numpy()
     assert (out.status.cpu().numpy() == 0).all()
     np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
     np.testing.assert_array_equal(out.n_rejected.cpu().numpy(), ref.n_rejected)
-    rel = np.abs(ys - ref.ys) / np.maximum(np.abs(ref.ys), 1e-300)
-    assert rel[np.abs(ref.ys) > 1e-12].max() <= 1e-6
+    _assert_close_f64(ys, ref.ys, atol=1e-5)
     assert np.abs(ys - ref.ys).max() <= 1e-9
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("T", [16, 200])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_mm_batch_per_row_theta(dtype):
+def test_mm_batch_per_row_theta(dtype, T, kernel):
     """BASELINE config 2 distributions at a size the oracle finishes in seconds."""
-    B = 2048
+    B = 2048 + 37  # ragged: not a multiple of the warp / block size
     y0, theta, consts = cases.mm_inputs(B, seed=0, dtype=dtype)
-    ts = np.linspace(0, 100, 16).astype(dtype)
-    ref, out = _run_pair(cases.michaelis_menten(), y0, theta, consts, ts, (0, 0, 0, None), dtype)
+    ts = np.linspace(0, 100, T).astype(dtype)
+    ref, out = _run_pair(cases.michaelis_menten(), y0, theta, consts, ts, (0, 0, 0, None), dtype,
+                         kernel=kernel)
     ys = out.ys.cpu().numpy()
-    assert (out.status.cpu().numpy() == ref.status).all()
+    assert (out.status.cpu().numpy() == ref.status).all() and (ref.status == 0).all()
     if dtype == np.float64:
         same = (out.n_accepted.cpu().numpy() == ref.n_accepted) & \
                (out.n_rejected.cpu().numpy() == ref.n_rejected)
         assert same.mean() > 0.999
-        denom = np.maximum(np.abs(ref.ys), 1e-6)
-        assert (np.abs(ys - ref.ys) / denom).max() <= 1e-6
+        _assert_close_f64(ys, ref.ys)
     else:
-        bound = 50 * (1e-6 + 1e-6 * np.abs(ref.ys)) + 2e-5 * np.abs(ref.ys)
-        assert (np.abs(ys - ref.ys) <= bound).all()
+        # f32 bound (stated): at rtol=atol=1e-6 the f32 error estimate is partly rounding noise,
+        # so two implementations of the same algorithm take different accept/reject paths.
+        # Measure both against an x64 truth: the CUDA result must be (a) within
+        # 200*(atol + rtol*|y|) of it and (b) as accurate as the f32 oracle, statistically.
+        from oracle import diffrax_oracle as do, symbolic as sy
+
+        m = cases.michaelis_menten()
+        rhs, *_ = sy.make_rhs(*m[:4], m[4])
+        truth = do.solve(rhs, y0.astype(np.float64), theta.astype(np.float64),
+                         consts.astype(np.float64), ts.astype(np.float64), rtol=1e-10,
+                         atol=1e-10, dtype=np.float64, max_steps=100000).ys
+        scale = 1e-6 + 1e-6 * np.abs(truth)
+        e_gpu = np.abs(ys.astype(np.float64) - truth) / scale
+        e_ref = np.abs(ref.ys.astype(np.float64) - truth) / scale
+        assert e_gpu.max() <= 200.0, e_gpu.max()
+        assert e_gpu.mean() <= 1.25 * e_ref.mean() + 0.05
+        assert np.percentile(e_gpu, 99.9) <= 1.5 * np.percentile(e_ref, 99.9) + 1.0
         steps_gpu = (out.n_accepted + out.n_rejected).cpu().numpy().sum()
         steps_ref = (ref.n_accepted + ref.n_rejected).sum()
         assert abs(steps_gpu - steps_ref) / steps_ref < 0.02
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("solver,dt0", [("tsit5", 0.1), ("dopri5", 0.1), ("euler", 0.01), ("heun", 0.02)])
-def test_nonautonomous_all_solvers_f64(solver, dt0):
+def test_nonautonomous_all_solvers_f64(solver, dt0, kernel):
     rng = np.random.default_rng(5)
     B = 64
     y0 = rng.uniform(0.2, 2.0, (B, 4))
@@ -84,20 +117,48 @@ def test_nonautonomous_all_solvers_f64(solver, dt0):
     ts[:, 0] = 0.0
     ref, out = _run_pair(cases.nonautonomous(), y0, theta, consts, ts, (0, None, 0, 0),
                          np.float64, solver=solver, dt0=dt0, rtol=1e-7, atol=1e-9,
-                         max_steps=100000)
+                         max_steps=100000, kernel=kernel)
     ys = out.ys.cpu().numpy()
     assert (out.status.cpu().numpy() == 0).all()
     np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
-    assert (np.abs(ys - ref.ys) / np.maximum(np.abs(ref.ys), 1e-3)).max() <= 1e-6
+    _assert_close_f64(ys, ref.ys, atol=1e-9 if solver in ("tsit5", "dopri5") else 1e-6)
 
 
-def test_max_steps_failure_fills_inf():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_stiff_rows_fail_like_the_reference(kernel):
+    """SURVEY's original K_m range: some rows exhaust max_steps; status + inf pattern must match."""
+    B = 1024
+    y0, theta, consts = cases.mm_inputs(B, seed=0, dtype=np.float64, km_range=(0.01, 1.0))
+    ts = np.linspace(0, 100, 16)
+    ref, out = _run_pair(cases.michaelis_menten(), y0, theta, consts, ts, (0, 0, 0, None),
+                         np.float64, kernel=kernel)
+    assert (ref.status == 1).sum() > 10
+    np.testing.assert_array_equal(out.status.cpu().numpy(), ref.status)
+    # thousands of stability-limited steps: the depleted component is +-atol noise that
+    # amplifies rounding differences chaotically -> compare it to the full atol
+    _assert_close_f64(out.ys.cpu().numpy(), ref.ys, abs_frac=1.0)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_degenerate_t0_equals_t1(kernel):
+    y0 = np.array([[10.0, 0.0, 100.0], [10.0, 1.0, 50.0]])
+    ts = np.zeros((2, 3))
+    ref, out = _run_pair(cases.michaelis_menten(), y0, np.array([0.05, 0.1]), np.zeros((2, 0)),
+                         ts, (0, None, 0, 0), np.float64, kernel=kernel)
+    ys = out.ys.cpu().numpy()
+    np.testing.assert_array_equal(ys, np.broadcast_to(y0[:, None, :], ys.shape))
+    np.testing.assert_array_equal(ys, ref.ys)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_max_steps_failure_fills_inf(kernel):
     """throw=False semantics (simulation.py:255-257): unsaved slots are inf, status says why."""
     y0 = np.array([[10.0, 0.0, 100.0]])
     theta = np.array([0.05, 0.1])
     ts = np.linspace(0, 100, 50)
     ref, out = _run_pair(cases.michaelis_menten(), y0, theta, np.zeros((1, 0)), ts,
-                         (0, None, 0, None), np.float64, rtol=1e-8, atol=1e-8, max_steps=20)
+                         (0, None, 0, None), np.float64, rtol=1e-8, atol=1e-8, max_steps=20,
+                         kernel=kernel)
     ys = out.ys.cpu().numpy()
     assert out.status.cpu().numpy()[0] == 1 == ref.status[0]
     np.testing.assert_array_equal(np.isinf(ys), np.isinf(ref.ys))
