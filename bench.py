@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched ODE-solve hot path (BASELINE.json configs[1]).
+
+Workload: README Michaelis-Menten model (states [E,P,S], parameters [K_m,k_cat]), 2^20
+initial-condition x parameter sets PER GPU, Tsit5, rtol=atol=1e-6, dt0=0.1, max_steps=4096,
+saved on linspace(0,100,T) with T=1000 ("same" grid as configs[0]).  One "step" = one pass of
+the hot path (ctx_solve) over the whole batch.  Multi-GPU: rows are sharded by rank, no
+data-path collective (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f32|f64] [--T 1000]
+  python bench.py --impl reference ...   # the reference ALGORITHM on the host cores (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+
+METRIC = "ODE trajectory-steps/s"
+UNIT = "steps/s"
+ROWS_PER_GPU = 1 << 20
+N_INPUT_SETS = 8          # rotate input sets so inputs (8 x 20 MB) are not L2-resident either
+CPU_SAMPLE_ROWS = 1 << 18
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nuts", action="store_true")
+    ap.add_argument("--nuts-chains", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"michaelis_menten_ode[E,P,S]_B{a.rows}_per_gpu_tsit5_rtol1e-6_atol1e-6_dt0.1_"
+            f"T{a.T}_linspace(0,100)")
+
+
+def np_dtype(a):
+    return np.float32 if a.dtype == "f32" else np.float64
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "50", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(a, rows, n_threads=None, repeats=1):
+    """Time the oracle's C port (the reference ALGORITHM) on host cores.  Returns steps/s."""
+    from oracle import c_oracle
+    from tests import cases
+
+    dt = np_dtype(a)
+    m = cases.michaelis_menten()
+    co = c_oracle.COracle(*m[:4], m[4], dtype=dt)
+    y0, th, c = cases.mm_inputs(rows, seed=0, dtype=dt)
+    ts = np.linspace(0, 100, a.T).astype(dt)
+    n_threads = n_threads or os.cpu_count() or 1
+    best = None
+    steps = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = co.solve(y0, th, c, ts, rtol=1e-6, atol=1e-6, dt0=0.1, max_steps=4096,
+                     n_threads=n_threads)
+        dt_s = time.perf_counter() - t0
+        steps = int((r.n_accepted.astype(np.int64) + r.n_rejected).sum())
+        best = dt_s if best is None else min(best, dt_s)
+    return steps / best, best, steps, n_threads
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = min(CPU_SAMPLE_ROWS, a.rows)
+    from oracle import c_oracle  # noqa: F401  (compiles on first use)
+
+    for _ in range(max(a.warmup, 0)):
+        cpu_oracle_run(a, min(rows, 1 << 14))
+    t_total, steps_total, threads = 0.0, 0, os.cpu_count() or 1
+    for _ in range(a.steps):
+        _, sec, steps, threads = cpu_oracle_run(a, rows)
+        t_total += sec
+        steps_total += steps
+    value = steps_total / t_total
+    sample = (f"first {rows} rows of the {a.rows}-row batch per step, C/OpenMP port of the "
+              f"reference algorithm (oracle/ctx_oracle_core.h), {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_total / max(a.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "rows_per_step": rows},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- NUTS leg
+def nuts_inputs(chains, M, T, dt, seed):
+    """BASELINE configs[3]: chains x 64 series x 20 points x 3 observables; data = trajectories at
+    theta* + noise; per-chain theta ~ theta* LogN(0, 0.2), sigma ~ LogN(log 0.5, 0.3).
+    theta* = (K_m=40, k_cat=0.3): with the README values the discrete tangents of the reference
+    algorithm blow up after substrate depletion (tests/test_gpu_parity_loglik.py)."""
+    from oracle import c_oracle
+    from tests import cases
+
+    rng = np.random.default_rng(seed)
+    m = cases.michaelis_menten()
+    y0s = np.stack([rng.uniform(5, 20, M), np.zeros(M), rng.uniform(50, 300, M)], axis=1)
+    ts = np.tile(np.linspace(0, 100, T), (M, 1))
+    theta_star = np.array([40.0, 0.3])
+    clean = c_oracle.COracle(*m[:4], m[4], dtype=np.float64).solve(
+        y0s, theta_star, np.zeros((M, 0)), ts, rtol=1e-8, atol=1e-8).ys
+    data = clean + rng.normal(size=clean.shape) * (0.05 * np.abs(clean) + 1e-3)
+    theta = theta_star * np.exp(rng.normal(0, 0.2, (chains, 2)))
+    sigma = np.exp(rng.normal(np.log(0.5), 0.3, (chains, 3)))
+    c = lambda x: np.ascontiguousarray(x, dtype=dt)
+    return c(y0s), c(theta), np.zeros((M, 0), dtype=dt), c(ts), c(data), c(sigma)
+
+
+def run_nuts_leg(a, model_field, dev, rank, world, dist):
+    """Chain-sharded (no collective): every rank evaluates its own `nuts_chains` chains over all
+    64 series.  value = chain-level (log-density, gradient) evaluations per second, all ranks."""
+    import torch
+
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+    from tests import cases
+
+    dt = np_dtype(a)
+    CH, M, T = a.nuts_chains, 64, 20
+    field = cg.generate_field(cases.field_spec(cases.michaelis_menten()), sens_theta=True)
+    model = engine.CompiledModel(field, np.dtype(dt).name)
+    y0s, theta, consts, ts, data, sigma = nuts_inputs(CH, M, T, dt, seed=2 + 100 * rank)
+    tt = lambda x: torch.as_tensor(x, device=dev)
+    args = [tt(x) for x in (y0s, theta, consts, ts, data, sigma)]
+    kw = dict(likelihood="softlaplace", rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096)
+    n_iter = max(3, min(a.steps, 20))
+    for _ in range(3):
+        out, partial, status = model.loglik_grad(*args, **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_iter):
+        out, partial, status = model.loglik_grad(*args, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    fails = int((status != 0).sum().item())
+    finite = bool(torch.isfinite(out).all().item())
+    return {"metric": "NUTS logp+grad evals/s", "value": CH * world * n_iter / (ms * 1e-3),
+            "unit": "evals/s", "ms_per_eval_batch": ms / n_iter,
+            "series_solves_with_gradient_per_s": CH * world * M * n_iter / (ms * 1e-3),
+            "config": {"chains_per_gpu": CH, "series": M, "points": T, "observables": 3,
+                       "likelihood": "SoftLaplace", "rtol": 1e-5, "atol": 1e-5,
+                       "sharding": "by chain (no collective)"},
+            "failed_series": fails, "all_finite": finite}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+    from tests import cases
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {a.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: catalax_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dt = np_dtype(a)
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+    w = 4 if a.dtype == "f32" else 8
+    B, T, S, P = a.rows, a.T, 3, 2
+    field = cg.generate_field(cases.field_spec(cases.michaelis_menten()))
+    model = engine.CompiledModel(field, np.dtype(dt).name)
+
+    # rows are sharded by rank: every rank draws its own seeds (no data-path collective)
+    sets = []
+    for k in range(N_INPUT_SETS):
+        y0, th, c = cases.mm_inputs(B, seed=1000 * rank + k, dtype=dt)
+        sets.append(tuple(torch.as_tensor(x, device=dev) for x in (y0, th, c)))
+    ts = torch.linspace(0, 100, T, dtype=tdt, device=dev)
+    out = torch.empty((B, T, S), dtype=tdt, device=dev)
+    kw = dict(solver="tsit5", in_axes=(0, 0, 0, None), rtol=1e-6, atol=1e-6, dt0=0.1,
+              max_steps=4096, kernel=a.kernel, out=out)
+
+    def step(i):
+        y0, th, c = sets[i % N_INPUT_SETS]
+        return model.solve(y0, th, c, ts, **kw)
+
+    # steps per input set (deterministic) -- counted outside the timed region
+    steps_of_set, fails = [], 0
+    for k in range(N_INPUT_SETS):
+        o = step(k)
+        steps_of_set.append(int((o.n_accepted.sum(dtype=torch.int64) + o.n_rejected.sum(dtype=torch.int64)).item()))
+        fails += int((o.status != 0).sum().item())
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(a.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = engine.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    my_steps = sum(steps_of_set[i % N_INPUT_SETS] for i in range(a.steps))
+
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tst = torch.tensor([float(my_steps), float(fails)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tst, op=dist.ReduceOp.SUM)
+    ms_max, total_steps, total_fails = float(tms.item()), float(tst[0].item()), int(tst[1].item())
+    value = total_steps / (ms_max * 1e-3)
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (copies inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        import psutil
+
+        out_bytes = B * T * S * w
+        e2e_rows = B
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        while e2e_rows > 4096 and (e2e_rows * T * S * w) * local_world * 3 > psutil.virtual_memory().available:
+            e2e_rows //= 2
+        y0h, thh, ch = cases.mm_inputs(e2e_rows, seed=1000 * rank, dtype=dt)
+        pin = lambda arr: torch.as_tensor(arr).pin_memory()
+        y0p, thp = pin(y0h), pin(thh)
+        chp = torch.empty((e2e_rows, 0), dtype=tdt).pin_memory()
+        tsp = torch.linspace(0, 100, T, dtype=tdt).pin_memory()
+        ysp = torch.empty((e2e_rows, T, S), dtype=tdt).pin_memory()
+        n_e2e = max(1, min(a.steps, 3))
+        run = lambda: model.solve_host(y0p.numpy(), thp.numpy(), chp.numpy(), tsp.numpy(),
+                                       in_axes=(0, 0, 0, None), rtol=1e-6, atol=1e-6, dt0=0.1,
+                                       max_steps=4096, kernel=a.kernel, out=ysp.numpy())
+        o = run()  # warm-up (allocates device staging)
+        e2e_steps = int(o.n_accepted.astype(np.int64).sum() + o.n_rejected.astype(np.int64).sum())
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            run()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+        ts_ = torch.tensor([float(e2e_steps * n_e2e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ts_, op=dist.ReduceOp.SUM)
+        h2d = e2e_rows * (S + P) * w + T * w
+        d2h = e2e_rows * T * S * w + 3 * 4 * e2e_rows
+        e2e = {"value": float(ts_.item()) / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "rows_per_step": e2e_rows,
+               "steps_timed": n_e2e, "api": "ctx_solve_host (C ABI, pinned host buffers)"}
+        del ysp
+
+    # ---- second headline metric: NUTS log-density + gradient evaluations / s (configs[3])
+    nuts = None
+    if not a.no_nuts:
+        nuts = run_nuts_leg(a, model_field=None, dev=dev, rank=rank, world=world, dist=dist)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo_bytes = B * (T * S * w + (S + P) * w + 12) + T * w     # per launch (per rank)
+    launch_ms = ms / a.steps                                     # rank 0's own average
+    achieved = algo_bytes / (launch_ms * 1e-3) / 1e9
+    prof = ROOT / "profiles" / f"r1_solve_{a.dtype}_T{T}.json"
+    traffic = None
+    if prof.exists():
+        try:
+            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a), "rows_total": B * world, "saved_points": T,
+                   "l2": f"outputs {B*T*S*w/1e9:.1f} GB/step >> 126 MB L2; inputs rotate over "
+                         f"{N_INPUT_SETS} sets",
+                   "kernel": "ctx_solve_v1 (persistent refill + cooperative dense output)",
+                   "failed_rows": total_fails, "steps_per_row": total_steps / (B * world * a.steps)},
+        "gpu_launches": launches, "clocks": clocks,
+        "saved_points_per_s": B * world * T * a.steps / (ms_max * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                     "algorithmic_bytes_per_launch": algo_bytes},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if nuts:
+        line["nuts"] = nuts
+    if not a.no_cpu_baseline and world == 1:
+        rows = min(CPU_SAMPLE_ROWS, B)
+        v, sec, steps, threads = cpu_oracle_run(a, rows)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {rows} rows of the batch, one pass ({sec:.2f} s), C/OpenMP port of "
+                      f"the reference algorithm (oracle/ctx_oracle_core.h)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,17 +109,26 @@ struct SolveArgs {
   real rtol, atol, dt0;
 };
 
-// Warps per CTA of the persistent kernel so that its static shared memory
-// (ctx_warp_smem in ctx_integrator.cuh) stays below 48 KB; 0 = record too large.
-int v1_warps(const ctx_model_desc& d, int solver, int tan) {
+// Shared memory of one warp of the persistent kernel = sizeof(ctx_warp_smem) in
+// ctx_integrator.cuh (step records + staging).
+size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan) {
   const size_t w = d.dtype == CTX_F64 ? 8 : 4;
   const size_t N = (size_t)d.n_states * (1 + (tan ? d.n_dirs : 0));
   const size_t deg = solver <= 1 ? 4 : 1;
   const size_t S = (size_t)d.n_states;
   const size_t rec = 2 + (deg + 1) * N;
-  const size_t per_warp = 32 * rec * w + 512 + 32 * S * w + (tan ? 32 * (N - S) * w : 0) + 256;
-  size_t warps = (48 * 1024) / per_warp;
+  return 32 * rec * w + 512 + 32 * S * w + (tan ? 32 * (N - S) * w : 0) + 256;
+}
+
+// Warps per CTA of the persistent kernel: 4 when that fits the default 48 KB, otherwise as many
+// as fit ~96 KB (opt-in dynamic shared memory, two CTAs per SM); 0 = a single warp's records do
+// not fit 200 KB, use the static kernel.
+int v1_warps(const ctx_model_desc& d, int solver, int tan) {
+  const size_t per_warp = v1_warp_smem(d, solver, tan);
+  if (4 * per_warp <= 48 * 1024) return 4;
+  size_t warps = (96 * 1024) / per_warp;
   if (warps > 4) warps = 4;
+  if (warps == 0 && per_warp <= 200 * 1024) warps = 1;
   return (int)warps;
 }
 
@@ -137,6 +146,7 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
       std::string("-DCTX_F64=") + (m->desc.dtype == CTX_F64 ? "1" : "0"),
       "-DCTX_SOLVER=" + std::to_string(solver), "-DCTX_TAN=" + std::to_string(tan),
       "-DCTX_WARPS=" + std::to_string(std::max(1, v1_warps(m->desc, solver, tan)))};
+  if (v1_warps(m->desc, solver, tan) <= 0) opts.push_back("-DCTX_NO_V1=1");
   const char* extra = getenv("CTX_B200_NVRTC_FLAGS");
   if (extra && *extra) {
     std::string e(extra), cur;
@@ -279,13 +289,19 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     int dev = 0, sms = 0, per_sm = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, 0));
+    const size_t smem = (size_t)warps * v1_warp_smem(m->desc, cfg->solver, tan);
+    if (smem > 48 * 1024)
+      CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block,
+                                                           smem));
     if (per_sm < 1) per_sm = 1;
     unsigned long long grid = (unsigned long long)sms * per_sm;
     const unsigned long long want = (cfg->batch + block - 1) / block;
     if (grid > want) grid = want;
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
-    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
+                              stream));
     g_launches++;
   } else if (kernel == 1) {
     int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v0", &k);
@@ -297,6 +313,81 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   } else {
     return fail(CTX_E_INVALID, "unknown kernel id");
   }
+  return CTX_OK;
+}
+
+template <typename real>
+struct LoglikArgs {
+  const real* y0s;
+  const real* theta;
+  const real* consts;
+  const real* ts;
+  const real* data;
+  const unsigned char* mask;
+  const real* sigma;
+  real* partial;
+  int* status;
+  int* n_accepted;
+  int* n_rejected;
+  unsigned long long* work_counter;
+  long long n_traj;
+  int M, T, likelihood, max_steps;
+  real rtol, atol, dt0;
+};
+
+template <typename real>
+int launch_loglik(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, const void* theta,
+                  const void* consts, const void* ts, const void* data, const uint8_t* mask,
+                  const void* sigma, void* out, void* partial, int32_t* status, void* ws,
+                  size_t ws_bytes, cudaStream_t stream) {
+  const ctx_model_desc& d = m->desc;
+  const long long n_traj = cfg->n_chains * (long long)cfg->n_series;
+  if (n_traj <= 0) return CTX_OK;
+  const size_t need = ctx_loglik_workspace_bytes(m, cfg);
+  if (ws_bytes < need || !ws) return fail(CTX_E_WORKSPACE, "workspace too small");
+  const int kp = 1 + d.n_theta_dirs + d.n_states + (d.n_dirs - d.n_theta_dirs);
+  char* p = (char*)ws;
+  LoglikArgs<real> a;
+  a.work_counter = (unsigned long long*)p; p += 256;
+  a.status = status ? status : (int*)p; p += sizeof(int) * n_traj;
+  a.n_accepted = (int*)p; p += sizeof(int) * n_traj;
+  a.n_rejected = (int*)p; p += sizeof(int) * n_traj;
+  p = (char*)(((uintptr_t)p + 255) / 256 * 256);
+  a.partial = partial ? (real*)partial : (real*)p;
+  a.y0s = (const real*)y0s; a.theta = (const real*)theta; a.consts = (const real*)consts;
+  a.ts = (const real*)ts; a.data = (const real*)data; a.mask = mask; a.sigma = (const real*)sigma;
+  a.n_traj = n_traj; a.M = cfg->n_series; a.T = cfg->n_times; a.likelihood = cfg->likelihood;
+  a.max_steps = cfg->max_steps;
+  a.rtol = (real)cfg->rtol; a.atol = (real)cfg->atol; a.dt0 = (real)cfg->dt0;
+  cudaKernel_t k;
+  int rc = get_kernel(m, cfg->solver, 1, "ctx_loglik_v1", &k);
+  if (rc) return rc;
+  const int warps = std::max(1, v1_warps(d, cfg->solver, 1));
+  const unsigned block = 32u * warps;
+  int dev = 0, sms = 0, per_sm = 0;
+  CTX_CUDA(cudaGetDevice(&dev));
+  CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, 0));
+  if (per_sm < 1) per_sm = 1;
+  unsigned long long grid = (unsigned long long)sms * per_sm;
+  const unsigned long long want = (n_traj + block - 1) / block;
+  if (grid > want) grid = want;
+  void* params[] = {&a};
+  CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+  CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
+  g_launches++;
+  cudaKernel_t kr;
+  rc = get_kernel(m, cfg->solver, 1, "ctx_loglik_reduce", &kr);
+  if (rc) return rc;
+  const real* part = a.partial;
+  real* outp = (real*)out;
+  long long nch = cfg->n_chains;
+  int M = cfg->n_series, KR = 1 + d.n_theta_dirs + d.n_states;
+  void* rparams[] = {(void*)&part, (void*)&outp, (void*)&nch, (void*)&M, (void*)&KR};
+  const unsigned long long rgrid = (nch * 32 + 127) / 128;
+  CTX_CUDA(cudaLaunchKernel((const void*)kr, dim3((unsigned)rgrid), dim3(128), rparams, 0, stream));
+  g_launches++;
+  (void)kp;
   return CTX_OK;
 }
 
@@ -402,6 +493,34 @@ int ctx_solve_sens(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
   if (!sens) return fail(CTX_E_INVALID, "sens output is null");
   return dispatch_solve(m, cfg, 1, y0, theta, consts, ts, ys, sens, status, nacc, nrej, ws,
                         ws_bytes, stream);
+}
+
+size_t ctx_loglik_workspace_bytes(const ctx_model* m, const ctx_loglik_cfg* cfg) {
+  if (!m || !cfg || cfg->n_chains <= 0 || cfg->n_series <= 0) return 0;
+  const ctx_model_desc& d = m->desc;
+  const size_t w = d.dtype == CTX_F64 ? 8 : 4;
+  const size_t n_traj = (size_t)cfg->n_chains * cfg->n_series;
+  const size_t kp = 1 + d.n_theta_dirs + d.n_states + (d.n_dirs - d.n_theta_dirs);
+  return 256 + 3 * sizeof(int32_t) * n_traj + 256 + n_traj * kp * w;
+}
+
+int ctx_loglik_grad(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, const void* theta,
+                    const void* consts, const void* ts, const void* data, const uint8_t* mask,
+                    const void* sigma, void* out, void* partial, int32_t* status, void* ws,
+                    size_t ws_bytes, void* stream) {
+  if (!m || !cfg || !out) return fail(CTX_E_INVALID, "null argument");
+  if (m->desc.n_theta_dirs != m->desc.n_params)
+    return fail(CTX_E_INVALID, "model must be generated with all parameter directions");
+  if (cfg->likelihood != CTX_LIK_NORMAL && cfg->likelihood != CTX_LIK_SOFTLAPLACE)
+    return fail(CTX_E_INVALID, "unknown likelihood id");
+  if (cfg->n_times <= 0) return fail(CTX_E_INVALID, "n_times must be >= 1");
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  if (m->desc.dtype == CTX_F64)
+    return launch_loglik<double>(m, cfg, y0s, theta, consts, ts, data, mask, sigma, out, partial,
+                                 status, ws, ws_bytes, (cudaStream_t)stream);
+  return launch_loglik<float>(m, cfg, y0s, theta, consts, ts, data, mask, sigma, out, partial,
+                              status, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,

@@ -364,7 +364,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
   {
     real inf[CTX_N];
 #pragma unroll
-    for (int i = 0; i < CTX_N; ++i) inf[i] = CTX_INF;
+    for (int i = 0; i < CTX_N; ++i) inf[i] = i < CTX_S ? CTX_INF : R(0.0);
     for (; idx < T; ++idx) ctx_store_point(a, b, idx, inf);
   }
   a.status[b] = status;
@@ -463,6 +463,7 @@ __device__ __forceinline__ void ctx_dense_coefs(const real dt, const real* y, co
   }
 }
 
+#ifndef CTX_NO_V1
 struct ctx_warp_smem {
   real rec[2 + CTX_NCOEF][32];   // tp, 1/dt, coefficients; one column per publishing lane
   long long ts_off[32];          // element offset into ts of the segment's save j = 0
@@ -476,8 +477,8 @@ struct ctx_warp_smem {
 
 extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
 ctx_solve_v1(const ctx_solve_args a) {
-  __shared__ ctx_warp_smem smem[CTX_WARPS];
-  ctx_warp_smem& w = smem[threadIdx.x >> 5];
+  extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];  // CTX_WARPS * sizeof(ctx_warp_smem)
+  ctx_warp_smem& w = reinterpret_cast<ctx_warp_smem*>(ctx_dyn_smem)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned le_mask = CTX_FULL >> (31 - lane);
@@ -603,7 +604,8 @@ ctx_solve_v1(const ctx_solve_args a) {
         if (filling) {
           const bool fill_inf = status != 0;
 #pragma unroll
-          for (int i = 0; i < CTX_N; ++i) coef[i] = fill_inf ? CTX_INF : y[i];
+          for (int i = 0; i < CTX_N; ++i)
+            coef[i] = fill_inf ? (i < CTX_S ? CTX_INF : R(0.0)) : y[i];
 #pragma unroll
           for (int i = CTX_N; i < CTX_NCOEF; ++i) coef[i] = R(0.0);
           w.rec[0][s] = R(0.0);
@@ -726,3 +728,232 @@ ctx_solve_v1(const ctx_solve_args a) {
     }
   }
 }
+
+#endif  // CTX_NO_V1
+
+// =====================================================================================
+// kernel K2: fused solve + forward tangents + masked log-likelihood and its gradient
+// =====================================================================================
+// Replaces, per NUTS leapfrog step, value_and_grad of the numpyro model
+//   catalax/mcmc/mcmc.py:405-491   states = sim_func(y0s, theta, constants, times)   (:448)
+//                                  loc = states[..., observables]                    (:461)
+//                                  sample("y", likelihood(loc, sqrt(sigma_y**2)), obs=data)
+//                                  under handlers.mask(mask)                         (:486-491)
+// One trajectory per (chain, series) pair, u = chain*M + m: theta and sigma are per chain,
+// y0 / constants / times / data / mask per series (in_axes=(0, None, 0, 0), mcmc.py:860).
+// Nothing of size [M,T,S] is written: every lane evaluates its own trajectory's requested
+// times right after the accepted step that covers them and accumulates
+//   ll, d ll/d theta_p = sum dlogp/dloc * d y_o/d theta_p, d ll/d sigma_o, d ll/d y0_i
+// in registers; one row of partial[u, :] is written when the trajectory retires and
+// ctx_loglik_reduce sums the M rows of every chain with warp shuffles (deterministic).
+// observables = all modeled states in state order (mcmc.py:393-395).
+//   likelihood 0: Normal       log p = -z^2/2 - log s - log(2 pi)/2
+//   likelihood 1: SoftLaplace  log p = log(2/pi) - log s - logaddexp(z, -z)   (numpyro)
+//   z = (x - loc)/s,  s = sqrt(sigma^2) = |sigma|
+#if CTX_TAN
+#define CTX_KP (1 + CTX_D_THETA + CTX_S + CTX_D_Y0)
+
+struct ctx_loglik_args {
+  const real* y0s;      // [M,S]
+  const real* theta;    // [CH,P]
+  const real* consts;   // [M,C]
+  const real* ts;       // [M,T]
+  const real* data;     // [M,T,S]
+  const unsigned char* mask;  // [M,T,S] 1 = observed; null -> isfinite(data)
+  const real* sigma;    // [CH,S]
+  real* partial;        // [CH*M, KP] = (ll, d/dtheta[D_THETA], d/dsigma[S], d/dy0[D_Y0])
+  int* status;          // [CH*M]
+  int* n_accepted;      // [CH*M]
+  int* n_rejected;      // [CH*M]
+  unsigned long long* work_counter;
+  long long n_traj;     // CH*M
+  int M, T, likelihood, max_steps;
+  real rtol, atol, dt0;
+};
+
+__device__ __forceinline__ real ctx_log1p_exp_neg2a(const real a) {  // log(1 + exp(-2a)), a >= 0
+  return log1p(exp(R(-2.0) * a));
+}
+
+extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
+ctx_loglik_v1(const ctx_loglik_args a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int T = a.T;
+
+  long long u = -1;
+  real y[CTX_N], ynew[CTX_N], y0[CTX_S];
+  real th[CTX_P > 0 ? CTX_P : 1], c[CTX_C > 0 ? CTX_C : 1], sg[CTX_S];
+  real K[CTX_NST][CTX_N];
+  real acc[CTX_KP];
+  real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
+  int idx = 0, nacc = 0, nrej = 0, status = 0, m = 0;
+  bool exhausted = false;
+  const real* tsr = a.ts;
+
+  while (true) {
+    const unsigned need = __ballot_sync(CTX_FULL, u < 0);
+    if (need && !exhausted) {
+      const int cnt = __popc(need);
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)cnt);
+      base = __shfl_sync(CTX_FULL, base, 0);
+      if (base + cnt >= (unsigned long long)a.n_traj) exhausted = true;
+      if (u < 0) {
+        const unsigned long long nu = base + __popc(need & lt_mask);
+        if (nu < (unsigned long long)a.n_traj) {
+          u = (long long)nu;
+          const long long ch = u / a.M;
+          m = (int)(u - ch * a.M);
+#pragma unroll
+          for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0s[(size_t)m * CTX_S + i];
+#pragma unroll
+          for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)ch * CTX_P + i];
+#pragma unroll
+          for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)m * CTX_C + i];
+#pragma unroll
+          for (int i = 0; i < CTX_S; ++i) sg[i] = a.sigma[(size_t)ch * CTX_S + i];
+#pragma unroll
+          for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
+#pragma unroll
+          for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
+#pragma unroll
+          for (int k = 0; k < CTX_KP; ++k) acc[k] = R(0.0);
+          tsr = a.ts + (size_t)m * T;
+          t_end = tsr[T - 1];
+          tprev = R(0.0);
+          tnext = fmin(tprev + a.dt0, t_end);
+          idx = 0; nacc = 0; nrej = 0; status = 0;
+          ctx_field(tprev, y, th, c, y0, K[0]);
+        }
+      }
+    }
+    if (__ballot_sync(CTX_FULL, u >= 0) == 0u) break;
+
+    if (u >= 0) {
+      bool keep = true, done = !(tprev < t_end);
+      const real tp = tprev, tn_step = tnext;
+      if (!done) {
+        const real dt = tnext - tprev;
+        ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
+        real dt_next = a.dt0;
+#if CTX_ADAPTIVE
+        const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
+        keep = scaled < R(1.0);
+        const real inv = R(1.0) / scaled;
+        real factor = R(0.9) * pow(inv, R(0.2));
+        factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
+        dt_next = dt * factor;
+        if (scaled != scaled) dt_next = scaled;
+#endif
+        real tp_new = keep ? tnext : tprev;
+        if (keep) ++nacc; else ++nrej;
+        tp_new = fmin(tp_new, t_end);
+        real tn = tp_new + dt_next;
+        if (tn > t_end - CTX_TOL_END) tn = keep ? t_end : tp_new + R(0.5) * (t_end - tp_new);
+        done = !(tp_new < t_end);
+        if (!done) {
+          if (!(fabs(tn) < CTX_INF)) status = CTX_ST_BAD;
+          else if (nacc + nrej >= a.max_steps) status = CTX_ST_MAX;
+        }
+        tprev = tp_new; tnext = tn;
+      } else {
+        // t0 == t1: every requested time is t0; interpolate a zero-length step at theta = 0
+#pragma unroll
+        for (int i = 0; i < CTX_N; ++i) ynew[i] = y[i];
+#pragma unroll
+        for (int k = 1; k < CTX_NST; ++k)
+#pragma unroll
+          for (int i = 0; i < CTX_N; ++i) K[k][i] = R(0.0);
+      }
+      // ---- requested times covered by this accepted step: likelihood terms
+      if (keep) {
+        while (idx < T) {
+          const real tq = tsr[idx];
+          if (!done && !(tq <= tn_step)) break;
+          real out[CTX_N];
+          ctx_dense(tq, tp, done && tp == tn_step ? tp : tn_step, y, ynew, K, out);
+          const real* drow = a.data + ((size_t)m * T + idx) * CTX_S;
+          const unsigned char* mrow = a.mask ? a.mask + ((size_t)m * T + idx) * CTX_S : nullptr;
+#pragma unroll
+          for (int o = 0; o < CTX_S; ++o) {
+            const real x = drow[o];
+            const bool use = mrow ? (mrow[o] != 0) : (fabs(x) < CTX_INF);
+            if (use) {
+              const real s = fabs(sg[o]);
+              const real z = (x - out[o]) / s;
+              real lp, dl_dloc, dl_ds;
+              if (a.likelihood == 0) {
+                lp = R(-0.5) * z * z - log(s) - R(0.9189385332046727418);
+                dl_dloc = z / s;
+                dl_ds = (z * z - R(1.0)) / s;
+              } else {
+                const real az = fabs(z);
+                lp = R(-0.4515827052894548647) - log(s) - (az + ctx_log1p_exp_neg2a(az));
+                const real tz = tanh(z);
+                dl_dloc = tz / s;
+                dl_ds = (z * tz - R(1.0)) / s;
+              }
+              acc[0] += lp;
+#pragma unroll
+              for (int d = 0; d < CTX_D_THETA; ++d) acc[1 + d] += dl_dloc * out[CTX_S + d * CTX_S + o];
+              acc[1 + CTX_D_THETA + o] += dl_ds * (sg[o] < R(0.0) ? R(-1.0) : R(1.0));
+#pragma unroll
+              for (int d = 0; d < CTX_D_Y0; ++d)
+                acc[1 + CTX_D_THETA + CTX_S + d] += dl_dloc * out[CTX_S + (CTX_D_THETA + d) * CTX_S + o];
+            }
+          }
+          ++idx;
+        }
+#pragma unroll
+        for (int i = 0; i < CTX_N; ++i) y[i] = ynew[i];
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#pragma unroll
+        for (int i = 0; i < CTX_N; ++i) K[0][i] = K[6][i];
+#else
+        ctx_field(tprev, y, th, c, y0, K[0]);
+#endif
+      }
+      if (done || status != 0) {
+        if (status != 0) {
+          // reference: unsaved states are inf (constant) -> log p = -inf, gradient inf * 0 = NaN
+          bool any_left = false;
+          for (int j = idx; j < T && !any_left; ++j)
+            for (int o = 0; o < CTX_S; ++o) {
+              const real x = a.data[((size_t)m * T + j) * CTX_S + o];
+              const bool use = a.mask ? (a.mask[((size_t)m * T + j) * CTX_S + o] != 0) : (fabs(x) < CTX_INF);
+              any_left |= use;
+            }
+          if (any_left) {
+            acc[0] = -CTX_INF;
+#pragma unroll
+            for (int k = 1; k < CTX_KP; ++k) acc[k] = CTX_INF - CTX_INF;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CTX_KP; ++k) a.partial[(size_t)u * CTX_KP + k] = acc[k];
+        a.status[u] = status;
+        a.n_accepted[u] = nacc;
+        a.n_rejected[u] = nrej;
+        u = -1;
+      }
+    }
+  }
+}
+
+// out[ch, k] = sum_m partial[ch*M + m, k] for k < KR; one warp per chain, double accumulation.
+extern "C" __global__ void __launch_bounds__(128)
+ctx_loglik_reduce(const real* partial, real* out, const long long n_chains, const int M,
+                  const int KR) {
+  const long long ch = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ch >= n_chains) return;
+  for (int k = 0; k < KR; ++k) {
+    double s = 0.0;
+    for (int mm = lane; mm < M; mm += 32) s += (double)partial[((size_t)ch * M + mm) * CTX_KP + k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(CTX_FULL, s, d);
+    if (lane == 0) out[(size_t)ch * KR + k] = (real)s;
+  }
+}
+#endif  // CTX_TAN

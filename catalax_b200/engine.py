@@ -42,6 +42,13 @@ class ctx_solve_cfg(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class ctx_loglik_cfg(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("likelihood", C.c_int32), ("n_chains", C.c_int64),
+                ("n_series", C.c_int32), ("n_times", C.c_int32), ("max_steps", C.c_int32),
+                ("reserved", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
+                ("dt0", C.c_double)]
+
+
 def lib() -> C.CDLL:
     """Load libctxb200.so (built in-tree by ``__graft_entry__.build()``)."""
     global _lib
@@ -72,6 +79,10 @@ def lib() -> C.CDLL:
     L.ctx_solve_sens.restype = C.c_int
     L.ctx_solve_sens.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  vp, C.c_size_t, vp]
+    L.ctx_loglik_workspace_bytes.restype = C.c_size_t
+    L.ctx_loglik_workspace_bytes.argtypes = [vp, C.POINTER(ctx_loglik_cfg)]
+    L.ctx_loglik_grad.restype = C.c_int
+    L.ctx_loglik_grad.argtypes = [vp, C.POINTER(ctx_loglik_cfg)] + [vp] * 11 + [C.c_size_t, vp]
     L.ctx_solve_host.restype = C.c_int
     L.ctx_solve_host.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -216,3 +227,48 @@ class CompiledModel:
         _check(lib().ctx_solve_host(self._h, C.byref(cfg), vp(y0), vp(theta), vp(consts), vp(ts),
                                     vp(ys), vp(status), vp(nacc), vp(nrej)))
         return SolveOutput(ys, status, nacc, nrej)
+
+    def loglik_grad(self, y0s, theta, consts, ts, data, sigma, *, mask=None,
+                    likelihood="softlaplace", solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,
+                    max_steps=4096):
+        """Fused log-likelihood + gradient for CH chains over M series (ctx_loglik_grad).
+
+        y0s [M,S], theta [CH,P], consts [M,C], ts [M,T], data [M,T,S], sigma [CH,S],
+        mask [M,T,S] bool or None (= isfinite(data)).  Returns (out [CH, 1+P+S],
+        partial [CH*M, 1+P+S+D_y0], status [CH*M]) as torch CUDA tensors.
+        """
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = theta.device
+        if dev.type != "cuda":
+            raise EngineError("loglik_grad() needs CUDA tensors: catalax_b200 has no CPU fallback")
+        S, P, Cn, D = self.field.S, self.field.P, self.field.C, self.field.D
+        if self.field.n_theta_dirs != P:
+            raise EngineError("model must be generated with sens_theta=True")
+        f = lambda x: x.to(device=dev, dtype=tdt).contiguous()
+        y0s, theta, consts, ts, data, sigma = map(f, (y0s, theta, consts, ts, data, sigma))
+        M, T = ts.shape
+        CH = theta.shape[0]
+        assert y0s.shape == (M, S) and theta.shape == (CH, P) and data.shape == (M, T, S)
+        assert sigma.shape == (CH, S) and consts.shape == (M, Cn)
+        if mask is not None:
+            mask = mask.to(device=dev, dtype=torch.uint8).contiguous()
+            assert mask.shape == (M, T, S)
+        cfg = ctx_loglik_cfg()
+        cfg.solver, cfg.likelihood = SOLVER_IDS[solver], LIKELIHOOD_IDS[likelihood]
+        cfg.n_chains, cfg.n_series, cfg.n_times, cfg.max_steps = CH, M, T, int(max_steps)
+        cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
+        kp = 1 + P + S + (D - P)
+        with torch.cuda.device(dev):
+            out = torch.empty((CH, 1 + P + S), dtype=tdt, device=dev)
+            partial = torch.empty((CH * M, kp), dtype=tdt, device=dev)
+            status = torch.empty(CH * M, dtype=torch.int32, device=dev)
+            wsb = int(lib().ctx_loglik_workspace_bytes(self._h, C.byref(cfg)))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            p = lambda t: C.c_void_p(t.data_ptr()) if (t is not None and t.numel()) else C.c_void_p(0)
+            _check(lib().ctx_loglik_grad(self._h, C.byref(cfg), p(y0s), p(theta), p(consts), p(ts),
+                                         p(data), p(mask), p(sigma), p(out), p(partial), p(status),
+                                         p(ws), wsb, C.c_void_p(stream)))
+        return out, partial, status

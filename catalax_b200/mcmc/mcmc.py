@@ -1,0 +1,172 @@
+"""The NUTS log-density + gradient entry point.
+
+Mirror of ``catalax/mcmc/mcmc.py``: ``MCMCConfig`` (:38-79), ``BayesianModel`` (:332-491),
+``_prepare_mcmc_data`` (:539-592), ``_extract_dataset_components`` (:759-790).  The reference
+hands a numpyro model to NUTS, which calls ``value_and_grad`` of its log-joint once per leapfrog
+step; the sampler itself (numpyro) is not part of this engine.  What is provided is that
+log-joint and its gradient, for MANY chains at once:
+
+    log p(theta, sigma_y | data) = sum_p log prior_p(theta_p) + log prior(sigma_y)
+                                   + sum_{mask} log L(data; loc = ys[..., obs], scale = |sigma_y|)
+
+The likelihood term and its gradient come from the fused CUDA kernel (ctx_loglik_grad); priors are
+scalar torch ops.  Multi-GPU: shard="chains" needs no collective; shard="series" all-reduces
+the [chains, 1+P+n_obs] block (catalax_b200.parallel).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Optional
+
+import numpy as np
+
+from ..config import default_dtype
+from ..model.simconfig import SimulationConfig
+from ..solvers import Tsit5, solver_name
+from . import priors as _priors
+from .error import DEFAULT_ERROR_MODEL, ErrorModel
+
+
+@dataclass
+class MCMCConfig:
+    """Fields and defaults of the reference's MCMCConfig (mcmc.py:57-71)."""
+
+    num_warmup: int
+    num_samples: int
+    likelihood: Any = "softlaplace"      # reference: dist.SoftLaplace (class); "normal" also used
+    dense_mass: bool = True
+    thinning: int = 1
+    max_tree_depth: int = 10
+    dt0: float = 0.1
+    chain_method: str = "sequential"
+    num_chains: int = 1
+    seed: int = 420
+    verbose: int = 1
+    max_steps: int = 64 ** 4
+    solver: Any = Tsit5
+    target_accept_prob: float = 0.8
+    error_model: Optional[ErrorModel] = None
+
+    def to_simulation_config(self) -> SimulationConfig:
+        # NB the reference forwards max_steps as t1 (mcmc.py:73-79): the solves really run
+        # with SimulationConfig's own defaults max_steps=4096, rtol=atol=1e-5.
+        return SimulationConfig(t1=self.max_steps, t0=0, dt0=self.dt0, solver=self.solver)
+
+
+def likelihood_name(lik) -> str:
+    name = lik if isinstance(lik, str) else getattr(lik, "__name__", type(lik).__name__)
+    name = name.lower()
+    if name not in ("normal", "softlaplace"):
+        raise NotImplementedError(f"likelihood {lik!r}: Normal and SoftLaplace are supported")
+    return name
+
+
+def extract_dataset_components(dataset, model):
+    """(data [M,T,n_obs], times [M,T], y0s [M,S], constants [M,C]) -- mcmc.py:759-790."""
+    data, times, _ = dataset.to_jax_arrays(model.get_observable_state_order(), inits_to_array=True)
+    constants = dataset.to_y0_matrix(state_order=model.get_constants_order())
+    order = model.get_state_order()
+    y0s = np.stack([np.array([m.initial_conditions[s] for s in order], dtype=default_dtype())
+                    for m in dataset.measurements])
+    return data, times, y0s, constants
+
+
+class BayesianModel:
+    """Batched log-density of the posterior the reference samples with NUTS (mcmc.py:332-491)."""
+
+    def __init__(self, model, dataset=None, *, yerrs=1.0, likelihood="softlaplace",
+                 config: Optional[SimulationConfig] = None, error_model: Optional[ErrorModel] = None,
+                 estimate_initials: bool = False, shard: str = "chains", arrays=None,
+                 device=None):
+        """arrays: optional (data, times, y0s, constants) instead of a Dataset (array seam)."""
+        from .. import engine, parallel
+        from ..tools import codegen as cg
+
+        self.model = model
+        self.config = config or MCMCConfig(0, 0).to_simulation_config()
+        self.likelihood = likelihood_name(likelihood)
+        self.error_model = error_model or DEFAULT_ERROR_MODEL
+        self.shard = shard
+        if shard not in ("chains", "series", "none"):
+            raise ValueError("shard must be 'chains', 'series' or 'none'")
+        self.dtype = default_dtype()
+        data, times, y0s, constants = arrays if arrays is not None else \
+            extract_dataset_components(dataset, model)
+        if data.shape[-1] != len(model.get_state_order()):
+            raise ValueError("observables must be all modeled states (mcmc.py:393-395, 772-775)")
+        self.priors = []
+        for name in model.get_parameter_order():
+            pr = model.parameters[name].prior
+            if isinstance(pr, dict):
+                pr = _priors.from_dict(pr)
+            if pr is None:
+                raise ValueError(f"Parameter '{name}' has no prior")
+            self.priors.append((name, pr))
+        rank, world = parallel.world()
+        self.rank, self.world = rank, world
+        M = data.shape[0]
+        lo, hi = parallel.shard_bounds(M, rank, world) if shard == "series" else (0, M)
+        self._series = slice(lo, hi)
+        self._arrays = tuple(np.asarray(a, dtype=self.dtype)[lo:hi] for a in (data, times, y0s, constants))
+        self.mask = np.isfinite(self._arrays[0])                       # mcmc.py:566
+        self.yerrs = np.broadcast_to(np.asarray(yerrs, dtype=np.float64), data.shape[-1:]).copy()
+        spec = model._replace_assignments().sim_input.field_spec()
+        self.field = cg.generate_field(spec, sens_theta=True, sens_y0=estimate_initials)
+        self._engine = engine
+        self._compiled = None
+        self._dev_arrays = None
+        self._device = device
+
+    # ------------------------------------------------------------------ likelihood block
+    def _local_loglik(self, theta, sigma):
+        """[CH, 1+P+S] (log L, dlogL/dtheta, dlogL/dsigma) over THIS rank's series (CUDA)."""
+        import torch
+
+        if self._compiled is None:
+            self._compiled = self._engine.CompiledModel(self.field, np.dtype(self.dtype).name)
+            dev = theta.device
+            data, times, y0s, constants = self._arrays
+            tt = lambda a: torch.as_tensor(a, device=dev)
+            self._dev_arrays = (tt(y0s), tt(constants), tt(times), tt(np.nan_to_num(data)),
+                                tt(self.mask.astype(np.uint8)))
+        y0s, constants, times, data, mask = self._dev_arrays
+        if y0s.shape[0] == 0:
+            return torch.zeros((theta.shape[0], 1 + self.field.P + self.field.S),
+                               dtype=theta.dtype, device=theta.device)
+        cfg = self.config
+        out, self._partial, self._status = self._compiled.loglik_grad(
+            y0s, theta, constants, times, data, sigma, mask=mask, likelihood=self.likelihood,
+            solver=solver_name(cfg.solver), rtol=cfg.rtol, atol=cfg.atol, dt0=cfg.dt0,
+            max_steps=cfg.max_steps)
+        return out
+
+    def log_likelihood(self, theta, sigma):
+        """Likelihood block summed over ALL series (all-reduced when series are sharded)."""
+        from .. import parallel
+
+        block = self._local_loglik(theta, sigma)
+        if self.shard == "series":
+            parallel.allreduce_sum_(block)
+        return block
+
+    # ------------------------------------------------------------------ log joint
+    def log_density(self, theta, sigma):
+        """theta [CH,P], sigma [CH,S] (torch, on the GPU) ->
+        (logp [CH], dlogp/dtheta [CH,P], dlogp/dsigma [CH,S])."""
+        import torch
+
+        block = self.log_likelihood(theta, sigma)
+        P = self.field.P
+        logp = block[:, 0].clone()
+        g_theta = block[:, 1:1 + P].clone()
+        g_sigma = block[:, 1 + P:].clone()
+        for j, (_name, prior) in enumerate(self.priors):
+            logp += prior.log_prob(theta[:, j])
+            g_theta[:, j] += prior.grad(theta[:, j])
+        hint = torch.as_tensor(self.yerrs, dtype=sigma.dtype, device=sigma.device)
+        if self.error_model.sampled:
+            logp += self.error_model.log_prob(sigma, hint.expand_as(sigma))
+            g_sigma += self.error_model.grad(sigma, hint.expand_as(sigma))
+        return logp, g_theta, g_sigma
+
+    __call__ = log_density

@@ -105,6 +105,37 @@ int ctx_solve_sens(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
                    int32_t* n_accepted, int32_t* n_rejected, void* workspace, size_t ws_bytes,
                    void* stream);
 
+/* ---- K2: fused log-likelihood + gradient ---------------------------------------------------
+ * Replaces value_and_grad of the numpyro model body, catalax/mcmc/mcmc.py:405-491:
+ *   states = sim_func(y0s, theta, constants, times)            (:448, in_axes=(0,None,0,0) :860)
+ *   log L  = sum over mask of log likelihood(data; loc = states[..., observables],
+ *                                            scale = sqrt(sigma_y**2))         (:461-491)
+ * for `n_chains` independent (theta, sigma_y) pairs at once over the same M series.
+ * The model must have been generated with parameter directions (and, to get d/dy0, initial
+ * value directions).  Shapes (device pointers, model dtype):
+ *   y0s [M,S]  theta [CH,P]  consts [M,C]  ts [M,T]  data [M,T,S]  mask [M,T,S] uint8 or NULL
+ *   (NULL = isfinite(data), mcmc.py:566)  sigma [CH,S]
+ *   out [CH, 1 + D_theta + S] = (log L, dlogL/dtheta, dlogL/dsigma_y) summed over the M series
+ *   partial [CH*M, 1 + D_theta + S + D_y0]: per-(chain, series) rows; its last D_y0 columns are
+ *   dlogL/dy0 of that series (init_estimator.py:47-58).  partial may be NULL (kept in workspace).
+ * Series-sharded multi-GPU runs all-reduce `out` (sum) across ranks; chain-sharded runs need no
+ * collective.  Prior terms (priors.py, error.py) are scalar and stay on the host side. */
+typedef struct ctx_loglik_cfg {
+  int32_t solver;
+  int32_t likelihood; /* CTX_LIK_NORMAL | CTX_LIK_SOFTLAPLACE */
+  int64_t n_chains;   /* CH */
+  int32_t n_series;   /* M */
+  int32_t n_times;    /* T */
+  int32_t max_steps;
+  int32_t reserved;
+  double rtol, atol, dt0;
+} ctx_loglik_cfg;
+size_t ctx_loglik_workspace_bytes(const ctx_model* m, const ctx_loglik_cfg* cfg);
+int ctx_loglik_grad(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, const void* theta,
+                    const void* consts, const void* ts, const void* data, const uint8_t* mask,
+                    const void* sigma, void* out, void* partial, int32_t* status, void* workspace,
+                    size_t ws_bytes, void* stream);
+
 /* ---- host-buffer convenience (the call a reference-side ctypes binding would make) --------
  * Same as ctx_solve but every array is a HOST pointer; device staging, the H2D / D2H copies
  * and one stream synchronisation happen inside. */

@@ -1,0 +1,78 @@
+"""CPU restatement of the NUTS log-likelihood and its gradient.  PARITY ORACLE (test infra).
+
+Follows ``catalax/mcmc/mcmc.py:405-491`` (``BayesianModel.__call__``):
+
+    states = sim_func(y0s, theta, constants, times)      # :448, in_axes=(0, None, 0, 0) (:860)
+    loc = states[..., observables]                        # :461, observables = all modeled states
+    sigma_total = sigma_y ** 2                            # :483
+    with mask(mask): sample("y", likelihood(loc, sqrt(sigma_total)), obs=data)   # :486-491
+
+and numpyro 0.19's distributions (un-vendored dependency, ``pyproject.toml:17``):
+``Normal.log_prob = -((x-loc)/s)^2/2 - log s - log sqrt(2 pi)`` and
+``SoftLaplace.log_prob = log(2/pi) - log s - logaddexp(z, -z)``, ``z = (x-loc)/s``.
+The gradient is what ``jax.value_and_grad`` of that log-density gives: the chain rule through
+the discrete tangents of the solve (``diffrax_oracle.solve`` with ``n_err``), ``d/dsigma``
+through ``s = sqrt(sigma^2)``.  PARITY UNPINNED against numpyro itself (the reference asserts
+no log-density or gradient value anywhere); pinned against finite differences of
+the frozen-step oracle and closed-form sensitivities in tests/.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import diffrax_oracle as do, symbolic as sy
+
+
+def logpdf_terms(x, loc, s, likelihood):
+    z = (x - loc) / s
+    if likelihood == "normal":
+        lp = -0.5 * z * z - np.log(s) - 0.5 * np.log(2 * np.pi)
+        dl_dloc = z / s
+        dl_ds = (z * z - 1.0) / s
+    elif likelihood == "softlaplace":
+        lp = np.log(2 / np.pi) - np.log(s) - np.logaddexp(z, -z)
+        dl_dloc = np.tanh(z) / s
+        dl_ds = (z * np.tanh(z) - 1.0) / s
+    else:
+        raise ValueError(likelihood)
+    return lp, dl_dloc, dl_ds
+
+
+def loglik_grad(model, y0s, theta, consts, ts, data, sigma, *, mask=None,
+                likelihood="softlaplace", sens_y0=False, dtype=np.float64, **solve_kw):
+    """model = (states, parameters, constants, odes, reactions); theta [CH,P]; sigma [CH,S].
+
+    Returns out [CH, 1+P+S], grad_y0 [CH, M, S] (zeros unless sens_y0), status [CH, M].
+    """
+    states, params, consts_n, odes, reactions = model
+    S, P = len(states), len(params)
+    rhs, N, D, init_aug = sy.make_rhs(states, params, consts_n, odes, reactions, sens_theta=True,
+                                      sens_y0=sens_y0)
+    y0s = np.asarray(y0s, dtype=dtype); ts = np.asarray(ts, dtype=dtype)
+    data = np.asarray(data, dtype=dtype); consts = np.asarray(consts, dtype=dtype)
+    M, T = ts.shape
+    if mask is None:
+        mask = np.isfinite(data)
+    CH = theta.shape[0]
+    out = np.zeros((CH, 1 + P + S), dtype=np.float64)
+    gy0 = np.zeros((CH, M, S), dtype=np.float64)
+    status = np.zeros((CH, M), dtype=np.int32)
+    for ch in range(CH):
+        r = do.solve(rhs, y0s, np.asarray(theta[ch], dtype=dtype), consts, ts, dtype=dtype,
+                     n_err=S, init_aug=init_aug(M, dtype), **solve_kw)
+        status[ch] = r.status
+        ys = r.ys[..., :S].astype(np.float64)
+        tang = r.ys[..., S:].astype(np.float64).reshape(M, T, D, S)   # [M,T,dir,state]
+        s = np.abs(np.asarray(sigma[ch], dtype=np.float64))
+        with np.errstate(all="ignore"):
+            lp, dl_dloc, dl_ds = logpdf_terms(np.where(mask, data, 0.0).astype(np.float64), ys,
+                                              s[None, None, :], likelihood)
+            out[ch, 0] = np.where(mask, lp, 0.0).sum()
+            w = np.where(mask, dl_dloc, 0.0)
+            for p in range(P):
+                out[ch, 1 + p] = (w * tang[:, :, p, :]).sum()
+            out[ch, 1 + P:] = (np.where(mask, dl_ds, 0.0) * np.sign(sigma[ch])[None, None, :]).sum(axis=(0, 1))
+            if sens_y0:
+                for i in range(S):
+                    gy0[ch, :, i] = (w * tang[:, :, P + i, :]).sum(axis=(1, 2))
+    return out, gy0, status

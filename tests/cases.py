@@ -75,3 +75,14 @@ def mm_inputs(B, seed=0, dtype=np.float64, km_range=(0.5, 50.0)):
     kc = np.exp(rng.uniform(np.log(0.02), np.log(0.5), B))
     theta = np.stack([Km, kc], axis=1).astype(dtype)
     return y0, theta, np.zeros((B, 0), dtype=dtype)
+
+
+def mm_closed_form(t, s0, V, K):
+    """S(t) of dS/dt = -V S/(K+S): u = S/K solves u + ln u = ln(s0/K) + (s0 - V t)/K
+    (Lambert W written so that it cannot overflow for small K)."""
+    L = np.log(s0 / K) + (s0 - V * np.asarray(t, dtype=np.float64)) / K
+    u = np.where(L > 1.0, L - np.log(np.maximum(L, 1.0)), np.exp(np.minimum(L, 1.0)))
+    for _ in range(60):
+        u = np.maximum(u, 1e-300)
+        u = u - (u + np.log(u) - L) / (1.0 + 1.0 / u)
+    return K * np.maximum(u, 0.0)

@@ -1,0 +1,94 @@
+"""The CUDA code generator, checked on the CPU: the generated field is compiled as host C++
+and compared with the oracle's independent sympy.lambdify evaluation (reference semantics of
+catalax/tools/stack.py + symbolicmodule.py)."""
+import numpy as np
+import pytest
+import sympy as sp
+
+from catalax_b200.tools import codegen as cg
+from oracle import symbolic as sy
+from tests import cases
+from tests.host_field import HostField
+
+MODELS = {
+    "mm": cases.michaelis_menten,
+    "menten_fixture": cases.menten_fixture,
+    "nonautonomous": cases.nonautonomous,
+    "mass_action_8": lambda: cases.mass_action_network(8),
+    "mass_action_32": lambda: cases.mass_action_network(32),
+}
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_generated_rhs_matches_lambdify(name):
+    model = MODELS[name]()
+    states, params, consts, odes, reactions = model
+    field = cg.generate_field(cases.field_spec(model))
+    hf = HostField(field)
+    rhs, *_ = sy.make_rhs(states, params, consts, odes, reactions)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        y = rng.uniform(0.1, 2.0, len(states)); th = rng.uniform(0.1, 1.5, len(params))
+        c = rng.uniform(0.1, 1.0, len(consts)); y0 = rng.uniform(0.1, 2.0, len(states))
+        t = rng.uniform(0, 3)
+        want = rhs(np.array([t]), y[None], th[None], c[None], y0[None])[0]
+        got = hf.rhs(t, y, th, c, y0)
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["mm", "nonautonomous", "mass_action_8"])
+def test_generated_tangent_field_matches_lambdify(name):
+    model = MODELS[name]()
+    states, params, consts, odes, reactions = model
+    S = len(states)
+    field = cg.generate_field(cases.field_spec(model), sens_theta=True, sens_y0=True)
+    assert field.D == len(params) + S and field.n_theta_dirs == len(params)
+    hf = HostField(field)
+    rhs, N, D, _ = sy.make_rhs(states, params, consts, odes, reactions, sens_theta=True, sens_y0=True)
+    rng = np.random.default_rng(1)
+    y = rng.uniform(0.1, 2.0, S); th = rng.uniform(0.1, 1.5, len(params))
+    c = rng.uniform(0.1, 1.0, len(consts)); y0 = rng.uniform(0.1, 2.0, S)
+    s = rng.normal(size=S * D)
+    Y = np.concatenate([y, s])
+    want = rhs(np.array([0.7]), Y[None], th[None], c[None], y0[None])[0]
+    dy, ds = hf.tan(0.7, y, s, th, c, y0)
+    np.testing.assert_allclose(dy, want[:S], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(ds, want[S:], rtol=1e-12, atol=1e-14)
+
+
+def test_stack_golden_values_through_the_generator():
+    """tests/unit/simulation/test_stack.py of the reference, through the CUDA generator."""
+    k1, k2, k3, s1, s2 = 1.0, 2.0, 3.0, 1.0, 2.0
+    r1 = ("r1", [(1.0, "s1")], [(1.0, "s2")], sp.sympify("k1 * s1"))
+    r2 = ("r2", [(1.0, "s2")], [(1.0, "s1")], sp.sympify("k2 * s2"))
+    f = cg.generate_field(cg.FieldSpec(["s1", "s2"], ["k1", "k2", "k3"], [], {"s1": sp.Symbol("k3")}, [r1, r2]))
+    np.testing.assert_allclose(HostField(f).rhs(1.0, [s1, s2], [k1, k2, k3], [], [s1, s2]),
+                               [-k1 * s1 + k2 * s2 + k3, k1 * s1 - k2 * s2])
+    f = cg.generate_field(cg.FieldSpec(["s1", "s2"], ["k1", "k2"], [], {}, [r1, r2]))
+    np.testing.assert_allclose(HostField(f).rhs(1.0, [s1, s2], [k1, k2], [], [s1, s2]),
+                               [-k1 * s1 + k2 * s2, k1 * s1 - k2 * s2])
+
+
+def test_operator_table_coverage():
+    """Every op of symbolicmodule.py:52-98 that makes sense for a scalar field prints."""
+    x, y, p = sp.symbols("x y p")
+    exprs = [sp.Abs(x - y), sp.sign(x - 1), sp.ceiling(x), sp.floor(y), sp.log(x + 1), sp.exp(-x),
+             sp.sqrt(x + y), sp.cos(x), sp.acos(x / 4), sp.sin(x), sp.asin(x / 4), sp.tan(x / 4),
+             sp.atan(x), sp.atan2(x, y), sp.cosh(x / 3), sp.acosh(x + 1), sp.sinh(x / 3),
+             sp.asinh(x), sp.tanh(x), sp.atanh(x / 4), x ** p, x ** -2, x ** sp.Rational(3, 2),
+             sp.erf(x), sp.Max(x, y, p), sp.Min(x, y), sp.Rational(2, 3) * x, sp.pi * x]
+    spec = cg.FieldSpec([f"s{i}" for i in range(len(exprs))], ["p"], [], {}, [])
+    names = {sp.Symbol("x"): sp.Symbol("s0"), sp.Symbol("y"): sp.Symbol("s1")}
+    spec.odes = {f"s{i}": e.xreplace(names) for i, e in enumerate(exprs)}
+    field = cg.generate_field(spec)
+    hf = HostField(field)
+    yv = np.linspace(0.6, 1.9, len(exprs)); th = np.array([1.3])
+    got = hf.rhs(0.0, yv, th, [], yv)
+    for i, e in enumerate(exprs):
+        want = float(e.xreplace(names).subs({sp.Symbol("s0"): yv[0], sp.Symbol("s1"): yv[1], p: th[0]}).evalf())
+        assert abs(got[i] - want) <= 1e-12 * max(1, abs(want)), (e, got[i], want)
+
+
+def test_missing_symbol_raises_like_the_reference():
+    with pytest.raises(KeyError, match="Missing input for symbol"):
+        cg.generate_field(cg.FieldSpec(["S"], ["k"], [], {"S": -sp.Symbol("k") * sp.Symbol("E") * sp.Symbol("S")}, []))

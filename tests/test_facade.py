@@ -1,0 +1,153 @@
+"""Host-side mirror of the reference's model / dataset interface (no GPU needed).
+Covers the ordering rules (model.py:882-999), scheme parser (reaction.py:31-181),
+parameter inference (equation.py:48-89), assignment inlining (model.py:788-820), dataset
+array export (dataset.py:390-451) and the stoichiometry conventions (stoich.py)."""
+import numpy as np
+import pytest
+import sympy as sp
+
+import catalax_b200 as ctx
+from catalax_b200.model.model import Reaction, resolve_assignments
+
+
+def _mm():
+    m = ctx.Model(name="MM")
+    m.add_state(S="Substrate", E="Enzyme", P="Product")
+    m.add_ode("S", "-k_cat * E * S / (K_m + S)")
+    m.add_ode("P", "k_cat * E * S / (K_m + S)")
+    m.add_ode("E", "0")
+    return m
+
+
+def test_ordering_is_python_sorted():
+    m = _mm()
+    assert m.get_state_order() == ["E", "P", "S"]           # 'E' < 'P' < 'S'
+    assert m.get_parameter_order() == ["K_m", "k_cat"]       # 'K' < 'k' (ASCII)
+    assert m.get_constants_order() == []
+    assert m.get_observable_state_order() == ["E", "P", "S"]
+    assert m.get_state_order(as_indices=True) == [0, 1, 2]
+
+
+def test_sympy_shadowed_names_parse_as_symbols():
+    m = _mm()
+    assert m.odes["S"].equation.free_symbols == {sp.Symbol(n) for n in ("k_cat", "E", "S", "K_m")}
+
+
+def test_parameter_inference_and_attribute_access():
+    m = _mm()
+    m.parameters.K_m.value = 0.05
+    m.parameters["k_cat"].value = 0.1
+    assert m.n_parameters() == 2
+    np.testing.assert_allclose(m._get_parameters(), [0.05, 0.1])
+    m2 = ctx.Model(name="x")
+    m2.add_state("a")
+    m2.add_ode("a", "k*a")
+    with pytest.raises(ValueError, match="Missing values for parameters: k"):
+        m2._get_parameters()
+    with pytest.raises(ValueError, match="already exists an ODE"):
+        m2.add_ode("a", "k")
+
+
+def test_constants_and_init_symbols():
+    m = ctx.Model(name="c")
+    m.add_state(s="Substrate", p="Product")
+    m.add_constant(e="Enzyme")
+    m.add_constant(s_init="Initial substrate")
+    m.add_ode("s", "-k*e*s")
+    m.add_ode("p", "s_init")
+    assert m.get_constants_order() == ["e"]
+    assert "s_init" not in m.parameters and "e" not in m.parameters
+    assert "s" in m.odes["p"].inits
+    with pytest.raises(ValueError, match="not found in the model for initial value"):
+        m.add_ode("q", "zz_init")
+
+
+def test_scheme_parser():
+    r = Reaction.from_scheme("r1", "2 H2 + O2 <=> 2 H2O", "k*H2*O2", True)
+    assert [(e.stoichiometry, e.state) for e in r.reactants] == [(2.0, "H2"), (1.0, "O2")]
+    assert [(e.stoichiometry, e.state) for e in r.products] == [(2.0, "H2O")]
+    for arrow in ("->", "<->", "=>", "<=>", "<==>", "<===>", ">"):
+        rr = Reaction.from_scheme("r", f"A {arrow} B", "k*A", False)
+        assert rr.reactants[0].state == "A" and rr.products[0].state == "B"
+    with pytest.raises(ValueError, match="No supported arrow"):
+        Reaction.from_scheme("r", "A B", "k", False)
+    with pytest.raises(ValueError, match="at least one reactant"):
+        Reaction.from_scheme("r", " -> B", "k", False)
+    with pytest.raises(ValueError, match="not found in states"):
+        Reaction.from_scheme("r", "A -> Z", "k", False, states=["A", "B"])
+
+
+def test_reaction_model_field_and_mixed_rule():
+    m = ctx.Model(name="r")
+    m.add_state("s1, s2")
+    m.add_reaction("s1 -> s2", symbol="r1", equation="k1 * s1")
+    m.add_reaction("s2 -> s1", symbol="r2", equation="k2 * s2")
+    assert m.sim_input.type == "reaction"
+    m.add_ode("s1", "k3")
+    assert m.sim_input.type == "mixed"
+    exprs = m.sim_input.field_spec().total_exprs()
+    k1, k2, k3, s1, s2 = sp.symbols("k1 k2 k3 s1 s2")
+    assert sp.simplify(exprs[0] - (-k1 * s1 + k2 * s2 + k3)) == 0
+    assert sp.simplify(exprs[1] - (k1 * s1 - k2 * s2)) == 0
+    with pytest.raises(ValueError, match="Cannot specify both"):
+        m.add_reaction("s1 -> s2", symbol="r3", reactants=[(1, "s1")], equation="k")
+    with pytest.raises(ValueError, match="not found in model"):
+        m.add_reaction(symbol="r4", reactants=[(1, "zz")], products=[(1, "s1")], equation="k")
+
+
+def test_assignment_inlining():
+    out = resolve_assignments({"a": sp.sympify("b + 1"), "b": sp.sympify("2*c"), "c": sp.sympify("k")})
+    assert out["a"] == sp.sympify("2*k + 1")
+    with pytest.raises(ValueError):
+        resolve_assignments({"a": sp.sympify("b"), "b": sp.sympify("a")})
+    m = ctx.Model(name="a")
+    m.add_state("s, p")
+    m.add_assignment("rate", "vmax * s / (km + s)")
+    m.add_ode("s", "-rate")
+    m.add_ode("p", "rate")
+    assert m.get_parameter_order() == ["km", "vmax"]
+    inl = m._replace_assignments()
+    assert sp.Symbol("rate") not in inl.odes["s"].equation.free_symbols
+    assert sp.Symbol("rate") in m.odes["s"].equation.free_symbols  # original untouched
+
+
+def test_dataset_array_export_and_roundtrip():
+    m = _mm()
+    ds = ctx.Dataset.from_model(m)
+    ds.add_initial(S=100.0, E=10.0, P=0.0)
+    ds.add_initial(S=200.0, E=10.0, P=0.0)
+    y0 = ds.to_y0_matrix(m.get_state_order())
+    np.testing.assert_array_equal(y0, [[10.0, 0.0, 100.0], [10.0, 0.0, 200.0]])
+    assert ds.to_y0_matrix(m.get_constants_order()).shape == (2, 0)
+    assert y0.dtype == np.float32
+    data = np.arange(2 * 5 * 3, dtype=np.float32).reshape(2, 5, 3)
+    time = np.tile(np.linspace(0, 1, 5, dtype=np.float32), (2, 1))
+    d2 = ctx.Dataset.from_jax_arrays(m.get_state_order(), data, time, y0)
+    dd, tt, ii = d2.to_jax_arrays(m.get_state_order(), inits_to_array=True)
+    np.testing.assert_array_equal(dd, data)
+    np.testing.assert_array_equal(tt, time)
+    np.testing.assert_array_equal(ii, y0)
+    cfg = d2.to_config(nsteps=7)
+    np.testing.assert_array_equal(cfg.t1, [1.0, 1.0])
+
+
+def test_inaxes_and_config_defaults():
+    assert ctx.InAxes.Y0.value == (0, None, 0, None)
+    assert ctx.InAxes.Y0 + ctx.InAxes.TIME == (0, None, 0, 0)
+    assert ctx.INITS is ctx.InAxes.Y0 and ctx.PARAMETERS is ctx.InAxes.PARAMETERS
+    c = ctx.SimulationConfig(t1=10)
+    assert (c.nsteps, c.t0, c.dt0, c.rtol, c.atol, c.max_steps, c.throw) == (None, 0, 0.1, 1e-5, 1e-5, 4096, True)
+    assert c.solver is ctx.Tsit5
+
+
+def test_reference_model_json_loads():
+    from pathlib import Path
+
+    m = ctx.Model.load(Path(__file__).parent / "golden" / "reference_fixtures" / "uode_model.json")
+    assert m.get_state_order() == ["s0", "s1", "s2", "s3"]
+    assert len(m.get_parameter_order()) == 10
+    spec = m._replace_assignments().sim_input.field_spec()
+    from catalax_b200.tools import codegen as cg
+
+    f = cg.generate_field(spec)
+    assert f.S == 4 and f.P == 10 and f.C == 1 and f.uses_t

@@ -165,3 +165,42 @@ def test_max_steps_failure_fills_inf(kernel):
     assert np.isinf(ys).any() and np.isfinite(ys[0, 0]).all()
     fin = np.isfinite(ref.ys)
     np.testing.assert_allclose(ys[fin], ref.ys[fin], rtol=1e-9)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("solver", ["tsit5", "dopri5", "heun"])
+def test_sensitivities_match_oracle_f64(solver, kernel):
+    """ctx_solve_sens = vmap(jax.jacobian(solve)) (simulation.py:279-323): discrete tangents
+    w.r.t. parameters and initial values, layout [B,T,S,D]."""
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+    from oracle import diffrax_oracle as do, symbolic as sy
+
+    model = cases.nonautonomous()
+    states, params, consts_n, odes, reactions = model
+    rng = np.random.default_rng(8)
+    B, S, P = 96, 4, 3
+    y0 = rng.uniform(0.3, 1.5, (B, S)); th = rng.uniform(0.2, 0.9, (B, P))
+    c = rng.uniform(0.0, 0.4, (B, 1)); ts = np.linspace(0, 5, 11)
+    dt0 = 0.1 if solver != "heun" else 0.02
+    kw = dict(solver=solver, rtol=1e-6, atol=1e-8, dt0=dt0, max_steps=100000)
+    rhs, N, D, init_aug = sy.make_rhs(states, params, consts_n, odes, reactions, sens_theta=True,
+                                      sens_y0=True)
+    ref = do.solve(rhs, y0, th, c, ts, dtype=np.float64, n_err=S, init_aug=init_aug(B, np.float64), **kw)
+    field = cg.generate_field(cases.field_spec(model), sens_theta=True, sens_y0=True)
+    m = engine.CompiledModel(field, "float64")
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    out = m.solve(tt(y0), tt(th), tt(c), tt(ts), in_axes=(0, 0, 0, None), tangents=True,
+                  kernel=kernel, **kw)
+    torch.cuda.synchronize()
+    ys, sens = out.ys.cpu().numpy(), out.sens.cpu().numpy()
+    assert sens.shape == (B, len(ts), S, P + S)
+    np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
+    _assert_close_f64(ys, ref.ys[..., :S], atol=1e-8)
+    ref_sens = ref.ys[..., S:].reshape(B, len(ts), D, S).transpose(0, 1, 3, 2)
+    scale = np.abs(ref_sens) + 1e-6 * np.abs(ref_sens).max()
+    assert (np.abs(sens - ref_sens) <= 1e-6 * scale).all()
+    # initial values: d y(0) / d y0 = identity, d y(0) / d theta = 0
+    np.testing.assert_array_equal(sens[:, 0, :, P:], np.broadcast_to(np.eye(S), (B, S, S)))
+    np.testing.assert_array_equal(sens[:, 0, :, :P], 0.0)

@@ -1,0 +1,157 @@
+"""The reference's own simulate tests (tests/integration/test_simulation.py), run unchanged in
+spirit through the drop-in facade on the GPU: same model-building calls, same asserts."""
+import numpy as np
+import pytest
+
+import catalax_b200 as ctx
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOLERANCE = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _f32_default():
+    ctx.enable_x64(False)
+    yield
+    ctx.enable_x64(False)
+
+
+def test_simulation():
+    model = ctx.Model(name="ExponentialGrowthModel")
+    model.add_state(s1="Substrate")
+    model.add_constant(e="Enzyme")
+    model.add_ode("s1", "e * s1 * q")
+    model.parameters["q"].value = 1.0
+    dataset = ctx.Dataset.from_model(model)
+    dataset.add_initial(s1=1.0, e=1.0)
+    dataset.add_initial(s1=1.0, e=2.0)
+    config = ctx.SimulationConfig(nsteps=3, t0=0, t1=3)
+    sim = model.simulate(dataset=dataset, config=config)
+    assert len(sim.measurements) == len(dataset.measurements)
+    assert np.abs(sim.measurements[0].data["s1"] - np.array([1.0, 4.481674, 20.08544])).sum() < TOLERANCE
+    assert sim.measurements[0].time.tolist() == [0.0, 1.5, 3.0]
+    assert sim.measurements[0].initial_conditions == {"s1": 1.0, "e": 1.0}
+    got2 = sim.measurements[1].data["s1"]
+    gold2 = np.array([1.0, 20.085447, 403.42603])
+    # see tests/test_oracle_golden.py: the golden 403.42603 is one f32 step path of diffrax
+    assert np.abs(got2 - gold2).sum() < 1.5 * TOLERANCE
+    assert (np.abs(got2 / gold2 - 1) < 2e-5).all()
+    assert sim.measurements[1].time.tolist() == [0.0, 1.5, 3.0]
+    assert sim.measurements[1].initial_conditions == {"s1": 1.0, "e": 2.0}
+
+
+def test_simulation_with_init_symbol():
+    model = ctx.Model(name="InitReuseModel")
+    model.add_state(s="Substrate", p="Product")
+    model.add_ode("s", "-k * s")
+    model.add_ode("p", "s_init")
+    model.parameters["k"].value = 1.0
+    assert "s" in model.odes["p"].inits
+    assert "s_init" not in model.parameters
+    dataset = ctx.Dataset.from_model(model)
+    dataset.add_initial(s=2.0, p=0.0)
+    dataset.add_initial(s=5.0, p=0.0)
+    sim = model.simulate(dataset=dataset, config=ctx.SimulationConfig(nsteps=4, t0=0, t1=3))
+    times = np.array([0.0, 1.0, 2.0, 3.0])
+    assert np.abs(sim.measurements[0].data["p"] - 2.0 * times).sum() < TOLERANCE
+    assert np.abs(sim.measurements[1].data["p"] - 5.0 * times).sum() < TOLERANCE
+    assert np.abs(sim.measurements[0].data["s"] - 2.0 * np.exp(-times)).sum() < TOLERANCE
+
+
+def test_init_symbol_declared_as_constant():
+    model = ctx.Model(name="InitConstantModel")
+    model.add_state(s="Substrate", p="Product")
+    model.add_constant(s_init="Initial substrate")
+    model.add_assignment(symbol="rate", equation="k * s_init")
+    model.add_ode("s", "-rate")
+    model.add_ode("p", "rate")
+    model.parameters["k"].value = 0.5
+    assert "s_init" not in model.get_constants_order()
+    assert model.get_constants_order() == []
+    dataset = ctx.Dataset.from_model(model)
+    dataset.add_initial(s=2.0, p=0.0)
+    dataset.add_initial(s=4.0, p=0.0)
+    assert dataset.to_y0_matrix(state_order=model.get_constants_order()).shape == (2, 0)
+    sim = model.simulate(dataset=dataset, config=ctx.SimulationConfig(nsteps=4, t0=0, t1=2))
+    times = np.linspace(0, 2, 4)
+    for i, s_init in enumerate([2.0, 4.0]):
+        assert np.abs(sim.measurements[i].data["p"] - 0.5 * s_init * times).sum() < TOLERANCE
+
+
+@pytest.mark.parametrize("x64", [False, True])
+def test_readme_model_config1(x64):
+    """BASELINE configs[0]: README Michaelis-Menten, 2 initial conditions, t1=100 nsteps=1000,
+    checked against the closed form (Lambert W) and the oracle."""
+    from tests import cases
+
+    ctx.enable_x64(x64)
+    model = ctx.Model(name="Michaelis-Menten")
+    model.add_state(S="Substrate", E="Enzyme", P="Product")
+    model.add_ode("S", "-k_cat * E * S / (K_m + S)")
+    model.add_ode("P", "k_cat * E * S / (K_m + S)")
+    model.add_ode("E", "0")
+    model.parameters.K_m.value = 0.05
+    model.parameters.k_cat.value = 0.1
+    assert model.get_state_order() == ["E", "P", "S"]
+    assert model.get_parameter_order() == ["K_m", "k_cat"]
+    dataset = ctx.Dataset.from_model(model)
+    dataset.add_initial(S=100.0, E=10.0, P=0.0)
+    dataset.add_initial(S=200.0, E=10.0, P=0.0)
+    config = ctx.SimulationConfig(t1=100, nsteps=1000)
+    ts, ys = model.simulate(dataset, config, return_array=True)
+    ys = np.asarray(ys, dtype=np.float64)
+    assert ys.shape == (2, 1000, 3)
+    t = np.linspace(0, 100, 1000)
+    for row, s0 in enumerate([100.0, 200.0]):
+        K, V = 0.05, 0.1 * 10.0
+        exact = cases.mm_closed_form(t, s0, V, K)
+        assert np.abs(ys[row, :, 2] - exact).max() < (2e-3 if not x64 else 1e-3)
+        np.testing.assert_allclose(ys[row, :, 0], 10.0, rtol=1e-6)
+        np.testing.assert_allclose(ys[row, :, 1] + ys[row, :, 2], s0, rtol=1e-5)
+    sim = model.simulate(dataset, config)
+    assert len(sim.measurements) == 2 and sim.measurements[0].data["S"].shape == (1000,)
+
+
+def test_throw_true_raises_and_throw_false_gives_inf():
+    from catalax_b200.tools.simulation import SolveError
+
+    ctx.enable_x64(True)
+    model = ctx.Model(name="stiff")
+    model.add_state("S")
+    model.add_ode("S", "-k * S")
+    model.parameters.k.value = 1000.0
+    dataset = ctx.Dataset.from_model(model)
+    dataset.add_initial(S=1.0)
+    with pytest.raises(SolveError, match="maximum number of solver steps"):
+        model.simulate(dataset, ctx.SimulationConfig(t1=100, nsteps=5, max_steps=64))
+    model.reset()
+    ts, ys = model.simulate(dataset, ctx.SimulationConfig(t1=100, nsteps=5, max_steps=64, throw=False),
+                            return_array=True)
+    assert np.isfinite(ys[0, 0, 0]) and np.isinf(ys[0, -1, 0])
+
+
+def test_reaction_model_and_time_axis():
+    """Reaction form (ReactionStack semantics) + per-measurement time grids (InAxes.TIME)."""
+    ctx.enable_x64(True)
+    model = ctx.Model(name="rev")
+    model.add_state("A, B")
+    model.add_reaction("A -> B", symbol="r1", equation="k1 * A")
+    model.add_reaction("B -> A", symbol="r2", equation="k2 * B")
+    model.parameters.k1.value = 0.7
+    model.parameters.k2.value = 0.3
+    dataset = ctx.Dataset.from_model(model)
+    dataset.add_initial(A=1.0, B=0.0)
+    dataset.add_initial(A=0.2, B=0.8)
+    config = ctx.SimulationConfig(t0=np.array([0.0, 0.0]), t1=np.array([2.0, 4.0]), nsteps=9,
+                                  rtol=1e-9, atol=1e-9)
+    ts, ys = model.simulate(dataset, config, return_array=True)
+    ys = np.asarray(ys)
+    assert ts.shape == (2, 9) and ys.shape == (2, 9, 2)
+    for row, (a0, b0) in enumerate([(1.0, 0.0), (0.2, 0.8)]):
+        tot, k = a0 + b0, 1.0
+        a_inf = 0.3 * tot
+        a = a_inf + (a0 - a_inf) * np.exp(-k * ts[row])
+        np.testing.assert_allclose(ys[row, :, 0], a, atol=1e-7)
+        np.testing.assert_allclose(ys[row].sum(axis=1), tot, atol=1e-9)
