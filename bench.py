@@ -39,7 +39,7 @@ CPU_SAMPLE_ROWS = 1 << 18
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
@@ -287,14 +287,22 @@ def run_b200(a):
         o = step(k)
         steps_of_set.append(int((o.n_accepted.sum(dtype=torch.int64) + o.n_rejected.sum(dtype=torch.int64)).item()))
         fails += int((o.status != 0).sum().item())
-    for i in range(max(a.warmup, 3)):
-        step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.start()           # nvidia-smi needs ~100 ms to start: begin before the warm-up
+    t_w = time.perf_counter()
+    i = 0
+    while i < max(a.warmup, 3) or time.perf_counter() - t_w < 0.3:   # >= 3 steps and >= 0.3 s
+        step(i)
+        i += 1
+        if i % 8 == 0:
+            torch.cuda.synchronize()
+    n_warm = i
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.lines.clear()      # keep only samples taken from here on (timed region)
+    if world > 1:
+        dist.barrier()
     launches0 = engine.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -387,7 +395,7 @@ def run_b200(a):
             traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": max(a.warmup, 3), "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+        "warmup": a.warmup, "warmup_done": n_warm, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a), "rows_total": B * world, "saved_points": T,
                    "l2": f"outputs {B*T*S*w/1e9:.1f} GB/step >> 126 MB L2; inputs rotate over "
