@@ -82,6 +82,8 @@ struct ctx_model {
   ctx_model_desc desc;
   std::mutex mu;
   std::map<int, Variant> variants;  // key = solver*2 + tan
+  bool theta_ptr = false;           // generated with CTX_THETA_PTR (shared weights in smem)
+  int p_pad = 0;
   // host-call staging (ctx_solve_host)
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -106,7 +108,20 @@ struct SolveArgs {
   int T;
   int max_steps;
   int stride_y0, stride_theta, stride_consts, stride_ts;
+  int t0_from_ts;
   real rtol, atol, dt0;
+};
+
+template <typename real>
+struct RatesArgs {
+  const real* t;
+  const real* y;
+  const real* theta;
+  const real* consts;
+  const real* y0;
+  real* out;
+  long long N;
+  int stride_t, stride_theta, stride_consts, stride_y0;
 };
 
 // Shared memory of one warp of the persistent kernel = sizeof(ctx_warp_smem) in
@@ -123,13 +138,18 @@ size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan) {
 // Warps per CTA of the persistent kernel: 4 when that fits the default 48 KB, otherwise as many
 // as fit ~96 KB (opt-in dynamic shared memory, two CTAs per SM); 0 = a single warp's records do
 // not fit 200 KB, use the static kernel.
-int v1_warps(const ctx_model_desc& d, int solver, int tan) {
+int v1_warps(const ctx_model_desc& d, int solver, int tan, size_t fixed = 0) {
   const size_t per_warp = v1_warp_smem(d, solver, tan);
-  if (4 * per_warp <= 48 * 1024) return 4;
-  size_t warps = (96 * 1024) / per_warp;
+  if (fixed + 4 * per_warp <= 48 * 1024) return 4;
+  if (fixed >= 96 * 1024) return per_warp + fixed <= 200 * 1024 ? 1 : 0;
+  size_t warps = (96 * 1024 - fixed) / per_warp;
   if (warps > 4) warps = 4;
-  if (warps == 0 && per_warp <= 200 * 1024) warps = 1;
+  if (warps == 0 && per_warp + fixed <= 200 * 1024) warps = 1;
   return (int)warps;
+}
+
+size_t theta_smem(const ctx_model* m) {
+  return m->theta_ptr ? (size_t)m->p_pad * (m->desc.dtype == CTX_F64 ? 8 : 4) : 0;
 }
 
 int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
@@ -145,8 +165,8 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
       "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
       std::string("-DCTX_F64=") + (m->desc.dtype == CTX_F64 ? "1" : "0"),
       "-DCTX_SOLVER=" + std::to_string(solver), "-DCTX_TAN=" + std::to_string(tan),
-      "-DCTX_WARPS=" + std::to_string(std::max(1, v1_warps(m->desc, solver, tan)))};
-  if (v1_warps(m->desc, solver, tan) <= 0) opts.push_back("-DCTX_NO_V1=1");
+      "-DCTX_WARPS=" + std::to_string(std::max(1, v1_warps(m->desc, solver, tan, theta_smem(m))))};
+  if (v1_warps(m->desc, solver, tan, theta_smem(m)) <= 0) opts.push_back("-DCTX_NO_V1=1");
   const char* extra = getenv("CTX_B200_NVRTC_FLAGS");
   if (extra && *extra) {
     std::string e(extra), cur;
@@ -271,12 +291,13 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.stride_theta = cfg->in_axes[1] == 0 ? d.n_params : 0;
   a.stride_consts = cfg->in_axes[2] == 0 ? d.n_consts : 0;
   a.stride_ts = cfg->in_axes[3] == 0 ? cfg->n_times : 0;
+  a.t0_from_ts = cfg->t0_from_ts ? 1 : 0;
   a.rtol = (real)cfg->rtol;
   a.atol = (real)cfg->atol;
   a.dt0 = (real)cfg->dt0;
 
   int kernel = cfg->kernel;
-  const int warps = v1_warps(m->desc, cfg->solver, tan);
+  const int warps = v1_warps(m->desc, cfg->solver, tan, theta_smem(m));
   if (kernel == 0) kernel = warps > 0 ? 2 : 1;
   cudaKernel_t k;
   void* params[] = {&a};
@@ -289,7 +310,9 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     int dev = 0, sms = 0, per_sm = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = (size_t)warps * v1_warp_smem(m->desc, cfg->solver, tan);
+    const size_t smem = theta_smem(m) + (size_t)warps * v1_warp_smem(m->desc, cfg->solver, tan);
+    if (m->theta_ptr && a.stride_theta != 0)
+      return fail(CTX_E_INVALID, "a weight-array model takes shared parameters (in_axes[1] = None)");
     if (smem > 48 * 1024)
       CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
@@ -304,6 +327,8 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
                               stream));
     g_launches++;
   } else if (kernel == 1) {
+    if (m->theta_ptr && warps > 0)
+      return fail(CTX_E_INVALID, "weight-array models run the persistent kernel (kernel 0 or 2)");
     int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v0", &k);
     if (rc) return rc;
     const unsigned block = 128;
@@ -362,7 +387,7 @@ int launch_loglik(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, cons
   cudaKernel_t k;
   int rc = get_kernel(m, cfg->solver, 1, "ctx_loglik_v1", &k);
   if (rc) return rc;
-  const int warps = std::max(1, v1_warps(d, cfg->solver, 1));
+  const int warps = std::max(1, v1_warps(d, cfg->solver, 1, theta_smem(m)));
   const unsigned block = 32u * warps;
   int dev = 0, sms = 0, per_sm = 0;
   CTX_CUDA(cudaGetDevice(&dev));
@@ -447,6 +472,12 @@ int ctx_model_compile(const char* field_src, const ctx_model_desc* desc, ctx_mod
   ctx_model* m = new ctx_model;
   m->field_src = field_src;
   m->desc = *desc;
+  m->theta_ptr = strstr(field_src, "#define CTX_THETA_PTR 1") != nullptr;
+  if (m->theta_ptr) {
+    const char* q = strstr(field_src, "#define CTX_P_PAD ");
+    m->p_pad = q ? atoi(q + 18) : desc->n_params;
+    if (m->p_pad < desc->n_params) m->p_pad = desc->n_params;
+  }
   *out = m;
   return CTX_OK;
 }
@@ -521,6 +552,37 @@ int ctx_loglik_grad(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, co
                                  status, ws, ws_bytes, (cudaStream_t)stream);
   return launch_loglik<float>(m, cfg, y0s, theta, consts, ts, data, mask, sigma, out, partial,
                               status, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ctx_rates(ctx_model* m, int64_t n, const void* t, int32_t stride_t, const void* y,
+              const void* theta, int32_t stride_theta, const void* consts, int32_t stride_consts,
+              const void* y0, int32_t stride_y0, void* out, void* stream) {
+  if (!m || !out) return fail(CTX_E_INVALID, "null argument");
+  if (n <= 0) return CTX_OK;
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  cudaKernel_t k;
+  int rc = get_kernel(m, CTX_TSIT5, 0, "ctx_rates", &k);
+  if (rc) return rc;
+  const unsigned block = 128;
+  const unsigned long long grid = (n + block - 1) / block;
+  if (m->desc.dtype == CTX_F64) {
+    RatesArgs<double> a{(const double*)t, (const double*)y, (const double*)theta,
+                        (const double*)consts, (const double*)y0, (double*)out, n,
+                        stride_t, stride_theta, stride_consts, stride_y0};
+    void* params[] = {&a};
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0,
+                              (cudaStream_t)stream));
+  } else {
+    RatesArgs<float> a{(const float*)t, (const float*)y, (const float*)theta,
+                       (const float*)consts, (const float*)y0, (float*)out, n,
+                       stride_t, stride_theta, stride_consts, stride_y0};
+    void* params[] = {&a};
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0,
+                              (cudaStream_t)stream));
+  }
+  g_launches++;
+  return CTX_OK;
 }
 
 int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,

@@ -64,8 +64,13 @@ struct ctx_solve_args {
   int T;
   int max_steps;
   int stride_y0, stride_theta, stride_consts, stride_ts;  // elements per row, 0 = shared
+  int t0_from_ts;  // 0: integrate from t0 = 0 (simulation.py:262); 1: from ts[0] (neuralode.py:52)
   real rtol, atol, dt0;
 };
+
+#ifndef CTX_THETA_PTR
+#define CTX_THETA_PTR 0   // 1: parameters are a shared array too large for registers (MLP weights)
+#endif
 
 // ------------------------------------------------------------------ vector field
 __device__ __forceinline__ void ctx_field(const real t, const real* Y, const real* th,
@@ -285,17 +290,26 @@ __device__ __forceinline__ void ctx_store_point(const ctx_solve_args& a, const l
 
 // ------------------------------------------------------------------ kernel v0
 // One thread per trajectory, static assignment, direct stores.
+#if !CTX_THETA_PTR || defined(CTX_NO_V1)   // weight-array models only get it when v1 cannot run
+#define CTX_HAVE_V0 1
+#endif
+#ifdef CTX_HAVE_V0
 extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_args a) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
 
   real y[CTX_N], ynew[CTX_N], y0[CTX_S];
-  real th[CTX_P > 0 ? CTX_P : 1], c[CTX_C > 0 ? CTX_C : 1];
+  real c[CTX_C > 0 ? CTX_C : 1];
   real K[CTX_NST][CTX_N];
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)b * a.stride_y0 + i];
+#if CTX_THETA_PTR
+  const real* th = a.theta + (size_t)b * a.stride_theta;
+#else
+  real th[CTX_P > 0 ? CTX_P : 1];
 #pragma unroll
   for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)b * a.stride_theta + i];
+#endif
 #pragma unroll
   for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)b * a.stride_consts + i];
 #if CTX_TAN
@@ -307,7 +321,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
   const real* ts = a.ts + (size_t)b * a.stride_ts;
   const int T = a.T;
   const real t_end = ts[T - 1];
-  real tprev = R(0.0);
+  real tprev = a.t0_from_ts ? ts[0] : R(0.0);
   real tnext = fmin(tprev + a.dt0, t_end);
   int idx = 0, nacc = 0, nrej = 0, status = 0;
 
@@ -371,6 +385,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
   a.n_accepted[b] = nacc;
   a.n_rejected[b] = nrej;
 }
+#endif  // CTX_HAVE_V0
 
 // =====================================================================================
 // kernel v1: persistent warps, lane refill, warp-cooperative dense output
@@ -477,8 +492,17 @@ struct ctx_warp_smem {
 
 extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
 ctx_solve_v1(const ctx_solve_args a) {
-  extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];  // CTX_WARPS * sizeof(ctx_warp_smem)
+  // dynamic smem: [CTX_THETA_PTR ? shared parameters (CTX_P_PAD reals)] [CTX_WARPS * ctx_warp_smem]
+  extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];
+#if CTX_THETA_PTR
+  real* th_smem = reinterpret_cast<real*>(ctx_dyn_smem);
+  for (int i = threadIdx.x; i < CTX_P; i += blockDim.x) th_smem[i] = a.theta[i];
+  __syncthreads();
+  const real* th = th_smem;
+  ctx_warp_smem& w = reinterpret_cast<ctx_warp_smem*>(ctx_dyn_smem + CTX_P_PAD * sizeof(real))[threadIdx.x >> 5];
+#else
   ctx_warp_smem& w = reinterpret_cast<ctx_warp_smem*>(ctx_dyn_smem)[threadIdx.x >> 5];
+#endif
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned le_mask = CTX_FULL >> (31 - lane);
@@ -488,7 +512,10 @@ ctx_solve_v1(const ctx_solve_args a) {
   long long b = -1;           // trajectory index, -1 = lane is free
   int phase = 0;              // 0 integrating | 1 emit a fill segment then retire
   real y[CTX_N], ynew[CTX_N], y0[CTX_S];
-  real th[CTX_P > 0 ? CTX_P : 1], c[CTX_C > 0 ? CTX_C : 1];
+#if !CTX_THETA_PTR
+  real th[CTX_P > 0 ? CTX_P : 1];
+#endif
+  real c[CTX_C > 0 ? CTX_C : 1];
   real K[CTX_NST][CTX_N];
   real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
   int idx = 0, nacc = 0, nrej = 0, status = 0;
@@ -510,8 +537,10 @@ ctx_solve_v1(const ctx_solve_args a) {
           b = (long long)nb;
 #pragma unroll
           for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)b * a.stride_y0 + i];
+#if !CTX_THETA_PTR
 #pragma unroll
           for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)b * a.stride_theta + i];
+#endif
 #pragma unroll
           for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)b * a.stride_consts + i];
 #if CTX_TAN
@@ -522,7 +551,7 @@ ctx_solve_v1(const ctx_solve_args a) {
 #endif
           tsr = a.ts + (size_t)b * a.stride_ts;
           t_end = tsr[T - 1];
-          tprev = R(0.0);
+          tprev = a.t0_from_ts ? tsr[0] : R(0.0);
           tnext = fmin(tprev + a.dt0, t_end);
           idx = 0; nacc = 0; nrej = 0; status = 0;
           phase = (tprev < t_end) ? 0 : 1;  // t0 == t1: emit y0 for every requested time
@@ -750,7 +779,7 @@ ctx_solve_v1(const ctx_solve_args a) {
 //   likelihood 0: Normal       log p = -z^2/2 - log s - log(2 pi)/2
 //   likelihood 1: SoftLaplace  log p = log(2/pi) - log s - logaddexp(z, -z)   (numpyro)
 //   z = (x - loc)/s,  s = sqrt(sigma^2) = |sigma|
-#if CTX_TAN
+#if CTX_TAN && !CTX_THETA_PTR
 #define CTX_KP (1 + CTX_D_THETA + CTX_S + CTX_D_Y0)
 
 struct ctx_loglik_args {
@@ -956,4 +985,43 @@ ctx_loglik_reduce(const real* partial, real* out, const long long n_chains, cons
     if (lane == 0) out[(size_t)ch * KR + k] = (real)s;
   }
 }
-#endif  // CTX_TAN
+#endif  // CTX_TAN && !CTX_THETA_PTR
+
+
+// =====================================================================================
+// kernel K4: right-hand-side evaluation at N points (no solve)
+// =====================================================================================
+// Replaces vmap(stack) / vmap(MLP): Model._setup_rate_function (model.py:1027-1051),
+// NeuralBase.rates (neuralbase.py:319-327), the surrogate branch mcmc.py:830-833.
+struct ctx_rates_args {
+  const real* t;       // [N] or [1]
+  const real* y;       // [N,S]
+  const real* theta;   // [N,P] or [P]
+  const real* consts;  // [N,C] or [C]
+  const real* y0;      // [N,S] or [S] ("{state}_init" values) or null -> y
+  real* out;           // [N,S]
+  long long N;
+  int stride_t, stride_theta, stride_consts, stride_y0;
+};
+
+extern "C" __global__ void __launch_bounds__(128) ctx_rates(const ctx_rates_args a) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  real y[CTX_S], y0[CTX_S], dy[CTX_S], c[CTX_C > 0 ? CTX_C : 1];
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) y[i] = a.y[(size_t)n * CTX_S + i];
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) y0[i] = a.y0 ? a.y0[(size_t)n * a.stride_y0 + i] : y[i];
+#pragma unroll
+  for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)n * a.stride_consts + i];
+#if CTX_THETA_PTR
+  const real* th = a.theta + (size_t)n * a.stride_theta;
+#else
+  real th[CTX_P > 0 ? CTX_P : 1];
+#pragma unroll
+  for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)n * a.stride_theta + i];
+#endif
+  ctx_rhs(a.t[(size_t)n * a.stride_t], y, th, c, y0, dy);
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) a.out[(size_t)n * CTX_S + i] = dy[i];
+}

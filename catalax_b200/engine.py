@@ -39,7 +39,7 @@ class ctx_solve_cfg(C.Structure):
     _fields_ = [("solver", C.c_int32), ("in_axes", C.c_int32 * 4), ("batch", C.c_int64),
                 ("n_times", C.c_int32), ("max_steps", C.c_int32), ("rtol", C.c_double),
                 ("atol", C.c_double), ("dt0", C.c_double), ("kernel", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("t0_from_ts", C.c_int32)]
 
 
 class ctx_loglik_cfg(C.Structure):
@@ -83,6 +83,9 @@ def lib() -> C.CDLL:
     L.ctx_loglik_workspace_bytes.argtypes = [vp, C.POINTER(ctx_loglik_cfg)]
     L.ctx_loglik_grad.restype = C.c_int
     L.ctx_loglik_grad.argtypes = [vp, C.POINTER(ctx_loglik_cfg)] + [vp] * 11 + [C.c_size_t, vp]
+    L.ctx_rates.restype = C.c_int
+    L.ctx_rates.argtypes = [vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, vp,
+                            C.c_int32, vp, vp]
     L.ctx_solve_host.restype = C.c_int
     L.ctx_solve_host.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -148,7 +151,8 @@ class CompiledModel:
         return C.string_at(ptr, n.value)
 
     # ------------------------------------------------------------------ compute
-    def make_cfg(self, *, solver, in_axes, batch, n_times, max_steps, rtol, atol, dt0, kernel=0):
+    def make_cfg(self, *, solver, in_axes, batch, n_times, max_steps, rtol, atol, dt0, kernel=0,
+                 t0_from_ts=False):
         cfg = ctx_solve_cfg()
         cfg.solver = SOLVER_IDS[solver]
         for i, a in enumerate(in_axes):
@@ -156,11 +160,12 @@ class CompiledModel:
         cfg.batch, cfg.n_times, cfg.max_steps = int(batch), int(n_times), int(max_steps)
         cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
         cfg.kernel = int(kernel)
+        cfg.t0_from_ts = int(bool(t0_from_ts))
         return cfg
 
     def solve(self, y0, theta, consts, ts, *, solver="tsit5", in_axes=(0, None, 0, None),
               rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096, tangents=False, kernel=0,
-              out=None):
+              out=None, t0_from_ts=False):
         """Device-resident solve.  All inputs are torch CUDA tensors of this model's dtype."""
         import torch
 
@@ -186,7 +191,8 @@ class CompiledModel:
         y0 = prep(y0, S, in_axes[0]); theta = prep(theta, P, in_axes[1])
         consts = prep(consts, Cn, in_axes[2]); ts = prep(ts, T, in_axes[3])
         cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
-                            max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel)
+                            max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel,
+                            t0_from_ts=t0_from_ts)
         with torch.cuda.device(dev):
             ys = out if out is not None else torch.empty((B, T, S), dtype=tdt, device=dev)
             status = torch.empty(B, dtype=torch.int32, device=dev)
@@ -272,3 +278,28 @@ class CompiledModel:
                                          p(data), p(mask), p(sigma), p(out), p(partial), p(status),
                                          p(ws), wsb, C.c_void_p(stream)))
         return out, partial, status
+
+    def rates(self, t, y, theta, consts, y0=None):
+        """Right-hand side at N points (ctx_rates): t [N]|scalar, y [N,S], theta [N,P]|[P],
+        consts [N,C]|[C], y0 [N,S]|[S]|None.  torch CUDA tensors in, [N,S] out."""
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = y.device
+        if dev.type != "cuda":
+            raise EngineError("rates() needs CUDA tensors: catalax_b200 has no CPU fallback")
+        f = lambda x: x.to(device=dev, dtype=tdt).contiguous()
+        y = f(y)
+        N = y.shape[0]
+        t = f(torch.as_tensor(t)).reshape(-1)
+        theta, consts = f(theta), f(consts)
+        y0 = None if y0 is None else f(y0)
+        st = lambda x, w: 0 if x is None or x.dim() == 1 else w
+        out = torch.empty((N, self.field.S), dtype=tdt, device=dev)
+        p = lambda x: C.c_void_p(x.data_ptr()) if (x is not None and x.numel()) else C.c_void_p(0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _check(lib().ctx_rates(self._h, N, p(t), 1 if t.numel() > 1 else 0, p(y), p(theta),
+                                   st(theta, theta.shape[-1]), p(consts), st(consts, self.field.C),
+                                   p(y0), st(y0, self.field.S), p(out), C.c_void_p(stream)))
+        return out

@@ -1,0 +1,218 @@
+"""NeuralODE / RateFlowODE / UniversalODE forward path on the B200 engine.
+
+Mirror of the forward (predict / rates) surface of ``catalax/neural``:
+``NeuralBase.__call__`` / ``predict`` (neuralbase.py:134-143, 252-317), ``rates`` (:319-327),
+the per-class solve calls (neuralode.py:38-59, rateflow.py:100-121, universalode.py:118-141) and
+the controller defaults (neuralbase.py:623-645: rtol=1e-3, atol=1e-6).  Training (optax loop,
+back-propagation through the solver, penalties) and the .eqx serialisation are out of scope.
+
+Weights follow equinox's convention (``Linear(x) = W @ x + b``, ``W: [out, in]``); they are given
+explicitly or drawn from ``numpy.random.default_rng(seed)`` with ``N(0, 1/fan_in)``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from ..config import default_dtype
+from ..solvers import Tsit5, solver_name
+from ..tools import codegen_mlp as cm
+
+
+def _act_name(a) -> str:
+    if a is None:
+        return "identity"
+    name = a if isinstance(a, str) else getattr(a, "__name__", str(a))
+    name = name.lower()
+    if name not in cm.ACTIVATIONS:
+        raise NotImplementedError(f"activation {a!r}; supported: {sorted(cm.ACTIVATIONS)}")
+    return name
+
+
+class NeuralBase:
+    kind = "neuralode"
+
+    def __init__(self, data_size: int, width_size: int, depth: int, state_order: List[str],
+                 observable_indices: Optional[List[int]] = None, solver=Tsit5,
+                 activation="softplus", final_activation=None, use_final_bias: bool = False,
+                 out_size: Optional[int] = None, max_time: float = 1.0, *, key=0,
+                 weights: Optional[Sequence[np.ndarray]] = None,
+                 biases: Optional[Sequence[Optional[np.ndarray]]] = None, mech=None):
+        self.data_size, self.width_size, self.depth = data_size, width_size, depth
+        self.state_order = list(state_order)
+        self.observable_indices = list(observable_indices) if observable_indices is not None \
+            else list(range(data_size))
+        self.solver = solver
+        self.max_time = float(max_time)
+        self.spec = cm.MLPSpec(kind=self.kind, data_size=data_size, width_size=width_size,
+                               depth=depth, out_size=out_size or data_size,
+                               activation=_act_name(activation),
+                               final_activation=_act_name(final_activation),
+                               use_final_bias=use_final_bias, mech=mech)
+        rng = np.random.default_rng(key)
+        dims = self.spec.layer_dims()
+        if weights is None:
+            weights = [rng.normal(0.0, 1.0 / np.sqrt(i), (o, i)) for i, o in dims]
+        if biases is None:
+            biases = [rng.normal(0.0, 1.0 / np.sqrt(i), (o,)) for i, o in dims]
+            if not use_final_bias:
+                biases[-1] = None
+        self.weights = [np.asarray(w, dtype=np.float64) for w in weights]
+        self.biases = [None if b is None else np.asarray(b, dtype=np.float64) for b in biases]
+        self._compiled = {}
+        self._rng = rng
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _extra(self):
+        return {}
+
+    def _t0_from_ts(self) -> bool:
+        return True     # neuralode.py:52 / rateflow.py:114: t0 = ts[0]
+
+    def _max_steps(self) -> int:
+        return 4096     # diffrax's default max_steps (the solve calls pass none)
+
+    def _model(self, dtype):
+        from .. import engine
+
+        key = np.dtype(dtype).name
+        if key not in self._compiled:
+            field = cm.generate_mlp_field(self.spec)
+            theta = cm.pack_parameters(self.spec, self.weights, self.biases, self.max_time,
+                                       np.dtype(dtype), **self._extra())
+            self._compiled[key] = (engine.CompiledModel(field, key), theta)
+        return self._compiled[key]
+
+    def get_weights_and_biases(self):
+        return [a for pair in zip(self.weights, self.biases) for a in pair if a is not None]
+
+    def n_parameters(self) -> int:
+        return int(sum(a.size for a in self.get_weights_and_biases()))
+
+    # ------------------------------------------------------------------ forward
+    def predict_arrays(self, ts, y0s, solver=None, rtol: Optional[float] = None,
+                       atol: Optional[float] = None, dt0: Optional[float] = None, kernel: int = 0):
+        """vmap(lambda ts, y0: self(ts, y0, ...)) (neuralbase.py:307-310): ts [B,T]|[T], y0s [B,S]
+        -> ys [B,T,S].  numpy in -> numpy out; torch CUDA in -> torch CUDA out."""
+        import torch
+
+        dtype = default_dtype()
+        model, theta = self._model(dtype)
+        on_device = isinstance(y0s, torch.Tensor) and y0s.is_cuda
+        dev = y0s.device if on_device else torch.device("cuda", torch.cuda.current_device())
+        tt = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=dtype))
+        ts_t, y0_t = tt(ts).to(dev), tt(y0s).to(dev)
+        if y0_t.dim() == 1:
+            y0_t = y0_t[None]
+        if dt0 is None:     # dt0 or ts[1] - ts[0]
+            first = ts_t if ts_t.dim() == 1 else ts_t[0]
+            dt0 = float((first[1] - first[0]).item())
+        out = model.solve(y0_t, torch.as_tensor(theta, device=dev),
+                          torch.empty((y0_t.shape[0], 0), dtype=y0_t.dtype, device=dev), ts_t,
+                          solver=solver_name(solver or self.solver),
+                          in_axes=(0, None, 0, 0 if ts_t.dim() == 2 else None),
+                          rtol=1e-3 if rtol is None else rtol, atol=1e-6 if atol is None else atol,
+                          dt0=dt0, max_steps=self._max_steps(), t0_from_ts=self._t0_from_ts(),
+                          kernel=kernel)
+        self.last = out
+        return out.ys if on_device else out.ys.cpu().numpy()
+
+    def __call__(self, ts, y0, solver=None, rtol=None, atol=None, dt0=None):
+        """One trajectory: ts [T], y0 [S] -> [T,S] (the per-class __call__ of the reference)."""
+        return self.predict_arrays(ts, np.asarray(y0)[None] if not hasattr(y0, "is_cuda") else y0[None],
+                                   solver, rtol, atol, dt0)[0]
+
+    def predict(self, dataset, config=None, n_steps: int = 100, use_times: bool = False):
+        """Dataset in, Dataset out (neuralbase.py:252-317); times come from the dataset."""
+        from ..dataset import Dataset
+
+        y0s = dataset.to_y0_matrix(self.state_order)
+        if use_times or config is None:
+            times = np.stack([m.time for m in dataset.measurements])
+        else:
+            times = np.linspace(np.asarray(config.t0, dtype=np.float64),
+                                np.asarray(config.t1, dtype=np.float64), config.nsteps or n_steps)
+            times = np.broadcast_to(np.asarray(times).T, (len(dataset), times.shape[0])) \
+                if np.ndim(times) == 1 else np.asarray(times).T
+        ys = self.predict_arrays(times.astype(default_dtype()), y0s)
+        return Dataset.from_jax_arrays(self.state_order, ys, times, y0s)
+
+    def rates(self, t, y, constants=None):
+        """vmap(field)(t, y) (neuralbase.py:319-327): t [N], y [N,S] -> [N,S]."""
+        import torch
+
+        dtype = default_dtype()
+        model, theta = self._model(dtype)
+        on_device = isinstance(y, torch.Tensor) and y.is_cuda
+        dev = y.device if on_device else torch.device("cuda", torch.cuda.current_device())
+        tt = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=dtype))).to(dev)
+        y_t = tt(y)
+        out = model.rates(tt(t), y_t, torch.as_tensor(theta, device=dev),
+                          torch.empty((0,), dtype=y_t.dtype, device=dev))
+        return out if on_device else out.cpu().numpy()
+
+
+class NeuralODE(NeuralBase):
+    """Plain MLP vector field (neuralode.py:25-59)."""
+
+    kind = "neuralode"
+
+
+class RateFlowODE(NeuralBase):
+    """``stoich_matrix @ relu(MLP)`` (rateflow.py:29-121)."""
+
+    kind = "rateflow"
+
+    def __init__(self, data_size: int, reaction_size: int, width_size: int, depth: int,
+                 state_order: List[str], observable_indices: Optional[List[int]] = None,
+                 solver=Tsit5, activation="celu", use_final_bias: bool = False,
+                 learn_stoich: bool = True, stoich_matrix=None, mass_constraint=None, *, key=0,
+                 **kw):
+        super().__init__(data_size=data_size, width_size=width_size, depth=depth,
+                         state_order=state_order, observable_indices=observable_indices,
+                         solver=solver, activation=activation, final_activation="relu",
+                         use_final_bias=use_final_bias, out_size=reaction_size, key=key, **kw)
+        self.reaction_size = reaction_size
+        self.learn_stoich = learn_stoich
+        self.mass_constraint = mass_constraint
+        self.stoich_matrix = (self._rng.normal(size=(data_size, reaction_size))
+                              if stoich_matrix is None else np.asarray(stoich_matrix, dtype=np.float64))
+
+    def _extra(self):
+        return {"stoich_matrix": self.stoich_matrix}
+
+
+class UniversalODE(NeuralBase):
+    """``mech + softplus(alpha) * sigmoid(10 G y) * MLP`` (universalode.py:28-141)."""
+
+    kind = "universalode"
+
+    def __init__(self, data_size: int, width_size: int, depth: int, model,
+                 observable_indices: Optional[List[int]] = None, solver=Tsit5,
+                 use_final_bias: bool = False, activation="celu", final_activation="identity",
+                 use_gate: bool = True, *, key=0, gate_matrix=None, alpha_residual=None, **kw):
+        resolved = model._replace_assignments()
+        state_order = model.get_state_order()
+        super().__init__(data_size=data_size, width_size=width_size, depth=depth,
+                         state_order=state_order, observable_indices=observable_indices,
+                         solver=solver, activation=activation, final_activation=final_activation,
+                         use_final_bias=use_final_bias, key=key,
+                         mech=resolved.sim_input.field_spec(), **kw)
+        self.use_gate = True          # effectively always True in the reference (universalode.py:65-68)
+        self.parameters = np.asarray(resolved._get_parameters(), dtype=np.float64)
+        S = len(state_order)
+        self.alpha_residual = (0.05 * self._rng.normal(size=(S,)) if alpha_residual is None
+                               else np.asarray(alpha_residual, dtype=np.float64))
+        self.gate_matrix = (0.01 * self._rng.normal(size=(S, S)) if gate_matrix is None
+                            else np.asarray(gate_matrix, dtype=np.float64))
+
+    def _extra(self):
+        return {"gate_matrix": self.gate_matrix, "alpha_residual": self.alpha_residual,
+                "mech_parameters": self.parameters}
+
+    def _t0_from_ts(self) -> bool:
+        return False    # universalode.py:133: t0 = 0.0
+
+    def _max_steps(self) -> int:
+        return 64 ** 4  # universalode.py:140

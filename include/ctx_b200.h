@@ -70,7 +70,8 @@ typedef struct ctx_solve_cfg {
   int32_t max_steps;   /* simconfig.py:19 */
   double rtol, atol, dt0;
   int32_t kernel;      /* 0 = auto, 1 = static one-thread-per-trajectory, 2 = persistent refill */
-  int32_t reserved;
+  int32_t t0_from_ts;  /* 0: integrate from t0 = 0 (simulation.py:262); 1: from time[0], as the
+                          neural solves do (neuralode.py:52, rateflow.py:114) */
 } ctx_solve_cfg;
 
 /* ---- model lifetime -------------------------------------------------------------------
@@ -135,6 +136,15 @@ int ctx_loglik_grad(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, co
                     const void* consts, const void* ts, const void* data, const uint8_t* mask,
                     const void* sigma, void* out, void* partial, int32_t* status, void* workspace,
                     size_t ws_bytes, void* stream);
+
+/* ---- K4: right-hand side only ---------------------------------------------------------------
+ * Replaces vmap(stack)(t, y, (theta, consts)) -- Model._setup_rate_function (model.py:1027-1051),
+ * NeuralBase.rates (neuralbase.py:319-327), surrogate rate matching (mcmc.py:830-833).
+ * t [N]|[1], y [N,S], theta [N,P]|[P], consts [N,C]|[C], y0 [N,S]|[S]|NULL -> out [N,S];
+ * a stride of 0 elements means "shared across the N points". */
+int ctx_rates(ctx_model* m, int64_t n, const void* t, int32_t stride_t, const void* y,
+              const void* theta, int32_t stride_theta, const void* consts, int32_t stride_consts,
+              const void* y0, int32_t stride_y0, void* out, void* stream);
 
 /* ---- host-buffer convenience (the call a reference-side ctypes binding would make) --------
  * Same as ctx_solve but every array is a HOST pointer; device staging, the H2D / D2H copies

@@ -73,7 +73,7 @@ def _bcast(a, B, dtype):
 
 def solve(rhs, y0, theta, consts, ts, *, solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,
           max_steps=4096, dtype=np.float64, n_err=None, init_aug=None,
-          record_steps=False, forced_steps=None):
+          record_steps=False, forced_steps=None, t0_from_ts=False):
     """Integrate a batch of trajectories the way the reference does.
 
     rhs(t[B], Y[B,N], theta[B,P], consts[B,C], y0[B,S]) -> dY[B,N]  (vectorised over B).
@@ -130,7 +130,9 @@ def solve(rhs, y0, theta, consts, ts, *, solver="tsit5", rtol=1e-5, atol=1e-5, d
     expo = R(1.0 / order)
 
     t_end = ts[:, -1].copy()                       # t1 = time[-1]
-    tprev = np.zeros(B, dtype=dtype)               # t0 = 0 (simulation.py:262)
+    # t0 = 0 for mechanistic models (simulation.py:262); the neural solves start at ts[0]
+    # (neuralode.py:52, rateflow.py:114); UniversalODE uses 0.0 again (universalode.py:133).
+    tprev = ts[:, 0].copy() if t0_from_ts else np.zeros(B, dtype=dtype)
     tnext = np.minimum(tprev + dt0, t_end)
     ys = np.full((B, T, N), np.inf, dtype=dtype)
     save_idx = np.zeros(B, dtype=np.int64)

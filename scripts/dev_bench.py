@@ -39,3 +39,26 @@ for dtype in a.dtype:
                                   steps=steps, steps_per_traj=round(steps / a.B, 1), rej_frac=round(float(o.n_rejected.sum().item()) / steps, 3),
                                   gsteps_s=round(steps / ms / 1e6, 2), out_GBs=round(byt / ms / 1e6, 1),
                                   fails=int((o.status != 0).sum().item()))), flush=True)
+
+# ---- config 5: neural vector field
+if "--neural" in sys.argv or True:
+    import catalax_b200 as ctx
+    from catalax_b200.neural import NeuralODE
+    for x64 in (False,):
+        ctx.enable_x64(x64)
+        net = NeuralODE(4, 64, 3, ["a", "b", "c", "d"], activation="tanh", max_time=10.0, key=3)
+        Bn = 1 << 19
+        rng = np.random.default_rng(3)
+        y0 = torch.as_tensor(rng.uniform(0, 2, (Bn, 4)).astype(np.float64 if x64 else np.float32), device=dev)
+        tsn = torch.linspace(0, 10, 16, dtype=y0.dtype, device=dev)
+        times = []
+        for it in range(3):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(); ys = net.predict_arrays(tsn, y0); e1.record(); torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        o = net.last
+        steps = int((o.n_accepted.sum() + o.n_rejected.sum()).item())
+        ms = min(times[1:])
+        print(json.dumps(dict(workload="neuralode 5-64-64-64-4 tanh", x64=x64, B=Bn, ms=round(ms, 2), first_ms=round(times[0], 1), steps=steps,
+                              gsteps_s=round(steps / ms / 1e6, 3), tflops=round(steps * 6 * 17536 / ms / 1e9, 2),
+                              fails=int((o.status != 0).sum().item()))), flush=True)
