@@ -37,7 +37,7 @@ def _oracle(net, ts, y0s, dtype, t0_from_ts, max_steps):
         kw["stoich_matrix"] = net.stoich_matrix
     if net.kind == "universalode":
         m = net.spec.mech
-        mech_rhs, *_ = sy.make_rhs(m.states, m.parameters, m.constants, m.odes, m.reactions)
+        mech_rhs, *_ = sy.make_rhs(m.states, m.parameters, [], m.odes, m.reactions)  # p0 is unused
         kw.update(gate_matrix=net.gate_matrix, alpha_residual=net.alpha_residual,
                   mech_rhs=mech_rhs, mech_parameters=net.parameters)
     rhs = mo.make_rhs(net.kind, net.weights, net.biases, net.spec.activation,
