@@ -298,7 +298,13 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
 
   int kernel = cfg->kernel;
   const int warps = v1_warps(m->desc, cfg->solver, tan, theta_smem(m));
-  if (kernel == 0) kernel = warps > 0 ? 2 : 1;
+  if (kernel == 0) {
+    // The persistent kernel wins while a trajectory's state fits registers (measured: S=3 f32
+    // 1.6x at T=16, 3.3x at T=1000); with S*(1+D) = 32 it spills and the static kernel is 3x
+    // faster (profiles/).  Weight-array (MLP) models always take it.
+    const size_t n_regs = (size_t)d.n_states * (1 + (tan ? d.n_dirs : 0)) * (d.dtype == CTX_F64 ? 2 : 1);
+    kernel = (warps > 0 && (n_regs <= 24 || m->theta_ptr)) ? 2 : 1;
+  }
   cudaKernel_t k;
   void* params[] = {&a};
   if (kernel == 2) {

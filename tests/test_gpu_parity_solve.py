@@ -204,3 +204,23 @@ def test_sensitivities_match_oracle_f64(solver, kernel):
     # initial values: d y(0) / d y0 = identity, d y(0) / d theta = 0
     np.testing.assert_array_equal(sens[:, 0, :, P:], np.broadcast_to(np.eye(S), (B, S, S)))
     np.testing.assert_array_equal(sens[:, 0, :, :P], 0.0)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("per_row_k", [True, False])
+def test_mass_action_network_config3(per_row_k, kernel):
+    """BASELINE configs[2] at test size: 32 states / 64 reactions (reaction form, stoichiometric
+    sums), per-row or shared rate constants, T=32 on [0,10], rtol=atol=1e-6."""
+    rng = np.random.default_rng(1)
+    B = 96
+    y0 = rng.uniform(0.1, 2.0, (B, 32))
+    k = np.exp(rng.uniform(np.log(0.01), np.log(1.0), (B, 64) if per_row_k else (64,)))
+    ts = np.linspace(0, 10, 32)
+    ref, out = _run_pair(cases.mass_action_network(32), y0, k, np.zeros((B, 0)), ts,
+                         (0, 0 if per_row_k else None, 0, None), np.float64, kernel=kernel)
+    ys = out.ys.cpu().numpy()
+    assert (out.status.cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
+    _assert_close_f64(ys, ref.ys)
+    # conservation: first-order steps conserve total mass, the A+B->C couplings remove one unit
+    assert (ys.sum(axis=2)[:, -1] <= ys.sum(axis=2)[:, 0] + 1e-9).all()
