@@ -22,6 +22,7 @@
 #include <unistd.h>
 
 extern const char ctx_integrator_src[];  // generated from ctx_integrator.cuh (embed step)
+extern const char ctx_mlp_tc_src[];      // generated from ctx_mlp_tc.cuh
 
 namespace {
 
@@ -84,6 +85,7 @@ struct ctx_model {
   std::map<int, Variant> variants;  // key = solver*2 + tan
   bool theta_ptr = false;           // generated with CTX_THETA_PTR (shared weights in smem)
   int p_pad = 0;
+  int mlp_tc_smem = 0;              // > 0: the tcgen05 MLP kernel is available (bytes of smem)
   // host-call staging (ctx_solve_host)
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -175,7 +177,7 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
       else cur += ch;
     }
   }
-  std::string keysrc = src + "\x01" + ctx_integrator_src;
+  std::string keysrc = src + "\x01" + ctx_integrator_src + "\x01" + ctx_mlp_tc_src;
   for (auto& o : opts) keysrc += "\x02" + o;
   int nv_major = 0, nv_minor = 0;
   nvrtcVersion(&nv_major, &nv_minor);
@@ -200,9 +202,9 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
     }
   }
   nvrtcProgram prog;
-  const char* hdr_src[] = {ctx_integrator_src};
-  const char* hdr_name[] = {"ctx_integrator.cuh"};
-  nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "ctx_model.cu", 1, hdr_src, hdr_name);
+  const char* hdr_src[] = {ctx_integrator_src, ctx_mlp_tc_src};
+  const char* hdr_name[] = {"ctx_integrator.cuh", "ctx_mlp_tc.cuh"};
+  nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "ctx_model.cu", 2, hdr_src, hdr_name);
   if (r != NVRTC_SUCCESS) return fail(CTX_E_NVRTC, nvrtcGetErrorString(r));
   std::vector<const char*> copts;
   for (auto& o : opts) copts.push_back(o.c_str());
@@ -331,6 +333,25 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
                               stream));
+    g_launches++;
+  } else if (kernel == 3) {
+    // K3: tcgen05 MLP tiles (ctx_mlp_tc.cuh); theta = [aux | UMMA weight pack]
+    if (m->mlp_tc_smem <= 0 || m->desc.dtype != CTX_F32 || tan || cfg->solver > CTX_DOPRI5)
+      return fail(CTX_E_INVALID, "tensor-core MLP kernel: f32 MLP model with Tsit5/Dopri5 only");
+    if (a.stride_theta != 0)
+      return fail(CTX_E_INVALID, "a weight-array model takes shared parameters (in_axes[1] = None)");
+    int rc = get_kernel(m, cfg->solver, 0, "ctx_solve_mlp_tc", &k);
+    if (rc) return rc;
+    int dev = 0, sms = 0;
+    CTX_CUDA(cudaGetDevice(&dev));
+    CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  m->mlp_tc_smem));
+    unsigned long long grid = (cfg->batch + 255) / 256;
+    if (grid > (unsigned long long)sms) grid = sms;
+    CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(256), params,
+                              (size_t)m->mlp_tc_smem, stream));
     g_launches++;
   } else if (kernel == 1) {
     if (m->theta_ptr && warps > 0)
@@ -484,6 +505,7 @@ int ctx_model_compile(const char* field_src, const ctx_model_desc* desc, ctx_mod
     m->p_pad = q ? atoi(q + 18) : desc->n_params;
     if (m->p_pad < desc->n_params) m->p_pad = desc->n_params;
   }
+  if (const char* q = strstr(field_src, "#define CTX_MLP_TC_SMEM ")) m->mlp_tc_smem = atoi(q + 24);
   *out = m;
   return CTX_OK;
 }

@@ -1025,3 +1025,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_rates(const ctx_rates_args
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) a.out[(size_t)n * CTX_S + i] = dy[i];
 }
+
+#ifdef CTX_MLP_TC
+#include "ctx_mlp_tc.cuh"
+#endif

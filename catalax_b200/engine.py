@@ -178,7 +178,7 @@ class CompiledModel:
         def prep(x, width, ax):
             x = x.to(device=dev, dtype=tdt).contiguous()
             want = 2 if ax == 0 else 1
-            if x.dim() != want or x.shape[-1] != width:
+            if x.dim() != want or (x.shape[-1] != width and width >= 0):
                 raise ValueError(f"expected a {want}-D array with last dim {width}, got {tuple(x.shape)}")
             return x
 
@@ -188,7 +188,8 @@ class CompiledModel:
         if any(b != B for b in Bs):
             raise ValueError(f"inconsistent batch sizes {Bs}")
         T = ts.shape[-1]
-        y0 = prep(y0, S, in_axes[0]); theta = prep(theta, P, in_axes[1])
+        # kernel 3 (tensor-core MLP) takes its own parameter pack [aux | UMMA weights]
+        y0 = prep(y0, S, in_axes[0]); theta = prep(theta, -1 if kernel == 3 else P, in_axes[1])
         consts = prep(consts, Cn, in_axes[2]); ts = prep(ts, T, in_axes[3])
         cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
                             max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel,

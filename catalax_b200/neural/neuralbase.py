@@ -84,6 +84,16 @@ class NeuralBase:
             self._compiled[key] = (engine.CompiledModel(field, key), theta)
         return self._compiled[key]
 
+    def tensor_core_eligible(self, dtype) -> bool:
+        """f32 models whose padded shapes fit tcgen05.mma tiles run on the tensor cores."""
+        return np.dtype(dtype) == np.float32 and cm.tc_dims(self.spec) is not None
+
+    def _tc_theta(self):
+        if "tc" not in self._compiled:
+            self._compiled["tc"] = cm.pack_tc_parameters(self.spec, self.weights, self.biases,
+                                                         self.max_time, **self._extra())
+        return self._compiled["tc"]
+
     def get_weights_and_biases(self):
         return [a for pair in zip(self.weights, self.biases) for a in pair if a is not None]
 
@@ -108,9 +118,14 @@ class NeuralBase:
         if dt0 is None:     # dt0 or ts[1] - ts[0]
             first = ts_t if ts_t.dim() == 1 else ts_t[0]
             dt0 = float((first[1] - first[0]).item())
+        sname = solver_name(solver or self.solver)
+        if kernel == 0:     # auto: tensor cores (kernel 3) when eligible, else CUDA cores (2)
+            kernel = 3 if (self.tensor_core_eligible(dtype) and sname in ("tsit5", "dopri5")) else 2
+        if kernel == 3:
+            theta = self._tc_theta()
         out = model.solve(y0_t, torch.as_tensor(theta, device=dev),
                           torch.empty((y0_t.shape[0], 0), dtype=y0_t.dtype, device=dev), ts_t,
-                          solver=solver_name(solver or self.solver),
+                          solver=sname,
                           in_axes=(0, None, 0, 0 if ts_t.dim() == 2 else None),
                           rtol=1e-3 if rtol is None else rtol, atol=1e-6 if atol is None else atol,
                           dt0=dt0, max_steps=self._max_steps(), t0_from_ts=self._t0_from_ts(),

@@ -123,6 +123,129 @@ def pack_parameters(spec: MLPSpec, weights: Sequence[np.ndarray], biases: Sequen
     return out.astype(dtype)
 
 
+ACT_IDS = {"tanh": 0, "softplus": 1, "celu": 2, "relu": 3, "identity": 4}
+
+
+def tc_dims(spec: MLPSpec):
+    """Padded dimensions of the tensor-core form, or None when the model does not qualify
+    (N must be a multiple of 16 for M=128 tcgen05.mma, K a multiple of 8 for tf32)."""
+    W = spec.width_size
+    if W % 16 or W > 64 or spec.depth < 1 or spec.data_size + 1 > 8 or spec.out_size > 16:
+        return None
+    in_pad, out_pad = 8, 16
+    layers = [(in_pad if l == 0 else W, out_pad if l == spec.depth else W) for l in range(spec.depth + 1)]
+    wpack = sum(2 * k * n for k, n in layers)
+    aux_bias = sum(n for _, n in layers)
+    extra = 4
+    S = spec.data_size
+    if spec.kind == "rateflow":
+        extra += S * spec.out_size
+    if spec.kind == "universalode":
+        extra += S * S + S + len(spec.mech.parameters)
+    aux = _pad4(aux_bias + extra)
+    kmax = max(W, in_pad)
+    smem = (wpack * 4 + 1023) // 1024 * 1024 + 4 * 128 * kmax * 4 + aux * 4 + 64
+    tmem_cols = 32
+    while tmem_cols < 2 * W:
+        tmem_cols *= 2
+    if smem > 227 * 1024:
+        return None
+    return dict(in_pad=in_pad, out_pad=out_pad, layers=layers, wpack=wpack, aux_bias=aux_bias,
+                aux=aux, smem=smem, tmem_cols=tmem_cols)
+
+
+def _umma_block(Wm: np.ndarray, n_pad: int, k_pad: int) -> np.ndarray:
+    """[N,K] weights -> K-major / no-swizzle UMMA canonical layout: 8x4-float core matrices,
+    consecutive along N (SBO = 128 B), k blocks n_pad/8 core matrices apart (LBO = n_pad*16 B)."""
+    full = np.zeros((n_pad, k_pad), dtype=np.float32)
+    full[: Wm.shape[0], : Wm.shape[1]] = Wm
+    blk = full.reshape(n_pad // 8, 8, k_pad // 4, 4)         # [nb, r, kb, c]
+    return np.ascontiguousarray(blk.transpose(2, 0, 1, 3)).ravel()   # [kb, nb, r, c]
+
+
+def _tf32_round(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest (ties away, like cvt.rna.tf32.f32) to 10 explicit mantissa bits."""
+    u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x1000) & 0xFFFFE000).astype(np.uint32)
+    return u.view(np.float32)
+
+
+def pack_tc_parameters(spec: MLPSpec, weights, biases, max_time, stoich_matrix=None,
+                       gate_matrix=None, alpha_residual=None, mech_parameters=None) -> np.ndarray:
+    """theta of ctx_solve_mlp_tc: [aux (biases, extras) | hi/lo TF32 weights in UMMA layout]."""
+    d = tc_dims(spec)
+    assert d is not None
+    aux = np.zeros(d["aux"], dtype=np.float32)
+    off = 0
+    for (k, n), b in zip(d["layers"], biases):
+        if b is not None:
+            aux[off: off + len(b)] = np.asarray(b, dtype=np.float32)
+        off += n
+    ex = off
+    aux[ex] = np.float32(1.0 / float(max_time))
+    S = spec.data_size
+    if spec.kind == "rateflow":
+        aux[ex + 4: ex + 4 + S * spec.out_size] = np.asarray(stoich_matrix, dtype=np.float32).ravel()
+    if spec.kind == "universalode":
+        aux[ex + 4: ex + 4 + S * S] = np.asarray(gate_matrix, dtype=np.float32).ravel()
+        aux[ex + 4 + S * S: ex + 4 + S * S + S] = np.logaddexp(np.asarray(alpha_residual, dtype=np.float64), 0.0)
+        mp = np.asarray(mech_parameters, dtype=np.float32)
+        aux[ex + 4 + S * S + S: ex + 4 + S * S + S + mp.size] = mp
+    packs = []
+    for (k, n), Wm in zip(d["layers"], weights):
+        Wm = np.asarray(Wm, dtype=np.float32)
+        hi = _tf32_round(Wm)
+        lo = _tf32_round(Wm - hi)
+        packs += [_umma_block(hi, n, k), _umma_block(lo, n, k)]
+    return np.concatenate([aux] + packs).astype(np.float32)
+
+
+def _tc_source(spec: MLPSpec) -> List[str]:
+    d = tc_dims(spec)
+    if d is None:
+        return []
+    S = spec.data_size
+    ex = 4   # extras start after [inv_max_time, pad x3]
+    out = [
+        "#if !CTX_F64",
+        "#define CTX_MLP_TC 1",
+        f"#define MLP_S {S}", f"#define MLP_IN_PAD {d['in_pad']}", f"#define MLP_W {spec.width_size}",
+        f"#define MLP_DEPTH {spec.depth}", f"#define MLP_OUT {spec.out_size}",
+        f"#define MLP_OUT_PAD {d['out_pad']}", f"#define MLP_ACT {ACT_IDS[spec.activation]}",
+        f"#define MLP_FINAL_ACT {ACT_IDS[spec.final_activation]}",
+        f"#define MLP_AUX_SIZE {d['aux']}", f"#define MLP_AUX_EXTRA {d['aux_bias']}",
+        f"#define MLP_WPACK_SIZE {d['wpack']}", f"#define TC_TMEM_COLS {d['tmem_cols']}",
+        f"#define CTX_MLP_TC_SMEM {d['smem']}",
+        "__device__ __forceinline__ void ctx_mlp_finish(const float t, const float* y, const float* y0,",
+        "                                               const float* ex, const float* o, float* dy) {",
+        "  (void)t; (void)y; (void)y0; (void)ex;",
+    ]
+    if spec.kind == "neuralode":
+        out += [f"  dy[{i}] = o[{i}];" for i in range(S)]
+    elif spec.kind == "rateflow":
+        R_ = spec.out_size
+        for i in range(S):
+            out.append(f"  dy[{i}] = " + " + ".join(
+                f"ex[{ex + i * R_ + r}] * fmaxf(o[{r}], 0.0f)" for r in range(R_)) + ";")
+    else:
+        names = {cg.T_SYM: "t"}
+        for i, s in enumerate(spec.mech.states):
+            names[sp.Symbol(s)] = f"y[{i}]"
+            names[sp.Symbol(f"{s}_init")] = f"y0[{i}]"
+        moff = ex + S * S + S
+        for i, p in enumerate(spec.mech.parameters):
+            names[sp.Symbol(p)] = f"ex[{moff + i}]"
+        lines, _ = cg._emit_block([(f"const real mech{i}", e) for i, e in
+                                   enumerate(spec.mech.total_exprs())], names, "q")
+        out += lines
+        for i in range(S):
+            g = " + ".join(f"ex[{ex + i * S + j}] * y[{j}]" for j in range(S))
+            out.append(f"  dy[{i}] = mech{i} + ex[{ex + S * S + i}] * "
+                       f"(1.0f / (1.0f + expf(-(10.0f * ({g}))))) * o[{i}];")
+    out += ["}", "#endif"]
+    return out
+
+
 def generate_mlp_field(spec: MLPSpec) -> cg.GeneratedField:
     S = spec.data_size
     lay = layout_of(spec)
@@ -218,6 +341,7 @@ def generate_mlp_field(spec: MLPSpec) -> cg.GeneratedField:
     else:
         raise ValueError(spec.kind)
     src += ["}", "#define CTX_D 0", "#define CTX_D_THETA 0", "#define CTX_D_Y0 0"]
+    src += _tc_source(spec)
     text = "\n".join(src) + "\n"
     key = hashlib.sha256(text.encode()).hexdigest()[:24]
     return cg.GeneratedField(text, S, lay.size, 0, 0, 0, 0, flops, 0, True, key)
