@@ -347,10 +347,10 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   m->mlp_tc_smem));
-    unsigned long long grid = (cfg->batch + 255) / 256;
+    unsigned long long grid = (cfg->batch + 255) / 256;   // 2 tiles x 128 trajectories per CTA
     if (grid > (unsigned long long)sms) grid = sms;
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
-    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(256), params,
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(512), params,
                               (size_t)m->mlp_tc_smem, stream));
     g_launches++;
   } else if (kernel == 1) {

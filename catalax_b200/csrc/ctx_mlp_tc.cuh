@@ -6,8 +6,10 @@
 //        vmap(diffeqsolve(ODETerm(field), solver, t0, t1, dt0, y0, PIDController, SaveAt(ts)))
 //   with field = MLP (catalax/neural/mlp.py:71-84) [+ stoichiometry / gate / mechanistic term].
 //
-// One CTA = 256 threads = two independent tiles of 128 trajectories (one per thread, thread r
-// of a tile <-> TMEM lane r).  Every RK stage evaluates the MLP for the whole tile as dense
+// One CTA = 512 threads = two independent tiles of 128 trajectories.  A tile has 8 warps: warps
+// 0-3 ("primary", thread r <-> trajectory r <-> TMEM lane r) own the integrator state; warps 4-7
+// ("helpers") only share the epilogue: warp q and warp q+4 may both read TMEM lanes 32q..32q+31,
+// so each half handles half of the hidden units (twice the warps to hide MUFU/FMA latency).  Every RK stage evaluates the MLP for the whole tile as dense
 // contractions  D[128 x N_l] = A[128 x K_l] . W_l[N_l x K_l]^T :
 //   * A (activations) is written by the owning threads into shared memory in the UMMA
 //     K-major / no-swizzle canonical layout (8x16B core matrices), W_l is staged there once;
@@ -31,7 +33,9 @@
 #endif
 
 #define TC_ROWS 128
-#define TC_THREADS 256
+#define TC_THREADS 512
+#define TC_TILE_THREADS 256
+#define TC_HALF_W (MLP_W / 2)                         // hidden units handled per half
 #define TC_NL (MLP_DEPTH + 1)
 #define TC_KMAX (MLP_W > MLP_IN_PAD ? MLP_W : MLP_IN_PAD)
 #define TC_A_BYTES (TC_ROWS * TC_KMAX * 4)          // one A tile (hi or lo)
@@ -80,13 +84,13 @@ __device__ __forceinline__ void tc_mbar_wait(const unsigned mbar, const unsigned
   } while (!done);
 }
 __device__ __forceinline__ void tc_bar(const int id) {  // the 128 threads of one tile
-  asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory");
+  asm volatile("bar.sync %0, 256;" :: "r"(id) : "memory");
 }
 __device__ __forceinline__ bool tc_tile_or(const int id, const bool pred) {
   unsigned out;
   asm volatile(
       "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\t"
-      "bar.red.or.pred q, %2, 128, p;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+      "bar.red.or.pred q, %2, 256, p;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
       : "=r"(out) : "r"((unsigned)pred), "r"(id) : "memory");
   return out != 0;
 }
@@ -117,6 +121,7 @@ struct tc_tile {
   const float* aux;       // biases + extras in shared memory
   int bar_id;             // named barrier of the tile's 128 threads
   int r;                  // row of this thread in the tile
+  int half;               // 0 = primary (owns the trajectory), 1 = epilogue helper
   unsigned parity;
 };
 
@@ -135,7 +140,7 @@ __device__ __forceinline__ void tc_store4(const tc_tile& T, const int k, const f
 __device__ __forceinline__ void tc_field(tc_tile& T, const float t, const float* y, const float* y0,
                                          float* dy) {
   // ---- layer-0 input row: [y, t/max_time, 0...]
-  {
+  if (T.half == 0) {
     float x[MLP_IN_PAD];
 #pragma unroll
     for (int i = 0; i < MLP_IN_PAD; ++i) x[i] = 0.0f;
@@ -155,7 +160,7 @@ __device__ __forceinline__ void tc_field(tc_tile& T, const float t, const float*
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tc_bar(T.bar_id);
-    if (T.r == 0) {
+    if (T.r == 0 && T.half == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const unsigned lbo_b = (unsigned)N * 16u;        // N/8 core matrices of 128 B per k block
       const unsigned w_hi = T.w_base + w_off, w_lo = w_hi + (unsigned)(N * K * 4);
@@ -178,19 +183,22 @@ __device__ __forceinline__ void tc_field(tc_tile& T, const float t, const float*
     // ---- epilogue: this thread's accumulator row (TMEM lane = 32*(warp%4) + lane)
     const unsigned taddr = T.tmem + ((unsigned)((T.r >> 5) * 32) << 16);
     if (l < TC_NL - 1) {
-      unsigned v[MLP_W];
+      // this half's hidden units [c, c + W/2)
+      const int c = T.half * TC_HALF_W;
+      unsigned v[TC_HALF_W];
 #pragma unroll
-      for (int c0 = 0; c0 < MLP_W; c0 += 16) TC_LD16(v, c0, taddr);
+      for (int c0 = 0; c0 < TC_HALF_W; c0 += 16) TC_LD16(v, c0, taddr + c);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const float* bias = T.aux + bias_off + c;
 #pragma unroll
-      for (int k = 0; k < MLP_W; k += 4) {
-        const float a0 = tc_act(__uint_as_float(v[k]) + T.aux[bias_off + k], MLP_ACT);
-        const float a1 = tc_act(__uint_as_float(v[k + 1]) + T.aux[bias_off + k + 1], MLP_ACT);
-        const float a2 = tc_act(__uint_as_float(v[k + 2]) + T.aux[bias_off + k + 2], MLP_ACT);
-        const float a3 = tc_act(__uint_as_float(v[k + 3]) + T.aux[bias_off + k + 3], MLP_ACT);
-        tc_store4(T, k, a0, a1, a2, a3);
+      for (int k = 0; k < TC_HALF_W; k += 4) {
+        const float a0 = tc_act(__uint_as_float(v[k]) + bias[k], MLP_ACT);
+        const float a1 = tc_act(__uint_as_float(v[k + 1]) + bias[k + 1], MLP_ACT);
+        const float a2 = tc_act(__uint_as_float(v[k + 2]) + bias[k + 2], MLP_ACT);
+        const float a3 = tc_act(__uint_as_float(v[k + 3]) + bias[k + 3], MLP_ACT);
+        tc_store4(T, c + k, a0, a1, a2, a3);
       }
-    } else {
+    } else if (T.half == 0) {
       unsigned v[MLP_OUT_PAD];
 #pragma unroll
       for (int c0 = 0; c0 < MLP_OUT_PAD; c0 += 16) TC_LD16(v, c0, taddr);
@@ -234,9 +242,11 @@ extern "C" __global__ void __launch_bounds__(TC_THREADS, 1) ctx_solve_mlp_tc(con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  const int wg = tid >> 7;
+  const int wg = tid >> 8;                         // tile
+  const int w_in = (tid >> 5) & 7;                 // warp within the tile
   tc_tile T;
-  T.r = tid & 127;
+  T.half = w_in >> 2;
+  T.r = (w_in & 3) * 32 + (tid & 31);
   T.bar_id = 1 + wg;
   T.a_hi = tc_smem_u32(a_sm + (2 * wg) * TC_A_BYTES);
   T.a_lo = tc_smem_u32(a_sm + (2 * wg + 1) * TC_A_BYTES);
@@ -260,8 +270,8 @@ extern "C" __global__ void __launch_bounds__(TC_THREADS, 1) ctx_solve_mlp_tc(con
   for (int i = 0; i < CTX_S; ++i) y[i] = y0[i] = 1.0f;
 
   while (true) {
-    // ---- refill free lanes (warp-aggregated claim)
-    const unsigned need = __ballot_sync(CTX_FULL, b < 0);
+    // ---- refill free lanes (warp-aggregated claim; helper warps own no trajectory)
+    const unsigned need = T.half == 0 ? __ballot_sync(CTX_FULL, b < 0) : 0u;
     if (need && !exhausted) {
       const int cnt = __popc(need);
       unsigned long long base = 0;

@@ -130,7 +130,7 @@ def tc_dims(spec: MLPSpec):
     """Padded dimensions of the tensor-core form, or None when the model does not qualify
     (N must be a multiple of 16 for M=128 tcgen05.mma, K a multiple of 8 for tf32)."""
     W = spec.width_size
-    if W % 16 or W > 64 or spec.depth < 1 or spec.data_size + 1 > 8 or spec.out_size > 16:
+    if W % 32 or W > 64 or spec.depth < 1 or spec.data_size + 1 > 8 or spec.out_size > 16:
         return None
     in_pad, out_pad = 8, 16
     layers = [(in_pad if l == 0 else W, out_pad if l == spec.depth else W) for l in range(spec.depth + 1)]

@@ -67,3 +67,24 @@ def test_nvrtc_compiles_all_variants_for_sm100a_without_gpu():
     for solver in ("tsit5", "dopri5", "euler", "heun"):
         cubin = m.cubin(solver, tangents=(solver == "tsit5"))
         assert cubin[:4] == b"\x7fELF" and len(cubin) > 1000
+
+
+def test_mlp_kernel_sass_uses_tcgen05_and_tmem():
+    """Evidence that K3 is Blackwell-native: UTC*MMA (tcgen05.mma) and LDTM (tcgen05.ld) in the
+    SASS of the NVRTC-compiled kernel (B200_PROFILING.md 'What proves a Blackwell-native kernel')."""
+    import subprocess
+    import tempfile
+
+    from catalax_b200 import engine
+    from catalax_b200.neural import NeuralODE
+    from catalax_b200.tools import codegen_mlp as cm
+
+    net = NeuralODE(4, 64, 3, ["a", "b", "c", "d"], activation="tanh", max_time=10.0, key=3)
+    m = engine.CompiledModel(cm.generate_mlp_field(net.spec), "float32")
+    cubin = m.cubin("tsit5", False)
+    with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
+        f.write(cubin); f.flush()
+        sass = subprocess.run(["cuobjdump", "-sass", f.name], capture_output=True, text=True).stdout
+    assert "ctx_solve_mlp_tc" in sass
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UTCBAR" in sass
+    assert "HMMA.16" not in sass  # no legacy mma.sync path
