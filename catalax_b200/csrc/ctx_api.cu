@@ -169,6 +169,17 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
       "-DCTX_SOLVER=" + std::to_string(solver), "-DCTX_TAN=" + std::to_string(tan),
       "-DCTX_WARPS=" + std::to_string(std::max(1, v1_warps(m->desc, solver, tan, theta_smem(m))))};
   if (v1_warps(m->desc, solver, tan, theta_smem(m)) <= 0) opts.push_back("-DCTX_NO_V1=1");
+  {
+    // Register cap of the persistent kernel (__launch_bounds__ min blocks).  Measured on the
+    // 3-state model: 4 CTAs/SM (128 regs) f32 and 3 CTAs/SM (170 regs) f64 are the sweet spots;
+    // tighter caps spill.  Budget ~96 registers + 10 per 32-bit word of trajectory state.
+    const size_t words = (size_t)m->desc.n_states * (1 + (tan ? m->desc.n_dirs : 0)) *
+                         (m->desc.dtype == CTX_F64 ? 2 : 1);
+    size_t mb = 512 / (96 + 10 * words);
+    mb = std::max<size_t>(1, std::min<size_t>(4, mb));
+    if (m->theta_ptr) mb = 1;
+    opts.push_back("-DCTX_MIN_BLOCKS=" + std::to_string(mb));
+  }
   const char* extra = getenv("CTX_B200_NVRTC_FLAGS");
   if (extra && *extra) {
     std::string e(extra), cur;
