@@ -111,6 +111,7 @@ struct SolveArgs {
   int max_steps;
   int stride_y0, stride_theta, stride_consts, stride_ts;
   int t0_from_ts;
+  int inner;
   real rtol, atol, dt0;
 };
 
@@ -305,6 +306,9 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.stride_consts = cfg->in_axes[2] == 0 ? d.n_consts : 0;
   a.stride_ts = cfg->in_axes[3] == 0 ? cfg->n_times : 0;
   a.t0_from_ts = cfg->t0_from_ts ? 1 : 0;
+  a.inner = cfg->inner > 0 ? cfg->inner : 0;
+  if (a.inner > 0 && cfg->batch % a.inner != 0)
+    return fail(CTX_E_INVALID, "two-level batch: batch must be a multiple of inner");
   a.rtol = (real)cfg->rtol;
   a.atol = (real)cfg->atol;
   a.dt0 = (real)cfg->dt0;
@@ -630,6 +634,7 @@ int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
   if (!m || !cfg) return fail(CTX_E_INVALID, "null model or config");
   if (ctx_device_count() <= 0)
     return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  if (cfg->inner > 0) return fail(CTX_E_INVALID, "ctx_solve_host: two-level batches take device buffers (ctx_solve)");
   const ctx_model_desc& d = m->desc;
   const size_t w = d.dtype == CTX_F64 ? 8 : 4;
   const size_t B = (size_t)cfg->batch, T = (size_t)cfg->n_times;

@@ -65,8 +65,14 @@ struct ctx_solve_args {
   int max_steps;
   int stride_y0, stride_theta, stride_consts, stride_ts;  // elements per row, 0 = shared
   int t0_from_ts;  // 0: integrate from t0 = 0 (simulation.py:262); 1: from ts[0] (neuralode.py:52)
+  int inner;       // M > 0: b = d*M + m, theta row d, y0 / consts / ts row m (predictive.py:150-154)
   real rtol, atol, dt0;
 };
+
+// operand rows of trajectory b: `ro` for the parameters, `ri` for y0 / constants / times
+#define CTX_ROWS(b, ro, ri)                                              \
+  const long long ro = a.inner > 0 ? (b) / a.inner : (b);               \
+  const long long ri = a.inner > 0 ? (b) - ro * a.inner : (b)
 
 #ifndef CTX_THETA_PTR
 #define CTX_THETA_PTR 0   // 1: parameters are a shared array too large for registers (MLP weights)
@@ -301,24 +307,25 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
   real y[CTX_N], ynew[CTX_N], y0[CTX_S];
   real c[CTX_C > 0 ? CTX_C : 1];
   real K[CTX_NST][CTX_N];
+  CTX_ROWS(b, ro, ri);
 #pragma unroll
-  for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)b * a.stride_y0 + i];
+  for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)ri * a.stride_y0 + i];
 #if CTX_THETA_PTR
-  const real* th = a.theta + (size_t)b * a.stride_theta;
+  const real* th = a.theta + (size_t)ro * a.stride_theta;
 #else
   real th[CTX_P > 0 ? CTX_P : 1];
 #pragma unroll
-  for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)b * a.stride_theta + i];
+  for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)ro * a.stride_theta + i];
 #endif
 #pragma unroll
-  for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)b * a.stride_consts + i];
+  for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)ri * a.stride_consts + i];
 #if CTX_TAN
 #pragma unroll
   for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
 #pragma unroll
   for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
 #endif
-  const real* ts = a.ts + (size_t)b * a.stride_ts;
+  const real* ts = a.ts + (size_t)ri * a.stride_ts;
   const int T = a.T;
   const real t_end = ts[T - 1];
   real tprev = a.t0_from_ts ? ts[0] : R(0.0);
@@ -548,6 +555,7 @@ ctx_solve_v1(const ctx_solve_args a) {
   int idx = 0, nacc = 0, nrej = 0, status = 0;
   bool exhausted = false;
   const real* tsr = a.ts;
+  long long ts_row = 0;       // element offset of this trajectory's time row
 
   while (true) {
     // ------------------------------------------------------------- refill free lanes
@@ -562,21 +570,23 @@ ctx_solve_v1(const ctx_solve_args a) {
         const unsigned long long nb = base + __popc(need & lt_mask);
         if (nb < (unsigned long long)a.B) {
           b = (long long)nb;
+          CTX_ROWS(b, ro, ri);
+          ts_row = ri * (long long)a.stride_ts;
 #pragma unroll
-          for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)b * a.stride_y0 + i];
+          for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)ri * a.stride_y0 + i];
 #if !CTX_THETA_PTR
 #pragma unroll
-          for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)b * a.stride_theta + i];
+          for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)ro * a.stride_theta + i];
 #endif
 #pragma unroll
-          for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)b * a.stride_consts + i];
+          for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)ri * a.stride_consts + i];
 #if CTX_TAN
 #pragma unroll
           for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
 #pragma unroll
           for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
 #endif
-          tsr = a.ts + (size_t)b * a.stride_ts;
+          tsr = a.ts + ts_row;
           t_end = tsr[T - 1];
           tprev = a.t0_from_ts ? tsr[0] : R(0.0);
           tnext = fmin(tprev + a.dt0, t_end);
@@ -679,7 +689,7 @@ ctx_solve_v1(const ctx_solve_args a) {
         }
 #pragma unroll
         for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
-        w.ts_off[s] = (long long)((size_t)b * a.stride_ts) + idx - off;
+        w.ts_off[s] = ts_row + idx - off;
         w.g_off[s] = b * (long long)T + idx - off;
       }
       __syncwarp();
@@ -690,11 +700,12 @@ ctx_solve_v1(const ctx_solve_args a) {
         const int n = __shfl_sync(CTX_FULL, nsave, src);
         const int i0 = __shfl_sync(CTX_FULL, idx, src);
         const long long bs = __shfl_sync(CTX_FULL, b, src);
+        const long long ts_row_s = __shfl_sync(CTX_FULL, ts_row, src);
         const real l_tp = w.rec[0][s], l_inv = w.rec[1][s];
         real lc[CTX_NCOEF];
 #pragma unroll
         for (int i = 0; i < CTX_NCOEF; ++i) lc[i] = w.rec[2 + i][s];
-        const real* tsp = a.ts + (size_t)bs * a.stride_ts;
+        const real* tsp = a.ts + ts_row_s;
         real* yp = a.ys + (size_t)bs * T * CTX_S;
         const int i1 = i0 + n;
         const int qe = (i1 + 3) >> 2;

@@ -282,9 +282,11 @@ extern "C" __global__ void __launch_bounds__(TC_THREADS, 1) ctx_solve_mlp_tc(con
         const unsigned long long nb = base + __popc(need & lt_mask);
         if (nb < (unsigned long long)a.B) {
           b = (long long)nb;
+          CTX_ROWS(b, ro, ri);
+          (void)ro;
 #pragma unroll
-          for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)b * a.stride_y0 + i];
-          tsr = a.ts + (size_t)b * a.stride_ts;
+          for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)ri * a.stride_y0 + i];
+          tsr = a.ts + (size_t)ri * a.stride_ts;
           t_end = tsr[Tn - 1];
           tprev = a.t0_from_ts ? tsr[0] : 0.0f;
           tnext = fminf(tprev + a.dt0, t_end);

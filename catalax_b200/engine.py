@@ -39,7 +39,7 @@ class ctx_solve_cfg(C.Structure):
     _fields_ = [("solver", C.c_int32), ("in_axes", C.c_int32 * 4), ("batch", C.c_int64),
                 ("n_times", C.c_int32), ("max_steps", C.c_int32), ("rtol", C.c_double),
                 ("atol", C.c_double), ("dt0", C.c_double), ("kernel", C.c_int32),
-                ("t0_from_ts", C.c_int32)]
+                ("t0_from_ts", C.c_int32), ("inner", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ctx_loglik_cfg(C.Structure):
@@ -152,7 +152,7 @@ class CompiledModel:
 
     # ------------------------------------------------------------------ compute
     def make_cfg(self, *, solver, in_axes, batch, n_times, max_steps, rtol, atol, dt0, kernel=0,
-                 t0_from_ts=False):
+                 t0_from_ts=False, inner=0):
         cfg = ctx_solve_cfg()
         cfg.solver = SOLVER_IDS[solver]
         for i, a in enumerate(in_axes):
@@ -161,12 +161,16 @@ class CompiledModel:
         cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
         cfg.kernel = int(kernel)
         cfg.t0_from_ts = int(bool(t0_from_ts))
+        cfg.inner = int(inner)
         return cfg
 
     def solve(self, y0, theta, consts, ts, *, solver="tsit5", in_axes=(0, None, 0, None),
               rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096, tangents=False, kernel=0,
-              out=None, t0_from_ts=False):
-        """Device-resident solve.  All inputs are torch CUDA tensors of this model's dtype."""
+              out=None, t0_from_ts=False, inner=0):
+        """Device-resident solve.  All inputs are torch CUDA tensors of this model's dtype.
+
+        inner=M > 0: two-level batch -- theta is [D,P] (one row per posterior draw), y0 / consts /
+        ts have M rows (one per series) and ys is [D*M, T, S] (predictive.py:150-154)."""
         import torch
 
         tdt = torch.float64 if self.dtype == np.float64 else torch.float32
@@ -182,18 +186,23 @@ class CompiledModel:
                 raise ValueError(f"expected a {want}-D array with last dim {width}, got {tuple(x.shape)}")
             return x
 
-        Bs = [a.shape[0] for a, ax in ((y0, in_axes[0]), (theta, in_axes[1]),
-                                       (consts, in_axes[2]), (ts, in_axes[3])) if ax == 0]
-        B = Bs[0] if Bs else 1
-        if any(b != B for b in Bs):
-            raise ValueError(f"inconsistent batch sizes {Bs}")
+        if inner:
+            if in_axes[1] != 0 or in_axes[0] != 0:
+                raise ValueError("two-level batch needs batched y0 and parameters")
+            B = theta.shape[0] * int(inner)
+        else:
+            Bs = [a.shape[0] for a, ax in ((y0, in_axes[0]), (theta, in_axes[1]),
+                                           (consts, in_axes[2]), (ts, in_axes[3])) if ax == 0]
+            B = Bs[0] if Bs else 1
+            if any(b != B for b in Bs):
+                raise ValueError(f"inconsistent batch sizes {Bs}")
         T = ts.shape[-1]
         # kernel 3 (tensor-core MLP) takes its own parameter pack [aux | UMMA weights]
         y0 = prep(y0, S, in_axes[0]); theta = prep(theta, -1 if kernel == 3 else P, in_axes[1])
         consts = prep(consts, Cn, in_axes[2]); ts = prep(ts, T, in_axes[3])
         cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
                             max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel,
-                            t0_from_ts=t0_from_ts)
+                            t0_from_ts=t0_from_ts, inner=inner)
         with torch.cuda.device(dev):
             ys = out if out is not None else torch.empty((B, T, S), dtype=tdt, device=dev)
             status = torch.empty(B, dtype=torch.int32, device=dev)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CTX_ABI_VERSION 1
+#define CTX_ABI_VERSION 2
 
 enum { CTX_F32 = 0, CTX_F64 = 1 };
 /* solver ids: simconfig.py:16 (`solver: Any = Tsit5`), simulation.py:23-26 (non-adaptive list) */
@@ -72,6 +72,11 @@ typedef struct ctx_solve_cfg {
   int32_t kernel;      /* 0 = auto, 1 = static one-thread-per-trajectory, 2 = persistent refill */
   int32_t t0_from_ts;  /* 0: integrate from t0 = 0 (simulation.py:262); 1: from time[0], as the
                           neural solves do (neuralode.py:52, rateflow.py:114) */
+  int32_t inner;       /* 0: one row index b for all operands.  M > 0: two-level batch
+                          b = d*M + m -- parameters are indexed by d, y0 / constants / time by m:
+                          vmap(per_draw)(thetas) over sim_func(y0s, theta, constants, times)
+                          (predictive.py:150-154, loo.py:180-193); ys is [D, M, T, S] */
+  int32_t reserved;
 } ctx_solve_cfg;
 
 /* ---- model lifetime -------------------------------------------------------------------

@@ -199,3 +199,35 @@ def test_bayesian_model_log_density_through_the_facade():
         np.testing.assert_allclose(g_sg.cpu().numpy(), want_gsg, rtol=2e-6)
     finally:
         ctx.enable_x64(False)
+
+
+def test_posterior_ensemble_two_level_batch():
+    """compute_ensemble's vmap(per_draw)(thetas) (predictive.py:150-154): [draws, M, T, S] from one
+    launch with ctx_solve_cfg.inner = M; compared with per-draw oracle solves, and its point-wise
+    log-likelihood summed over the data equals the fused K2 kernel's."""
+    import catalax_b200 as ctx
+    from catalax_b200.mcmc.predictive import EnsembleIntegrator, ensemble_times
+    from oracle import diffrax_oracle as do, symbolic as sy
+
+    ctx.enable_x64(True)
+    try:
+        model = ctx.Model(name="MM")
+        model.add_state(S="Substrate", E="Enzyme", P="Product")
+        model.add_ode("S", "-k_cat * E * S / (K_m + S)")
+        model.add_ode("P", "k_cat * E * S / (K_m + S)")
+        model.add_ode("E", "0")
+        D, M = 7, 9
+        mm, y0s, theta, consts, ts, data, sigma = _config4(D, M, seed=31)
+        grid = ensemble_times(ts, 33)
+        ens = EnsembleIntegrator(model)
+        ys = ens.integrate(y0s, theta, consts, grid).cpu().numpy()
+        assert ys.shape == (D, M, 33, 3)
+        rhs, *_ = sy.make_rhs(*mm[:4], mm[4])
+        for d in range(D):
+            ref = do.solve(rhs, y0s, theta[d], consts, grid, rtol=1e-5, atol=1e-5, dtype=np.float64)
+            np.testing.assert_allclose(ys[d], ref.ys, rtol=1e-6, atol=1e-9)
+        lp = ens.pointwise_log_likelihood(y0s, theta, sigma, consts, ts, data, "normal").cpu().numpy()
+        out, _, _ = _gpu(mm, y0s, theta, consts, ts, data, sigma, "normal", np.float64)
+        np.testing.assert_allclose(np.nansum(lp, axis=(1, 2, 3)), out[:, 0], rtol=1e-9)
+    finally:
+        ctx.enable_x64(False)
