@@ -230,7 +230,28 @@ def run_nuts_leg(a, model_field, dev, rank, world, dist):
     ms = float(t.item())
     fails = int((status != 0).sum().item())
     finite = bool(torch.isfinite(out).all().item())
+    # compute roofline of K2 (rank 0's numbers): algorithmic flops = sympy count_ops of the
+    # CSE'd field + tangent field, Tsit5 stage / error / controller arithmetic, dense output and
+    # likelihood terms vs the MEASURED FFMA/DFMA peak of this GPU.
+    roof = None
+    if rank == 0:
+        S, D = field.S, field.D
+        N = S * (1 + D)
+        F = field.flops_rhs + field.flops_tan
+        nacc, nrej = model.last_loglik_counts
+        steps = int((nacc.sum(dtype=torch.int64) + nrej.sum(dtype=torch.int64)).item())
+        flops_step = 6 * F + 56 * N + 8 * S + 11
+        flops_point = 40 + 14 * N + 25 * S
+        flops = steps * flops_step + CH * M * T * flops_point
+        peak = engine.measure_fma_peak(np.dtype(dt).name)
+        achieved = flops / (ms / n_iter * 1e-3) / 1e12
+        roof = {"bound": "fp32" if a.dtype == "f32" else "fp64", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "ctx_measure_fma_peak (FMA loop measured on this GPU)",
+                "flops_per_step": flops_step, "flops_per_saved_point": flops_point,
+                "steps_per_eval_batch": steps}
     return {"metric": "NUTS logp+grad evals/s", "value": CH * world * n_iter / (ms * 1e-3),
+            "roofline": roof,
             "unit": "evals/s", "ms_per_eval_batch": ms / n_iter,
             "series_solves_with_gradient_per_s": CH * world * M * n_iter / (ms * 1e-3),
             "config": {"chains_per_gpu": CH, "series": M, "points": T, "observables": 3,

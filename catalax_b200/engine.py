@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
     L.ctx_loglik_workspace_bytes.argtypes = [vp, C.POINTER(ctx_loglik_cfg)]
     L.ctx_loglik_grad.restype = C.c_int
     L.ctx_loglik_grad.argtypes = [vp, C.POINTER(ctx_loglik_cfg)] + [vp] * 11 + [C.c_size_t, vp]
+    L.ctx_measure_fma_peak.restype = C.c_int
+    L.ctx_measure_fma_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     L.ctx_rates.restype = C.c_int
     L.ctx_rates.argtypes = [vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, vp,
                             C.c_int32, vp, vp]
@@ -105,6 +107,13 @@ def _check(rc: int) -> None:
 
 def device_count() -> int:
     return int(lib().ctx_device_count())
+
+
+def measure_fma_peak(dtype: str = "float32") -> float:
+    """Measured FFMA (float32) / DFMA (float64) peak of the current GPU in TFLOP/s."""
+    v = C.c_double()
+    _check(lib().ctx_measure_fma_peak(F64 if np.dtype(dtype) == np.float64 else F32, C.byref(v)))
+    return float(v.value)
 
 
 def launch_count() -> int:
@@ -287,6 +296,10 @@ class CompiledModel:
             _check(lib().ctx_loglik_grad(self._h, C.byref(cfg), p(y0s), p(theta), p(consts), p(ts),
                                          p(data), p(mask), p(sigma), p(out), p(partial), p(status),
                                          p(ws), wsb, C.c_void_p(stream)))
+            # step counters live in the workspace: [256 B][status slot][n_accepted][n_rejected]
+            n = CH * M
+            counts = ws[256 + 4 * n: 256 + 12 * n].view(torch.int32)
+            self.last_loglik_counts = (counts[:n], counts[n:])
         return out, partial, status
 
     def rates(self, t, y, theta, consts, y0=None):

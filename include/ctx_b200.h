@@ -162,6 +162,9 @@ int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
 int ctx_abi_version(void);
 int ctx_device_count(void); /* 0 when no GPU is visible; never throws */
 size_t ctx_last_error(char* buf, size_t n);
+/* Measured dense FMA peak of the current device in TFLOP/s (2 flops per FMA; FFMA for CTX_F32,
+ * DFMA for CTX_F64): the roofline denominator of the compute-bound kernels. */
+int ctx_measure_fma_peak(int32_t dtype, double* tflops);
 /* number of kernel launches this library has issued in this process (bench "gpu_launches") */
 int64_t ctx_launch_count(void);
 
