@@ -1,0 +1,129 @@
+"""Edge cases of the solve seam against the oracle: every in_axes combination the reference's
+InAxes enum produces (inaxes.py:5-27), single-point and repeated-time grids, negative / early
+save times (Appendix A: integration always starts at t0 = 0), the unbatched call, ragged sizes."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _pair(model, y0, theta, consts, ts, in_axes, kernel, **kw):
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+    from oracle import diffrax_oracle as do, symbolic as sy
+
+    rhs, *_ = sy.make_rhs(*model[:4], model[4])
+    ref = do.solve(rhs, y0, theta, consts, ts, dtype=np.float64, **kw)
+    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), "float64")
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
+    out = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), in_axes=in_axes, kernel=kernel, **kw)
+    torch.cuda.synchronize()
+    return ref, out
+
+
+def _close(ys, ref, atol=1e-5):
+    np.testing.assert_array_equal(np.isinf(ys), np.isinf(ref))
+    fin = np.isfinite(ref)
+    assert (np.abs(ys[fin] - ref[fin]) <= 1e-6 * np.abs(ref[fin]) + 1e-3 * atol).all()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("in_axes", [(0, None, 0, None), (None, 0, None, None), (None, None, 0, None),
+                                     (None, None, None, 0), (0, 0, 0, 0), (0, None, 0, 0)])
+def test_every_in_axes_combination(in_axes, kernel):
+    rng = np.random.default_rng(12)
+    B = 37
+    model = cases.menten_fixture()            # 1 state, 2 parameters, 1 constant
+    y0 = rng.uniform(50, 150, (B, 1)) if in_axes[0] == 0 else np.array([100.0])
+    th = np.stack([rng.uniform(50, 150, B), rng.uniform(-2, -0.5, B)], 1) if in_axes[1] == 0 else np.array([100.0, -1.0])
+    c = rng.uniform(5, 15, (B, 1)) if in_axes[2] == 0 else np.array([10.0])
+    ts = np.sort(rng.uniform(0, 20, (B, 9)), axis=1) if in_axes[3] == 0 else np.linspace(0, 20, 9)
+    ref, out = _pair(model, y0, th, c, ts, in_axes, kernel, rtol=1e-5, atol=1e-5)
+    assert out.ys.shape == (B, 9, 1)
+    np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
+    _close(out.ys.cpu().numpy(), ref.ys)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_single_time_point_and_repeated_times(kernel):
+    model = cases.michaelis_menten()
+    y0 = np.array([[10.0, 0.0, 100.0], [12.0, 1.0, 80.0]])
+    th = np.array([40.0, 0.3])
+    ref, out = _pair(model, y0, th, np.zeros((2, 0)), np.array([7.5]), (0, None, 0, None), kernel)
+    _close(out.ys.cpu().numpy(), ref.ys)
+    ts = np.array([0.0, 0.0, 2.0, 2.0, 2.0, 9.0, 9.0])
+    ref, out = _pair(model, y0, th, np.zeros((2, 0)), ts, (0, None, 0, None), kernel)
+    ys = out.ys.cpu().numpy()
+    _close(ys, ref.ys)
+    np.testing.assert_array_equal(ys[:, 2], ys[:, 3])
+    np.testing.assert_array_equal(ys[:, 0], y0)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_save_times_before_t0_are_extrapolated_from_the_first_step(kernel):
+    """config.t0 only shapes the grid (model.py:664-665); the solve starts at 0 (simulation.py:262),
+    so earlier times are evaluated with the first step's interpolant."""
+    model = cases.michaelis_menten()
+    y0 = np.array([[10.0, 0.0, 100.0]])
+    ts = np.linspace(-0.05, 5.0, 12)
+    ref, out = _pair(model, y0, np.array([40.0, 0.3]), np.zeros((1, 0)), ts, (0, None, 0, None), kernel)
+    _close(out.ys.cpu().numpy(), ref.ys)
+    assert out.ys[0, 0, 2].item() > 100.0      # extrapolated backwards: more substrate than y0
+
+
+def test_unbatched_call_and_ragged_sizes_through_the_facade():
+    import catalax_b200 as ctx
+    from catalax_b200.tools.simulation import Simulation
+
+    ctx.enable_x64(True)
+    try:
+        model = ctx.Model(name="m")
+        model.add_state("s1")
+        model.add_constant("e")
+        model.add_ode("s1", "kcat * e * s1 / (k_m + s1)")
+        sim_input = model.sim_input
+        cfg = ctx.SimulationConfig(t1=10, nsteps=5)
+        f, _ = Simulation(sim_input=sim_input, config=cfg)._prepare_func(in_axes=None)
+        ys = f(np.array([100.0]), np.array([100.0, -1.0]), np.array([10.0]), np.linspace(0, 10, 5))
+        assert ys.shape == (5, 1) and ys[0, 0] == 100.0 and ys[-1, 0] < 100.0
+        for B in (1, 31, 33, 129):
+            f, _ = Simulation(sim_input=sim_input, config=cfg)._prepare_func(in_axes=(0, None, 0, None))
+            out = f(np.full((B, 1), 100.0), np.array([100.0, -1.0]), np.full((B, 1), 10.0),
+                    np.linspace(0, 10, 5))
+            assert out.shape == (B, 5, 1)
+            np.testing.assert_allclose(out, np.broadcast_to(ys, (B, 5, 1)), rtol=1e-12)
+    finally:
+        ctx.enable_x64(False)
+
+
+def test_long_segments_with_unaligned_rows_f32_and_f64():
+    """The warp-wide 128-bit store path needs 16-byte aligned groups of 4 points; T*S*w that is
+    not a multiple of 16 exercises its scalar fallback, T=1000 the vector path."""
+    model = cases.michaelis_menten()
+    rng = np.random.default_rng(3)
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+    from oracle import c_oracle
+
+    for dtype in (np.float32, np.float64):
+        co = c_oracle.COracle(*model[:4], model[4], dtype=dtype)
+        m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), np.dtype(dtype).name)
+        for T in (1000, 333, 50):
+            B = 70
+            y0, th, c = cases.mm_inputs(B, seed=T, dtype=dtype)
+            ts = np.linspace(0, 100, T).astype(dtype)
+            ref = co.solve(y0, th, c, ts, rtol=1e-6, atol=1e-6)
+            dev = torch.device("cuda:0")
+            tt = lambda a: torch.as_tensor(a, device=dev)
+            out = m.solve(tt(y0), tt(th), tt(c), tt(ts), in_axes=(0, 0, 0, None), rtol=1e-6, atol=1e-6, kernel=2)
+            ys = out.ys.cpu().numpy().astype(np.float64)
+            if dtype == np.float64:
+                _close(ys, ref.ys, atol=1e-6)
+            else:
+                scale = 1e-6 + 1e-6 * np.abs(ref.ys)
+                assert np.median(np.abs(ys - ref.ys) / scale) < 2.0
+                assert (np.abs(ys - ref.ys) <= 500 * scale).all()
