@@ -135,7 +135,7 @@ size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan) {
   const size_t deg = solver <= 1 ? 4 : 1;
   const size_t S = (size_t)d.n_states;
   const size_t rec = 2 + (deg + 1) * N;
-  return 32 * rec * w + 512 + 32 * S * w + (tan ? 32 * (N - S) * w : 0) + 256;
+  return 32 * rec * w + 512 + 32 * S * w + (tan ? 32 * (N - S) * w : 0) + 256 + 384;
 }
 
 // Warps per CTA of the persistent kernel: 4 when that fits the default 48 KB, otherwise as many

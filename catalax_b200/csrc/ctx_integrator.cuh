@@ -498,6 +498,8 @@ struct ctx_warp_smem {
   real stage_s[32 * CTX_S * CTX_D];  // tangents of one round, [point][state][direction]
 #endif
   long long gpt[32];             // element index (point*S) of each staged point (mixed rounds)
+  int seg_i0[32], seg_i1[32];    // [first, last) requested-time index of the segment
+  int seg_gf[32];                // (first group of the segment) - (its offset in the flat list)
 };
 
 // First index in [lo, T) with ts[index] > t (ts ascending, ts[T-1] = t_end > t).  Requested
@@ -649,6 +651,112 @@ ctx_solve_v1(const ctx_solve_args a) {
     if (filling) { nsave = T - idx; retire = true; }
 
     // ------------------------------------------------------------- cooperative saves
+#if !CTX_TAN
+    // Unified group path.  The pending save points of every lane are cut into groups of 4
+    // consecutive points aligned to multiples of 4 within their trajectory; all groups of all
+    // lanes are flattened and dealt out to the 32 lanes (consecutive lanes = consecutive groups
+    // of one segment), so every lane evaluates <= 4 points per pass from a register-cached
+    // record and writes them with 128-bit stores when the group is full and 16-byte aligned
+    // (scalar, masked stores at segment ends).  Loads of ts and the stores of a pass are
+    // contiguous across lanes; nothing is staged in shared memory.
+    const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
+    if (nz) {
+      const int gq0 = idx >> 2;
+      const int ng = nsave > 0 ? ((idx + nsave + 3) >> 2) - gq0 : 0;
+      int incl = ng;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(CTX_FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int goff = incl - ng;
+      const int gtotal = __shfl_sync(CTX_FULL, incl, 31);
+      if (nsave > 0) {
+        const int s = __popc(nz & lt_mask);
+        real coef[CTX_NCOEF];
+        if (filling) {
+          const bool fill_inf = status != 0;
+#pragma unroll
+          for (int i = 0; i < CTX_N; ++i) coef[i] = fill_inf ? CTX_INF : y[i];
+#pragma unroll
+          for (int i = CTX_N; i < CTX_NCOEF; ++i) coef[i] = R(0.0);
+          w.rec[0][s] = R(0.0);
+          w.rec[1][s] = R(0.0);
+        } else {
+          ctx_dense_coefs(rec_dt, y, ynew, K, coef);
+          w.rec[0][s] = rec_tp;
+          w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+        }
+#pragma unroll
+        for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
+        w.ts_off[s] = ts_row;
+        w.g_off[s] = b * (long long)T;
+        w.seg_i0[s] = idx;
+        w.seg_i1[s] = idx + nsave;
+        w.seg_gf[s] = gq0 - goff;
+      }
+      __syncwarp();
+      const unsigned myoff = nsave > 0 ? (unsigned)goff : 0xffffffffu;
+      int seg_base = 0, s_have = -1;
+      real r_tp = R(0.0), r_inv = R(0.0), r_coef[CTX_NCOEF];
+      int r_i0 = 0, r_i1 = 0, r_gf = 0;
+      const real* r_ts = a.ts;
+      real* r_ys = a.ys;
+      for (int g0 = 0; g0 < gtotal; g0 += 32) {
+        const unsigned dpos = myoff - (unsigned)g0;
+        const unsigned bits = __reduce_or_sync(CTX_FULL, dpos < 32u ? (1u << dpos) : 0u);
+        const int s = seg_base + __popc(bits & le_mask) - 1;
+        seg_base += __popc(bits);
+        const int g = g0 + lane;
+        if (s != s_have) {  // (lanes past gtotal follow the last segment: harmless)
+          s_have = s;
+          r_tp = w.rec[0][s]; r_inv = w.rec[1][s];
+#pragma unroll
+          for (int i = 0; i < CTX_NCOEF; ++i) r_coef[i] = w.rec[2 + i][s];
+          r_i0 = w.seg_i0[s]; r_i1 = w.seg_i1[s]; r_gf = w.seg_gf[s];
+          r_ts = a.ts + w.ts_off[s];
+          r_ys = a.ys + w.g_off[s] * CTX_S;
+        }
+        if (g < gtotal) {
+          const int p0 = (r_gf + g) << 2;
+          const real* tq = r_ts + p0;
+          real o[4 * CTX_S];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ok[u] = (p0 + u >= r_i0) && (p0 + u < r_i1);
+            const real th_ = ((ok[u] ? tq[u] : r_tp) - r_tp) * r_inv;
+#pragma unroll
+            for (int i = 0; i < CTX_S; ++i) {
+              real v = r_coef[CTX_DEG * CTX_N + i];
+#pragma unroll
+              for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + r_coef[mm * CTX_N + i];
+              o[u * CTX_S + i] = v;
+            }
+          }
+          real* dst = r_ys + (size_t)p0 * CTX_S;
+          if (ok[0] && ok[3] && (reinterpret_cast<size_t>(dst) & 15) == 0) {
+#if CTX_F64
+#pragma unroll
+            for (int k = 0; k < 2 * CTX_S; ++k)
+              reinterpret_cast<double2*>(dst)[k] = make_double2(o[2 * k], o[2 * k + 1]);
+#else
+#pragma unroll
+            for (int k = 0; k < CTX_S; ++k)
+              reinterpret_cast<float4*>(dst)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+#endif
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (ok[u]) {
+#pragma unroll
+                for (int i = 0; i < CTX_S; ++i) dst[u * CTX_S + i] = o[u * CTX_S + i];
+              }
+          }
+        }
+      }
+    }
+#else   // CTX_TAN: batched point path (states + tangents staged through shared memory)
     const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
     if (nz) {
       // Long segments (one accepted step covering >= CTX_LONG_SEG requested times) are written
@@ -833,6 +941,8 @@ ctx_solve_v1(const ctx_solve_args a) {
       }
       }  // total > 0
     }
+
+#endif  // CTX_TAN
 
     // ------------------------------------------------------------- advance / retire
     if (accepted) {
