@@ -373,7 +373,8 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
       return fail(CTX_E_INVALID, "weight-array models run the persistent kernel (kernel 0 or 2)");
     int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v0", &k);
     if (rc) return rc;
-    const unsigned block = 128;
+    unsigned block = 128;
+    if (const char* e = getenv("CTX_B200_V0_BLOCK")) block = (unsigned)std::max(32, std::min(128, atoi(e)));
     const unsigned long long grid = (cfg->batch + block - 1) / block;
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
     g_launches++;

@@ -403,11 +403,12 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 //   accepted / rejected steps their trajectories need ("step-count compaction").
 // * Dense output is not evaluated by the lane that owns the step.  Each lane with an accepted
 //   step that covers requested times publishes the step's interpolant as polynomial
-//   coefficients in theta = (t - tprev)/dt in shared memory; the warp then spreads ALL pending
-//   save points of ALL its lanes evenly over its 32 lanes (consecutive lanes = consecutive
-//   save points of one trajectory), evaluates the polynomial (Horner), stages the results in
-//   shared memory and copies them out as contiguous runs: fully coalesced stores into
-//   ys[B,T,S] although neighbouring lanes integrate unrelated trajectories.
+//   coefficients in theta = (t - tprev)/dt in shared memory; the warp then cuts ALL pending save
+//   points of ALL its lanes into groups of 4 consecutive points, deals the flattened groups out
+//   to its 32 lanes (consecutive lanes = consecutive groups of one trajectory), evaluates the
+//   polynomial (Horner) and writes each group with 128-bit stores: coalesced stores into
+//   ys[B,T,S] although neighbouring lanes integrate unrelated trajectories.  (Kernels that also
+//   write tangents use a point-wise variant staged through shared memory.)
 // * inf-fill of failed trajectories and the t0 == t1 case reuse the same path (a constant
 //   polynomial inf / y0).
 //
@@ -424,9 +425,6 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #endif
 #ifndef CTX_MIN_BLOCKS
 #define CTX_MIN_BLOCKS 1
-#endif
-#ifndef CTX_LONG_SEG
-#define CTX_LONG_SEG 32   // requested times per accepted step from which the warp-wide path pays
 #endif
 #define CTX_FULL 0xffffffffu
 
@@ -759,27 +757,16 @@ ctx_solve_v1(const ctx_solve_args a) {
 #else   // CTX_TAN: batched point path (states + tangents staged through shared memory)
     const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
     if (nz) {
-      // Long segments (one accepted step covering >= CTX_LONG_SEG requested times) are written
-      // by the whole warp, 4 consecutive points per lane, straight from registers with 128-bit
-      // stores; everything else goes through the batched path below.
-#if CTX_TAN
-      const bool is_long = false;
-#else
-      const bool is_long = nsave >= CTX_LONG_SEG;
-#endif
-      const unsigned nzl = __ballot_sync(CTX_FULL, is_long);
-      const int nshort = is_long ? 0 : nsave;
-      int incl = nshort;
+      int incl = nsave;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const int v = __shfl_up_sync(CTX_FULL, incl, d);
         if (lane >= d) incl += v;
       }
-      const int off = incl - nshort;
+      const int off = incl - nsave;
       const int total = __shfl_sync(CTX_FULL, incl, 31);
       if (nsave > 0) {
-        // short segments take slots 0,1,.. in lane order, long ones 31,30,..
-        const int s = is_long ? 31 - __popc(nzl & lt_mask) : __popc((nz & ~nzl) & lt_mask);
+        const int s = __popc(nz & lt_mask);
         real coef[CTX_NCOEF];
         if (filling) {
           const bool fill_inf = status != 0;
@@ -801,62 +788,9 @@ ctx_solve_v1(const ctx_solve_args a) {
         w.g_off[s] = b * (long long)T + idx - off;
       }
       __syncwarp();
-#if !CTX_TAN
-      for (unsigned lm = nzl; lm; lm &= lm - 1u) {
-        const int src = __ffs(lm) - 1;
-        const int s = 31 - __popc(nzl & ((1u << src) - 1u));
-        const int n = __shfl_sync(CTX_FULL, nsave, src);
-        const int i0 = __shfl_sync(CTX_FULL, idx, src);
-        const long long bs = __shfl_sync(CTX_FULL, b, src);
-        const long long ts_row_s = __shfl_sync(CTX_FULL, ts_row, src);
-        const real l_tp = w.rec[0][s], l_inv = w.rec[1][s];
-        real lc[CTX_NCOEF];
-#pragma unroll
-        for (int i = 0; i < CTX_NCOEF; ++i) lc[i] = w.rec[2 + i][s];
-        const real* tsp = a.ts + ts_row_s;
-        real* yp = a.ys + (size_t)bs * T * CTX_S;
-        const int i1 = i0 + n;
-        const int qe = (i1 + 3) >> 2;
-        for (int q = (i0 >> 2) + lane; q < qe; q += 32) {
-          const int p0 = q << 2;
-          real o[4 * CTX_S];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int pc = min(max(p0 + u, i0), i1 - 1);
-            const real th_ = (tsp[pc] - l_tp) * l_inv;
-#pragma unroll
-            for (int i = 0; i < CTX_S; ++i) {
-              real v = lc[CTX_DEG * CTX_N + i];
-#pragma unroll
-              for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + lc[mm * CTX_N + i];
-              o[u * CTX_S + i] = v;
-            }
-          }
-          real* dst = yp + (size_t)p0 * CTX_S;
-          if (p0 >= i0 && p0 + 3 < i1 && (reinterpret_cast<size_t>(dst) & 15) == 0) {
-#if CTX_F64
-#pragma unroll
-            for (int k = 0; k < 2 * CTX_S; ++k)
-              reinterpret_cast<double2*>(dst)[k] = make_double2(o[2 * k], o[2 * k + 1]);
-#else
-#pragma unroll
-            for (int k = 0; k < CTX_S; ++k)
-              reinterpret_cast<float4*>(dst)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-#endif
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (p0 + u >= i0 && p0 + u < i1) {
-#pragma unroll
-                for (int i = 0; i < CTX_S; ++i) dst[u * CTX_S + i] = o[u * CTX_S + i];
-              }
-          }
-        }
-      }
-#endif
       if (total > 0) {
       // myoff: where this lane's segment starts in the flattened list (none: never matches)
-      const unsigned myoff = nshort > 0 ? (unsigned)off : 0xffffffffu;
+      const unsigned myoff = nsave > 0 ? (unsigned)off : 0xffffffffu;
       int seg_base = 0, s_have = -1;
       real r_tp = R(0.0), r_inv = R(0.0), r_coef[CTX_NCOEF];
       const real* tq_ptr = a.ts;       // &ts[segment offset + j] of this lane's point
