@@ -94,6 +94,53 @@ class NeuralBase:
                                                          self.max_time, **self._extra())
         return self._compiled["tc"]
 
+    # ------------------------------------------------------------------ reference checkpoints
+    @classmethod
+    def from_eqx(cls, path, **overrides):
+        """Load a model saved by the reference's ``save_to_eqx`` (neuralbase.py:481-571).
+
+        File layout (equinox ``tree_serialise_leaves``): one JSON line with the constructor
+        hyper-parameters, then every array leaf as consecutive ``numpy.save`` blobs in pytree
+        order -- for the MLP classes: ``W_0, b_0, W_1, b_1, ..., W_last[, b_last]`` followed by
+        the scalar ``max_time`` and static fields (ignored).  Plain NeuralODE checkpoints are
+        supported; RateFlow / Universal checkpoints carry extra leaves and raise."""
+        import json
+
+        with open(path, "rb") as f:
+            header = json.loads(f.readline().decode())
+            hp = dict(header["hyperparameters"])
+            leaves = []
+            while True:
+                try:
+                    leaves.append(np.load(f, allow_pickle=False))
+                except (EOFError, ValueError):
+                    break
+        if cls.kind != "neuralode" or hp.get("rbf"):
+            raise NotImplementedError("only plain NeuralODE .eqx checkpoints are supported")
+        S, W, depth = int(hp["data_size"]), int(hp["width_size"]), int(hp["depth"])
+        out = int(hp["out_size"]) if hp.get("out_size") else S
+        dims = [S + 1] + [W] * depth + [out]
+        weights, biases, k = [], [], 0
+        for l, (i, o) in enumerate(zip(dims[:-1], dims[1:])):
+            Wm = leaves[k]; k += 1
+            if Wm.shape != (o, i):
+                raise ValueError(f"{path}: layer {l} weight has shape {Wm.shape}, expected {(o, i)}")
+            weights.append(Wm)
+            has_bias = l < depth or bool(hp.get("use_final_bias"))
+            if has_bias:
+                biases.append(leaves[k]); k += 1
+            else:
+                biases.append(None)
+        max_time = float(leaves[k]) if k < len(leaves) and leaves[k].shape == () else 1.0
+        kw = dict(data_size=S, width_size=W, depth=depth, state_order=hp["state_order"],
+                  observable_indices=hp.get("observable_indices"),
+                  activation=hp.get("activation", "softplus"),
+                  final_activation=hp.get("final_activation"),
+                  use_final_bias=bool(hp.get("use_final_bias")), out_size=hp.get("out_size"),
+                  max_time=max_time, weights=weights, biases=biases)
+        kw.update(overrides)
+        return cls(**kw)
+
     def get_weights_and_biases(self):
         return [a for pair in zip(self.weights, self.biases) for a in pair if a is not None]
 
