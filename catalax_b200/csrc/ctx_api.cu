@@ -86,6 +86,7 @@ struct ctx_model {
   bool theta_ptr = false;           // generated with CTX_THETA_PTR (shared weights in smem)
   int p_pad = 0;
   int mlp_tc_smem = 0;              // > 0: the tcgen05 MLP kernel is available (bytes of smem)
+  int warp_warps = 0;               // > 0: lane-parallel form present (ctx_solve_w), warps per CTA
   // host-call staging (ctx_solve_host)
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -321,6 +322,9 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     // faster (profiles/).  Weight-array (MLP) models always take it.
     const size_t n_regs = (size_t)d.n_states * (1 + (tan ? d.n_dirs : 0)) * (d.dtype == CTX_F64 ? 2 : 1);
     kernel = (warps > 0 && (n_regs <= 24 || m->theta_ptr)) ? 2 : 1;
+    // ... and a warp per trajectory (lane = state) beats both once the generated field has a
+    // lane-parallel form (config 3, 32 states: 2.4x over the static kernel).
+    if (kernel == 1 && m->warp_warps > 0 && !tan) kernel = 4;
   }
   cudaKernel_t k;
   void* params[] = {&a};
@@ -367,6 +371,25 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(512), params,
                               (size_t)m->mlp_tc_smem, stream));
+    g_launches++;
+  } else if (kernel == 4) {
+    // K1w: one warp per trajectory, persistent warps (ctx_integrator.cuh ctx_solve_w)
+    if (m->warp_warps <= 0 || tan)
+      return fail(CTX_E_INVALID, "warp-per-trajectory kernel: model has no lane-parallel form "
+                                 "(or tangents were requested)");
+    int rc = get_kernel(m, cfg->solver, 0, "ctx_solve_w", &k);
+    if (rc) return rc;
+    const unsigned block = 32u * m->warp_warps;
+    int dev = 0, sms = 0, per_sm = 0;
+    CTX_CUDA(cudaGetDevice(&dev));
+    CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, 0));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long grid = (unsigned long long)sms * per_sm;
+    const unsigned long long want = (cfg->batch + m->warp_warps - 1) / m->warp_warps;
+    if (grid > want) grid = want;
+    CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
     g_launches++;
   } else if (kernel == 1) {
     if (m->theta_ptr && warps > 0)
@@ -522,6 +545,8 @@ int ctx_model_compile(const char* field_src, const ctx_model_desc* desc, ctx_mod
     if (m->p_pad < desc->n_params) m->p_pad = desc->n_params;
   }
   if (const char* q = strstr(field_src, "#define CTX_MLP_TC_SMEM ")) m->mlp_tc_smem = atoi(q + 24);
+  if (strstr(field_src, "#define CTX_HAVE_WARP 1"))
+    if (const char* q = strstr(field_src, "#define CTXW_WARPS ")) m->warp_warps = atoi(q + 19);
   *out = m;
   return CTX_OK;
 }

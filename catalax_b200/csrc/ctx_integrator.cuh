@@ -1168,6 +1168,248 @@ extern "C" __global__ void __launch_bounds__(128) ctx_rates(const ctx_rates_args
   for (int i = 0; i < CTX_S; ++i) a.out[(size_t)n * CTX_S + i] = dy[i];
 }
 
+
+// =====================================================================================
+// kernel K1w: one WARP per trajectory (lane = state) for models whose state does not fit the
+// registers of one thread
+// =====================================================================================
+// Same algorithm as ctx_solve_v0 / v1 (simulation.py:259-273 under vmap :346-355), laid out for
+// large S: lane l owns states l, l+32, ... (CTXW_NSS per lane) with their 7 stage slopes in
+// registers; the vector field is the generated lane-parallel form (tools/codegen.py
+// generate_warp_form): stage state -> shared memory, every lane evaluates its terms (ODE
+// right-hand sides / reaction rates, one structural class per slot so the instruction stream is
+// shared), terms -> shared memory, every lane sums its ELL row of the stoichiometric matrix.
+// The error norm is a warp-shuffle reduction, so accept / reject, the step size and the number
+// of requested times covered by a step are warp-uniform: no divergence at all.  Saved points
+// are written by all lanes at once: S contiguous values per requested time.
+// Persistent warps claim trajectories from a global counter.
+#if defined(CTX_HAVE_WARP) && !CTX_TAN
+#define CTXW_NY (CTXW_NSS * 32)
+#define CTXW_NRS (CTXW_NTS * 32 + 32)
+#ifndef CTXW_MIN_BLOCKS
+#define CTXW_MIN_BLOCKS 1
+#endif
+
+struct ctxw_ctx {
+  int it[CTXW_NI];
+  real rt[CTXW_NR];
+  real pre[CTXW_NPRE];
+  real* sy;
+  real* sr;
+  int lane;
+};
+
+__device__ __forceinline__ void ctxw_field(const ctxw_ctx& w, const real t, const real* yv,
+                                           real* dy) {
+#pragma unroll
+  for (int u = 0; u < CTXW_NSS; ++u) w.sy[u * 32 + w.lane] = yv[u];
+  __syncwarp();
+  ctxw_terms(w.it, w.pre, t, w.sy, w.sr, w.lane);
+  __syncwarp();
+  ctxw_dy(w.it, w.rt, w.sr, dy);
+}
+
+extern "C" __global__ void __launch_bounds__(CTXW_WARPS * 32, CTXW_MIN_BLOCKS)
+ctx_solve_w(const ctx_solve_args a) {
+  __shared__ real sm_y[CTXW_WARPS][CTXW_NY];
+  __shared__ real sm_r[CTXW_WARPS][CTXW_NRS];
+  ctxw_ctx w;
+  w.lane = threadIdx.x & 31;
+  w.sy = sm_y[threadIdx.x >> 5];
+  w.sr = sm_r[threadIdx.x >> 5];
+  const int lane = w.lane;
+#pragma unroll
+  for (int k = 0; k < CTXW_NI; ++k) w.it[k] = ctxw_itab[k * 32 + lane];
+#pragma unroll
+  for (int k = 0; k < CTXW_NR; ++k) w.rt[k] = ctxw_rtab[k * 32 + lane];
+  w.sr[CTXW_NTS * 32 + lane] = R(0.0);   // the column padded ELL entries point at
+  const int T = a.T;
+  bool valid[CTXW_NSS];
+#pragma unroll
+  for (int u = 0; u < CTXW_NSS; ++u) valid[u] = (u * 32 + lane) < CTX_S;
+
+  while (true) {
+    unsigned long long bb = 0;
+    if (lane == 0) bb = atomicAdd(a.work_counter, 1ull);
+    bb = __shfl_sync(CTX_FULL, bb, 0);
+    if (bb >= (unsigned long long)a.B) break;
+    const long long b = (long long)bb;
+    CTX_ROWS(b, ro, ri);
+    real y[CTXW_NSS], ynew[CTXW_NSS], yt[CTXW_NSS];
+    real K[CTX_NST][CTXW_NSS];
+#pragma unroll
+    for (int u = 0; u < CTXW_NSS; ++u)
+      y[u] = valid[u] ? a.y0[(size_t)ri * a.stride_y0 + u * 32 + lane] : R(0.0);
+    ctxw_preload(w.it, a.theta + (size_t)ro * a.stride_theta,
+                 a.consts + (size_t)ri * a.stride_consts, a.y0 + (size_t)ri * a.stride_y0, w.pre);
+    const real* ts = a.ts + (size_t)ri * a.stride_ts;
+    real* out = a.ys + (size_t)b * T * CTX_S;
+    const real t_end = ts[T - 1];
+    real tprev = a.t0_from_ts ? ts[0] : R(0.0);
+    real tnext = fmin(tprev + a.dt0, t_end);
+    int idx = 0, nacc = 0, nrej = 0, status = 0;
+
+    if (!(tprev < t_end)) {   // t0 == t1: every requested time is t0
+      for (; idx < T; ++idx) {
+#pragma unroll
+        for (int u = 0; u < CTXW_NSS; ++u)
+          if (valid[u]) out[(size_t)idx * CTX_S + u * 32 + lane] = y[u];
+      }
+    }
+    ctxw_field(w, tprev, y, K[0]);
+
+    for (int n = 0; tprev < t_end; ++n) {
+      if (n >= a.max_steps) { status = CTX_ST_MAX; break; }
+      const real dt = tnext - tprev;
+      // ---- stages (same tableau macros as ctx_rk_stages; K holds f_i)
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u) yt[u] = y[u] + dt * (A21 * K[0][u]);
+      ctxw_field(w, tprev + C2 * dt, yt, K[1]);
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u) yt[u] = y[u] + dt * (A31 * K[0][u] + A32 * K[1][u]);
+      ctxw_field(w, tprev + C3 * dt, yt, K[2]);
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u)
+        yt[u] = y[u] + dt * (A41 * K[0][u] + A42 * K[1][u] + A43 * K[2][u]);
+      ctxw_field(w, tprev + C4 * dt, yt, K[3]);
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u)
+        yt[u] = y[u] + dt * (A51 * K[0][u] + A52 * K[1][u] + A53 * K[2][u] + A54 * K[3][u]);
+      ctxw_field(w, tprev + C5 * dt, yt, K[4]);
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u)
+        yt[u] = y[u] + dt * (A61 * K[0][u] + A62 * K[1][u] + A63 * K[2][u] + A64 * K[3][u] +
+                             A65 * K[4][u]);
+      ctxw_field(w, tprev + dt, yt, K[5]);
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u)
+        ynew[u] = y[u] + dt * (A71 * K[0][u] + A72 * K[1][u] + A73 * K[2][u] + A74 * K[3][u] +
+                               A75 * K[4][u] + A76 * K[5][u]);
+      ctxw_field(w, tprev + dt, ynew, K[6]);
+#elif CTX_SOLVER == 2
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u) ynew[u] = y[u] + dt * K[0][u];
+#else
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u) yt[u] = y[u] + dt * K[0][u];
+      ctxw_field(w, tprev + dt, yt, K[1]);
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u) ynew[u] = y[u] + dt * (R(0.5) * K[0][u] + R(0.5) * K[1][u]);
+#endif
+      bool keep = true;
+      real dt_next = a.dt0;
+#if CTX_ADAPTIVE
+      {
+        bool my_nan = false;
+#pragma unroll
+        for (int u = 0; u < CTXW_NSS; ++u) my_nan |= valid[u] && (ynew[u] != ynew[u]);
+        const bool has_nan = __any_sync(CTX_FULL, my_nan);
+        real ssq = R(0.0);
+#pragma unroll
+        for (int u = 0; u < CTXW_NSS; ++u) {
+          real e = dt * (E1 * K[0][u] + E2 * K[1][u] + E3 * K[2][u] + E4 * K[3][u] +
+                         E5 * K[4][u] + E6 * K[5][u] + E7 * K[6][u]);
+          if (e != e) e = CTX_INF;
+          const real y1 = has_nan ? y[u] : ynew[u];
+          const real sc = a.atol + fmax(fabs(y[u]), fabs(y1)) * a.rtol;
+          const real r = e / sc;
+          if (valid[u]) ssq += r * r;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ssq += __shfl_xor_sync(CTX_FULL, ssq, d);
+        ssq = __shfl_sync(CTX_FULL, ssq, 0);
+        const real scaled = sqrt(ssq / (real)CTX_S);
+        keep = scaled < R(1.0);
+        const real inv = R(1.0) / scaled;
+        real factor = R(0.9) * pow(inv, R(0.2));
+        factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
+        if (factor != factor) factor = inv;
+        dt_next = dt * factor;
+      }
+#endif
+      if (keep) {
+        // ---- dense output: polynomial in theta of every owned state, evaluated for the
+        // requested times this step covers (lanes prefetch 32 times, then broadcast them)
+        real cf[CTXW_NSS][CTX_DEG + 1];
+#pragma unroll
+        for (int u = 0; u < CTXW_NSS; ++u) {
+#if CTX_SOLVER == 0
+          const real d2 = K[1][u] - K[0][u], d3 = K[2][u] - K[0][u], d4 = K[3][u] - K[0][u],
+                     d5 = K[4][u] - K[0][u], d6 = K[5][u] - K[0][u], d7 = K[6][u] - K[0][u];
+          cf[u][0] = y[u];
+          cf[u][1] = dt * K[0][u];
+          cf[u][2] = dt * (TB22 * d2 + TB32 * d3 + TB42 * d4 + TB52 * d5 + TB62 * d6 + TB72 * d7);
+          cf[u][3] = dt * (TB23 * d2 + TB33 * d3 + TB43 * d4 + TB53 * d5 + TB63 * d6 + TB73 * d7);
+          cf[u][4] = dt * (TB24 * d2 + TB34 * d3 + TB44 * d4 + TB54 * d5 + TB64 * d6 + TB74 * d7);
+#elif CTX_SOLVER == 1
+          const real ymid = y[u] + dt * (M1 * K[0][u] + M2 * K[1][u] + M3 * K[2][u] + M4 * K[3][u] +
+                                         M5 * K[4][u] + M6 * K[5][u] + M7 * K[6][u]);
+          const real f0 = dt * K[0][u], f1 = dt * K[6][u];
+          cf[u][0] = y[u];
+          cf[u][1] = f0;
+          cf[u][2] = f1 - R(4.0) * f0 - R(11.0) * y[u] - R(5.0) * ynew[u] + R(16.0) * ymid;
+          cf[u][3] = R(5.0) * f0 - R(3.0) * f1 + R(18.0) * y[u] + R(14.0) * ynew[u] - R(32.0) * ymid;
+          cf[u][4] = R(2.0) * (f1 - f0) - R(8.0) * (ynew[u] + y[u]) + R(16.0) * ymid;
+#else
+          cf[u][0] = y[u];
+          cf[u][1] = ynew[u] - y[u];
+#endif
+        }
+        const real inv_dt = (dt == R(0.0)) ? R(0.0) : R(1.0) / dt;
+        while (idx < T) {
+          const int j = idx + lane;
+          const real tq = (j < T) ? ts[j] : R(0.0);
+          const unsigned m = __ballot_sync(CTX_FULL, (j < T) && (tq <= tnext));
+          const int cnt = (m == CTX_FULL) ? 32 : __ffs((int)~m) - 1;
+          for (int q = 0; q < cnt; ++q) {
+            const real th_ = (__shfl_sync(CTX_FULL, tq, q) - tprev) * inv_dt;
+#pragma unroll
+            for (int u = 0; u < CTXW_NSS; ++u) {
+              real v = cf[u][CTX_DEG];
+#pragma unroll
+              for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + cf[u][mm];
+              if (valid[u]) out[(size_t)(idx + q) * CTX_S + u * 32 + lane] = v;
+            }
+          }
+          idx += cnt;
+          if (cnt < 32) break;
+        }
+#pragma unroll
+        for (int u = 0; u < CTXW_NSS; ++u) y[u] = ynew[u];
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#pragma unroll
+        for (int u = 0; u < CTXW_NSS; ++u) K[0][u] = K[6][u];
+#endif
+        tprev = tnext;
+        ++nacc;
+      } else {
+        ++nrej;
+      }
+#if !(CTX_SOLVER == 0 || CTX_SOLVER == 1)
+      if (keep) ctxw_field(w, tprev, y, K[0]);
+#endif
+      tprev = fmin(tprev, t_end);
+      real tn = tprev + dt_next;
+      if (tn > t_end - CTX_TOL_END) tn = keep ? t_end : tprev + R(0.5) * (t_end - tprev);
+      tnext = tn;
+      if (tprev < t_end && !(fabs(tnext) < CTX_INF)) { status = CTX_ST_BAD; break; }
+    }
+    if (tprev < t_end && status == 0) status = CTX_ST_MAX;
+    for (; idx < T; ++idx) {
+#pragma unroll
+      for (int u = 0; u < CTXW_NSS; ++u)
+        if (valid[u]) out[(size_t)idx * CTX_S + u * 32 + lane] = CTX_INF;
+    }
+    if (lane == 0) {
+      a.status[b] = status;
+      a.n_accepted[b] = nacc;
+      a.n_rejected[b] = nrej;
+    }
+  }
+}
+#endif  // CTX_HAVE_WARP
+
 #ifdef CTX_MLP_TC
 #include "ctx_mlp_tc.cuh"
 #endif

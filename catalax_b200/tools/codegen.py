@@ -224,6 +224,8 @@ class GeneratedField:
     flops_tan: int
     uses_t: bool
     key: str             # content hash (NVRTC cache key)
+    warp_form: bool = False   # lane-parallel form for the warp-per-trajectory kernel emitted
+    warp_info: dict = field(default_factory=dict)
 
 
 def _emit_block(exprs_out: Sequence[Tuple[str, sp.Expr]], names, tmp_prefix: str):
@@ -245,8 +247,13 @@ def _emit_block(exprs_out: Sequence[Tuple[str, sp.Expr]], names, tmp_prefix: str
     return lines, flops
 
 
-def generate_field(spec: FieldSpec, sens_theta: bool = False, sens_y0: bool = False) -> GeneratedField:
-    """Generate the CUDA device functions of one model."""
+def generate_field(spec: FieldSpec, sens_theta: bool = False, sens_y0: bool = False,
+                   warp_form="auto") -> GeneratedField:
+    """Generate the CUDA device functions of one model.
+
+    warp_form: "auto" emits the lane-parallel form (``generate_warp_form``) when a trajectory's
+    state no longer fits the registers of one thread (S > 24) and the equations fall into few
+    structural classes; True forces it (raises if impossible), False never emits it."""
     S, P, C = len(spec.states), len(spec.parameters), len(spec.constants)
     names = spec.symbol_names()
     f = [sp.sympify(e) for e in spec.total_exprs()]
@@ -318,6 +325,209 @@ def generate_field(spec: FieldSpec, sens_theta: bool = False, sens_y0: bool = Fa
         ]
     else:
         src += ["#define CTX_D 0", "#define CTX_D_THETA 0", "#define CTX_D_Y0 0"]
+    winfo = {}
+    if warp_form is True or (warp_form == "auto" and S > WARP_FORM_MIN_STATES):
+        wsrc, winfo = generate_warp_form(spec)
+        if wsrc is None:
+            if warp_form is True:
+                raise UnsupportedExpression(f"no lane-parallel form: {winfo.get('reason')}")
+            winfo = {}
+        else:
+            src += wsrc
     text = "\n".join(src) + "\n"
     key = hashlib.sha256(text.encode()).hexdigest()[:24]
-    return GeneratedField(text, S, P, C, D, n_theta, D - n_theta, flops_rhs, flops_tan, uses_t, key)
+    return GeneratedField(text, S, P, C, D, n_theta, D - n_theta, flops_rhs, flops_tan, uses_t, key,
+                          bool(winfo), winfo)
+
+
+# ---------------------------------------------------------------- lane-parallel ("warp") form
+WARP_FORM_MIN_STATES = 24     # below this a trajectory lives in the registers of one thread
+WARP_FORM_MAX_TERM_SLOTS = 12
+
+
+def _structural_key(expr: sp.Expr, kinds: Dict[sp.Symbol, Tuple[str, int]]):
+    """Rename the leaves of ``expr`` to typed placeholders in order of first appearance.
+
+    Returns (key, template expression over placeholder symbols, [(kind, index)] per placeholder).
+    Two equations with the same key differ only in WHICH state / parameter / constant / initial
+    value they read, so the 32 lanes of a warp can evaluate 32 of them with one instruction
+    stream and per-lane index tables."""
+    order: List[sp.Symbol] = []
+    for node in sp.preorder_traversal(expr):
+        if isinstance(node, sp.Symbol) and node != T_SYM and node not in order:
+            if node not in kinds:
+                raise KeyError(f"Missing input for symbol {node}")
+            order.append(node)
+    counters: Dict[str, int] = {}
+    sub, leaves = {}, []
+    for sym in order:
+        kind, index = kinds[sym]
+        n = counters.get(kind, 0)
+        counters[kind] = n + 1
+        sub[sym] = sp.Symbol(f"__{kind}{n}")
+        leaves.append((kind, index))
+    templ = expr.xreplace(sub)
+    return sp.srepr(templ), templ, [sub[s] for s in order], leaves
+
+
+def generate_warp_form(spec: FieldSpec):
+    """Lane-parallel form of the vector field for the warp-per-trajectory kernel ``ctx_solve_w``.
+
+    The field is the same ``dy = odes + S_mat @ rates`` as ``ctx_rhs`` (stack.py:159-173,
+    232-250, 332-349) but laid out for 32 lanes working on ONE trajectory:
+
+    * every non-zero ODE right-hand side and every reaction rate is a *term*; terms are grouped
+      by structural class (``_structural_key``) and each class is padded to whole slots of 32
+      terms, so slot q of lane l evaluates term ``32 q + l`` with straight-line code shared by
+      all lanes (state values gathered from shared memory through per-lane index registers;
+      parameters / constants / initial values pre-loaded into per-lane registers once per
+      trajectory);
+    * ``dy_i = sum_k coef[i][k] * term[col[i][k]]`` in ELL format (rows padded to the slot's
+      longest row with a column that always holds 0), lane l owning states ``l, l+32, ...``.
+
+    Returns (lines, info) or (None, {"reason": ...}) when the equations do not share structure.
+    """
+    S = len(spec.states)
+    kinds: Dict[sp.Symbol, Tuple[str, int]] = {}
+    for i, s_ in enumerate(spec.states):
+        kinds[sp.Symbol(s_)] = ("Y", i)
+        kinds[sp.Symbol(f"{s_}_init")] = ("I", i)
+    for i, p_ in enumerate(spec.parameters):
+        kinds[sp.Symbol(p_)] = ("P", i)
+    for i, c_ in enumerate(spec.constants):
+        kinds[sp.Symbol(c_)] = ("C", i)
+    sidx = {s_: i for i, s_ in enumerate(spec.states)}
+
+    # ---- terms: (expression, {state index: coefficient})
+    terms = []
+    for s_, e in spec.odes.items():
+        e = sp.sympify(e)
+        if e != 0 and s_ in sidx:
+            terms.append((e, {sidx[s_]: 1.0}))
+    for _sym, reactants, products, expr in sorted(spec.reactions, key=lambda r: r[0]):
+        row: Dict[int, float] = {}
+        for coef, st in reactants:
+            if st in sidx:
+                row[sidx[st]] = row.get(sidx[st], 0.0) - float(np.float32(coef))
+        for coef, st in products:
+            if st in sidx:
+                row[sidx[st]] = row.get(sidx[st], 0.0) + float(np.float32(coef))
+        row = {i: v for i, v in row.items() if v != 0.0}
+        if row:
+            terms.append((sp.sympify(expr), row))
+
+    # ---- structural classes -> slots
+    classes: Dict[str, dict] = {}
+    for n, (e, _row) in enumerate(terms):
+        key, templ, placeholders, leaves = _structural_key(e, kinds)
+        cl = classes.setdefault(key, {"templ": templ, "ph": placeholders, "members": []})
+        cl["members"].append((n, leaves))
+    n_term_slots = sum((len(c["members"]) + 31) // 32 for c in classes.values())
+    if n_term_slots > WARP_FORM_MAX_TERM_SLOTS:
+        return None, {"reason": f"{len(classes)} structural classes need {n_term_slots} term slots"}
+    NSS = (S + 31) // 32
+    zero_col = n_term_slots * 32          # rs[zero_col] == 0 always
+
+    itab: List[List[int]] = []            # [entry][lane]
+    rtab: List[List[float]] = []
+    pre_lines, term_lines = [], []
+    pos_of_term: Dict[int, int] = {}
+    n_pre = 0
+    flops = 0
+    slot = 0
+    for cl in classes.values():
+        members = cl["members"]
+        for s0 in range(0, len(members), 32):
+            chunk = members[s0:s0 + 32]
+            names: Dict[sp.Symbol, str] = {T_SYM: "t"}
+            for q, ph in enumerate(cl["ph"]):
+                col = [chunk[l][1][q][1] if l < len(chunk) else 0 for l in range(32)]
+                kind = chunk[0][1][q][0]
+                e_idx = len(itab)
+                itab.append(col)
+                if kind == "Y":
+                    names[ph] = f"ys[it[{e_idx}]]"
+                else:
+                    src_arr = {"P": "th", "C": "c", "I": "y0"}[kind]
+                    pre_lines.append(f"  pre[{n_pre}] = {src_arr}[it[{e_idx}]];")
+                    names[ph] = f"pre[{n_pre}]"
+                    n_pre += 1
+            lines, fl = _emit_block([(f"rs[{slot * 32} + lane]", cl["templ"])], names, f"w{slot}_")
+            term_lines += lines
+            flops += fl * len(chunk)
+            for l, (n, _leaves) in enumerate(chunk):
+                pos_of_term[n] = slot * 32 + l
+            slot += 1
+
+    # ---- ELL rows of dy = S_mat @ terms
+    rows: List[List[Tuple[int, float]]] = [[] for _ in range(NSS * 32)]
+    for n, (_e, row) in enumerate(terms):
+        for i, v in row.items():
+            rows[i].append((pos_of_term[n], v))
+    for r in rows:                          # equal coefficients line up across lanes -> literals
+        r.sort(key=lambda cv: (cv[1], cv[0]))
+    dy_lines = []
+    for u in range(NSS):
+        width = max((len(rows[u * 32 + l]) for l in range(32)), default=0)
+        parts = []
+        for k in range(width):
+            cols, coefs = [], []
+            for l in range(32):
+                r = rows[u * 32 + l]
+                cols.append(r[k][0] if k < len(r) else zero_col)
+                coefs.append(r[k][1] if k < len(r) else 0.0)
+            ei = len(itab)
+            itab.append(cols)
+            live = {v for v, cc in zip(coefs, cols) if cc != zero_col}
+            if len(live) == 1:              # same coefficient in every lane that has the entry
+                parts.append(f"{_lit(live.pop())} * rs[it[{ei}]]")
+            else:
+                parts.append(f"rt[{len(rtab)}] * rs[it[{ei}]]")
+                rtab.append(coefs)
+        dy_lines.append(f"  dy[{u}] = " + (" + ".join(parts) if parts else "R(0.0)") + ";")
+        flops += 2 * sum(len(rows[u * 32 + l]) for l in range(32))
+
+    NI, NR = max(len(itab), 1), max(len(rtab), 1)
+    if not itab:
+        itab = [[0] * 32]
+    if not rtab:
+        rtab = [[0.0] * 32]
+    per_warp_bytes = (NSS * 32 + n_term_slots * 32 + 32) * 8
+    warps = max(1, min(8, (40 * 1024) // per_warp_bytes))
+    if per_warp_bytes > 40 * 1024:
+        return None, {"reason": "term table does not fit shared memory"}
+    fl = lambda v: _lit(v)
+    out = [
+        "#define CTX_HAVE_WARP 1",
+        f"#define CTXW_NSS {NSS}",
+        f"#define CTXW_NTS {n_term_slots}",
+        f"#define CTXW_NI {NI}",
+        f"#define CTXW_NR {NR}",
+        f"#define CTXW_NPRE {max(n_pre, 1)}",
+        f"#define CTXW_WARPS {warps}",
+        "__device__ const int ctxw_itab[CTXW_NI * 32] = {",
+        *["  " + ", ".join(str(v) for v in row) + "," for row in itab],
+        "};",
+        "__device__ const real ctxw_rtab[CTXW_NR * 32] = {",
+        *["  " + ", ".join(fl(v) for v in row) + "," for row in rtab],
+        "};",
+        "__device__ __forceinline__ void ctxw_preload(const int* it, const real* th, const real* c,",
+        "                                             const real* y0, real* pre) {",
+        "  (void)it; (void)th; (void)c; (void)y0; (void)pre;",
+        *pre_lines,
+        "}",
+        "__device__ __forceinline__ void ctxw_terms(const int* it, const real* pre, const real t,",
+        "                                           const real* ys, real* rs, const int lane) {",
+        "  (void)it; (void)pre; (void)t; (void)ys;",
+        *term_lines,
+        "}",
+        "__device__ __forceinline__ void ctxw_dy(const int* it, const real* rt, const real* rs,",
+        "                                        real* dy) {",
+        "  (void)it; (void)rt; (void)rs;",
+        *dy_lines,
+        "}",
+    ]
+    info = {"classes": len(classes), "term_slots": n_term_slots, "state_slots": NSS,
+            "terms": len(terms), "flops_rhs": flops, "warps": warps,
+            "lane_utilisation": S / (NSS * 32.0)}
+    return out, info

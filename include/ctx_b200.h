@@ -69,7 +69,8 @@ typedef struct ctx_solve_cfg {
   int32_t n_times;     /* T = len(time) */
   int32_t max_steps;   /* simconfig.py:19 */
   double rtol, atol, dt0;
-  int32_t kernel;      /* 0 = auto, 1 = static one-thread-per-trajectory, 2 = persistent refill */
+  int32_t kernel;      /* 0 = auto, 1 = static one-thread-per-trajectory, 2 = persistent refill,
+                          3 = tcgen05 MLP tiles, 4 = one warp per trajectory (lane = state) */
   int32_t t0_from_ts;  /* 0: integrate from t0 = 0 (simulation.py:262); 1: from time[0], as the
                           neural solves do (neuralode.py:52, rateflow.py:114) */
   int32_t inner;       /* 0: one row index b for all operands.  M > 0: two-level batch

@@ -16,7 +16,7 @@ for dtype in ("float32", "float64"):
     k = torch.as_tensor(np.exp(rng.uniform(np.log(0.01), np.log(1.0), (B, 64))).astype(dtype), device=dev)
     c = torch.empty((B, 0), dtype=y0.dtype, device=dev)
     ts = torch.linspace(0, 10, 32, dtype=y0.dtype, device=dev)
-    for kernel in (1, 2):
+    for kernel in [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['1', '4'])]:
         times = []
         for it in range(3):
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)

@@ -27,6 +27,30 @@ extern "C" void eval_tan(double t, const double* y, const double* s, const doubl
   ctx_rhs_tan(t, y, s, th, c, y0, dy, ds);
 }
 #endif
+#ifdef CTX_HAVE_WARP
+// the lane-parallel form, emulated lane by lane exactly as ctx_solve_w runs it
+extern "C" void eval_warp(double t, const double* y, const double* th, const double* c,
+                          const double* y0, double* dy) {
+  static double ys[CTXW_NSS * 32], rs[CTXW_NTS * 32 + 32];
+  for (int i = 0; i < CTXW_NSS * 32; ++i) ys[i] = i < CTX_S ? y[i] : 0.0;
+  for (int i = 0; i < CTXW_NTS * 32 + 32; ++i) rs[i] = 0.0;
+  int it[CTXW_NI]; double rt[CTXW_NR], pre[CTXW_NPRE];
+  for (int lane = 0; lane < 32; ++lane) {
+    for (int k = 0; k < CTXW_NI; ++k) it[k] = ctxw_itab[k * 32 + lane];
+    ctxw_preload(it, th, c, y0, pre);
+    ctxw_terms(it, pre, t, ys, rs, lane);
+  }
+  for (int i = CTXW_NTS * 32; i < CTXW_NTS * 32 + 32; ++i) rs[i] = 0.0;
+  for (int lane = 0; lane < 32; ++lane) {
+    for (int k = 0; k < CTXW_NI; ++k) it[k] = ctxw_itab[k * 32 + lane];
+    for (int k = 0; k < CTXW_NR; ++k) rt[k] = ctxw_rtab[k * 32 + lane];
+    double d[CTXW_NSS];
+    ctxw_dy(it, rt, rs, d);
+    for (int u = 0; u < CTXW_NSS; ++u)
+      if (u * 32 + lane < CTX_S) dy[u * 32 + lane] = d[u];
+  }
+}
+#endif
 """
 
 
@@ -48,6 +72,8 @@ class HostField:
         self.lib.eval_rhs.argtypes = [C.c_double, dp, dp, dp, dp, dp]
         if field.D:
             self.lib.eval_tan.argtypes = [C.c_double, dp, dp, dp, dp, dp, dp, dp]
+        if getattr(field, "warp_form", False):
+            self.lib.eval_warp.argtypes = [C.c_double, dp, dp, dp, dp, dp]
 
     @staticmethod
     def _p(a):
@@ -57,6 +83,13 @@ class HostField:
         y, th, c, y0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (y, th, c, y0))
         dy = np.zeros(self.field.S)
         self.lib.eval_rhs(float(t), self._p(y), self._p(th), self._p(c), self._p(y0), self._p(dy))
+        return dy
+
+    def warp(self, t, y, th, c, y0):
+        """The lane-parallel form (generate_warp_form), emulated lane by lane."""
+        y, th, c, y0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (y, th, c, y0))
+        dy = np.zeros(self.field.S)
+        self.lib.eval_warp(float(t), self._p(y), self._p(th), self._p(c), self._p(y0), self._p(dy))
         return dy
 
     def tan(self, t, y, s, th, c, y0):

@@ -92,3 +92,47 @@ def test_operator_table_coverage():
 def test_missing_symbol_raises_like_the_reference():
     with pytest.raises(KeyError, match="Missing input for symbol"):
         cg.generate_field(cg.FieldSpec(["S"], ["k"], [], {"S": -sp.Symbol("k") * sp.Symbol("E") * sp.Symbol("S")}, []))
+
+
+WARP_MODELS = {
+    "nonautonomous": cases.nonautonomous,          # 4 classes, t, constants, *_init
+    "mm": cases.michaelis_menten,                  # ODE form, a zero right-hand side
+    "mass_action_32": lambda: cases.mass_action_network(32),   # 2 classes x 32 terms
+    "mass_action_40": lambda: cases.mass_action_network(40),   # ragged second state slot
+}
+
+
+@pytest.mark.parametrize("name", list(WARP_MODELS))
+def test_lane_parallel_form_equals_the_thread_form(name):
+    """generate_warp_form (the field of the warp-per-trajectory kernel ctx_solve_w), emulated
+    lane by lane on the host, equals ctx_rhs and the oracle's lambdify evaluation."""
+    model = WARP_MODELS[name]()
+    states, params, consts, odes, reactions = model
+    field = cg.generate_field(cases.field_spec(model), warp_form=True)
+    assert field.warp_form and field.warp_info["state_slots"] == (len(states) + 31) // 32
+    hf = HostField(field)
+    rhs, *_ = sy.make_rhs(states, params, consts, odes, reactions)
+    rng = np.random.default_rng(4)
+    for _ in range(4):
+        y = rng.uniform(0.1, 2.0, len(states)); th = rng.uniform(0.1, 1.5, len(params))
+        c = rng.uniform(0.1, 1.0, len(consts)); y0 = rng.uniform(0.1, 2.0, len(states))
+        t = rng.uniform(0, 3)
+        want = rhs(np.array([t]), y[None], th[None], c[None], y0[None])[0]
+        np.testing.assert_allclose(hf.warp(t, y, th, c, y0), want, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(hf.warp(t, y, th, c, y0), hf.rhs(t, y, th, c, y0), rtol=1e-13, atol=1e-15)
+
+
+def test_lane_parallel_form_is_automatic_only_for_large_structured_models():
+    small = cg.generate_field(cases.field_spec(cases.michaelis_menten()))
+    assert not small.warp_form and "CTX_HAVE_WARP" not in small.source
+    big = cg.generate_field(cases.field_spec(cases.mass_action_network(32)))
+    assert big.warp_form and big.warp_info["classes"] == 2 and big.warp_info["term_slots"] == 2
+    # 40 unrelated rate laws: too many structural classes -> thread form only
+    n = 40
+    states = [f"s{i:02d}" for i in range(n)]
+    odes = {s: sum(sp.Symbol(states[(i + j) % n]) ** (j + 1) for j in range(i % 13 + 1)) * sp.Symbol("k")
+            for i, s in enumerate(states)}
+    odd = cg.generate_field(cg.FieldSpec(states, ["k"], [], odes, []))
+    assert not odd.warp_form
+    with pytest.raises(cg.UnsupportedExpression):
+        cg.generate_field(cg.FieldSpec(states, ["k"], [], odes, []), warp_form=True)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_pair(model, y0, theta, consts, ts, in_axes, dtype, solver="tsit5", rtol=1e-6,
-              atol=1e-6, dt0=0.1, max_steps=4096, kernel=0):
+              atol=1e-6, dt0=0.1, max_steps=4096, kernel=0, warp_form="auto"):
     from catalax_b200 import engine
     from catalax_b200.tools import codegen as cg
     from oracle import diffrax_oracle as do, symbolic as sy
@@ -23,7 +23,7 @@ def _run_pair(model, y0, theta, consts, ts, in_axes, dtype, solver="tsit5", rtol
     rhs, N, D, _ = sy.make_rhs(states, params, consts_n, odes, reactions)
     ref = do.solve(rhs, y0, theta, consts, ts, solver=solver, rtol=rtol, atol=atol, dt0=dt0,
                    max_steps=max_steps, dtype=dtype)
-    field = cg.generate_field(cases.field_spec(model))
+    field = cg.generate_field(cases.field_spec(model), warp_form=warp_form)
     m = engine.CompiledModel(field, np.dtype(dtype).name)
     dev = torch.device("cuda:0")
     tt = lambda a: torch.as_tensor(np.asarray(a, dtype=dtype), device=dev)
@@ -206,7 +206,7 @@ def test_sensitivities_match_oracle_f64(solver, kernel):
     np.testing.assert_array_equal(sens[:, 0, :, :P], 0.0)
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", KERNELS + [4, 0])
 @pytest.mark.parametrize("per_row_k", [True, False])
 def test_mass_action_network_config3(per_row_k, kernel):
     """BASELINE configs[2] at test size: 32 states / 64 reactions (reaction form, stoichiometric
@@ -224,3 +224,89 @@ def test_mass_action_network_config3(per_row_k, kernel):
     _assert_close_f64(ys, ref.ys)
     # conservation: first-order steps conserve total mass, the A+B->C couplings remove one unit
     assert (ys.sum(axis=2)[:, -1] <= ys.sum(axis=2)[:, 0] + 1e-9).all()
+
+
+# ----------------------------------------------------------------------------- K1w (kernel 4)
+@pytest.mark.parametrize("solver,dt0", [("tsit5", 0.1), ("dopri5", 0.1), ("euler", 0.01), ("heun", 0.02)])
+def test_warp_kernel_general_field_all_solvers_f64(solver, dt0):
+    """ctx_solve_w with a field that has 4 structural classes, t, constants and *_init symbols,
+    per-row time grids (forced lane-parallel form; 4 of 32 lanes own a state)."""
+    rng = np.random.default_rng(5)
+    B = 67
+    y0 = rng.uniform(0.2, 2.0, (B, 4))
+    theta = rng.uniform(0.1, 1.0, (3,))
+    consts = rng.uniform(0.0, 0.5, (B, 1))
+    ts = np.sort(rng.uniform(0, 6.0, (B, 12)), axis=1)
+    ts[:, 0] = 0.0
+    ref, out = _run_pair(cases.nonautonomous(), y0, theta, consts, ts, (0, None, 0, 0),
+                         np.float64, solver=solver, dt0=dt0, rtol=1e-7, atol=1e-9,
+                         max_steps=100000, kernel=4, warp_form=True)
+    ys = out.ys.cpu().numpy()
+    assert (out.status.cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
+    np.testing.assert_array_equal(out.n_rejected.cpu().numpy(), ref.n_rejected)
+    _assert_close_f64(ys, ref.ys, atol=1e-9 if solver in ("tsit5", "dopri5") else 1e-6)
+
+
+@pytest.mark.parametrize("n_states", [40, 64])
+def test_warp_kernel_more_states_than_lanes(n_states):
+    """S > 32: every lane owns two states (the second slot ragged for S=40); T=70 > 32 so the
+    requested times of one step span more than one prefetch round."""
+    rng = np.random.default_rng(11)
+    B = 33
+    y0 = rng.uniform(0.1, 2.0, (B, n_states))
+    k = np.exp(rng.uniform(np.log(0.01), np.log(1.0), (B, 2 * n_states)))
+    ts = np.linspace(0, 10, 70)
+    ref, out = _run_pair(cases.mass_action_network(n_states), y0, k, np.zeros((B, 0)), ts,
+                         (0, 0, 0, None), np.float64, kernel=4)
+    assert (out.status.cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
+    _assert_close_f64(out.ys.cpu().numpy(), ref.ys)
+
+
+def test_warp_kernel_failure_semantics_and_degenerate_grid():
+    """max_steps exhaustion -> status 1 + inf fill; t0 == t1 -> y0 everywhere (kernel 4)."""
+    model = cases.mass_action_network(32)
+    rng = np.random.default_rng(3)
+    y0 = rng.uniform(0.1, 2.0, (5, 32))
+    k = np.exp(rng.uniform(np.log(0.01), np.log(1.0), (64,)))
+    ts = np.linspace(0, 10, 32)
+    ref, out = _run_pair(model, y0, k, np.zeros((5, 0)), ts, (0, None, 0, None), np.float64,
+                         rtol=1e-9, atol=1e-9, max_steps=12, kernel=4)
+    ys = out.ys.cpu().numpy()
+    np.testing.assert_array_equal(out.status.cpu().numpy(), ref.status)
+    assert (ref.status == 1).all()
+    np.testing.assert_array_equal(np.isinf(ys), np.isinf(ref.ys))
+    fin = np.isfinite(ref.ys)
+    np.testing.assert_allclose(ys[fin], ref.ys[fin], rtol=1e-9)
+    ref, out = _run_pair(model, y0, k, np.zeros((5, 0)), np.zeros((5, 3)), (0, None, 0, 0),
+                         np.float64, kernel=4)
+    np.testing.assert_array_equal(out.ys.cpu().numpy(),
+                                  np.broadcast_to(y0[:, None, :], (5, 3, 32)))
+
+
+def test_warp_kernel_f32_config3_statistical_bound():
+    """f32 (stated bound, as for kernels 1/2): error against an x64 truth within
+    200*(atol+rtol*|y|) and statistically no worse than the f32 oracle."""
+    from oracle import diffrax_oracle as do, symbolic as sy
+
+    model = cases.mass_action_network(32)
+    rng = np.random.default_rng(1)
+    B = 256
+    y0 = rng.uniform(0.1, 2.0, (B, 32)).astype(np.float32)
+    k = np.exp(rng.uniform(np.log(0.01), np.log(1.0), (B, 64))).astype(np.float32)
+    ts = np.linspace(0, 10, 32).astype(np.float32)
+    ref, out = _run_pair(model, y0, k, np.zeros((B, 0), np.float32), ts, (0, 0, 0, None),
+                         np.float32, kernel=4)
+    rhs, *_ = sy.make_rhs(*model[:4], model[4])
+    truth = do.solve(rhs, y0.astype(np.float64), k.astype(np.float64), np.zeros((B, 0)),
+                     ts.astype(np.float64), rtol=1e-10, atol=1e-10, dtype=np.float64,
+                     max_steps=100000).ys
+    ys = out.ys.cpu().numpy()
+    scale = 1e-6 + 1e-6 * np.abs(truth)
+    e_gpu = np.abs(ys.astype(np.float64) - truth) / scale
+    e_ref = np.abs(ref.ys.astype(np.float64) - truth) / scale
+    assert (out.status.cpu().numpy() == 0).all()
+    assert e_gpu.max() <= 200.0, e_gpu.max()
+    assert e_gpu.mean() <= 1.25 * e_ref.mean() + 0.05
+    assert np.percentile(e_gpu, 99.9) <= 1.5 * np.percentile(e_ref, 99.9) + 1.0
