@@ -74,6 +74,7 @@ struct Variant {
   cudaLibrary_t lib = nullptr;
   std::map<std::string, cudaKernel_t> kernels;
   int loaded_device = -1;
+  long v1_warp_smem = -1;   // sizeof(ctx_warp_smem) read back from the loaded module
 };
 
 }  // namespace
@@ -113,6 +114,8 @@ struct SolveArgs {
   int stride_y0, stride_theta, stride_consts, stride_ts;
   int t0_from_ts;
   int inner;
+  int q_div;
+  int ts_smem;
   real rtol, atol, dt0;
 };
 
@@ -128,22 +131,29 @@ struct RatesArgs {
   int stride_t, stride_theta, stride_consts, stride_y0;
 };
 
-// Shared memory of one warp of the persistent kernel = sizeof(ctx_warp_smem) in
-// ctx_integrator.cuh (step records + staging).
-size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan) {
+// Upper bound of sizeof(ctx_warp_smem) in ctx_integrator.cuh (input queue + step records +
+// staging); used to choose CTX_WARPS before compiling.  The launch uses the exact size the
+// module exports (ctx_v1_warp_smem_bytes).
+size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan, bool theta_ptr = false) {
   const size_t w = d.dtype == CTX_F64 ? 8 : 4;
-  const size_t N = (size_t)d.n_states * (1 + (tan ? d.n_dirs : 0));
-  const size_t deg = solver <= 1 ? 4 : 1;
   const size_t S = (size_t)d.n_states;
+  const size_t N = S * (1 + (tan ? d.n_dirs : 0));
+  const size_t deg = solver <= 1 ? 4 : 1;
+  const size_t qw = S + (theta_ptr ? 0 : (size_t)d.n_params) + (size_t)d.n_consts + 2;
+  const size_t q_in = 2 * qw * 32 * w;
+  if (!tan) {   // ctx_rec records (16-byte aligned) + one pending group per lane
+    const size_t rec = (((2 + (deg + 1) * N) * w + 6 * 4) + 15) / 16 * 16;
+    return q_in + 32 * rec + 32 * 4 * S * w + 64;
+  }
   const size_t rec = 2 + (deg + 1) * N;
-  return 32 * rec * w + 512 + 32 * S * w + (tan ? 32 * (N - S) * w : 0) + 256 + 384;
+  return q_in + 32 * rec * w + 3 * 32 * 8 + 32 * S * w + 32 * (N - S) * w + 64;
 }
 
 // Warps per CTA of the persistent kernel: 4 when that fits the default 48 KB, otherwise as many
 // as fit ~96 KB (opt-in dynamic shared memory, two CTAs per SM); 0 = a single warp's records do
 // not fit 200 KB, use the static kernel.
 int v1_warps(const ctx_model_desc& d, int solver, int tan, size_t fixed = 0) {
-  const size_t per_warp = v1_warp_smem(d, solver, tan);
+  const size_t per_warp = v1_warp_smem(d, solver, tan, fixed > 0);
   if (fixed + 4 * per_warp <= 48 * 1024) return 4;
   if (fixed >= 96 * 1024) return per_warp + fixed <= 200 * 1024 ? 1 : 0;
   size_t warps = (96 * 1024 - fixed) / per_warp;
@@ -180,7 +190,9 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
     size_t mb = 512 / (96 + 10 * words);
     mb = std::max<size_t>(1, std::min<size_t>(4, mb));
     if (m->theta_ptr) mb = 1;
-    opts.push_back("-DCTX_MIN_BLOCKS=" + std::to_string(mb));
+    const char* ex = getenv("CTX_B200_NVRTC_FLAGS");
+    if (!(ex && strstr(ex, "-DCTX_MIN_BLOCKS=")))   // developer override for A/B runs
+      opts.push_back("-DCTX_MIN_BLOCKS=" + std::to_string(mb));
   }
   const char* extra = getenv("CTX_B200_NVRTC_FLAGS");
   if (extra && *extra) {
@@ -272,6 +284,22 @@ int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_
   return CTX_OK;
 }
 
+// sizeof(ctx_warp_smem) of the loaded ctx_solve_v1 module (call after get_kernel)
+int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out) {
+  std::lock_guard<std::mutex> lk(m->mu);
+  Variant& v = m->variants[solver * 2 + tan];
+  if (v.v1_warp_smem < 0) {
+    void* dptr = nullptr;
+    size_t nbytes = 0;
+    unsigned val = 0;
+    CTX_CUDA(cudaLibraryGetGlobal(&dptr, &nbytes, v.lib, "ctx_v1_warp_smem_bytes"));
+    CTX_CUDA(cudaMemcpy(&val, dptr, sizeof(val), cudaMemcpyDeviceToHost));
+    v.v1_warp_smem = (long)val;
+  }
+  *out = (size_t)v.v1_warp_smem;
+  return CTX_OK;
+}
+
 template <typename real>
 int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0,
                  const void* theta, const void* consts, const void* ts, void* ys, void* sens,
@@ -308,6 +336,8 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.stride_ts = cfg->in_axes[3] == 0 ? cfg->n_times : 0;
   a.t0_from_ts = cfg->t0_from_ts ? 1 : 0;
   a.inner = cfg->inner > 0 ? cfg->inner : 0;
+  a.q_div = 1;
+  a.ts_smem = 0;
   if (a.inner > 0 && cfg->batch % a.inner != 0)
     return fail(CTX_E_INVALID, "two-level batch: batch must be a multiple of inner");
   a.rtol = (real)cfg->rtol;
@@ -331,15 +361,27 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   if (kernel == 2) {
     if (warps <= 0)
       return fail(CTX_E_INVALID, "persistent kernel: step record does not fit shared memory");
+    if (cfg->batch >= (1ll << 31))
+      return fail(CTX_E_INVALID, "persistent kernel: batch must be < 2^31 rows per call");
     int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k);
     if (rc) return rc;
     const unsigned block = 32u * warps;
     int dev = 0, sms = 0, per_sm = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = theta_smem(m) + (size_t)warps * v1_warp_smem(m->desc, cfg->solver, tan);
+    size_t per_warp = 0;
+    rc = v1_exact_warp_smem(m, cfg->solver, tan, &per_warp);
+    if (rc) return rc;
+    size_t smem = theta_smem(m) + (size_t)warps * per_warp;
     if (m->theta_ptr && a.stride_theta != 0)
       return fail(CTX_E_INVALID, "a weight-array model takes shared parameters (in_axes[1] = None)");
+    // a time grid shared by all trajectories is staged in shared memory (<= 32 KB)
+    const size_t ts_bytes = (((size_t)cfg->n_times + 3) & ~(size_t)3) * sizeof(real);
+    if (a.stride_ts == 0 && ts_bytes <= 32 * 1024 && smem + ts_bytes <= 200 * 1024 &&
+        !getenv("CTX_B200_NO_TS_SMEM")) {
+      a.ts_smem = 1;
+      smem += ts_bytes;
+    }
     if (smem > 48 * 1024)
       CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
@@ -349,6 +391,9 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     unsigned long long grid = (unsigned long long)sms * per_sm;
     const unsigned long long want = (cfg->batch + block - 1) / block;
     if (grid > want) grid = want;
+    // guided self-scheduling of the input queue: a warp claims remaining / (4 * warps in the
+    // grid) trajectories at a time, clamped to [1, 32]
+    a.q_div = (int)std::min<unsigned long long>(1u << 30, 4ull * grid * (unsigned long long)warps);
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
                               stream));

@@ -66,6 +66,8 @@ struct ctx_solve_args {
   int stride_y0, stride_theta, stride_consts, stride_ts;  // elements per row, 0 = shared
   int t0_from_ts;  // 0: integrate from t0 = 0 (simulation.py:262); 1: from ts[0] (neuralode.py:52)
   int inner;       // M > 0: b = d*M + m, theta row d, y0 / consts / ts row m (predictive.py:150-154)
+  int q_div;       // persistent kernels: a warp claims clamp(remaining / q_div, 1, 32) trajectories
+  int ts_smem;     // 1: the shared time grid (stride_ts == 0) is staged in shared memory
   real rtol, atol, dt0;
 };
 
@@ -423,6 +425,9 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #ifndef CTX_WARPS
 #define CTX_WARPS 4
 #endif
+#ifndef CTX_QUEUE
+#define CTX_QUEUE 1   // 1: cp.async input queue | 0: lanes load their next trajectory directly
+#endif
 #ifndef CTX_MIN_BLOCKS
 #define CTX_MIN_BLOCKS 1
 #endif
@@ -487,17 +492,62 @@ __device__ __forceinline__ void ctx_dense_coefs(const real dt, const real* y, co
 }
 
 #ifndef CTX_NO_V1
+// Input queue of a persistent warp.  A finished lane must not wait ~1 us for the y0 / parameter
+// rows of its next trajectory to arrive from HBM (the whole warp would wait with it, once per
+// iteration: 32 lanes / ~30 steps per trajectory).  Every warp therefore claims trajectories in
+// batches of q_batch, copies their operands with cp.async into one of two shared-memory buffers
+// (lane = entry) and consumes one buffer while the other is in flight; the atomicAdd that claims
+// the batch after next is issued a whole buffer ahead of its use as well.
+#if CTX_THETA_PTR
+#define CTX_QTH 0
+#else
+#define CTX_QTH CTX_P
+#endif
+#define CTX_QW (CTX_S + CTX_QTH + CTX_C + 2)   // y0, theta, constants, ts[0], ts[T-1]
+
+__device__ __forceinline__ void ctx_cp_async(real* dst_smem, const real* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+#if CTX_F64
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+#endif
+}
+#define CTX_CP_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define CTX_CP_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
+
+#if !CTX_TAN
+// One published step ("segment"): everything a lane needs to evaluate 4 requested times of it,
+// as one 16-byte-aligned record so that it moves with 128-bit shared-memory accesses.
+struct alignas(16) ctx_rec {
+  real v[2 + CTX_NCOEF];   // tp, 1/dt, polynomial coefficients [power][component]
+  int i0, i1;              // [first, last) requested-time index covered by the step
+  int gf;                  // (first group of the segment) - (its offset in the flat group list)
+  int owner;               // publishing lane (index of the trajectory's pending-point buffer)
+  int b, ri;               // trajectory index, row of its time grid
+};
+#define CTX_REC_Q ((int)(sizeof(ctx_rec) / 16))
+union ctx_rec_u {
+  ctx_rec r;
+  uint4 q[CTX_REC_Q];
+  __device__ __forceinline__ ctx_rec_u() {}
+};
+#define CTX_PEND_Q ((int)(4 * CTX_S * sizeof(real) / 16))   // 16-byte chunks of one group
+#endif
+
 struct ctx_warp_smem {
+  real q_in[2][CTX_QW][32];      // input queue: two buffers, one column per entry
+#if !CTX_TAN
+  ctx_rec rec[32];               // one record per publishing lane of this iteration
+  uint4 pend[32][CTX_PEND_Q];    // per lane: the group of 4 points its trajectory has not completed
+#else
   real rec[2 + CTX_NCOEF][32];   // tp, 1/dt, coefficients; one column per publishing lane
   long long ts_off[32];          // element offset into ts of the segment's save j = 0
   long long g_off[32];           // point index (b*T + idx) of the segment's save j = 0
   real stage_y[32 * CTX_S];      // interpolated states of one round, [point][state]
-#if CTX_TAN
   real stage_s[32 * CTX_S * CTX_D];  // tangents of one round, [point][state][direction]
-#endif
   long long gpt[32];             // element index (point*S) of each staged point (mixed rounds)
-  int seg_i0[32], seg_i1[32];    // [first, last) requested-time index of the segment
-  int seg_gf[32];                // (first group of the segment) - (its offset in the flat list)
+#endif
 };
 
 // First index in [lo, T) with ts[index] > t (ts ascending, ts[T-1] = t_end > t).  Requested
@@ -524,23 +574,61 @@ __device__ __forceinline__ int ctx_upper_bound(const real* ts, int lo, const int
   return hi;
 }
 
-extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
-ctx_solve_v1(const ctx_solve_args a) {
-  // dynamic smem: [CTX_THETA_PTR ? shared parameters (CTX_P_PAD reals)] [CTX_WARPS * ctx_warp_smem]
-  extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];
-#if CTX_THETA_PTR
-  real* th_smem = reinterpret_cast<real*>(ctx_dyn_smem);
-  for (int i = threadIdx.x; i < CTX_P; i += blockDim.x) th_smem[i] = a.theta[i];
-  __syncthreads();
-  const real* th = th_smem;
-  ctx_warp_smem& w = reinterpret_cast<ctx_warp_smem*>(ctx_dyn_smem + CTX_P_PAD * sizeof(real))[threadIdx.x >> 5];
-#else
-  ctx_warp_smem& w = reinterpret_cast<ctx_warp_smem*>(ctx_dyn_smem)[threadIdx.x >> 5];
+// issue the operand copies of the batch [base, base + q_batch) into queue buffer `buf`
+__device__ __forceinline__ void ctx_queue_fetch(const ctx_solve_args& a, ctx_warp_smem& w,
+                                                const int buf, const unsigned long long base,
+                                                const int count, const int lane) {
+  const unsigned long long u = base + (unsigned long long)lane;
+  if (lane < count && u < (unsigned long long)a.B) {
+    CTX_ROWS((long long)u, ro, ri);
+    (void)ro;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.y0 + (size_t)ri * a.stride_y0 + i);
+#if !CTX_THETA_PTR
+#pragma unroll
+    for (int i = 0; i < CTX_P; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.theta + (size_t)ro * a.stride_theta + i);
 #endif
+#pragma unroll
+    for (int i = 0; i < CTX_C; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.consts + (size_t)ri * a.stride_consts + i);
+    const real* tr = a.ts + (size_t)ri * a.stride_ts;
+    ctx_cp_async(&w.q_in[buf][k++][lane], tr);
+    ctx_cp_async(&w.q_in[buf][k++][lane], tr + (a.T - 1));
+  }
+  CTX_CP_COMMIT();
+}
+
+// TSM: the time grid is shared by all trajectories and staged in shared memory (ts_sm).
+template <bool TSM>
+__device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
+  // dynamic smem: [CTX_THETA_PTR ? shared parameters (CTX_P_PAD reals)]
+  //               [TSM ? time grid, padded to a multiple of 4 reals] [CTX_WARPS * ctx_warp_smem]
+  extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];
+  unsigned char* sm_cur = ctx_dyn_smem;
+#if CTX_THETA_PTR
+  real* th_smem = reinterpret_cast<real*>(sm_cur);
+  for (int i = threadIdx.x; i < CTX_P; i += blockDim.x) th_smem[i] = a.theta[i];
+  const real* th = th_smem;
+  sm_cur += CTX_P_PAD * sizeof(real);
+#endif
+  const int T = a.T;
+  const real* ts_base = a.ts;     // base of all time rows (shared memory copy when TSM)
+  if (TSM) {
+    real* ts_sm = reinterpret_cast<real*>(sm_cur);
+    const int Tpad = (T + 3) & ~3;
+    for (int i = threadIdx.x; i < Tpad; i += blockDim.x) ts_sm[i] = a.ts[min(i, T - 1)];
+    sm_cur += (size_t)Tpad * sizeof(real);
+    ts_base = ts_sm;
+  }
+#if CTX_THETA_PTR
+  __syncthreads();
+#else
+  if (TSM) __syncthreads();
+#endif
+  ctx_warp_smem& w = reinterpret_cast<ctx_warp_smem*>(sm_cur)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned le_mask = CTX_FULL >> (31 - lane);
-  const int T = a.T;
 
   // per-lane trajectory state
   long long b = -1;           // trajectory index, -1 = lane is free
@@ -553,25 +641,106 @@ ctx_solve_v1(const ctx_solve_args a) {
   real K[CTX_NST][CTX_N];
   real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
   int idx = 0, nacc = 0, nrej = 0, status = 0;
-  bool exhausted = false;
-  const real* tsr = a.ts;
+  const real* tsr = ts_base;
   long long ts_row = 0;       // element offset of this trajectory's time row
+  int ri_row = 0;             // row of its y0 / constants / time grid
+
+#if CTX_QUEUE
+  // input queue (warp-uniform state).  Claim sizes follow the work that is left (guided
+  // self-scheduling): whole warps of 32 while the batch is large, single trajectories at the
+  // end, so that no warp sits on a private backlog while others have run dry.
+  const unsigned long long Bq = (unsigned long long)a.B;
+  const unsigned long long qdiv = (unsigned long long)a.q_div;
+#define CTX_CLAIM(done) ((int)min(32ull, max(1ull, (Bq > (done) ? Bq - (done) : 0ull) / qdiv)))
+  unsigned long long qb_cur = 0, qb_nxt = 0, qb_pend = 0;
+  int qn_cur = CTX_CLAIM(0ull), qn_nxt = qn_cur, qn_pend = qn_cur;
+  int q_cur = 0, q_pos = 0;
+  bool q_empty = false;
+  {
+    if (lane == 0) qb_cur = atomicAdd(a.work_counter, (unsigned long long)(2 * qn_cur));
+    qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
+    qb_nxt = qb_cur + qn_cur;
+    ctx_queue_fetch(a, w, 0, qb_cur, qn_cur, lane);
+    ctx_queue_fetch(a, w, 1, qb_nxt, qn_nxt, lane);
+    qn_pend = CTX_CLAIM(qb_nxt + qn_nxt);
+    if (lane == 0) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);  // read one buffer later
+    CTX_CP_WAIT(1);
+    __syncwarp();
+    q_empty = qb_cur >= Bq;
+  }
 
   while (true) {
     // ------------------------------------------------------------- refill free lanes
     const unsigned need = __ballot_sync(CTX_FULL, b < 0);
-    if (need && !exhausted) {
+    if (need && !q_empty) {
+      const int nval = (int)min((unsigned long long)qn_cur, Bq - qb_cur);   // entries of this buffer
+      const int take = min(__popc(need), nval - q_pos);
+      const int rank = __popc(need & lt_mask);
+      if (b < 0 && rank < take) {
+        const int e = q_pos + rank;
+        b = (long long)qb_cur + e;
+        CTX_ROWS(b, ro, ri);
+        (void)ro;
+        ts_row = TSM ? 0 : ri * (long long)a.stride_ts;
+        ri_row = (int)ri;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = w.q_in[q_cur][k++][e];
+#if !CTX_THETA_PTR
+#pragma unroll
+        for (int i = 0; i < CTX_P; ++i) th[i] = w.q_in[q_cur][k++][e];
+#endif
+#pragma unroll
+        for (int i = 0; i < CTX_C; ++i) c[i] = w.q_in[q_cur][k++][e];
+        const real t_first = w.q_in[q_cur][k++][e];
+        t_end = w.q_in[q_cur][k++][e];
+#if CTX_TAN
+#pragma unroll
+        for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
+#pragma unroll
+        for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
+#endif
+        tsr = ts_base + ts_row;
+        tprev = a.t0_from_ts ? t_first : R(0.0);
+        tnext = fmin(tprev + a.dt0, t_end);
+        idx = 0; nacc = 0; nrej = 0; status = 0;
+        phase = (tprev < t_end) ? 0 : 1;  // t0 == t1: emit y0 for every requested time
+        ctx_field(tprev, y, th, c, y0, K[0]);
+      }
+      q_pos += take;
+      if (q_pos >= nval) {
+        // buffer consumed: the other one has been in flight for a whole buffer's worth of
+        // trajectories; recycle this one for the batch claimed one rotation ago
+        CTX_CP_WAIT(0);
+        __syncwarp();
+        const unsigned long long nbase = __shfl_sync(CTX_FULL, qb_pend, 0);
+        ctx_queue_fetch(a, w, q_cur, nbase, qn_pend, lane);
+        qb_cur = qb_nxt; qn_cur = qn_nxt;
+        qb_nxt = nbase; qn_nxt = qn_pend;
+        qn_pend = CTX_CLAIM(nbase + qn_nxt);
+        if (lane == 0 && nbase < Bq) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);
+        q_cur ^= 1; q_pos = 0;
+        q_empty = qb_cur >= Bq;
+      }
+    }
+#else   // direct refill: every lane loads its next trajectory from global memory itself
+  bool q_empty = false;
+  while (true) {
+    const unsigned need = __ballot_sync(CTX_FULL, b < 0);
+    if (need && !q_empty) {
       const int cnt = __popc(need);
       unsigned long long base = 0;
       if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)cnt);
       base = __shfl_sync(CTX_FULL, base, 0);
-      if (base + cnt >= (unsigned long long)a.B) exhausted = true;
+      if (base + cnt >= (unsigned long long)a.B) q_empty = true;
       if (b < 0) {
         const unsigned long long nb = base + __popc(need & lt_mask);
         if (nb < (unsigned long long)a.B) {
           b = (long long)nb;
           CTX_ROWS(b, ro, ri);
-          ts_row = ri * (long long)a.stride_ts;
+          (void)ro;
+          ts_row = TSM ? 0 : ri * (long long)a.stride_ts;
+          ri_row = (int)ri;
 #pragma unroll
           for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0[(size_t)ri * a.stride_y0 + i];
 #if !CTX_THETA_PTR
@@ -586,17 +755,21 @@ ctx_solve_v1(const ctx_solve_args a) {
 #pragma unroll
           for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
 #endif
-          tsr = a.ts + ts_row;
+          tsr = ts_base + ts_row;
           t_end = tsr[T - 1];
           tprev = a.t0_from_ts ? tsr[0] : R(0.0);
           tnext = fmin(tprev + a.dt0, t_end);
           idx = 0; nacc = 0; nrej = 0; status = 0;
-          phase = (tprev < t_end) ? 0 : 1;  // t0 == t1: emit y0 for every requested time
+          phase = (tprev < t_end) ? 0 : 1;
           ctx_field(tprev, y, th, c, y0, K[0]);
         }
       }
     }
-    if (__ballot_sync(CTX_FULL, b >= 0) == 0u) break;
+#endif  // CTX_QUEUE
+    if (__ballot_sync(CTX_FULL, b >= 0) == 0u) {
+      if (q_empty) break;
+      continue;
+    }
 
     // ------------------------------------------------------------- one step attempt
     const bool stepping = (b >= 0) && phase == 0;
@@ -650,13 +823,14 @@ ctx_solve_v1(const ctx_solve_args a) {
 
     // ------------------------------------------------------------- cooperative saves
 #if !CTX_TAN
-    // Unified group path.  The pending save points of every lane are cut into groups of 4
-    // consecutive points aligned to multiples of 4 within their trajectory; all groups of all
-    // lanes are flattened and dealt out to the 32 lanes (consecutive lanes = consecutive groups
-    // of one segment), so every lane evaluates <= 4 points per pass from a register-cached
-    // record and writes them with 128-bit stores when the group is full and 16-byte aligned
-    // (scalar, masked stores at segment ends).  Loads of ts and the stores of a pass are
-    // contiguous across lanes; nothing is staged in shared memory.
+    // Unified group path.  The requested times of every trajectory are cut into groups of 4
+    // consecutive points aligned to multiples of 4; the groups touched by the accepted steps of
+    // all lanes are flattened and dealt out to the 32 lanes (consecutive lanes = consecutive
+    // groups of one segment).  A lane fetches its segment's record (6 x LDS.128 for 3 states),
+    // evaluates the 4 points by Horner and writes a COMPLETE group with 128-bit stores.  A group
+    // a step only partly covers is parked in the owner lane's pending buffer in shared memory
+    // and merged by the step that completes it, so global memory only sees whole, aligned
+    // 16-byte stores (scalar stores remain for unaligned rows and a ragged last group).
     const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
     if (nz) {
       const int gq0 = idx >> 2;
@@ -671,85 +845,120 @@ ctx_solve_v1(const ctx_solve_args a) {
       const int gtotal = __shfl_sync(CTX_FULL, incl, 31);
       if (nsave > 0) {
         const int s = __popc(nz & lt_mask);
-        real coef[CTX_NCOEF];
+        ctx_rec_u u;
         if (filling) {
           const bool fill_inf = status != 0;
 #pragma unroll
-          for (int i = 0; i < CTX_N; ++i) coef[i] = fill_inf ? CTX_INF : y[i];
+          for (int i = 0; i < CTX_N; ++i) u.r.v[2 + i] = fill_inf ? CTX_INF : y[i];
 #pragma unroll
-          for (int i = CTX_N; i < CTX_NCOEF; ++i) coef[i] = R(0.0);
-          w.rec[0][s] = R(0.0);
-          w.rec[1][s] = R(0.0);
+          for (int i = CTX_N; i < CTX_NCOEF; ++i) u.r.v[2 + i] = R(0.0);
+          u.r.v[0] = R(0.0);
+          u.r.v[1] = R(0.0);
         } else {
-          ctx_dense_coefs(rec_dt, y, ynew, K, coef);
-          w.rec[0][s] = rec_tp;
-          w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+          ctx_dense_coefs(rec_dt, y, ynew, K, u.r.v + 2);
+          u.r.v[0] = rec_tp;
+          u.r.v[1] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
         }
+        u.r.i0 = idx;
+        u.r.i1 = idx + nsave;
+        u.r.gf = gq0 - goff;
+        u.r.owner = lane;
+        u.r.b = (int)b;
+        u.r.ri = ri_row;
+        uint4* dstq = reinterpret_cast<uint4*>(&w.rec[s]);
 #pragma unroll
-        for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
-        w.ts_off[s] = ts_row;
-        w.g_off[s] = b * (long long)T;
-        w.seg_i0[s] = idx;
-        w.seg_i1[s] = idx + nsave;
-        w.seg_gf[s] = gq0 - goff;
+        for (int k = 0; k < CTX_REC_Q; ++k) dstq[k] = u.q[k];
       }
       __syncwarp();
       const unsigned myoff = nsave > 0 ? (unsigned)goff : 0xffffffffu;
       int seg_base = 0, s_have = -1;
-      real r_tp = R(0.0), r_inv = R(0.0), r_coef[CTX_NCOEF];
-      int r_i0 = 0, r_i1 = 0, r_gf = 0;
-      const real* r_ts = a.ts;
-      real* r_ys = a.ys;
+      ctx_rec_u rr;
+      rr.r.i0 = 0; rr.r.i1 = 0; rr.r.gf = 0; rr.r.owner = 0; rr.r.b = 0; rr.r.ri = 0;
       for (int g0 = 0; g0 < gtotal; g0 += 32) {
         const unsigned dpos = myoff - (unsigned)g0;
         const unsigned bits = __reduce_or_sync(CTX_FULL, dpos < 32u ? (1u << dpos) : 0u);
         const int s = seg_base + __popc(bits & le_mask) - 1;
         seg_base += __popc(bits);
         const int g = g0 + lane;
-        if (s != s_have) {  // (lanes past gtotal follow the last segment: harmless)
+        const bool act = g < gtotal;
+        if (act && s != s_have) {
           s_have = s;
-          r_tp = w.rec[0][s]; r_inv = w.rec[1][s];
+          const uint4* srcq = reinterpret_cast<const uint4*>(&w.rec[s]);
 #pragma unroll
-          for (int i = 0; i < CTX_NCOEF; ++i) r_coef[i] = w.rec[2 + i][s];
-          r_i0 = w.seg_i0[s]; r_i1 = w.seg_i1[s]; r_gf = w.seg_gf[s];
-          r_ts = a.ts + w.ts_off[s];
-          r_ys = a.ys + w.g_off[s] * CTX_S;
+          for (int k = 0; k < CTX_REC_Q; ++k) rr.q[k] = srcq[k];
         }
-        if (g < gtotal) {
-          const int p0 = (r_gf + g) << 2;
-          const real* tq = r_ts + p0;
-          real o[4 * CTX_S];
-          bool ok[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            ok[u] = (p0 + u >= r_i0) && (p0 + u < r_i1);
-            const real th_ = ((ok[u] ? tq[u] : r_tp) - r_tp) * r_inv;
-#pragma unroll
-            for (int i = 0; i < CTX_S; ++i) {
-              real v = r_coef[CTX_DEG * CTX_N + i];
-#pragma unroll
-              for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + r_coef[mm * CTX_N + i];
-              o[u * CTX_S + i] = v;
-            }
-          }
-          real* dst = r_ys + (size_t)p0 * CTX_S;
-          if (ok[0] && ok[3] && (reinterpret_cast<size_t>(dst) & 15) == 0) {
+        const int p0 = (rr.r.gf + g) << 2;
+        real o[4 * CTX_S];
+        if (act) {
+          const real* r_ts = TSM ? ts_base : ts_base + (size_t)rr.r.ri * a.stride_ts;
+          real tq[4];
+          if (TSM) {   // padded to a multiple of 4 and 16-byte aligned
 #if CTX_F64
-#pragma unroll
-            for (int k = 0; k < 2 * CTX_S; ++k)
-              reinterpret_cast<double2*>(dst)[k] = make_double2(o[2 * k], o[2 * k + 1]);
+            const double2 t01 = reinterpret_cast<const double2*>(r_ts + p0)[0];
+            const double2 t23 = reinterpret_cast<const double2*>(r_ts + p0)[1];
+            tq[0] = t01.x; tq[1] = t01.y; tq[2] = t23.x; tq[3] = t23.y;
 #else
-#pragma unroll
-            for (int k = 0; k < CTX_S; ++k)
-              reinterpret_cast<float4*>(dst)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            const float4 t4 = *reinterpret_cast<const float4*>(r_ts + p0);
+            tq[0] = t4.x; tq[1] = t4.y; tq[2] = t4.z; tq[3] = t4.w;
 #endif
           } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (ok[u]) {
+            for (int u = 0; u < 4; ++u) tq[u] = (p0 + u < rr.r.i1) ? r_ts[p0 + u] : rr.r.v[0];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const real th_ = (tq[u] - rr.r.v[0]) * rr.r.v[1];
+#pragma unroll
+            for (int i = 0; i < CTX_S; ++i) {
+              real v = rr.r.v[2 + CTX_DEG * CTX_N + i];
+#pragma unroll
+              for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + rr.r.v[2 + mm * CTX_N + i];
+              o[u * CTX_S + i] = v;
+            }
+          }
+          if (p0 < rr.r.i0) {   // points of this group that earlier steps evaluated
+            union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
+#pragma unroll
+            for (int k = 0; k < CTX_PEND_Q; ++k) pd.q[k] = w.pend[rr.r.owner][k];
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+              if (p0 + u < rr.r.i0) {
+#pragma unroll
+                for (int i = 0; i < CTX_S; ++i) o[u * CTX_S + i] = pd.v[u * CTX_S + i];
+              }
+          }
+        }
+        __syncwarp();   // every read of a pending buffer precedes the writes below
+        if (act) {
+          real* dst = a.ys + ((size_t)rr.r.b * T + p0) * CTX_S;
+          if (p0 + 4 <= rr.r.i1) {
+            if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
+#if CTX_F64
+#pragma unroll
+              for (int k = 0; k < 2 * CTX_S; ++k)
+                reinterpret_cast<double2*>(dst)[k] = make_double2(o[2 * k], o[2 * k + 1]);
+#else
+#pragma unroll
+              for (int k = 0; k < CTX_S; ++k)
+                reinterpret_cast<float4*>(dst)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+#endif
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4 * CTX_S; ++k) dst[k] = o[k];
+            }
+          } else if (rr.r.i1 == T) {   // ragged last group of the trajectory
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+              if (p0 + u < T) {
 #pragma unroll
                 for (int i = 0; i < CTX_S; ++i) dst[u * CTX_S + i] = o[u * CTX_S + i];
               }
+          } else {                      // incomplete: park it for the step that completes it
+            union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
+#pragma unroll
+            for (int k = 0; k < 4 * CTX_S; ++k) pd.v[k] = o[k];
+#pragma unroll
+            for (int k = 0; k < CTX_PEND_Q; ++k) w.pend[rr.r.owner][k] = pd.q[k];
           }
         }
       }
@@ -793,7 +1002,7 @@ ctx_solve_v1(const ctx_solve_args a) {
       const unsigned myoff = nsave > 0 ? (unsigned)off : 0xffffffffu;
       int seg_base = 0, s_have = -1;
       real r_tp = R(0.0), r_inv = R(0.0), r_coef[CTX_NCOEF];
-      const real* tq_ptr = a.ts;       // &ts[segment offset + j] of this lane's point
+      const real* tq_ptr = ts_base;    // &ts[segment offset + j] of this lane's point
       long long r_ebase = 0;           // (g_off[s]) * S: element index of the segment's j = 0
       for (int r0 = 0; r0 < total; r0 += 32) {
         const unsigned dpos = myoff - (unsigned)r0;
@@ -808,7 +1017,7 @@ ctx_solve_v1(const ctx_solve_args a) {
           r_tp = w.rec[0][s]; r_inv = w.rec[1][s];
 #pragma unroll
           for (int i = 0; i < CTX_NCOEF; ++i) r_coef[i] = w.rec[2 + i][s];
-          tq_ptr = a.ts + (w.ts_off[s] + j);
+          tq_ptr = ts_base + (w.ts_off[s] + j);
           r_ebase = w.g_off[s] * CTX_S;
         }
         if (j < total) {
@@ -899,6 +1108,15 @@ ctx_solve_v1(const ctx_solve_args a) {
     }
   }
 }
+
+extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
+ctx_solve_v1(const ctx_solve_args a) {
+  if (a.ts_smem) ctx_solve_v1_body<true>(a);
+  else ctx_solve_v1_body<false>(a);
+}
+
+// bytes of dynamic shared memory one warp of ctx_solve_v1 needs (read by the host at load time)
+extern "C" __device__ const unsigned ctx_v1_warp_smem_bytes = sizeof(ctx_warp_smem);
 
 #endif  // CTX_NO_V1
 
