@@ -440,6 +440,26 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #endif
 #define CTX_NCOEF ((CTX_DEG + 1) * CTX_N)
 
+// States with dy/dt == 0 identically (CTX_CONST_MASK, from the code generator) have the constant
+// interpolant y: the step records of the non-tangent save path carry only the theta^0 coefficient
+// for them ("packed" layout: [theta^0: all components][theta^m, m >= 1: dynamic components]).
+#ifndef CTX_CONST_MASK
+#define CTX_CONST_MASK 0u
+#endif
+#if CTX_TAN || CTX_S > 32
+#define CTX_CMASK 0u
+#else
+#define CTX_CMASK (CTX_CONST_MASK)
+#endif
+__host__ __device__ constexpr int ctx_popc_c(unsigned m) { return m ? (int)(m & 1u) + ctx_popc_c(m >> 1) : 0; }
+#define CTX_NDYN (CTX_N - ctx_popc_c(CTX_CMASK))
+#define CTX_NPACK (CTX_N + CTX_DEG * CTX_NDYN)
+__host__ __device__ constexpr bool ctx_is_const(int i) { return i < 32 && ((CTX_CMASK >> i) & 1u); }
+// position of the theta^m coefficient of component i in the packed layout (i dynamic when m >= 1)
+__host__ __device__ constexpr int ctx_pidx(int m, int i) {
+  return m == 0 ? i : CTX_N + (m - 1) * CTX_NDYN + (i - ctx_popc_c(CTX_CMASK & ((1u << i) - 1u)));
+}
+
 #if CTX_SOLVER == 0
 #define TB22 R(0.13169999999999999727)
 #define TB23 R(-0.22339999999999999818)
@@ -491,6 +511,21 @@ __device__ __forceinline__ void ctx_dense_coefs(const real dt, const real* y, co
   }
 }
 
+// the same coefficients in the packed layout (constant states: theta^0 only)
+__device__ __forceinline__ void ctx_dense_coefs_packed(const real dt, const real* y, const real* ynew,
+                                                       const real (*K)[CTX_N], real* pk) {
+  real coef[CTX_NCOEF];
+  ctx_dense_coefs(dt, y, ynew, K, coef);
+#pragma unroll
+  for (int i = 0; i < CTX_N; ++i) {
+    pk[ctx_pidx(0, i)] = coef[i];
+    if (!ctx_is_const(i)) {
+#pragma unroll
+      for (int m = 1; m <= CTX_DEG; ++m) pk[ctx_pidx(m, i)] = coef[m * CTX_N + i];
+    }
+  }
+}
+
 #ifndef CTX_NO_V1
 // Input queue of a persistent warp.  A finished lane must not wait ~1 us for the y0 / parameter
 // rows of its next trajectory to arrive from HBM (the whole warp would wait with it, once per
@@ -520,11 +555,12 @@ __device__ __forceinline__ void ctx_cp_async(real* dst_smem, const real* src) {
 // One published step ("segment"): everything a lane needs to evaluate 4 requested times of it,
 // as one 16-byte-aligned record so that it moves with 128-bit shared-memory accesses.
 struct alignas(16) ctx_rec {
-  real v[2 + CTX_NCOEF];   // tp, 1/dt, polynomial coefficients [power][component]
+  real v[2 + CTX_NPACK];   // tp, 1/dt, polynomial coefficients (packed layout, ctx_pidx)
   int i0, i1;              // [first, last) requested-time index covered by the step
   int gf;                  // (first group of the segment) - (its offset in the flat group list)
   int owner;               // publishing lane (index of the trajectory's pending-point buffer)
-  int b, ri;               // trajectory index, row of its time grid
+  unsigned row_lo, row_hi; // address of the trajectory's output row ys[b, 0, 0]
+  int ri;                  // row of its time grid (per-row grids only)
 };
 #define CTX_REC_Q ((int)(sizeof(ctx_rec) / 16))
 union ctx_rec_u {
@@ -550,26 +586,44 @@ struct ctx_warp_smem {
 #endif
 };
 
+// Requested times.  SM: the grid is shared by all trajectories and staged in shared memory; it
+// is then read through its 32-bit shared-space address `sa` (ld.shared: a generic pointer would
+// cost a generic-to-shared conversion and the long-scoreboard path on every access).
+template <bool SM>
+__device__ __forceinline__ real ctx_ts_at(const real* row, const unsigned sa, const int i) {
+  if (SM) {
+    real v;
+#if CTX_F64
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa + 8u * (unsigned)i));
+#else
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa + 4u * (unsigned)i));
+#endif
+    return v;
+  }
+  return row[i];
+}
+
 // First index in [lo, T) with ts[index] > t (ts ascending, ts[T-1] = t_end > t).  Requested
 // times are usually an (almost) uniform grid: interpolate the position, fix it up with a few
 // probes, and fall back to bisection of the remaining bracket for irregular grids.
-__device__ __forceinline__ int ctx_upper_bound(const real* ts, int lo, const int T, const real t,
-                                               const real t_end) {
+template <bool SM>
+__device__ __forceinline__ int ctx_upper_bound(const real* ts, const unsigned sa, int lo,
+                                               const int T, const real t, const real t_end) {
   int hi = T - 1;                       // ts[hi] = t_end > t: the answer is in [lo, hi]
-  const real t_lo = ts[lo];
+  const real t_lo = ctx_ts_at<SM>(ts, sa, lo);
   if (t_lo > t) return lo;
   // invariant from here: ts[lo] <= t < ts[hi]
   int g = lo + 1 + (int)((t - t_lo) / (t_end - t_lo) * (real)(hi - lo));
   g = min(max(g, lo + 1), hi);
 #pragma unroll 1
   for (int probe = 0; probe < 3 && hi - lo > 1; ++probe) {
-    if (ts[g] > t) { hi = g; g = max(g - 1, lo + 1); }
+    if (ctx_ts_at<SM>(ts, sa, g) > t) { hi = g; g = max(g - 1, lo + 1); }
     else { lo = g; g = min(g + 1, hi); }
     if (hi - lo == 1) break;
   }
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if (ts[mid] > t) hi = mid; else lo = mid;
+    if (ctx_ts_at<SM>(ts, sa, mid) > t) hi = mid; else lo = mid;
   }
   return hi;
 }
@@ -613,8 +667,11 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #endif
   const int T = a.T;
   const real* ts_base = a.ts;     // base of all time rows (shared memory copy when TSM)
+  unsigned ts_sa = 0;             // ... and its shared-space address
   if (TSM) {
     real* ts_sm = reinterpret_cast<real*>(sm_cur);
+    ts_sa = (unsigned)__cvta_generic_to_shared(ts_sm);
+    asm volatile("mov.u32 %0, %0;" : "+r"(ts_sa));   // opaque: keep it in a register
     const int Tpad = (T + 3) & ~3;
     for (int i = threadIdx.x; i < Tpad; i += blockDim.x) ts_sm[i] = a.ts[min(i, T - 1)];
     sm_cur += (size_t)Tpad * sizeof(real);
@@ -797,7 +854,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
         if (!(tnext < t_end)) {
           nsave = T - idx;
         } else {
-          nsave = ctx_upper_bound(tsr, idx, T, tnext, t_end) - idx;
+          nsave = ctx_upper_bound<TSM && !CTX_TAN>(tsr, ts_sa, idx, T, tnext, t_end) - idx;
         }
         tp_new = tnext;
         accepted = true;
@@ -849,13 +906,13 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
         if (filling) {
           const bool fill_inf = status != 0;
 #pragma unroll
-          for (int i = 0; i < CTX_N; ++i) u.r.v[2 + i] = fill_inf ? CTX_INF : y[i];
+          for (int i = 0; i < CTX_N; ++i) u.r.v[2 + ctx_pidx(0, i)] = fill_inf ? CTX_INF : y[i];
 #pragma unroll
-          for (int i = CTX_N; i < CTX_NCOEF; ++i) u.r.v[2 + i] = R(0.0);
+          for (int i = CTX_N; i < CTX_NPACK; ++i) u.r.v[2 + i] = R(0.0);
           u.r.v[0] = R(0.0);
           u.r.v[1] = R(0.0);
         } else {
-          ctx_dense_coefs(rec_dt, y, ynew, K, u.r.v + 2);
+          ctx_dense_coefs_packed(rec_dt, y, ynew, K, u.r.v + 2);
           u.r.v[0] = rec_tp;
           u.r.v[1] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
         }
@@ -863,7 +920,15 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
         u.r.i1 = idx + nsave;
         u.r.gf = gq0 - goff;
         u.r.owner = lane;
-        u.r.b = (int)b;
+#ifdef CTX_DBG_ROWMASK    // developer experiment: all rows alias a small, L2-resident region
+        const unsigned long long rowp = reinterpret_cast<unsigned long long>(
+            a.ys + (size_t)(b & CTX_DBG_ROWMASK) * (size_t)T * CTX_S);
+#else
+        const unsigned long long rowp =
+            reinterpret_cast<unsigned long long>(a.ys + (size_t)b * (size_t)T * CTX_S);
+#endif
+        u.r.row_lo = (unsigned)rowp;
+        u.r.row_hi = (unsigned)(rowp >> 32);
         u.r.ri = ri_row;
         uint4* dstq = reinterpret_cast<uint4*>(&w.rec[s]);
 #pragma unroll
@@ -871,94 +936,163 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       }
       __syncwarp();
       const unsigned myoff = nsave > 0 ? (unsigned)goff : 0xffffffffu;
-      int seg_base = 0, s_have = -1;
-      ctx_rec_u rr;
-      rr.r.i0 = 0; rr.r.i1 = 0; rr.r.gf = 0; rr.r.owner = 0; rr.r.b = 0; rr.r.ri = 0;
-      for (int g0 = 0; g0 < gtotal; g0 += 32) {
-        const unsigned dpos = myoff - (unsigned)g0;
-        const unsigned bits = __reduce_or_sync(CTX_FULL, dpos < 32u ? (1u << dpos) : 0u);
-        const int s = seg_base + __popc(bits & le_mask) - 1;
-        seg_base += __popc(bits);
-        const int g = g0 + lane;
-        const bool act = g < gtotal;
-        if (act && s != s_have) {
-          s_have = s;
-          const uint4* srcq = reinterpret_cast<const uint4*>(&w.rec[s]);
-#pragma unroll
-          for (int k = 0; k < CTX_REC_Q; ++k) rr.q[k] = srcq[k];
-        }
-        const int p0 = (rr.r.gf + g) << 2;
-        real o[4 * CTX_S];
-        if (act) {
-          const real* r_ts = TSM ? ts_base : ts_base + (size_t)rr.r.ri * a.stride_ts;
-          real tq[4];
-          if (TSM) {   // padded to a multiple of 4 and 16-byte aligned
-#if CTX_F64
-            const double2 t01 = reinterpret_cast<const double2*>(r_ts + p0)[0];
-            const double2 t23 = reinterpret_cast<const double2*>(r_ts + p0)[1];
-            tq[0] = t01.x; tq[1] = t01.y; tq[2] = t23.x; tq[3] = t23.y;
-#else
-            const float4 t4 = *reinterpret_cast<const float4*>(r_ts + p0);
-            tq[0] = t4.x; tq[1] = t4.y; tq[2] = t4.z; tq[3] = t4.w;
+      // One pass = 32 consecutive flat groups, one per lane.  CTX_PASSES passes can be kept in
+      // flight together (all evaluate, then all store).  Measured on B200 (config 2, T=1000):
+      // 2 passes need 144 registers (3 CTAs/SM) and gain 6 % in f32 but lose 15 % at T=16 and
+      // 25 % in f64, so the default stays 1.
+#ifndef CTX_PASSES
+#define CTX_PASSES 1
 #endif
-          } else {
+#ifndef CTX_ST_OP
+#define CTX_ST_OP ""      // cache operator of the 128-bit trajectory stores (".cs", ".cg", ...)
+#endif
+      struct pass_t {
+        ctx_rec_u rr;
+        real o[4 * CTX_S];
+        int s_have, p0;
+        bool act;
+      } ps[CTX_PASSES];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) tq[u] = (p0 + u < rr.r.i1) ? r_ts[p0 + u] : rr.r.v[0];
+      for (int k = 0; k < CTX_PASSES; ++k) {
+        ps[k].s_have = -1;
+        ps[k].rr.r.i0 = 0; ps[k].rr.r.i1 = 0; ps[k].rr.r.gf = 0; ps[k].rr.r.owner = 0;
+        ps[k].rr.r.row_lo = 0; ps[k].rr.r.row_hi = 0; ps[k].rr.r.ri = 0;
+      }
+      int seg_base = 0;
+      // bit j of bits[k]: a segment starts at flat group g0 + 32 k + j.  The masks of a round are
+      // reduced one round ahead of their use, so that the REDUX latency is off the critical path.
+      unsigned bits[CTX_PASSES];
+#pragma unroll
+      for (int k = 0; k < CTX_PASSES; ++k) {
+        bits[k] = 0u;
+        if (32 * k < gtotal) {
+          const unsigned dn = myoff - (unsigned)(32 * k);
+          bits[k] = __reduce_or_sync(CTX_FULL, dn < 32u ? (1u << dn) : 0u);
+        }
+      }
+      for (int g0 = 0; g0 < gtotal; g0 += 32 * CTX_PASSES) {
+        unsigned bits_cur[CTX_PASSES];
+#pragma unroll
+        for (int k = 0; k < CTX_PASSES; ++k) {
+          bits_cur[k] = bits[k];
+          if (g0 + 32 * (CTX_PASSES + k) < gtotal) {   // (warp-uniform)
+            const unsigned dn = myoff - (unsigned)(g0 + 32 * (CTX_PASSES + k));
+            bits[k] = __reduce_or_sync(CTX_FULL, dn < 32u ? (1u << dn) : 0u);
           }
+        }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const real th_ = (tq[u] - rr.r.v[0]) * rr.r.v[1];
+        for (int k = 0; k < CTX_PASSES; ++k) {
+          pass_t& q = ps[k];
+          ctx_rec_u& rr = q.rr;
+          if (k > 0 && g0 + 32 * k >= gtotal) {   // (warp-uniform) no groups left for this pass
+            q.act = false;
+            continue;
+          }
+          const int s = seg_base + __popc(bits_cur[k] & le_mask) - 1;
+          seg_base += __popc(bits_cur[k]);
+          const int g = g0 + 32 * k + lane;
+          const bool act = g < gtotal;
+          q.act = act;
+          if (act && s != q.s_have) {
+            q.s_have = s;
+            const uint4* srcq = reinterpret_cast<const uint4*>(&w.rec[s]);
 #pragma unroll
-            for (int i = 0; i < CTX_S; ++i) {
-              real v = rr.r.v[2 + CTX_DEG * CTX_N + i];
+            for (int j = 0; j < CTX_REC_Q; ++j) rr.q[j] = srcq[j];
+          }
+          const int p0 = (rr.r.gf + g) << 2;
+          q.p0 = p0;
+          real* o = q.o;
+          if (act) {
+            real tq[4];
+            if (TSM) {   // padded to a multiple of 4 and 16-byte aligned
+#if CTX_F64
+              asm("ld.shared.v2.f64 {%0, %1}, [%2];"
+                  : "=d"(tq[0]), "=d"(tq[1]) : "r"(ts_sa + 8u * (unsigned)p0));
+              asm("ld.shared.v2.f64 {%0, %1}, [%2];"
+                  : "=d"(tq[2]), "=d"(tq[3]) : "r"(ts_sa + 8u * (unsigned)p0 + 16u));
+#else
+              asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                  : "=f"(tq[0]), "=f"(tq[1]), "=f"(tq[2]), "=f"(tq[3])
+                  : "r"(ts_sa + 4u * (unsigned)p0));
+#endif
+            } else {
+              const real* r_ts = ts_base + (size_t)rr.r.ri * a.stride_ts;
 #pragma unroll
-              for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + rr.r.v[2 + mm * CTX_N + i];
-              o[u * CTX_S + i] = v;
+              for (int u = 0; u < 4; ++u) tq[u] = (p0 + u < rr.r.i1) ? r_ts[p0 + u] : rr.r.v[0];
             }
-          }
-          if (p0 < rr.r.i0) {   // points of this group that earlier steps evaluated
-            union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
 #pragma unroll
-            for (int k = 0; k < CTX_PEND_Q; ++k) pd.q[k] = w.pend[rr.r.owner][k];
+            for (int u = 0; u < 4; ++u) {
+              const real th_ = (tq[u] - rr.r.v[0]) * rr.r.v[1];
 #pragma unroll
-            for (int u = 0; u < 3; ++u)
-              if (p0 + u < rr.r.i0) {
+              for (int i = 0; i < CTX_S; ++i) {
+                if (ctx_is_const(i)) {
+                  o[u * CTX_S + i] = rr.r.v[2 + ctx_pidx(0, i)];
+                } else {
+                  real v = rr.r.v[2 + ctx_pidx(CTX_DEG, i)];
 #pragma unroll
-                for (int i = 0; i < CTX_S; ++i) o[u * CTX_S + i] = pd.v[u * CTX_S + i];
+                  for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + rr.r.v[2 + ctx_pidx(mm, i)];
+                  o[u * CTX_S + i] = v;
+                }
               }
+            }
+            if (p0 < rr.r.i0) {   // points of this group that earlier steps evaluated
+              union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
+#pragma unroll
+              for (int j = 0; j < CTX_PEND_Q; ++j) pd.q[j] = w.pend[rr.r.owner][j];
+#pragma unroll
+              for (int u = 0; u < 3; ++u)
+                if (p0 + u < rr.r.i0) {
+#pragma unroll
+                  for (int i = 0; i < CTX_S; ++i) o[u * CTX_S + i] = pd.v[u * CTX_S + i];
+                }
+            }
           }
         }
         __syncwarp();   // every read of a pending buffer precedes the writes below
-        if (act) {
-          real* dst = a.ys + ((size_t)rr.r.b * T + p0) * CTX_S;
-          if (p0 + 4 <= rr.r.i1) {
-            if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < CTX_PASSES; ++k) {
+          pass_t& q = ps[k];
+          const ctx_rec_u& rr = q.rr;
+          const int p0 = q.p0;
+          const real* o = q.o;
+          if (q.act) {
+            real* dst = reinterpret_cast<real*>(((unsigned long long)rr.r.row_hi << 32) |
+                                                (unsigned long long)rr.r.row_lo) + p0 * CTX_S;
+#ifdef CTX_DBG_NOSTORE   // developer experiment: everything but the global stores
+            if (o[0] != R(-12345.678)) continue;
+#endif
+            if (p0 + 4 <= rr.r.i1) {
+              if ((rr.r.row_lo & 15u) == 0u) {   // p0 * S reals = a multiple of 16 bytes
 #if CTX_F64
 #pragma unroll
-              for (int k = 0; k < 2 * CTX_S; ++k)
-                reinterpret_cast<double2*>(dst)[k] = make_double2(o[2 * k], o[2 * k + 1]);
+                for (int j = 0; j < 2 * CTX_S; ++j)
+                  asm volatile("st.global" CTX_ST_OP ".v2.f64 [%0], {%1, %2};" ::"l"(dst + 2 * j), "d"(o[2 * j]),
+                               "d"(o[2 * j + 1]) : "memory");
 #else
 #pragma unroll
-              for (int k = 0; k < CTX_S; ++k)
-                reinterpret_cast<float4*>(dst)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+                for (int j = 0; j < CTX_S; ++j)   // st.global: the address was rebuilt from integers
+                  asm volatile("st.global" CTX_ST_OP ".v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                               "f"(o[4 * j]), "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                               : "memory");
 #endif
-            } else {
+              } else {
 #pragma unroll
-              for (int k = 0; k < 4 * CTX_S; ++k) dst[k] = o[k];
-            }
-          } else if (rr.r.i1 == T) {   // ragged last group of the trajectory
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-              if (p0 + u < T) {
-#pragma unroll
-                for (int i = 0; i < CTX_S; ++i) dst[u * CTX_S + i] = o[u * CTX_S + i];
+                for (int j = 0; j < 4 * CTX_S; ++j) dst[j] = o[j];
               }
-          } else {                      // incomplete: park it for the step that completes it
-            union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
+            } else if (rr.r.i1 == T) {   // ragged last group of the trajectory
 #pragma unroll
-            for (int k = 0; k < 4 * CTX_S; ++k) pd.v[k] = o[k];
+              for (int u = 0; u < 3; ++u)
+                if (p0 + u < T) {
 #pragma unroll
-            for (int k = 0; k < CTX_PEND_Q; ++k) w.pend[rr.r.owner][k] = pd.q[k];
+                  for (int i = 0; i < CTX_S; ++i) dst[u * CTX_S + i] = o[u * CTX_S + i];
+                }
+            } else {                      // incomplete: park it for the step that completes it
+              union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
+#pragma unroll
+              for (int j = 0; j < 4 * CTX_S; ++j) pd.v[j] = o[j];
+#pragma unroll
+              for (int j = 0; j < CTX_PEND_Q; ++j) w.pend[rr.r.owner][j] = pd.q[j];
+            }
           }
         }
       }

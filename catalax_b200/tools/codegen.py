@@ -247,6 +247,17 @@ def _emit_block(exprs_out: Sequence[Tuple[str, sp.Expr]], names, tmp_prefix: str
     return lines, flops
 
 
+def _const_state_mask(f) -> int:
+    """Bit i set <=> dy_i/dt == 0 identically (only reported for models of <= 32 states)."""
+    if len(f) > 32:
+        return 0
+    mask = 0
+    for i, e in enumerate(f):
+        if e == 0 or sp.expand(e) == 0:
+            mask |= 1 << i
+    return mask
+
+
 def generate_field(spec: FieldSpec, sens_theta: bool = False, sens_y0: bool = False,
                    warp_form="auto") -> GeneratedField:
     """Generate the CUDA device functions of one model.
@@ -268,6 +279,9 @@ def generate_field(spec: FieldSpec, sens_theta: bool = False, sens_y0: bool = Fa
         f"#define CTX_S {S}",
         f"#define CTX_P {P}",
         f"#define CTX_C {C}",
+        # states whose right-hand side is identically zero (conserved catalysts, ...): their
+        # dense-output polynomial is the constant y, the save path skips the Horner evaluation
+        f"#define CTX_CONST_MASK 0x{_const_state_mask(f):x}u",
         "__device__ __forceinline__ void ctx_rhs(const real t, const real* y, const real* th,",
         "                                        const real* c, const real* y0, real* dy) {",
         "  (void)t; (void)th; (void)c; (void)y0;",
