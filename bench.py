@@ -210,7 +210,8 @@ def run_nuts_leg(a, model_field, dev, rank, world, dist):
     y0s, theta, consts, ts, data, sigma = nuts_inputs(CH, M, T, dt, seed=2 + 100 * rank)
     tt = lambda x: torch.as_tensor(x, device=dev)
     args = [tt(x) for x in (y0s, theta, consts, ts, data, sigma)]
-    kw = dict(likelihood="softlaplace", rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096)
+    kw = dict(likelihood="softlaplace", rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096,
+              kernel=int(os.environ.get("CTX_BENCH_LL_KERNEL", "0")))
     n_iter = max(3, min(a.steps, 20))
     for _ in range(3):
         out, partial, status = model.loglik_grad(*args, **kw)

@@ -75,6 +75,7 @@ struct Variant {
   std::map<std::string, cudaKernel_t> kernels;
   int loaded_device = -1;
   long v1_warp_smem = -1;   // sizeof(ctx_warp_smem) read back from the loaded module
+  long ll_warp_smem = -1;   // sizeof(ctx_ll_warp_smem) (cooperative log-likelihood kernel)
 };
 
 }  // namespace
@@ -300,6 +301,22 @@ int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out) {
   return CTX_OK;
 }
 
+// sizeof(ctx_ll_warp_smem) of the loaded tangent module (call after get_kernel)
+int ll_exact_warp_smem(ctx_model* m, int solver, size_t* out) {
+  std::lock_guard<std::mutex> lk(m->mu);
+  Variant& v = m->variants[solver * 2 + 1];
+  if (v.ll_warp_smem < 0) {
+    void* dptr = nullptr;
+    size_t nbytes = 0;
+    unsigned val = 0;
+    CTX_CUDA(cudaLibraryGetGlobal(&dptr, &nbytes, v.lib, "ctx_ll_warp_smem_bytes"));
+    CTX_CUDA(cudaMemcpy(&val, dptr, sizeof(val), cudaMemcpyDeviceToHost));
+    v.ll_warp_smem = (long)val;
+  }
+  *out = (size_t)v.ll_warp_smem;
+  return CTX_OK;
+}
+
 template <typename real>
 int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0,
                  const void* theta, const void* consts, const void* ts, void* ys, void* sens,
@@ -495,22 +512,40 @@ int launch_loglik(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, cons
   a.n_traj = n_traj; a.M = cfg->n_series; a.T = cfg->n_times; a.likelihood = cfg->likelihood;
   a.max_steps = cfg->max_steps;
   a.rtol = (real)cfg->rtol; a.atol = (real)cfg->atol; a.dt0 = (real)cfg->dt0;
+  // kernel (cfg->kernel): 0 = automatic, 1 = per-lane likelihood terms (ctx_loglik_v1),
+  // 2 = warp-cooperative likelihood terms (ctx_loglik_v2, the default)
+  const int which = cfg->kernel == 1 ? 1 : 2;
+  if (cfg->kernel < 0 || cfg->kernel > 2) return fail(CTX_E_INVALID, "unknown log-likelihood kernel id");
   cudaKernel_t k;
-  int rc = get_kernel(m, cfg->solver, 1, "ctx_loglik_v1", &k);
+  int rc = get_kernel(m, cfg->solver, 1, which == 1 ? "ctx_loglik_v1" : "ctx_loglik_v2", &k);
   if (rc) return rc;
   const int warps = std::max(1, v1_warps(d, cfg->solver, 1, theta_smem(m)));
   const unsigned block = 32u * warps;
+  size_t smem = 0;
+  if (which == 2) {
+    if ((long long)cfg->n_series * cfg->n_times >= (1ll << 31))
+      return fail(CTX_E_INVALID, "log-likelihood: n_series * n_times must be < 2^31");
+    size_t per_warp = 0;
+    rc = ll_exact_warp_smem(m, cfg->solver, &per_warp);
+    if (rc) return rc;
+    smem = (size_t)warps * per_warp;
+    if (smem > 200 * 1024)
+      return fail(CTX_E_INVALID, "log-likelihood: step records do not fit shared memory");
+    if (smem > 48 * 1024)
+      CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  }
   int dev = 0, sms = 0, per_sm = 0;
   CTX_CUDA(cudaGetDevice(&dev));
   CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, 0));
+  CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, smem));
   if (per_sm < 1) per_sm = 1;
   unsigned long long grid = (unsigned long long)sms * per_sm;
   const unsigned long long want = (n_traj + block - 1) / block;
   if (grid > want) grid = want;
   void* params[] = {&a};
   CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
-  CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
+  CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem, stream));
   g_launches++;
   cudaKernel_t kr;
   rc = get_kernel(m, cfg->solver, 1, "ctx_loglik_reduce", &kr);

@@ -1464,6 +1464,292 @@ ctx_loglik_v1(const ctx_loglik_args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// ctx_loglik_v2: the same computation with WARP-COOPERATIVE likelihood terms.
+// In ctx_loglik_v1 every lane evaluates the requested times of its own accepted step in a
+// data-dependent loop; a step covers ~1 of the 20 requested times on average, so that loop runs
+// with a handful of active lanes (ncu: 10 of 32 threads per instruction over the whole kernel).
+// Here a lane with an accepted step publishes the step's interpolant (polynomial coefficients of
+// all S*(1+D) components) in shared memory; the requested times covered by all lanes' steps are
+// flattened and dealt out one per lane (full warps), each lane evaluates one time point: Horner,
+// the likelihood of the S observables and their gradient contributions.  The contributions are
+// added to the owning trajectory's accumulators (shared memory) by the last lane of every
+// segment, sequentially in time order starting from the accumulator's value: the summation order
+// of a trajectory is independent of which lanes evaluated it, so results are reproducible.
+#define CTX_LL_RW (2 + CTX_NCOEF + CTX_S)   // tp, 1/dt, coefficients [power][component], sigma
+struct ctx_ll_warp_smem {
+  real rec[CTX_LL_RW][32];   // one column per publishing lane of this iteration
+  real acc[CTX_KP][32];      // accumulators of the trajectory each lane integrates
+  int pt0[32];               // point index (m*T + idx) of the segment's first time - its flat offset
+  int off[32];               // flat offset of the segment
+  int cnt[32];               // requested times it covers
+  int owner[32];             // publishing lane
+};
+
+extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
+ctx_loglik_v2(const ctx_loglik_args a) {
+  extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];
+  ctx_ll_warp_smem& w = reinterpret_cast<ctx_ll_warp_smem*>(ctx_dyn_smem)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned le_mask = CTX_FULL >> (31 - lane);
+  const int T = a.T;
+
+  long long u = -1;
+  real y[CTX_N], ynew[CTX_N], y0[CTX_S];
+  real th[CTX_P > 0 ? CTX_P : 1], c[CTX_C > 0 ? CTX_C : 1], sg[CTX_S];
+  real K[CTX_NST][CTX_N];
+  real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
+  int idx = 0, nacc = 0, nrej = 0, status = 0, m = 0;
+  bool exhausted = false;
+  const real* tsr = a.ts;
+
+  while (true) {
+    const unsigned need = __ballot_sync(CTX_FULL, u < 0);
+    if (need && !exhausted) {
+      const int cnt = __popc(need);
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)cnt);
+      base = __shfl_sync(CTX_FULL, base, 0);
+      if (base + cnt >= (unsigned long long)a.n_traj) exhausted = true;
+      if (u < 0) {
+        const unsigned long long nu = base + __popc(need & lt_mask);
+        if (nu < (unsigned long long)a.n_traj) {
+          u = (long long)nu;
+          const long long ch = u / a.M;
+          m = (int)(u - ch * a.M);
+#pragma unroll
+          for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = a.y0s[(size_t)m * CTX_S + i];
+#pragma unroll
+          for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)ch * CTX_P + i];
+#pragma unroll
+          for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)m * CTX_C + i];
+#pragma unroll
+          for (int i = 0; i < CTX_S; ++i) sg[i] = a.sigma[(size_t)ch * CTX_S + i];
+#pragma unroll
+          for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
+#pragma unroll
+          for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
+#pragma unroll
+          for (int k = 0; k < CTX_KP; ++k) w.acc[k][lane] = R(0.0);
+          tsr = a.ts + (size_t)m * T;
+          t_end = tsr[T - 1];
+          tprev = R(0.0);
+          tnext = fmin(tprev + a.dt0, t_end);
+          idx = 0; nacc = 0; nrej = 0; status = 0;
+          ctx_field(tprev, y, th, c, y0, K[0]);
+        }
+      }
+    }
+    if (__ballot_sync(CTX_FULL, u >= 0) == 0u) break;
+
+    // ------------------------------------------------------------- one step attempt
+    bool keep = false, done = false;
+    int nsave = 0;
+    real rec_tp = R(0.0), rec_dt = R(0.0);
+    if (u >= 0) {
+      keep = true;
+      done = !(tprev < t_end);
+      rec_tp = tprev;
+      if (!done) {
+        const real dt = tnext - tprev;
+        const real tn_step = tnext;
+        rec_dt = dt;
+        ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
+        real dt_next = a.dt0;
+#if CTX_ADAPTIVE
+        const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
+        keep = scaled < R(1.0);
+        const real inv = R(1.0) / scaled;
+        real factor = R(0.9) * pow(inv, R(0.2));
+        factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
+        dt_next = dt * factor;
+        if (scaled != scaled) dt_next = scaled;
+#endif
+        real tp_new = keep ? tnext : tprev;
+        if (keep) ++nacc; else ++nrej;
+        tp_new = fmin(tp_new, t_end);
+        real tn = tp_new + dt_next;
+        if (tn > t_end - CTX_TOL_END) tn = keep ? t_end : tp_new + R(0.5) * (t_end - tp_new);
+        done = !(tp_new < t_end);
+        if (!done) {
+          if (!(fabs(tn) < CTX_INF)) status = CTX_ST_BAD;
+          else if (nacc + nrej >= a.max_steps) status = CTX_ST_MAX;
+        }
+        tprev = tp_new; tnext = tn;
+        if (keep)
+          nsave = done ? T - idx : ctx_upper_bound<false>(tsr, 0u, idx, T, tn_step, t_end) - idx;
+      } else {
+        // t0 == t1: every requested time is t0 (a zero-length step evaluated at theta = 0)
+#pragma unroll
+        for (int i = 0; i < CTX_N; ++i) ynew[i] = y[i];
+#pragma unroll
+        for (int k = 1; k < CTX_NST; ++k)
+#pragma unroll
+          for (int i = 0; i < CTX_N; ++i) K[k][i] = R(0.0);
+        nsave = T - idx;
+      }
+    }
+
+    // ------------------------------------------------------------- cooperative likelihood terms
+    const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
+    if (nz) {
+      int incl = nsave;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(CTX_FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int off = incl - nsave;
+      const int total = __shfl_sync(CTX_FULL, incl, 31);
+      if (nsave > 0) {
+        const int s = __popc(nz & lt_mask);
+        real coef[CTX_NCOEF];
+        ctx_dense_coefs(rec_dt, y, ynew, K, coef);
+        w.rec[0][s] = rec_tp;
+        w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+#pragma unroll
+        for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
+#pragma unroll
+        for (int i = 0; i < CTX_S; ++i) w.rec[2 + CTX_NCOEF + i][s] = sg[i];
+        w.pt0[s] = m * T + idx - off;
+        w.off[s] = off;
+        w.cnt[s] = nsave;
+        w.owner[s] = lane;
+      }
+      __syncwarp();
+      const unsigned myoff = nsave > 0 ? (unsigned)off : 0xffffffffu;
+      int seg_base = 0;
+      for (int r0 = 0; r0 < total; r0 += 32) {
+        const unsigned dpos = myoff - (unsigned)r0;
+        const unsigned bits = __reduce_or_sync(CTX_FULL, dpos < 32u ? (1u << dpos) : 0u);
+        const int s = seg_base + __popc(bits & le_mask) - 1;   // >= 0: flat position 0 starts one
+        seg_base += __popc(bits);
+        const int j = r0 + lane;
+        const bool act = j < total;
+        real cv[CTX_KP];
+#pragma unroll
+        for (int k = 0; k < CTX_KP; ++k) cv[k] = R(0.0);
+        int my_len = 0, s_owner = 0;
+        bool is_tail = false;
+        if (act) {
+          const int s_off = w.off[s], s_cnt = w.cnt[s];
+          s_owner = w.owner[s];
+          const int first = max(s_off - r0, 0);                 // this segment's lanes in the pass
+          const int last = min(s_off + s_cnt - r0, 32) - 1;
+          is_tail = lane == last;
+          my_len = last - first + 1;
+          const int pt = w.pt0[s] + j;
+          const real tq = a.ts[pt];
+          const real th_ = (tq - w.rec[0][s]) * w.rec[1][s];
+          real out[CTX_N];
+#pragma unroll
+          for (int i = 0; i < CTX_N; ++i) {
+            real v = w.rec[2 + CTX_DEG * CTX_N + i][s];
+#pragma unroll
+            for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + w.rec[2 + mm * CTX_N + i][s];
+            out[i] = v;
+          }
+          const real* drow = a.data + (size_t)pt * CTX_S;
+          const unsigned char* mrow = a.mask ? a.mask + (size_t)pt * CTX_S : nullptr;
+#pragma unroll
+          for (int o = 0; o < CTX_S; ++o) {
+            const real x = drow[o];
+            const bool use = mrow ? (mrow[o] != 0) : (fabs(x) < CTX_INF);
+            if (use) {
+              const real sgo = w.rec[2 + CTX_NCOEF + o][s];
+              const real sd = fabs(sgo);
+              const real z = (x - out[o]) / sd;
+              real lp, dl_dloc, dl_ds;
+              if (a.likelihood == 0) {
+                lp = R(-0.5) * z * z - log(sd) - R(0.9189385332046727418);
+                dl_dloc = z / sd;
+                dl_ds = (z * z - R(1.0)) / sd;
+              } else {
+                const real az = fabs(z);
+                lp = R(-0.4515827052894548647) - log(sd) - (az + ctx_log1p_exp_neg2a(az));
+                const real tz = tanh(z);
+                dl_dloc = tz / sd;
+                dl_ds = (z * tz - R(1.0)) / sd;
+              }
+              cv[0] += lp;
+#pragma unroll
+              for (int d = 0; d < CTX_D_THETA; ++d) cv[1 + d] += dl_dloc * out[CTX_S + d * CTX_S + o];
+              cv[1 + CTX_D_THETA + o] += dl_ds * (sgo < R(0.0) ? R(-1.0) : R(1.0));
+#pragma unroll
+              for (int d = 0; d < CTX_D_Y0; ++d)
+                cv[1 + CTX_D_THETA + CTX_S + d] += dl_dloc * out[CTX_S + (CTX_D_THETA + d) * CTX_S + o];
+            }
+          }
+        }
+        // the last lane of a segment adds the segment's terms to the owner's accumulators in
+        // time order: acc = (((acc + c_first) + ...) + c_last)
+        const int maxlen = __reduce_max_sync(CTX_FULL, my_len);
+        real av[CTX_KP];
+        if (is_tail) {
+#pragma unroll
+          for (int k = 0; k < CTX_KP; ++k) av[k] = w.acc[k][s_owner];
+        }
+        for (int q = maxlen - 1; q >= 0; --q) {
+#pragma unroll
+          for (int k = 0; k < CTX_KP; ++k) {
+            const real t = __shfl_sync(CTX_FULL, cv[k], (lane - q) & 31);
+            if (is_tail && q < my_len) av[k] += t;
+          }
+        }
+        if (is_tail) {
+#pragma unroll
+          for (int k = 0; k < CTX_KP; ++k) w.acc[k][s_owner] = av[k];
+        }
+        __syncwarp();   // a segment that continues in the next pass reads what this one wrote
+      }
+    }
+
+    // ------------------------------------------------------------- advance / retire
+    if (u >= 0) {
+      if (keep) {
+        idx += nsave;
+#pragma unroll
+        for (int i = 0; i < CTX_N; ++i) y[i] = ynew[i];
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#pragma unroll
+        for (int i = 0; i < CTX_N; ++i) K[0][i] = K[6][i];
+#else
+        ctx_field(tprev, y, th, c, y0, K[0]);
+#endif
+      }
+      if (done || status != 0) {
+        real acc[CTX_KP];
+#pragma unroll
+        for (int k = 0; k < CTX_KP; ++k) acc[k] = w.acc[k][lane];
+        if (status != 0) {
+          // reference: unsaved states are inf (constant) -> log p = -inf, gradient inf * 0 = NaN
+          bool any_left = false;
+          for (int j = idx; j < T && !any_left; ++j)
+            for (int o = 0; o < CTX_S; ++o) {
+              const real x = a.data[((size_t)m * T + j) * CTX_S + o];
+              const bool use = a.mask ? (a.mask[((size_t)m * T + j) * CTX_S + o] != 0) : (fabs(x) < CTX_INF);
+              any_left |= use;
+            }
+          if (any_left) {
+            acc[0] = -CTX_INF;
+#pragma unroll
+            for (int k = 1; k < CTX_KP; ++k) acc[k] = CTX_INF - CTX_INF;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CTX_KP; ++k) a.partial[(size_t)u * CTX_KP + k] = acc[k];
+        a.status[u] = status;
+        a.n_accepted[u] = nacc;
+        a.n_rejected[u] = nrej;
+        u = -1;
+      }
+    }
+  }
+}
+
+extern "C" __device__ const unsigned ctx_ll_warp_smem_bytes = sizeof(ctx_ll_warp_smem);
+
 // out[ch, k] = sum_m partial[ch*M + m, k] for k < KR; one warp per chain, double accumulation.
 extern "C" __global__ void __launch_bounds__(128)
 ctx_loglik_reduce(const real* partial, real* out, const long long n_chains, const int M,

@@ -45,7 +45,7 @@ class ctx_solve_cfg(C.Structure):
 class ctx_loglik_cfg(C.Structure):
     _fields_ = [("solver", C.c_int32), ("likelihood", C.c_int32), ("n_chains", C.c_int64),
                 ("n_series", C.c_int32), ("n_times", C.c_int32), ("max_steps", C.c_int32),
-                ("reserved", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
+                ("kernel", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("dt0", C.c_double)]
 
 
@@ -255,8 +255,9 @@ class CompiledModel:
 
     def loglik_grad(self, y0s, theta, consts, ts, data, sigma, *, mask=None,
                     likelihood="softlaplace", solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,
-                    max_steps=4096):
+                    max_steps=4096, kernel=0):
         """Fused log-likelihood + gradient for CH chains over M series (ctx_loglik_grad).
+        kernel: 0 automatic | 1 per-lane likelihood terms | 2 warp-cooperative likelihood terms.
 
         y0s [M,S], theta [CH,P], consts [M,C], ts [M,T], data [M,T,S], sigma [CH,S],
         mask [M,T,S] bool or None (= isfinite(data)).  Returns (out [CH, 1+P+S],
@@ -284,6 +285,7 @@ class CompiledModel:
         cfg.solver, cfg.likelihood = SOLVER_IDS[solver], LIKELIHOOD_IDS[likelihood]
         cfg.n_chains, cfg.n_series, cfg.n_times, cfg.max_steps = CH, M, T, int(max_steps)
         cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
+        cfg.kernel = int(kernel)
         kp = 1 + P + S + (D - P)
         with torch.cuda.device(dev):
             out = torch.empty((CH, 1 + P + S), dtype=tdt, device=dev)

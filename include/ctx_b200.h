@@ -134,7 +134,7 @@ typedef struct ctx_loglik_cfg {
   int32_t n_series;   /* M */
   int32_t n_times;    /* T */
   int32_t max_steps;
-  int32_t reserved;
+  int32_t kernel;     /* 0 = automatic (cooperative), 1 = per-lane likelihood terms, 2 = cooperative */
   double rtol, atol, dt0;
 } ctx_loglik_cfg;
 size_t ctx_loglik_workspace_bytes(const ctx_model* m, const ctx_loglik_cfg* cfg);
