@@ -251,7 +251,40 @@ def run_nuts_leg(a, model_field, dev, rank, world, dist):
                 "peak_source": "ctx_measure_fma_peak (FMA loop measured on this GPU)",
                 "flops_per_step": flops_step, "flops_per_saved_point": flops_point,
                 "steps_per_eval_batch": steps}
+    # series-sharded form of the SAME posterior (SURVEY 8d config 4 asks for both): all ranks
+    # evaluate the same CH chains (rank 0's parameters) over M/world series each, followed by the
+    # path's only collective, an NCCL all-reduce(sum) of the [CH, 1+P+S] block.
+    series = None
+    if world > 1 and M % world == 0:
+        y0s0, theta0, consts0, ts0, data0, sigma0 = nuts_inputs(CH, M, T, dt, seed=2)
+        lo, hi = rank * (M // world), (rank + 1) * (M // world)
+        sargs = [tt(x) for x in (y0s0[lo:hi], theta0, consts0[lo:hi], ts0[lo:hi], data0[lo:hi], sigma0)]
+
+        def series_eval():
+            o, _, st = model.loglik_grad(*sargs, **kw)
+            dist.all_reduce(o, op=dist.ReduceOp.SUM)
+            return o, st
+
+        for _ in range(3):
+            series_eval()
+        torch.cuda.synchronize()
+        dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_iter):
+            so, sst = series_eval()
+        s1.record()
+        torch.cuda.synchronize()
+        st_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(st_ms, op=dist.ReduceOp.MAX)
+        sms = float(st_ms.item())
+        series = {"value": CH * n_iter / (sms * 1e-3), "unit": "evals/s",
+                  "ms_per_eval_batch": sms / n_iter, "series_per_rank": M // world,
+                  "collective": f"NCCL all-reduce(sum) of [{CH}, {1 + 2 + 3}] {a.dtype} per evaluation",
+                  "scaling": "strong (one posterior, series split over ranks)",
+                  "all_finite": bool(torch.isfinite(so).all().item())}
     return {"metric": "NUTS logp+grad evals/s", "value": CH * world * n_iter / (ms * 1e-3),
+            "series_sharded": series,
             "roofline": roof,
             "unit": "evals/s", "ms_per_eval_batch": ms / n_iter,
             "series_solves_with_gradient_per_s": CH * world * M * n_iter / (ms * 1e-3),
@@ -436,7 +469,7 @@ def run_b200(a):
     if nuts:
         line["nuts"] = nuts
     if not a.no_cpu_baseline and world == 1:
-        rows = min(CPU_SAMPLE_ROWS, B)
+        rows = B                       # the whole batch once: ~1.5 s on 16 cores (~20 core-seconds)
         v, sec, steps, threads = cpu_oracle_run(a, rows)
         line["cpu_baseline"] = {
             "value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -231,3 +231,43 @@ def test_posterior_ensemble_two_level_batch():
         np.testing.assert_allclose(np.nansum(lp, axis=(1, 2, 3)), out[:, 0], rtol=1e-9)
     finally:
         ctx.enable_x64(False)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_both_loglik_kernels_match_oracle(kernel):
+    """ctx_loglik_v1 (per-lane terms) and ctx_loglik_v2 (warp-cooperative terms) are the same
+    computation: both meet the x64 bound against the oracle, incl. the y0 directions."""
+    from oracle import loglik_oracle as lo
+
+    CH, M = 9, 21   # ragged: 189 trajectories, not a multiple of the warp size
+    model, y0s, theta, consts, ts, data, sigma = _config4(CH, M, seed=11)
+    out, partial, status = _gpu(model, y0s, theta, consts, ts, data, sigma, "softlaplace",
+                                np.float64, sens_y0=True, kernel=kernel)
+    ref, gy0, rstat = lo.loglik_grad(model, y0s, theta, consts, ts, data, sigma,
+                                     likelihood="softlaplace", rtol=1e-5, atol=1e-5, sens_y0=True)
+    assert (status == 0).all() and (rstat == 0).all()
+    scale = np.abs(ref) + 1e-3 * np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(out - ref) <= 1e-6 * scale).all(), float((np.abs(out - ref) / scale).max())
+    g = partial.reshape(CH, M, -1)[:, :, 1 + 2 + 3:]
+    gs = np.abs(gy0) + 1e-3 * np.abs(gy0).max()
+    assert (np.abs(g - gy0) <= 1e-6 * gs).all()
+
+
+def test_cooperative_loglik_is_reproducible_and_handles_long_segments():
+    """Run-to-run bit reproducibility of the cooperative kernel (time-ordered accumulation), on a
+    grid where one step covers many requested times (segments longer than a warp pass) and on
+    one where t0 == t1 for every point."""
+    CH, M, T = 64, 8, 150
+    model, y0s, theta, consts, ts, data, sigma = _config4(CH, M, T=T, seed=5)
+    a = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float32, kernel=2)
+    b = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float32, kernel=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    v1 = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float32, kernel=1)
+    scale = np.abs(v1[0]) + 1e-3 * np.abs(v1[0]).max(axis=1, keepdims=True)
+    assert (np.abs(a[0] - v1[0]) <= 2e-4 * scale).all()
+    # degenerate grid: all requested times are t0 = 0
+    ts0 = np.zeros_like(ts)
+    z2 = _gpu(model, y0s, theta, consts, ts0, data, sigma, "normal", np.float64, kernel=2)
+    z1 = _gpu(model, y0s, theta, consts, ts0, data, sigma, "normal", np.float64, kernel=1)
+    assert np.allclose(z2[0], z1[0], rtol=1e-12, atol=1e-12)
+    assert (z2[2] == 0).all()
