@@ -132,6 +132,23 @@ struct RatesArgs {
   int stride_t, stride_theta, stride_consts, stride_y0;
 };
 
+template <typename real>
+struct RateLlArgs {
+  const real* t;
+  const real* y;
+  const real* theta;
+  const real* consts;
+  const real* inits;
+  const real* data;
+  const unsigned char* mask;
+  const real* jac2;
+  const real* extra2;
+  const real* sigma;
+  real* out;
+  long long n_chains;
+  int N, n_time, likelihood;
+};
+
 // Upper bound of sizeof(ctx_warp_smem) in ctx_integrator.cuh (input queue + step records +
 // staging); used to choose CTX_WARPS before compiling.  The launch uses the exact size the
 // module exports (ctx_v1_warp_smem_bytes).
@@ -726,6 +743,47 @@ int ctx_rates(ctx_model* m, int64_t n, const void* t, int32_t stride_t, const vo
     RatesArgs<float> a{(const float*)t, (const float*)y, (const float*)theta,
                        (const float*)consts, (const float*)y0, (float*)out, n,
                        stride_t, stride_theta, stride_consts, stride_y0};
+    void* params[] = {&a};
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0,
+                              (cudaStream_t)stream));
+  }
+  g_launches++;
+  return CTX_OK;
+}
+
+int ctx_rate_loglik_grad(ctx_model* m, int32_t likelihood, int64_t n_chains, int32_t n_points,
+                         int32_t n_time, const void* t, const void* y, const void* theta,
+                         const void* consts, const void* inits, const void* data,
+                         const uint8_t* mask, const void* jac2, const void* extra2,
+                         const void* sigma, void* out, void* stream) {
+  if (!m || !out) return fail(CTX_E_INVALID, "null argument");
+  if (m->desc.n_theta_dirs != m->desc.n_params || m->desc.n_dirs <= 0)
+    return fail(CTX_E_INVALID, "model must be generated with all parameter directions");
+  if (likelihood != CTX_LIK_NORMAL && likelihood != CTX_LIK_SOFTLAPLACE)
+    return fail(CTX_E_INVALID, "unknown likelihood id");
+  if (n_time <= 0 || n_points < 0 || (n_points % n_time) != 0)
+    return fail(CTX_E_INVALID, "n_points must be a multiple of n_time (points grouped per measurement)");
+  if (n_chains <= 0) return CTX_OK;
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  cudaKernel_t k;
+  int rc = get_kernel(m, CTX_TSIT5, 1, "ctx_rate_loglik", &k);
+  if (rc) return rc;
+  const unsigned block = 128;
+  const unsigned long long grid = ((unsigned long long)n_chains * 32 + block - 1) / block;
+  if (m->desc.dtype == CTX_F64) {
+    RateLlArgs<double> a{(const double*)t, (const double*)y, (const double*)theta,
+                         (const double*)consts, (const double*)inits, (const double*)data, mask,
+                         (const double*)jac2, (const double*)extra2, (const double*)sigma,
+                         (double*)out, n_chains, n_points, n_time, likelihood};
+    void* params[] = {&a};
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0,
+                              (cudaStream_t)stream));
+  } else {
+    RateLlArgs<float> a{(const float*)t, (const float*)y, (const float*)theta,
+                        (const float*)consts, (const float*)inits, (const float*)data, mask,
+                        (const float*)jac2, (const float*)extra2, (const float*)sigma,
+                        (float*)out, n_chains, n_points, n_time, likelihood};
     void* params[] = {&a};
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0,
                               (cudaStream_t)stream));

@@ -1765,6 +1765,105 @@ ctx_loglik_reduce(const real* partial, real* out, const long long n_chains, cons
     if (lane == 0) out[(size_t)ch * KR + k] = (real)s;
   }
 }
+
+// =====================================================================================
+// kernel K5: surrogate (rate-matching) log-likelihood + gradient -- no solve
+// =====================================================================================
+// Replaces value_and_grad of the numpyro model in Modes.SURROGATE:
+//   catalax/mcmc/mcmc.py:819-847  sim_func = vmap(rate_fun)(y_points, theta, constants, t, inits)
+//                                 (measured states as evaluation points, "{state}_init" from the
+//                                 first time of each measurement, data = surrogate rates)
+//   catalax/mcmc/mcmc.py:469-480  sigma_total[p,j] = sum_k J[p,j,k]^2 sigma_y[k]^2
+//                                 (+ sigma_surr^2 + rate_sigma^2) + 1e-8
+//   catalax/mcmc/mcmc.py:486-491  sample("y", likelihood(loc, sqrt(sigma_total)), obs=data) | mask
+// One warp per chain; lanes stride over the N = M * n_time points, evaluate the generated field
+// and its parameter derivatives (ctx_rhs_tan with zero tangents: ds = df/dtheta), accumulate
+//   (ll, d ll/d theta[P], d ll/d sigma_y[S])
+// and reduce with warp shuffles in double precision (fixed order: reproducible).
+struct ctx_rate_ll_args {
+  const real* t;        // [N]
+  const real* y;        // [N,S]     evaluation points (measured states), p = m * n_time + j
+  const real* theta;    // [CH,P]
+  const real* consts;   // [M,C]     row p / n_time
+  const real* inits;    // [M,S]     "{state}_init" values, row p / n_time
+  const real* data;     // [N,S]     surrogate rates
+  const unsigned char* mask;  // [N,S] or null -> isfinite(data)
+  const real* jac2;     // [N,S,S]   squared surrogate rate-Jacobian J[p,j,k]^2
+  const real* extra2;   // [N,S] or null: sigma_surr^2 + rate_sigma^2
+  const real* sigma;    // [CH,S]
+  real* out;            // [CH, 1+P+S]
+  long long n_chains;
+  int N, n_time, likelihood;
+};
+#define CTX_KR (1 + CTX_D_THETA + CTX_S)
+
+extern "C" __global__ void __launch_bounds__(128) ctx_rate_loglik(const ctx_rate_ll_args a) {
+  const long long ch = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ch >= a.n_chains) return;
+  real th[CTX_P > 0 ? CTX_P : 1], sg[CTX_S], acc[CTX_KR];
+#pragma unroll
+  for (int i = 0; i < CTX_P; ++i) th[i] = a.theta[(size_t)ch * CTX_P + i];
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) sg[i] = a.sigma[(size_t)ch * CTX_S + i];
+#pragma unroll
+  for (int k = 0; k < CTX_KR; ++k) acc[k] = R(0.0);
+  for (int p = lane; p < a.N; p += 32) {
+    const int mrow = p / a.n_time;
+    real y[CTX_S], y0[CTX_S], c[CTX_C > 0 ? CTX_C : 1], dy[CTX_S];
+    real s[CTX_S * CTX_D], ds[CTX_S * CTX_D];
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) y[i] = a.y[(size_t)p * CTX_S + i];
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) y0[i] = a.inits[(size_t)mrow * CTX_S + i];
+#pragma unroll
+    for (int i = 0; i < CTX_C; ++i) c[i] = a.consts[(size_t)mrow * CTX_C + i];
+#pragma unroll
+    for (int i = 0; i < CTX_S * CTX_D; ++i) s[i] = R(0.0);
+    ctx_rhs_tan(a.t[p], y, s, th, c, y0, dy, ds);
+#pragma unroll
+    for (int j = 0; j < CTX_S; ++j) {
+      const real x = a.data[(size_t)p * CTX_S + j];
+      const bool use = a.mask ? (a.mask[(size_t)p * CTX_S + j] != 0) : (fabs(x) < CTX_INF);
+      if (use) {
+        real j2[CTX_S];
+        real s2 = a.extra2 ? a.extra2[(size_t)p * CTX_S + j] : R(0.0);
+#pragma unroll
+        for (int k = 0; k < CTX_S; ++k) {
+          j2[k] = a.jac2[((size_t)p * CTX_S + j) * CTX_S + k];
+          s2 += j2[k] * (sg[k] * sg[k]);
+        }
+        s2 += R(1e-8);
+        const real sd = sqrt(s2);
+        const real z = (x - dy[j]) / sd;
+        real lp, dl_dloc, dl_ds;
+        if (a.likelihood == 0) {
+          lp = R(-0.5) * z * z - log(sd) - R(0.9189385332046727418);
+          dl_dloc = z / sd;
+          dl_ds = (z * z - R(1.0)) / sd;
+        } else {
+          const real az = fabs(z);
+          lp = R(-0.4515827052894548647) - log(sd) - (az + ctx_log1p_exp_neg2a(az));
+          const real tz = tanh(z);
+          dl_dloc = tz / sd;
+          dl_ds = (z * tz - R(1.0)) / sd;
+        }
+        acc[0] += lp;
+#pragma unroll
+        for (int d = 0; d < CTX_D_THETA; ++d) acc[1 + d] += dl_dloc * ds[d * CTX_S + j];
+#pragma unroll
+        for (int k = 0; k < CTX_S; ++k) acc[1 + CTX_D_THETA + k] += dl_ds * (j2[k] * sg[k] / sd);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CTX_KR; ++k) {
+    double v = (double)acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(CTX_FULL, v, d);
+    if (lane == 0) a.out[(size_t)ch * CTX_KR + k] = (real)v;
+  }
+}
 #endif  // CTX_TAN && !CTX_THETA_PTR
 
 

@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
     L.ctx_rates.restype = C.c_int
     L.ctx_rates.argtypes = [vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, vp,
                             C.c_int32, vp, vp]
+    L.ctx_rate_loglik_grad.restype = C.c_int
+    L.ctx_rate_loglik_grad.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [vp] * 12
     L.ctx_solve_host.restype = C.c_int
     L.ctx_solve_host.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -303,6 +305,50 @@ class CompiledModel:
             counts = ws[256 + 4 * n: 256 + 12 * n].view(torch.int32)
             self.last_loglik_counts = (counts[:n], counts[n:])
         return out, partial, status
+
+    def rate_loglik_grad(self, t, y, theta, consts, inits, data, jac2, sigma, *, n_time,
+                         mask=None, extra2=None, likelihood="softlaplace"):
+        """Surrogate (rate-matching) log-likelihood + gradient for CH chains (ctx_rate_loglik_grad).
+
+        t [N], y [N,S] (measured states, grouped per measurement: p = m*n_time + j), theta [CH,P],
+        consts [M,C], inits [M,S], data [N,S] (surrogate rates), jac2 [N,S,S] (squared surrogate
+        rate-Jacobian), sigma [CH,S], mask [N,S] or None (= isfinite(data)), extra2 [N,S] or None.
+        Returns out [CH, 1+P+S] = (log L, d/dtheta, d/dsigma_y) as a torch CUDA tensor."""
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = theta.device
+        if dev.type != "cuda":
+            raise EngineError("rate_loglik_grad() needs CUDA tensors: catalax_b200 has no CPU fallback")
+        S, P, Cn = self.field.S, self.field.P, self.field.C
+        if self.field.n_theta_dirs != P or P == 0:
+            raise EngineError("model must be generated with sens_theta=True")
+        f = lambda x: x.to(device=dev, dtype=tdt).contiguous()
+        t, y, theta, consts, inits, data, jac2, sigma = map(
+            f, (t, y, theta, consts, inits, data, jac2, sigma))
+        N, CH = y.shape[0], theta.shape[0]
+        n_time = int(n_time)
+        if n_time <= 0 or N % n_time:
+            raise ValueError("the N points must be grouped per measurement: N = M * n_time")
+        M = N // n_time
+        assert t.shape == (N,) and y.shape == (N, S) and data.shape == (N, S)
+        assert jac2.shape == (N, S, S) and sigma.shape == (CH, S) and theta.shape == (CH, P)
+        assert inits.shape == (M, S) and consts.shape == (M, Cn)
+        if mask is not None:
+            mask = mask.to(device=dev, dtype=torch.uint8).contiguous()
+            assert mask.shape == (N, S)
+        if extra2 is not None:
+            extra2 = f(extra2)
+            assert extra2.shape == (N, S)
+        out = torch.empty((CH, 1 + P + S), dtype=tdt, device=dev)
+        p = lambda x: C.c_void_p(x.data_ptr()) if (x is not None and x.numel()) else C.c_void_p(0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _check(lib().ctx_rate_loglik_grad(
+                self._h, LIKELIHOOD_IDS[likelihood], CH, N, n_time, p(t), p(y), p(theta), p(consts),
+                p(inits), p(data), p(mask), p(jac2), p(extra2), p(sigma), p(out),
+                C.c_void_p(stream)))
+        return out
 
     def rates(self, t, y, theta, consts, y0=None):
         """Right-hand side at N points (ctx_rates): t [N]|scalar, y [N,S], theta [N,P]|[P],

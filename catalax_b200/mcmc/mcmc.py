@@ -71,14 +71,45 @@ def extract_dataset_components(dataset, model):
     return data, times, y0s, constants
 
 
+def surrogate_rate_jacobian(surrogate, states_flat, times_flat):
+    """``J[p, i, k] = d rate_i / d y_k`` of a surrogate at every measured point
+    (``_surrogate_rate_jacobian``, mcmc.py:865-894; computed once, the surrogate is fixed).
+
+    Uses ``surrogate.rate_jacobian(t, y)`` when the surrogate provides one, otherwise central
+    differences of its public ``rates`` API (the reference takes ``jax.jacfwd`` of the same
+    function; the result feeds a first-order delta method, mcmc.py:469-480)."""
+    y = np.asarray(states_flat, dtype=np.float64)
+    t = np.asarray(times_flat, dtype=np.float64)
+    if hasattr(surrogate, "rate_jacobian"):
+        return np.asarray(surrogate.rate_jacobian(t, y), dtype=np.float64)
+    N, S = y.shape
+    J = np.empty((N, S, S))
+    probe = np.asarray(surrogate.rates(t, y))
+    eps = np.finfo(probe.dtype if probe.dtype.kind == "f" else np.float64).eps ** (1.0 / 3.0)
+    for k in range(S):
+        h = eps * np.maximum(1.0, np.abs(y[:, k]))
+        yp, ym = y.copy(), y.copy()
+        yp[:, k] += h
+        ym[:, k] -= h
+        J[:, :, k] = (np.asarray(surrogate.rates(t, yp), dtype=np.float64)
+                      - np.asarray(surrogate.rates(t, ym), dtype=np.float64)) / (2.0 * h)[:, None]
+    return J
+
+
 class BayesianModel:
-    """Batched log-density of the posterior the reference samples with NUTS (mcmc.py:332-491)."""
+    """Batched log-density of the posterior the reference samples with NUTS (mcmc.py:332-491).
+
+    ``surrogate`` switches to the reference's Modes.SURROGATE (mcmc.py:819-847, 469-480): no
+    solve; the mechanistic rates at the measured states are matched to the surrogate's rates,
+    with the concentration noise ``sigma_y`` pushed forward through the surrogate's Jacobian."""
 
     def __init__(self, model, dataset=None, *, yerrs=1.0, likelihood="softlaplace",
                  config: Optional[SimulationConfig] = None, error_model: Optional[ErrorModel] = None,
                  estimate_initials: bool = False, shard: str = "chains", arrays=None,
-                 device=None):
-        """arrays: optional (data, times, y0s, constants) instead of a Dataset (array seam)."""
+                 device=None, surrogate=None, surrogate_arrays=None):
+        """arrays: optional (data, times, y0s, constants) instead of a Dataset (array seam).
+        surrogate: object with ``predict_rates(dataset)`` / ``rates(t, y)`` (catalax/surrogate.py);
+        surrogate_arrays: optional (rates [N,S], jac [N,S,S], extra2 [N,S] | None) instead."""
         from .. import engine, parallel
         from ..tools import codegen as cg
 
@@ -110,6 +141,34 @@ class BayesianModel:
         self._arrays = tuple(np.asarray(a, dtype=self.dtype)[lo:hi] for a in (data, times, y0s, constants))
         self.mask = np.isfinite(self._arrays[0])                       # mcmc.py:566
         self.yerrs = np.broadcast_to(np.asarray(yerrs, dtype=np.float64), data.shape[-1:]).copy()
+        self.mode = "surrogate" if (surrogate is not None or surrogate_arrays is not None) else "integrated"
+        self._surr = None
+        if self.mode == "surrogate":
+            if estimate_initials:
+                raise NotImplementedError("surrogate mode evaluates rates at the measured states; "
+                                          "initial conditions are not sampled")
+            T_, S_ = data.shape[1], data.shape[2]
+            if surrogate_arrays is not None:
+                rates, jac, extra2 = surrogate_arrays
+            else:
+                if dataset is None:
+                    raise ValueError("a surrogate needs the Dataset (predict_rates) or surrogate_arrays")
+                rates = np.asarray(surrogate.predict_rates(dataset), dtype=np.float64)
+                jac = surrogate_rate_jacobian(surrogate, np.asarray(data).reshape(-1, S_),
+                                              np.asarray(times).ravel())
+                extra2 = None
+                if getattr(surrogate, "has_uncertainty", False):      # mcmc.py:225-230, 472-475
+                    extra2 = np.asarray(surrogate.rate_uncertainty(dataset=dataset)).reshape(-1, S_) ** 2 \
+                        + np.asarray(surrogate.rate_sigma(dataset=dataset)).reshape(1, S_) ** 2
+            rates = np.asarray(rates, dtype=self.dtype).reshape(M, T_, S_)[lo:hi].reshape(-1, S_)
+            jac2 = (np.asarray(jac, dtype=np.float64) ** 2).astype(self.dtype) \
+                .reshape(M, T_, S_, S_)[lo:hi].reshape(-1, S_, S_)
+            if extra2 is not None:
+                extra2 = np.asarray(extra2, dtype=self.dtype).reshape(M, T_, S_)[lo:hi].reshape(-1, S_)
+            self._surr = (rates, jac2, extra2)
+            # mean |J| row-norm per state: sigma_y is identifiable where >> 0 (mcmc.py:240-246)
+            self.jac_rownorm = np.sqrt((np.asarray(jac, dtype=np.float64).reshape(-1, S_, S_) ** 2)
+                                       .sum(-1)).mean(0)
         spec = model._replace_assignments().sim_input.field_spec()
         self.field = cg.generate_field(spec, sens_theta=True, sens_y0=estimate_initials)
         self._engine = engine
@@ -133,12 +192,36 @@ class BayesianModel:
         if y0s.shape[0] == 0:
             return torch.zeros((theta.shape[0], 1 + self.field.P + self.field.S),
                                dtype=theta.dtype, device=theta.device)
+        if self.mode == "surrogate":
+            return self._local_rate_loglik(theta, sigma)
         cfg = self.config
         out, self._partial, self._status = self._compiled.loglik_grad(
             y0s, theta, constants, times, data, sigma, mask=mask, likelihood=self.likelihood,
             solver=solver_name(cfg.solver), rtol=cfg.rtol, atol=cfg.atol, dt0=cfg.dt0,
             max_steps=cfg.max_steps)
         return out
+
+    def _local_rate_loglik(self, theta, sigma):
+        """Surrogate mode: [CH, 1+P+S] over THIS rank's measurements (ctx_rate_loglik_grad)."""
+        import torch
+
+        y0s, constants, times, data, mask = self._dev_arrays
+        if getattr(self, "_dev_surr", None) is None:
+            dev = theta.device
+            rates, jac2, extra2 = self._surr
+            tt = lambda a: None if a is None else torch.as_tensor(a, device=dev)
+            # evaluation points = the measured states; "{state}_init" = first state of each
+            # measurement (mcmc.py:833-842); unobserved (NaN) points are masked out
+            Mloc, T, S = data.shape
+            pts_ok = mask.reshape(Mloc * T, S).bool().all(dim=1, keepdim=True)
+            rmask = (torch.isfinite(tt(rates)) & pts_ok).to(torch.uint8)
+            self._dev_surr = (times.reshape(-1).contiguous(), data.reshape(Mloc * T, S).contiguous(),
+                              data[:, 0, :].contiguous(), tt(np.nan_to_num(rates)), rmask, tt(jac2),
+                              tt(extra2), T)
+        t_pts, y_pts, inits, rates, rmask, jac2, extra2, T = self._dev_surr
+        return self._compiled.rate_loglik_grad(t_pts, y_pts, theta, constants, inits, rates, jac2,
+                                               sigma, n_time=T, mask=rmask, extra2=extra2,
+                                               likelihood=self.likelihood)
 
     def log_likelihood(self, theta, sigma):
         """Likelihood block summed over ALL series (all-reduced when series are sharded)."""

@@ -215,6 +215,38 @@ class NeuralBase:
         return out if on_device else out.cpu().numpy()
 
 
+    # ---- Surrogate protocol (catalax/surrogate.py:13-73), used by BayesianModel(surrogate=...)
+    has_uncertainty = False            # neuralbase.py:146-152 (ensembles only)
+
+    def predict_rates(self, dataset):
+        """Rates at every measured point of a Dataset, [M*T, S] (neuralbase.py:329-344)."""
+        data, times, _ = dataset.to_jax_arrays(self.state_order)
+        M, T, S = data.shape
+        return np.asarray(self.rates(np.asarray(times).ravel(), np.asarray(data).reshape(M * T, S)))
+
+    def rate_jacobian(self, t, y, rel_step: float = 1e-6):
+        """``J[p, i, k] = d rate_i / d y_k`` at N points, [N,S,S] float64.  The reference takes
+        ``jax.jacfwd`` of ``rates`` (mcmc.py:865-894); here: central differences of the SAME
+        field evaluated in float64 by the generated kernel (ctx_rates), accurate to ~1e-9."""
+        import torch
+
+        model, theta = self._model(np.float64)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        y = torch.as_tensor(np.asarray(y, dtype=np.float64), device=dev)
+        t = torch.as_tensor(np.asarray(t, dtype=np.float64), device=dev)
+        th = torch.as_tensor(np.asarray(theta, dtype=np.float64), device=dev)
+        c = torch.empty((0,), dtype=torch.float64, device=dev)
+        N, S = y.shape
+        J = torch.empty((N, S, S), dtype=torch.float64, device=dev)
+        for k in range(S):
+            h = rel_step * torch.clamp(y[:, k].abs(), min=1.0)
+            yp, ym = y.clone(), y.clone()
+            yp[:, k] += h
+            ym[:, k] -= h
+            J[:, :, k] = (model.rates(t, yp, th, c) - model.rates(t, ym, th, c)) / (2.0 * h)[:, None]
+        return J.cpu().numpy()
+
+
 class NeuralODE(NeuralBase):
     """Plain MLP vector field (neuralode.py:25-59)."""
 

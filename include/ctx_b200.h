@@ -152,6 +152,21 @@ int ctx_rates(ctx_model* m, int64_t n, const void* t, int32_t stride_t, const vo
               const void* theta, int32_t stride_theta, const void* consts, int32_t stride_consts,
               const void* y0, int32_t stride_y0, void* out, void* stream);
 
+/* ---- K5: surrogate (rate-matching) log-likelihood + gradient, no solve ----------------------
+ * Replaces value_and_grad of the numpyro model in Modes.SURROGATE -- catalax/mcmc/mcmc.py:819-847
+ * (sim_func = vmap(rate_fun) at the measured states, "{state}_init" = first state of each
+ * measurement, data = surrogate rates), :469-480 (sigma_total[p,j] = sum_k J[p,j,k]^2 sigma_y[k]^2
+ * + extra + 1e-8) and :486-491 (masked likelihood).  Points are grouped per measurement:
+ * p = m * n_time + j.  t [N], y [N,S], theta [CH,P], consts [M,C], inits [M,S], data [N,S],
+ * mask [N,S] or NULL (= isfinite(data)), jac2 [N,S,S] = J^2, extra2 [N,S] or NULL
+ * (sigma_surr^2 + rate_sigma^2), sigma [CH,S] -> out [CH, 1+P+S] = (log L, d/dtheta, d/dsigma_y).
+ * The model must have been generated with all parameter directions (as for ctx_loglik_grad). */
+int ctx_rate_loglik_grad(ctx_model* m, int32_t likelihood, int64_t n_chains, int32_t n_points,
+                         int32_t n_time, const void* t, const void* y, const void* theta,
+                         const void* consts, const void* inits, const void* data,
+                         const uint8_t* mask, const void* jac2, const void* extra2,
+                         const void* sigma, void* out, void* stream);
+
 /* ---- host-buffer convenience (the call a reference-side ctypes binding would make) --------
  * Same as ctx_solve but every array is a HOST pointer; device staging, the H2D / D2H copies
  * and one stream synchronisation happen inside. */

@@ -76,3 +76,53 @@ def loglik_grad(model, y0s, theta, consts, ts, data, sigma, *, mask=None,
                 for i in range(S):
                     gy0[ch, :, i] = (w * tang[:, :, P + i, :]).sum(axis=(1, 2))
     return out, gy0, status
+
+
+def surrogate_loglik_grad(model, t, y, theta, consts, inits, data, jac2, sigma, *, n_time,
+                          mask=None, extra2=None, likelihood="softlaplace"):
+    """Surrogate (rate-matching) mode of the same numpyro model.  PARITY ORACLE (test infra).
+
+    Follows ``catalax/mcmc/mcmc.py``:
+      * :819-847  ``sim_func = vmap(rate_fun, in_axes=(0, None, 0, 0, 0))``: the mechanistic
+        right-hand side evaluated at the measured states ``y [N,S]`` (``N = M * n_time`` points,
+        grouped per measurement), constants repeated per time point, ``{state}_init`` symbols
+        from each measurement's first state (``inits [M,S]``); ``data`` = surrogate rates;
+      * :469-480  ``sigma_total[p,j] = sum_k J[p,j,k]^2 sigma_y[k]^2 (+ extra) + 1e-8``;
+      * :486-491  masked ``likelihood(loc, sqrt(sigma_total))``.
+    Gradient = chain rule through ``d rate / d theta`` (sympy derivative, numpy evaluation) and
+    through ``sqrt(sigma_total)``.  Returns out [CH, 1+P+S] (float64).
+    """
+    states, params, consts_n, odes, reactions = model
+    S, P = len(states), len(params)
+    rhs, _N, D, _ = sy.make_rhs(states, params, consts_n, odes, reactions, sens_theta=True)
+    t = np.asarray(t, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    N = y.shape[0]
+    M = N // n_time
+    rows = np.repeat(np.arange(M), n_time)
+    c_pts = np.asarray(consts, dtype=np.float64).reshape(M, -1)[rows]
+    i_pts = np.asarray(inits, dtype=np.float64)[rows]
+    data = np.asarray(data, dtype=np.float64)
+    jac2 = np.asarray(jac2, dtype=np.float64)
+    if mask is None:
+        mask = np.isfinite(data)
+    ex = np.zeros((N, S)) if extra2 is None else np.asarray(extra2, dtype=np.float64)
+    CH = theta.shape[0]
+    out = np.zeros((CH, 1 + P + S))
+    Y = np.concatenate([y, np.zeros((N, D * S))], axis=1)      # zero tangents: ds = d f / d theta
+    for ch in range(CH):
+        th = np.broadcast_to(np.asarray(theta[ch], dtype=np.float64), (N, P))
+        r = rhs(t, Y, th, c_pts, i_pts)
+        loc = r[:, :S]
+        dloc = r[:, S:].reshape(N, D, S)                         # [N, dir, state]
+        sg = np.asarray(sigma[ch], dtype=np.float64)
+        s2 = np.einsum("pjk,k->pj", jac2, sg ** 2) + ex + 1e-8
+        sd = np.sqrt(s2)
+        with np.errstate(all="ignore"):
+            lp, dl_dloc, dl_ds = logpdf_terms(np.where(mask, data, 0.0), loc, sd, likelihood)
+        out[ch, 0] = np.where(mask, lp, 0.0).sum()
+        w = np.where(mask, dl_dloc, 0.0)
+        for p in range(P):
+            out[ch, 1 + p] = (w * dloc[:, p, :]).sum()
+        ws = np.where(mask, dl_ds / sd, 0.0)                     # d lp / d s2 * 2 ... via sd
+        out[ch, 1 + P:] = np.einsum("pj,pjk->k", ws, jac2) * sg
+    return out

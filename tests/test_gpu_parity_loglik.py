@@ -262,9 +262,13 @@ def test_cooperative_loglik_is_reproducible_and_handles_long_segments():
     a = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float32, kernel=2)
     b = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float32, kernel=2)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-    v1 = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float32, kernel=1)
+    # same grid in x64: both kernels agree far below the solver tolerance (they differ only in the
+    # algebraic form of the interpolant and in the summation order)
+    v2 = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float64, kernel=2)
+    v1 = _gpu(model, y0s, theta, consts, ts, data, sigma, "normal", np.float64, kernel=1)
     scale = np.abs(v1[0]) + 1e-3 * np.abs(v1[0]).max(axis=1, keepdims=True)
-    assert (np.abs(a[0] - v1[0]) <= 2e-4 * scale).all()
+    assert (np.abs(v2[0] - v1[0]) <= 1e-8 * scale).all(), float((np.abs(v2[0] - v1[0]) / scale).max())
+    assert (v2[2] == 0).all() and (v1[2] == 0).all()
     # degenerate grid: all requested times are t0 = 0
     ts0 = np.zeros_like(ts)
     z2 = _gpu(model, y0s, theta, consts, ts0, data, sigma, "normal", np.float64, kernel=2)

@@ -137,3 +137,39 @@ def test_series_sharded_loglik_allreduce_world2_gloo(tmp_path):
     for rank, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o[-3000:]
         assert f"ok {rank}" in o
+
+
+def test_surrogate_rate_jacobian_by_central_differences_and_series_slicing():
+    """Host side of the surrogate mode (mcmc.py:865-894, 819-847): the Jacobian helper works on
+    any object with the public ``rates`` API; surrogate arrays follow the series sharding."""
+    import catalax_b200 as ctx
+    from catalax_b200.mcmc import BayesianModel
+    from catalax_b200.mcmc.mcmc import surrogate_rate_jacobian
+
+    class Fake:
+        def rates(self, t, y, constants=None):
+            y = np.asarray(y, dtype=np.float64)
+            return np.stack([y[:, 0] * y[:, 1], np.sin(y[:, 1]) + np.asarray(t)], axis=1)
+
+    rng = np.random.default_rng(0)
+    y = rng.uniform(0.5, 2.0, (11, 2)); t = rng.uniform(0, 1, 11)
+    J = surrogate_rate_jacobian(Fake(), y, t)
+    want = np.zeros((11, 2, 2))
+    want[:, 0, 0] = y[:, 1]; want[:, 0, 1] = y[:, 0]; want[:, 1, 1] = np.cos(y[:, 1])
+    np.testing.assert_allclose(J, want, rtol=1e-8, atol=1e-9)
+
+    model = ctx.Model(name="decay")
+    model.add_state(s="s", p="p")
+    model.add_ode("s", "-k * s"); model.add_ode("p", "k * s_init")
+    model.parameters.k.prior = priors.Uniform(0.1, 2.0)
+    M, T = 4, 3
+    data = rng.uniform(1, 2, (M, T, 2)); times = np.tile(np.linspace(0, 1, T), (M, 1))
+    rates = rng.normal(size=(M * T, 2)); jac = rng.normal(size=(M * T, 2, 2))
+    bm = BayesianModel(model, arrays=(data, times, data[:, 0, :], np.zeros((M, 0))), shard="none",
+                       surrogate_arrays=(rates, jac, None))
+    assert bm.mode == "surrogate" and bm._surr[0].shape == (M * T, 2) and bm._surr[1].shape == (M * T, 2, 2)
+    np.testing.assert_allclose(bm._surr[1], jac ** 2, rtol=1e-6)
+    assert bm.jac_rownorm.shape == (2,)
+    with pytest.raises(NotImplementedError):
+        BayesianModel(model, arrays=(data, times, data[:, 0, :], np.zeros((M, 0))), shard="none",
+                      surrogate_arrays=(rates, jac, None), estimate_initials=True)
