@@ -10,9 +10,10 @@ from .config import enable_x64, set_host_count, set_platform, x64_enabled
 from .dataset import Dataset, Measurement
 from .model import InAxes, Model, SimulationConfig
 from .solvers import Dopri5, Euler, Heun, Tsit5
+from .tools.optimization import optimize
 
 __all__ = ["SimulationConfig", "Dataset", "Measurement", "InAxes", "Model", "enable_x64",
-           "set_platform", "set_host_count", "Tsit5", "Dopri5", "Euler", "Heun"]
+           "set_platform", "set_host_count", "optimize", "Tsit5", "Dopri5", "Euler", "Heun"]
 __version__ = "0.1.0"
 
 PARAMETERS = InAxes.PARAMETERS

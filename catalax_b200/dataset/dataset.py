@@ -63,6 +63,20 @@ class Dataset:
                                   initial_condition={s: float(y0s[i, j]) for j, s in enumerate(state_order)})
         return ds
 
+    def get_observable_states_order(self) -> List[str]:
+        """Sorted states that carry data in every measurement (dataset.py:133-172)."""
+        if not self.measurements:
+            return []
+        common = set(self.measurements[0].data.keys())
+        for meas in self.measurements[1:]:
+            if set(meas.data.keys()) != common:
+                common &= set(meas.data.keys())
+                warnings.warn("Inconsistent observables across measurements. "
+                              f"Using the common ones: {sorted(common)}")
+        if not common:
+            raise ValueError("No common observable states across measurements")
+        return sorted(common)
+
     def to_jax_arrays(self, state_order: List[str], inits_to_array: bool = False):
         data, time, inits = [], [], []
         for meas in self.measurements:
