@@ -23,6 +23,7 @@
 
 extern const char ctx_integrator_src[];  // generated from ctx_integrator.cuh (embed step)
 extern const char ctx_mlp_tc_src[];      // generated from ctx_mlp_tc.cuh
+extern const char ctx_mlp_adjoint_src[]; // generated from ctx_mlp_adjoint.cuh
 
 namespace {
 
@@ -88,6 +89,7 @@ struct ctx_model {
   bool theta_ptr = false;           // generated with CTX_THETA_PTR (shared weights in smem)
   int p_pad = 0;
   int mlp_tc_smem = 0;              // > 0: the tcgen05 MLP kernel is available (bytes of smem)
+  bool has_adjoint = false;         // weight-gradient kernels were generated (ctx_mlp_adjoint.cuh)
   int warp_warps = 0;               // > 0: lane-parallel form present (ctx_solve_w), warps per CTA
   // host-call staging (ctx_solve_host)
   void* stage = nullptr;
@@ -220,7 +222,8 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
       else cur += ch;
     }
   }
-  std::string keysrc = src + "\x01" + ctx_integrator_src + "\x01" + ctx_mlp_tc_src;
+  std::string keysrc = src + "\x01" + ctx_integrator_src + "\x01" + ctx_mlp_tc_src + "\x01" +
+                       ctx_mlp_adjoint_src;
   for (auto& o : opts) keysrc += "\x02" + o;
   int nv_major = 0, nv_minor = 0;
   nvrtcVersion(&nv_major, &nv_minor);
@@ -245,9 +248,9 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
     }
   }
   nvrtcProgram prog;
-  const char* hdr_src[] = {ctx_integrator_src, ctx_mlp_tc_src};
-  const char* hdr_name[] = {"ctx_integrator.cuh", "ctx_mlp_tc.cuh"};
-  nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "ctx_model.cu", 2, hdr_src, hdr_name);
+  const char* hdr_src[] = {ctx_integrator_src, ctx_mlp_tc_src, ctx_mlp_adjoint_src};
+  const char* hdr_name[] = {"ctx_integrator.cuh", "ctx_mlp_tc.cuh", "ctx_mlp_adjoint.cuh"};
+  nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "ctx_model.cu", 3, hdr_src, hdr_name);
   if (r != NVRTC_SUCCESS) return fail(CTX_E_NVRTC, nvrtcGetErrorString(r));
   std::vector<const char*> copts;
   for (auto& o : opts) copts.push_back(o.c_str());
@@ -579,6 +582,128 @@ int launch_loglik(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, cons
   return CTX_OK;
 }
 
+// ---------------------------------------------------------------------------- MLP adjoint
+template <typename real>
+struct AdjArgs {
+  const real* y0;
+  const real* theta;
+  const real* ts;
+  real* ys;
+  const real* gys;
+  real* ck_real;
+  int* ck_int;
+  int* n_steps;
+  int* status;
+  int* n_accepted;
+  int* n_rejected;
+  real* partial;
+  real* gy0;
+  unsigned long long* work_counter;
+  long long B;
+  int T, cap, max_steps, stride_ts;
+  real rtol, atol, dt0;
+};
+
+struct AdjPlan {
+  unsigned spack = 0, nact = 0, warps = 0, n_params = 0, wmax = 0;   // ctx_adj_info of the module
+  unsigned grid = 0;
+  size_t smem_fwd = 0, smem_bwd = 0;
+  size_t off_ck_real = 0, off_ck_int = 0, off_nsteps = 0, off_counts = 0, off_partial = 0, total = 0;
+};
+
+int adj_plan(ctx_model* m, const ctx_adjoint_cfg* cfg, AdjPlan& p) {
+  if (!m->has_adjoint)
+    return fail(CTX_E_INVALID, "model has no weight-gradient kernels (plain NeuralODE fields only)");
+  if (cfg->batch <= 0 || cfg->n_times <= 0 || cfg->cap <= 0)
+    return fail(CTX_E_INVALID, "adjoint: batch, n_times and cap must be positive");
+  cudaKernel_t k;
+  int rc = get_kernel(m, CTX_TSIT5, 0, "ctx_mlp_adj_forward", &k);
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    Variant& v = m->variants[CTX_TSIT5 * 2 + 0];
+    void* dptr = nullptr;
+    size_t nbytes = 0;
+    unsigned info[5] = {0, 0, 0, 0, 0};
+    CTX_CUDA(cudaLibraryGetGlobal(&dptr, &nbytes, v.lib, "ctx_adj_info"));
+    CTX_CUDA(cudaMemcpy(info, dptr, sizeof(info), cudaMemcpyDeviceToHost));
+    p.spack = info[0]; p.nact = info[1]; p.warps = info[2]; p.n_params = info[3];
+    p.wmax = info[4];
+  }
+  const size_t w = m->desc.dtype == CTX_F64 ? 8 : 4;
+  int dev = 0, sms = 0;
+  CTX_CUDA(cudaGetDevice(&dev));
+  CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  unsigned long long grid = ((unsigned long long)cfg->batch + p.warps - 1) / p.warps;
+  if (grid > (unsigned long long)sms) grid = sms;
+  p.grid = (unsigned)grid;
+  p.smem_fwd = ((size_t)p.spack + (size_t)p.warps * p.nact) * w;
+  p.smem_bwd = ((size_t)p.spack + (size_t)p.warps * (p.spack + 7 * (size_t)p.nact + 2 * (size_t)p.wmax)) * w;
+  auto al = [](size_t n) { return (n + 255) / 256 * 256; };
+  const size_t B = (size_t)cfg->batch, cap = (size_t)cfg->cap, S = (size_t)m->desc.n_states;
+  size_t off = 256;
+  p.off_ck_real = off; off += al(B * cap * (2 + S) * w);
+  p.off_ck_int = off;  off += al(B * cap * 2 * sizeof(int));
+  p.off_nsteps = off;  off += al(B * sizeof(int));
+  p.off_counts = off;  off += al(3 * B * sizeof(int));
+  p.off_partial = off; off += al((size_t)p.grid * p.warps * p.n_params * w);
+  p.total = off;
+  return CTX_OK;
+}
+
+template <typename real>
+int launch_adjoint(ctx_model* m, const ctx_adjoint_cfg* cfg, bool backward, const void* y0,
+                   const void* theta, const void* ts, void* ys, const void* gys, int32_t* status,
+                   int32_t* nacc, int32_t* nrej, void* grad_theta, void* grad_y0, void* ws,
+                   size_t ws_bytes, cudaStream_t stream) {
+  AdjPlan p;
+  int rc = adj_plan(m, cfg, p);
+  if (rc) return rc;
+  if (!ws || ws_bytes < p.total) return fail(CTX_E_WORKSPACE, "workspace too small");
+  char* base = (char*)ws;
+  AdjArgs<real> a;
+  a.y0 = (const real*)y0; a.theta = (const real*)theta; a.ts = (const real*)ts;
+  a.ys = (real*)ys; a.gys = (const real*)gys;
+  a.ck_real = (real*)(base + p.off_ck_real);
+  a.ck_int = (int*)(base + p.off_ck_int);
+  a.n_steps = (int*)(base + p.off_nsteps);
+  int* counts = (int*)(base + p.off_counts);
+  a.status = status ? status : counts;
+  a.n_accepted = nacc ? nacc : counts + cfg->batch;
+  a.n_rejected = nrej ? nrej : counts + 2 * cfg->batch;
+  a.partial = (real*)(base + p.off_partial);
+  a.gy0 = (real*)grad_y0;
+  a.work_counter = (unsigned long long*)base;
+  a.B = cfg->batch; a.T = cfg->n_times; a.cap = cfg->cap; a.max_steps = cfg->max_steps;
+  a.stride_ts = cfg->ts_per_row ? cfg->n_times : 0;
+  a.rtol = (real)cfg->rtol; a.atol = (real)cfg->atol; a.dt0 = (real)cfg->dt0;
+  cudaKernel_t k;
+  rc = get_kernel(m, CTX_TSIT5, 0, backward ? "ctx_mlp_adj_backward" : "ctx_mlp_adj_forward", &k);
+  if (rc) return rc;
+  const size_t smem = backward ? p.smem_bwd : p.smem_fwd;
+  if (smem > 227 * 1024) return fail(CTX_E_INVALID, "adjoint: the network does not fit shared memory");
+  if (smem > 48 * 1024)
+    CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  void* params[] = {&a};
+  CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+  CTX_CUDA(cudaLaunchKernel((const void*)k, dim3(p.grid), dim3(32 * p.warps), params, smem, stream));
+  g_launches++;
+  if (backward) {
+    cudaKernel_t kr;
+    rc = get_kernel(m, CTX_TSIT5, 0, "ctx_mlp_adj_reduce", &kr);
+    if (rc) return rc;
+    const real* part = a.partial;
+    real* g = (real*)grad_theta;
+    int rows = (int)(p.grid * p.warps);
+    void* rparams[] = {(void*)&part, (void*)&g, (void*)&rows};
+    CTX_CUDA(cudaLaunchKernel((const void*)kr, dim3((p.n_params + 127) / 128), dim3(128), rparams,
+                              0, stream));
+    g_launches++;
+  }
+  return CTX_OK;
+}
+
 int dispatch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0,
                    const void* theta, const void* consts, const void* ts, void* ys, void* sens,
                    int32_t* status, int32_t* nacc, int32_t* nrej, void* ws, size_t ws_bytes,
@@ -642,6 +767,7 @@ int ctx_model_compile(const char* field_src, const ctx_model_desc* desc, ctx_mod
     if (m->p_pad < desc->n_params) m->p_pad = desc->n_params;
   }
   if (const char* q = strstr(field_src, "#define CTX_MLP_TC_SMEM ")) m->mlp_tc_smem = atoi(q + 24);
+  m->has_adjoint = strstr(field_src, "#define CTX_MLP_ADJ 1") != nullptr;
   if (strstr(field_src, "#define CTX_HAVE_WARP 1"))
     if (const char* q = strstr(field_src, "#define CTXW_WARPS ")) m->warp_warps = atoi(q + 19);
   *out = m;
@@ -790,6 +916,44 @@ int ctx_rate_loglik_grad(ctx_model* m, int32_t likelihood, int64_t n_chains, int
   }
   g_launches++;
   return CTX_OK;
+}
+
+size_t ctx_mlp_adjoint_workspace_bytes(ctx_model* m, const ctx_adjoint_cfg* cfg) {
+  if (!m || !cfg || ctx_device_count() <= 0) return 0;
+  AdjPlan p;
+  if (adj_plan(m, cfg, p)) return 0;
+  return p.total;
+}
+
+int ctx_mlp_adjoint_forward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void* y0,
+                            const void* theta, const void* ts, void* ys, int32_t* status,
+                            int32_t* n_accepted, int32_t* n_rejected, void* workspace,
+                            size_t ws_bytes, void* stream) {
+  if (!m || !cfg || !ys) return fail(CTX_E_INVALID, "null argument");
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  if (m->desc.dtype == CTX_F64)
+    return launch_adjoint<double>(m, cfg, false, y0, theta, ts, ys, nullptr, status, n_accepted,
+                                  n_rejected, nullptr, nullptr, workspace, ws_bytes,
+                                  (cudaStream_t)stream);
+  return launch_adjoint<float>(m, cfg, false, y0, theta, ts, ys, nullptr, status, n_accepted,
+                               n_rejected, nullptr, nullptr, workspace, ws_bytes,
+                               (cudaStream_t)stream);
+}
+
+int ctx_mlp_adjoint_backward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void* theta,
+                             const void* ts, const void* gys, int32_t* status, void* grad_theta,
+                             void* grad_y0, void* workspace, size_t ws_bytes, void* stream) {
+  if (!m || !cfg || !gys || !grad_theta || !status) return fail(CTX_E_INVALID, "null argument");
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  if (m->desc.dtype == CTX_F64)
+    return launch_adjoint<double>(m, cfg, true, nullptr, theta, ts, nullptr, gys, status, nullptr,
+                                  nullptr, grad_theta, grad_y0, workspace, ws_bytes,
+                                  (cudaStream_t)stream);
+  return launch_adjoint<float>(m, cfg, true, nullptr, theta, ts, nullptr, gys, status, nullptr,
+                               nullptr, grad_theta, grad_y0, workspace, ws_bytes,
+                               (cudaStream_t)stream);
 }
 
 int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,

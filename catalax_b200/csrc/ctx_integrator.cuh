@@ -2150,3 +2150,6 @@ ctx_solve_w(const ctx_solve_args a) {
 #ifdef CTX_MLP_TC
 #include "ctx_mlp_tc.cuh"
 #endif
+#ifdef CTX_MLP_ADJ
+#include "ctx_mlp_adjoint.cuh"
+#endif

@@ -42,6 +42,12 @@ class ctx_solve_cfg(C.Structure):
                 ("t0_from_ts", C.c_int32), ("inner", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ctx_adjoint_cfg(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("n_times", C.c_int32), ("max_steps", C.c_int32),
+                ("cap", C.c_int32), ("ts_per_row", C.c_int32), ("rtol", C.c_double),
+                ("atol", C.c_double), ("dt0", C.c_double)]
+
+
 class ctx_loglik_cfg(C.Structure):
     _fields_ = [("solver", C.c_int32), ("likelihood", C.c_int32), ("n_chains", C.c_int64),
                 ("n_series", C.c_int32), ("n_times", C.c_int32), ("max_steps", C.c_int32),
@@ -90,6 +96,12 @@ def lib() -> C.CDLL:
                             C.c_int32, vp, vp]
     L.ctx_rate_loglik_grad.restype = C.c_int
     L.ctx_rate_loglik_grad.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [vp] * 12
+    L.ctx_mlp_adjoint_workspace_bytes.restype = C.c_size_t
+    L.ctx_mlp_adjoint_workspace_bytes.argtypes = [vp, C.POINTER(ctx_adjoint_cfg)]
+    L.ctx_mlp_adjoint_forward.restype = C.c_int
+    L.ctx_mlp_adjoint_forward.argtypes = [vp, C.POINTER(ctx_adjoint_cfg)] + [vp] * 8 + [C.c_size_t, vp]
+    L.ctx_mlp_adjoint_backward.restype = C.c_int
+    L.ctx_mlp_adjoint_backward.argtypes = [vp, C.POINTER(ctx_adjoint_cfg)] + [vp] * 7 + [C.c_size_t, vp]
     L.ctx_solve_host.restype = C.c_int
     L.ctx_solve_host.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -349,6 +361,59 @@ class CompiledModel:
                 p(inits), p(data), p(mask), p(jac2), p(extra2), p(sigma), p(out),
                 C.c_void_p(stream)))
         return out
+
+    # ------------------------------------------------------------------ NeuralODE training
+    def adjoint_forward(self, y0, theta, ts, *, rtol=1e-3, atol=1e-6, dt0=0.1, max_steps=4096,
+                        cap=512):
+        """Forward solve that records every accepted step (ctx_mlp_adjoint_forward).
+        y0 [B,S], theta [P] (flat layout), ts [B,T] or [T].  Returns a context dict holding ys
+        [B,T,S], status / step counts and the workspace `adjoint_backward` needs."""
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = y0.device
+        if dev.type != "cuda":
+            raise EngineError("adjoint_forward() needs CUDA tensors: catalax_b200 has no CPU fallback")
+        f = lambda x: x.to(device=dev, dtype=tdt).contiguous()
+        y0, theta, ts = f(y0), f(theta), f(ts)
+        B, S = y0.shape
+        T = ts.shape[-1]
+        cfg = ctx_adjoint_cfg()
+        cfg.batch, cfg.n_times, cfg.max_steps, cfg.cap = B, T, int(max_steps), int(cap)
+        cfg.ts_per_row = 1 if ts.dim() == 2 else 0
+        cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
+        p = lambda t: C.c_void_p(t.data_ptr()) if (t is not None and t.numel()) else C.c_void_p(0)
+        with torch.cuda.device(dev):
+            wsb = int(lib().ctx_mlp_adjoint_workspace_bytes(self._h, C.byref(cfg)))
+            if wsb == 0:
+                raise EngineError(last_error() or "adjoint workspace query failed")
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            ys = torch.empty((B, T, S), dtype=tdt, device=dev)
+            counts = torch.empty((3, B), dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _check(lib().ctx_mlp_adjoint_forward(self._h, C.byref(cfg), p(y0), p(theta), p(ts), p(ys),
+                                                 p(counts[0]), p(counts[1]), p(counts[2]), p(ws),
+                                                 wsb, C.c_void_p(stream)))
+        return dict(cfg=cfg, ws=ws, wsb=wsb, ys=ys, status=counts[0], n_accepted=counts[1],
+                    n_rejected=counts[2], theta=theta, ts=ts)
+
+    def adjoint_backward(self, ctx, gys, want_y0: bool = False):
+        """d loss / d theta [P] (and d loss / d y0 [B,S]) from gys = d loss / d ys [B,T,S]."""
+        import torch
+
+        ys = ctx["ys"]
+        gys = gys.to(device=ys.device, dtype=ys.dtype).contiguous()
+        assert gys.shape == ys.shape
+        p = lambda t: C.c_void_p(t.data_ptr()) if (t is not None and t.numel()) else C.c_void_p(0)
+        with torch.cuda.device(ys.device):
+            g = torch.empty(ctx["theta"].shape, dtype=ys.dtype, device=ys.device)
+            gy0 = torch.empty((ys.shape[0], ys.shape[2]), dtype=ys.dtype, device=ys.device) \
+                if want_y0 else None
+            stream = torch.cuda.current_stream(ys.device).cuda_stream
+            _check(lib().ctx_mlp_adjoint_backward(self._h, C.byref(ctx["cfg"]), p(ctx["theta"]),
+                                                  p(ctx["ts"]), p(gys), p(ctx["status"]), p(g), p(gy0),
+                                                  p(ctx["ws"]), ctx["wsb"], C.c_void_p(stream)))
+        return (g, gy0) if want_y0 else g
 
     def rates(self, t, y, theta, consts, y0=None):
         """Right-hand side at N points (ctx_rates): t [N]|scalar, y [N,S], theta [N,P]|[P],

@@ -252,6 +252,102 @@ class NeuralODE(NeuralBase):
 
     kind = "neuralode"
 
+    # ---- training: value and gradient of the loss (trainer.py:268-306)
+    def value_and_grad(self, ts, y0, data, *, loss="l2", mask=None, rtol=None, atol=None, dt0=None,
+                       want_y0: bool = False, cap: int = 512):
+        """Loss of ``vmap(self)(ts, y0)`` against ``data`` and its gradient w.r.t. every weight.
+
+        ts [B,T] (or [T]), y0 [B,S], data [B,T,S]; ``mask`` [T] weights the time points (temporal
+        dropout, trainer.py:300-306): ``loss = sum(mask * per_point) / (sum(mask) * B * S)``.
+        ``loss``: "l2" (``optax.l2_loss``, 0.5 (p - y)^2), "l1", or a callable
+        ``(pred, target) -> per-point loss`` written with torch operators.
+        Returns ``(value, grads)`` with ``grads = {"weights": [...], "biases": [...]}`` in the
+        equinox convention (W [out, in]; None where the model has no bias)."""
+        import torch
+
+        dtype = default_dtype()
+        model, theta = self._model(dtype)
+        if not model.field.source.count("#define CTX_MLP_ADJ 1"):
+            raise NotImplementedError("weight gradients: plain NeuralODE fields of <= 8 states")
+        if solver_name(self.solver) != "tsit5":
+            raise NotImplementedError("weight gradients are implemented for Tsit5")
+        dev = y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda else \
+            torch.device("cuda", torch.cuda.current_device())
+        tt = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=dtype))).to(dev)
+        ts_t, y0_t, data_t = tt(ts), tt(y0), tt(data)
+        if dt0 is None:
+            dt0 = 0.0        # kernel: ts[1] - ts[0] of every trajectory (neuralode.py:44-47)
+        ctx = model.adjoint_forward(y0_t, torch.as_tensor(theta, device=dev), ts_t,
+                                    rtol=1e-3 if rtol is None else rtol,
+                                    atol=1e-6 if atol is None else atol, dt0=dt0,
+                                    max_steps=self._max_steps(), cap=cap)
+        self.last = ctx
+        bad = int((ctx["status"] != 0).sum().item())
+        if bad:
+            raise RuntimeError(f"{bad} trajectories failed in the training solve "
+                               f"(status {int(ctx['status'].max().item())}; 3 = more than cap={cap} steps)")
+        pred = ctx["ys"].detach().clone().requires_grad_(True)
+        if callable(loss):
+            per_point = loss(pred, data_t.to(pred.dtype))
+        elif loss == "l2":
+            per_point = 0.5 * (pred - data_t.to(pred.dtype)) ** 2
+        elif loss == "l1":
+            per_point = (pred - data_t.to(pred.dtype)).abs()
+        else:
+            raise ValueError(f"unknown loss {loss!r}")
+        B, T, S = pred.shape
+        m = torch.ones(T, dtype=pred.dtype, device=dev) if mask is None else tt(mask).to(pred.dtype)
+        value = (per_point * m[None, :, None]).sum() / (m.sum() * B * S)
+        (gys,) = torch.autograd.grad(value, pred)
+        g = model.adjoint_backward(ctx, gys, want_y0=want_y0)
+        g, gy0 = g if want_y0 else (g, None)
+        g = g.to(torch.float64).cpu().numpy()
+        lay = cm.layout_of(self.spec)
+        gW, gb = [], []
+        for l, (n_in, n_out) in enumerate(self.spec.layer_dims()):
+            ip = lay.in_pad[l]
+            gW.append(g[lay.w_off[l]: lay.w_off[l] + n_out * ip].reshape(n_out, ip)[:, :n_in].copy())
+            gb.append(None if self.biases[l] is None else g[lay.b_off[l]: lay.b_off[l] + n_out].copy())
+        grads = {"weights": gW, "biases": gb}
+        if want_y0:
+            grads["y0"] = gy0
+        return float(value.item()), grads
+
+    def apply_updates(self, dW, db):
+        """weights += dW, biases += db; the compiled parameter packs are rebuilt lazily."""
+        self.weights = [w + np.asarray(d, dtype=np.float64) for w, d in zip(self.weights, dW)]
+        self.biases = [None if b is None else b + np.asarray(d, dtype=np.float64)
+                       for b, d in zip(self.biases, db)]
+        for key in list(self._compiled):
+            if key == "tc":
+                del self._compiled[key]
+            else:
+                model, _ = self._compiled[key]
+                self._compiled[key] = (model, cm.pack_parameters(
+                    self.spec, self.weights, self.biases, self.max_time, np.dtype(key), **self._extra()))
+
+    def train(self, ts, y0, data, *, steps: int = 100, lr: float = 1e-3, loss="l2", **kw):
+        """Minimal Adam loop over ``value_and_grad`` (the role of trainer.py:173-253's optax loop;
+        strategies, penalties and batching are left to the caller).  Returns the loss history."""
+        m = [[np.zeros_like(w) for w in self.weights], [None if b is None else np.zeros_like(b) for b in self.biases]]
+        v = [[np.zeros_like(w) for w in self.weights], [None if b is None else np.zeros_like(b) for b in self.biases]]
+        b1, b2, eps, hist = 0.9, 0.999, 1e-8, []
+        for k in range(1, steps + 1):
+            val, g = self.value_and_grad(ts, y0, data, loss=loss, **kw)
+            hist.append(val)
+            upd = [[], []]
+            for grp, (params, grads) in enumerate(((self.weights, g["weights"]), (self.biases, g["biases"]))):
+                for i, (p_, g_) in enumerate(zip(params, grads)):
+                    if p_ is None:
+                        upd[grp].append(None)
+                        continue
+                    m[grp][i] = b1 * m[grp][i] + (1 - b1) * g_
+                    v[grp][i] = b2 * v[grp][i] + (1 - b2) * g_ * g_
+                    mh, vh = m[grp][i] / (1 - b1 ** k), v[grp][i] / (1 - b2 ** k)
+                    upd[grp].append(-lr * mh / (np.sqrt(vh) + eps))
+            self.apply_updates(upd[0], upd[1])
+        return hist
+
 
 class RateFlowODE(NeuralBase):
     """``stoich_matrix @ relu(MLP)`` (rateflow.py:29-121)."""

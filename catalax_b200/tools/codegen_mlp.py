@@ -246,6 +246,51 @@ def _tc_source(spec: MLPSpec) -> List[str]:
     return out
 
 
+def adjoint_dims(spec: MLPSpec):
+    """Shared-memory pack of the weight-gradient kernels (csrc/ctx_mlp_adjoint.cuh), or None when
+    the model is not a plain NeuralODE of at most 8 states (RateFlow / Universal fields: next)."""
+    if spec.kind != "neuralode" or spec.data_size > 8 or spec.out_size != spec.data_size:
+        return None
+    dims = spec.layer_dims()
+    wmax = max(max(ni, no) for ni, no in dims)
+    wmax = (wmax + 31) // 32 * 32
+    soff, off = [], 0
+    for ni, no in dims:
+        soff.append(off)
+        off += ni * (no + 1) + no
+    nact = (len(dims) + 1) * wmax
+    per_warp_bwd = off + 7 * nact + 2 * wmax
+
+    def warps(word):
+        w = (227 * 1024 // word - off) // per_warp_bwd
+        return max(0, min(4, w))
+    return dict(dims=dims, wmax=wmax, soff=soff, spack=off, nact=nact, per_warp_bwd=per_warp_bwd,
+                warps32=warps(4), warps64=warps(8))
+
+
+def _adjoint_source(spec: MLPSpec) -> List[str]:
+    d = adjoint_dims(spec)
+    if d is None or d["warps32"] < 1:
+        return []
+    lay = layout_of(spec)
+    arr = lambda name, vals: f"__device__ const int {name}[{len(vals)}] = {{" + ", ".join(map(str, vals)) + "};"
+    out = [
+        "#define CTX_MLP_ADJ 1",
+        f"#define ADJ_L {len(d['dims'])}", f"#define ADJ_WMAX {d['wmax']}",
+        f"#define ADJ_SPACK {d['spack']}", f"#define ADJ_P {lay.size}",
+        f"#define ADJ_INVT {lay.inv_max_time}",
+        f"#define ADJ_ACT {ACT_IDS[spec.activation]}", f"#define ADJ_FACT {ACT_IDS[spec.final_activation]}",
+        "#if CTX_F64", f"#define ADJ_WARPS {max(1, d['warps64'])}", "#else",
+        f"#define ADJ_WARPS {d['warps32']}", "#endif",
+        arr("adj_nin", [ni for ni, _ in d["dims"]]), arr("adj_nout", [no for _, no in d["dims"]]),
+        arr("adj_woff", lay.w_off), arr("adj_boff", lay.b_off), arr("adj_inpad", lay.in_pad),
+        arr("adj_soff", d["soff"]),
+    ]
+    if d["warps64"] < 1:
+        out = ["#if !CTX_F64"] + out + ["#endif"]
+    return out
+
+
 def generate_mlp_field(spec: MLPSpec) -> cg.GeneratedField:
     S = spec.data_size
     lay = layout_of(spec)
@@ -342,6 +387,7 @@ def generate_mlp_field(spec: MLPSpec) -> cg.GeneratedField:
         raise ValueError(spec.kind)
     src += ["}", "#define CTX_D 0", "#define CTX_D_THETA 0", "#define CTX_D_Y0 0"]
     src += _tc_source(spec)
+    src += _adjoint_source(spec)
     text = "\n".join(src) + "\n"
     key = hashlib.sha256(text.encode()).hexdigest()[:24]
     return cg.GeneratedField(text, S, lay.size, 0, 0, 0, 0, flops, 0, True, key)

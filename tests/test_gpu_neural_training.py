@@ -1,0 +1,119 @@
+"""NeuralODE training gradient (catalax/neural/trainer.py:268-306 through
+neuralode.py:38-59) -- ctx_mlp_adj_forward / ctx_mlp_adj_backward vs the torch-autograd
+restatement of the discrete adjoint (oracle/adjoint_oracle.py)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _problem(S, width, depth, activation, B, T, seed, t1=4.0, use_final_bias=False):
+    from catalax_b200.neural import NeuralODE
+
+    rng = np.random.default_rng(seed)
+    net = NeuralODE(S, width, depth, [f"s{i}" for i in range(S)], activation=activation,
+                    max_time=t1, key=seed, use_final_bias=use_final_bias)
+    # damp the random field so trajectories stay O(1) over [0, t1]
+    net.weights[-1] = net.weights[-1] * 0.3
+    y0 = rng.uniform(0.2, 1.5, (B, S))
+    ts = np.tile(np.linspace(0.0, t1, T), (B, 1))
+    ts[1:] += rng.uniform(0, 0.05, (B - 1, 1)) * np.arange(T)[None, :] / T   # per-row grids
+    data = y0[:, None, :] * np.exp(-0.4 * ts)[:, :, None] + 0.01 * rng.normal(size=(B, T, S))
+    return net, ts, y0, data
+
+
+def _oracle(net, ts, y0, data, mask=None, loss="l2", rtol=1e-3, atol=1e-6):
+    from oracle import adjoint_oracle as ao
+
+    d = torch.tensor(data)
+    B, T, S = data.shape
+    m = torch.ones(T, dtype=torch.float64) if mask is None else torch.tensor(mask, dtype=torch.float64)
+
+    def loss_fn(ys):
+        pp = 0.5 * (ys - d) ** 2 if loss == "l2" else (ys - d).abs()
+        return (pp * m[None, :, None]).sum() / (m.sum() * B * S)
+
+    return ao.neuralode_value_and_grad(net.weights, net.biases, net.spec.activation,
+                                       net.spec.final_activation, net.max_time, ts, y0, loss_fn,
+                                       rtol=rtol, atol=atol)
+
+
+def _check(g, ref_W, ref_b, rtol):
+    for l, (a, b) in enumerate(zip(g["weights"], ref_W)):
+        scale = np.abs(b).max() + 1e-300
+        assert np.abs(a - b).max() <= rtol * scale, (l, float(np.abs(a - b).max() / scale))
+    for l, (a, b) in enumerate(zip(g["biases"], ref_b)):
+        assert (a is None) == (b is None)
+        if a is not None:
+            scale = np.abs(b).max() + 1e-300
+            assert np.abs(a - b).max() <= rtol * scale, (l, float(np.abs(a - b).max() / scale))
+
+
+@pytest.mark.parametrize("S,width,depth,activation,B,fb", [
+    (2, 32, 2, "tanh", 5, False),
+    (4, 64, 3, "softplus", 9, True),      # BASELINE configs[4] shape (5->64->64->64->4)
+    (3, 64, 1, "celu", 3, False),
+])
+def test_weight_gradient_matches_autograd_of_the_discrete_scheme_f64(S, width, depth, activation, B, fb):
+    import catalax_b200 as ctx
+
+    ctx.enable_x64(True)
+    try:
+        net, ts, y0, data = _problem(S, width, depth, activation, B, 8, seed=S + depth, use_final_bias=fb)
+        # tight tolerances: many steps per trajectory, with rejections
+        val, g = net.value_and_grad(ts, y0, data, want_y0=True, rtol=1e-7, atol=1e-9)
+        rv, rys, rW, rb, rgy0, rna, rnr = _oracle(net, ts, y0, data, rtol=1e-7, atol=1e-9)
+        assert rna.min() >= 3 and rna.max() >= 4
+        assert np.array_equal(net.last["n_accepted"].cpu().numpy(), rna)
+        assert np.array_equal(net.last["n_rejected"].cpu().numpy(), rnr)
+        np.testing.assert_allclose(net.last["ys"].cpu().numpy(), rys, rtol=1e-9, atol=1e-11)
+        assert abs(val - rv) <= 1e-10 * abs(rv)
+        _check(g, rW, rb, 1e-8)
+        gy0 = g["y0"].cpu().numpy()
+        assert np.abs(gy0 - rgy0).max() <= 1e-8 * np.abs(rgy0).max()
+    finally:
+        ctx.enable_x64(False)
+
+
+def test_mask_l1_loss_and_reproducibility_f64():
+    import catalax_b200 as ctx
+
+    ctx.enable_x64(True)
+    try:
+        net, ts, y0, data = _problem(2, 32, 2, "tanh", 6, 10, seed=11)
+        mask = np.array([1, 0, 1, 1, 0, 1, 1, 1, 0, 1], dtype=np.float64)   # temporal dropout
+        val, g = net.value_and_grad(ts, y0, data, loss="l1", mask=mask)
+        val2, g2 = net.value_and_grad(ts, y0, data, loss="l1", mask=mask)
+        assert val == val2 and all(np.array_equal(a, b) for a, b in zip(g["weights"], g2["weights"]))
+        rv, _, rW, rb, *_ = _oracle(net, ts, y0, data, mask=mask, loss="l1")
+        assert abs(val - rv) <= 1e-10 * abs(rv)
+        _check(g, rW, rb, 1e-8)
+    finally:
+        ctx.enable_x64(False)
+
+
+def test_weight_gradient_f32_stated_bound():
+    """f32 (the reference's training dtype): 2e-3 of each layer's largest gradient entry."""
+    net, ts, y0, data = _problem(4, 64, 3, "softplus", 16, 8, seed=5)
+    val, g = net.value_and_grad(ts.astype(np.float32), y0.astype(np.float32), data.astype(np.float32))
+    rv, _, rW, rb, *_ = _oracle(net, ts, y0, data)
+    assert abs(val - rv) <= 1e-4 * abs(rv)
+    _check(g, rW, rb, 2e-3)
+
+
+def test_adam_steps_on_the_gradient_reduce_the_loss():
+    net, ts, y0, data = _problem(2, 32, 2, "tanh", 32, 8, seed=2)
+    hist = net.train(ts, y0, data, steps=40, lr=3e-3)
+    assert hist[-1] < 0.5 * hist[0], (hist[0], hist[-1])
+    # the forward (predict) path sees the updated weights
+    pred = net.predict_arrays(ts.astype(np.float32), y0.astype(np.float32))
+    mse = float(0.5 * np.mean((np.asarray(pred) - data) ** 2))
+    assert abs(mse - hist[-1]) < 0.2 * hist[-1] + 1e-4
+
+
+def test_unsupported_fields_say_so():
+    from catalax_b200.neural import RateFlowODE
+
+    net = RateFlowODE(3, 2, 16, 2, ["a", "b", "c"], max_time=1.0, key=0)
+    assert not hasattr(net, "value_and_grad")     # RateFlow / Universal gradients: next
