@@ -12,7 +12,7 @@ python bench.py $ARGS > gpurun_out/${TAG}_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:ctx_solve_v1 -s 12 -c 1 \
     -o gpurun_out/${TAG}_solve_full python bench.py $ARGS > gpurun_out/${TAG}_ncu_full.log 2>&1
 python scripts/dev_bench_nuts.py f32 > gpurun_out/${TAG}_nuts_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:ctx_loglik_v1 -s 2 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:ctx_loglik_v2 -s 2 -c 1 \
     -o gpurun_out/${TAG}_loglik_full python scripts/dev_bench_nuts.py f32 > gpurun_out/${TAG}_nuts_ncu.log 2>&1
 python scripts/dev_bench5.py 262144 3 > gpurun_out/${TAG}_mlp_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:ctx_solve_mlp_tc -s 1 -c 1 \
