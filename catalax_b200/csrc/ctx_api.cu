@@ -163,7 +163,7 @@ size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan, bool theta_ptr
   const size_t q_in = 2 * qw * 32 * w;
   if (!tan) {   // ctx_rec records (16-byte aligned) + one pending group per lane
     const size_t rec = (((2 + (deg + 1) * N) * w + 7 * 4) + 15) / 16 * 16;
-    return q_in + 32 * rec + 32 * 4 * S * w + 64;
+    return q_in + 32 * rec + 32 * 4 * S * w + 2 * 32 * 4 * S * w + 64;   // + bulk-store staging
   }
   const size_t rec = 2 + (deg + 1) * N;
   return q_in + 32 * rec * w + 3 * 32 * 8 + 32 * S * w + 32 * (N - S) * w + 64;

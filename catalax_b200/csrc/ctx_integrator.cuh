@@ -431,6 +431,16 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #ifndef CTX_MIN_BLOCKS
 #define CTX_MIN_BLOCKS 1
 #endif
+#ifndef CTX_PASSES
+#define CTX_PASSES 1      // save passes kept in flight together (see the save loop)
+#endif
+#ifndef CTX_BULK
+// 1: complete groups leave through shared memory + one cp.async.bulk (TMA) per run of groups of
+// one trajectory.  Measured on B200 (config 2, T=1000): 4.68 ms vs 4.44 ms (f32), 9.5 vs 8.1 ms
+// (f64) for the direct 128-bit stores -- the runs are short (~480 B) and every copy is issued
+// from uniform registers, one lane at a time -- so the direct stores stay the default.
+#define CTX_BULK 0
+#endif
 #define CTX_FULL 0xffffffffu
 
 #if CTX_SOLVER == 0 || CTX_SOLVER == 1
@@ -576,6 +586,9 @@ struct ctx_warp_smem {
 #if !CTX_TAN
   ctx_rec rec[32];               // one record per publishing lane of this iteration
   uint4 pend[32][CTX_PEND_Q];    // per lane: the group of 4 points its trajectory has not completed
+#if CTX_BULK
+  uint4 stg[2 * CTX_PASSES][32][CTX_PEND_Q];   // staging of complete groups for the bulk stores
+#endif
 #else
   real rec[2 + CTX_NCOEF][32];   // tp, 1/dt, coefficients; one column per publishing lane
   long long ts_off[32];          // element offset into ts of the segment's save j = 0
@@ -701,6 +714,9 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
   const real* tsr = ts_base;
   long long ts_row = 0;       // element offset of this trajectory's time row
   int ri_row = 0;             // row of its y0 / constants / time grid
+#if CTX_BULK && !CTX_TAN
+  unsigned stg_round = 0;     // save rounds so far (selects the staging slots)
+#endif
 
 #if CTX_QUEUE
   // input queue (warp-uniform state).  Claim sizes follow the work that is left (guided
@@ -940,9 +956,6 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       // flight together (all evaluate, then all store).  Measured on B200 (config 2, T=1000):
       // 2 passes need 144 registers (3 CTAs/SM) and gain 6 % in f32 but lose 15 % at T=16 and
       // 25 % in f64, so the default stays 1.
-#ifndef CTX_PASSES
-#define CTX_PASSES 1
-#endif
 #ifndef CTX_ST_OP
 #define CTX_ST_OP ""      // cache operator of the 128-bit trajectory stores (".cs", ".cg", ...)
 #endif
@@ -1048,13 +1061,20 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
             }
           }
         }
+#if CTX_BULK
+        // The staging slots of this round were last read by the bulk copies committed two
+        // rounds ago: at most one committed group (the previous round's) may still be pending.
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+#endif
         __syncwarp();   // every read of a pending buffer precedes the writes below
+        bool ok[CTX_PASSES];
 #pragma unroll
         for (int k = 0; k < CTX_PASSES; ++k) {
           pass_t& q = ps[k];
           const ctx_rec_u& rr = q.rr;
           const int p0 = q.p0;
           const real* o = q.o;
+          ok[k] = false;
           if (q.act) {
             real* dst = reinterpret_cast<real*>(((unsigned long long)rr.r.row_hi << 32) |
                                                 (unsigned long long)rr.r.row_lo) + p0 * CTX_S;
@@ -1063,7 +1083,15 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #endif
             if (p0 + 4 <= rr.r.i1) {
               if ((rr.r.row_lo & 15u) == 0u) {   // p0 * S reals = a multiple of 16 bytes
-#if CTX_F64
+#if CTX_BULK
+                // stage the group; lanes are 4*S reals apart (conflict-free 128-bit stores)
+                union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } sg;
+#pragma unroll
+                for (int j = 0; j < 4 * CTX_S; ++j) sg.v[j] = o[j];
+#pragma unroll
+                for (int j = 0; j < CTX_PEND_Q; ++j) w.stg[(stg_round & 1u) * CTX_PASSES + k][lane][j] = sg.q[j];
+                ok[k] = true;
+#elif CTX_F64
 #pragma unroll
                 for (int j = 0; j < 2 * CTX_S; ++j)
                   asm volatile("st.global" CTX_ST_OP ".v2.f64 [%0], {%1, %2};" ::"l"(dst + 2 * j), "d"(o[2 * j]),
@@ -1095,6 +1123,32 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
             }
           }
         }
+#if CTX_BULK
+        // One bulk copy (TMA) per run of staged groups of one trajectory: consecutive lanes =
+        // consecutive groups = one contiguous, 16-byte aligned piece of ys[b].  The copy is
+        // asynchronous (no store queue back-pressure on the warp) and L2 receives whole lines.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < CTX_PASSES; ++k) {
+          const pass_t& q = ps[k];
+          const int s_prev = __shfl_up_sync(CTX_FULL, q.s_have, 1);
+          const unsigned okm = __ballot_sync(CTX_FULL, ok[k]);
+          const unsigned brk = __ballot_sync(CTX_FULL, lane == 0 || s_prev != q.s_have) | ~okm;
+          if (ok[k] && (lane == 0 || s_prev != q.s_have || !((okm >> (lane - 1)) & 1u))) {
+            const unsigned above = brk & ~(CTX_FULL >> (31 - lane));     // breaks at lanes > lane
+            const int len = (above ? __ffs((int)above) - 1 : 32) - lane;
+            real* dst = reinterpret_cast<real*>(((unsigned long long)q.rr.r.row_hi << 32) |
+                                                (unsigned long long)q.rr.r.row_lo) + q.p0 * CTX_S;
+            const unsigned src = (unsigned)__cvta_generic_to_shared(
+                &w.stg[(stg_round & 1u) * CTX_PASSES + k][lane][0]);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                         "r"(src), "r"(len * (int)(4 * CTX_S * sizeof(real))) : "memory");
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        ++stg_round;
+#endif
       }
     }
 #else   // CTX_TAN: batched point path (states + tangents staged through shared memory)
@@ -1241,6 +1295,9 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       phase = 0;
     }
   }
+#if CTX_BULK && !CTX_TAN
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores have landed
+#endif
 }
 
 extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
