@@ -103,7 +103,43 @@ __device__ __forceinline__ bool tc_tile_or(const int id, const bool pred) {
                  "=r"(v[off + 12]), "=r"(v[off + 13]), "=r"(v[off + 14]), "=r"(v[off + 15])     \
                : "r"((taddr) + (off)))
 
+// Activations of the tensor-core form.  The epilogue, not the MMAs, bounds this kernel (ncu:
+// libdevice tanhf = 60 % of all instructions), and the operands already carry the 3xTF32
+// splitting error (~5e-7 relative), so the transcendental part is evaluated with the SFU
+// approximations (ex2 / lg2 / rcp .approx: <= 2 ulp each): absolute error <= ~3e-7 per
+// activation, far inside the f32 bound of the solve (rtol 1e-3) and of the same order as the
+// splitting error.  MLP_FAST_ACT=0 restores the libdevice functions.
+#ifndef MLP_FAST_ACT
+#define MLP_FAST_ACT 1
+#endif
+__device__ __forceinline__ float tc_ex2(const float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tc_lg2(const float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tc_rcp(const float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float tc_act(const float x, const int kind) {
+#if MLP_FAST_ACT
+  switch (kind) {
+    case 0:   // tanh = 1 - 2 / (exp(2x) + 1): saturates correctly (ex2 -> inf | 0)
+      return fmaf(-2.0f, tc_rcp(tc_ex2(x * 2.8853900817779268f) + 1.0f), 1.0f);
+    case 1:   // softplus = max(x, 0) + log(1 + exp(-|x|))
+      return fmaf(0.69314718055994531f, tc_lg2(1.0f + tc_ex2(-1.4426950408889634f * fabsf(x))),
+                  fmaxf(x, 0.0f));
+    case 2: return x > 0.0f ? x : tc_ex2(1.4426950408889634f * x) - 1.0f;   // celu, alpha = 1
+    case 3: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+#else
   switch (kind) {
     case 0: return tanhf(x);
     case 1: return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
@@ -111,6 +147,7 @@ __device__ __forceinline__ float tc_act(const float x, const int kind) {
     case 3: return fmaxf(x, 0.0f);
     default: return x;
   }
+#endif
 }
 
 struct tc_tile {
