@@ -214,6 +214,18 @@ __device__ __forceinline__ void ctx_rk_stages(const real tp, const real dt, cons
 }
 
 #if CTX_ADAPTIVE
+// scaled^(-1/5) of the I-controller.  The factor only scales the next step size (it is clipped
+// to [0.2 | 1, 10] and never enters the accept / reject decision), so f32 uses the SFU form
+// exp2(0.2 * log2(x)) (~1e-7 relative, i.e. f32 rounding level; libdevice powf costs ~70
+// instructions per step attempt); f64 keeps pow().  inf -> inf, 0 -> 0, NaN -> NaN as pow does.
+__device__ __forceinline__ real ctx_pow02(const real x) {
+#if CTX_F64
+  return pow(x, 0.2);
+#else
+  return __powf(x, 0.2f);
+#endif
+}
+
 // scaled error norm of PIDController: rms(y_err / (atol + rtol*max(|y0|,|y1|))) over the S
 // model states only (tangents never enter the norm: the factor is under stop_gradient).
 __device__ __forceinline__ real ctx_scaled_error(const real dt, const real* y, const real* ynew,
@@ -349,7 +361,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
     const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
     keep = scaled < R(1.0);
     const real inv = R(1.0) / scaled;
-    real factor = R(0.9) * pow(inv, R(0.2));
+    real factor = R(0.9) * ctx_pow02(inv);
     factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
     if (factor != factor) factor = inv;  // clip(NaN) stays NaN in the reference
     dt_next = dt * factor;
@@ -858,7 +870,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
       keep = scaled < R(1.0);
       const real inv = R(1.0) / scaled;
-      real factor = R(0.9) * pow(inv, R(0.2));
+      real factor = R(0.9) * ctx_pow02(inv);
       factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
       dt_next = dt * factor;
       if (scaled != scaled) dt_next = scaled;  // NaN error norm poisons the step size
@@ -1421,7 +1433,7 @@ ctx_loglik_v1(const ctx_loglik_args a) {
         const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
         keep = scaled < R(1.0);
         const real inv = R(1.0) / scaled;
-        real factor = R(0.9) * pow(inv, R(0.2));
+        real factor = R(0.9) * ctx_pow02(inv);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         dt_next = dt * factor;
         if (scaled != scaled) dt_next = scaled;
@@ -1618,7 +1630,7 @@ ctx_loglik_v2(const ctx_loglik_args a) {
         const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
         keep = scaled < R(1.0);
         const real inv = R(1.0) / scaled;
-        real factor = R(0.9) * pow(inv, R(0.2));
+        real factor = R(0.9) * ctx_pow02(inv);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         dt_next = dt * factor;
         if (scaled != scaled) dt_next = scaled;
@@ -2116,7 +2128,7 @@ ctx_solve_w(const ctx_solve_args a) {
         const real scaled = sqrt(ssq / (real)CTX_S);
         keep = scaled < R(1.0);
         const real inv = R(1.0) / scaled;
-        real factor = R(0.9) * pow(inv, R(0.2));
+        real factor = R(0.9) * ctx_pow02(inv);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         if (factor != factor) factor = inv;
         dt_next = dt * factor;

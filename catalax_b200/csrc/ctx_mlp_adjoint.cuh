@@ -282,7 +282,7 @@ ctx_mlp_adj_forward(const ctx_adj_args a) {
       const real scaled = sqrt(ssq / (real)CTX_S);
       const bool keep = scaled < R(1.0);
       const real inv = R(1.0) / scaled;
-      real factor = R(0.9) * pow(inv, R(0.2));
+      real factor = R(0.9) * ctx_pow02(inv);
       factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
       if (factor != factor) factor = inv;
       const real dt_next = dt * factor;

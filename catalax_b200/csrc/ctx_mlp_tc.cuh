@@ -373,7 +373,7 @@ extern "C" __global__ void __launch_bounds__(TC_THREADS, 1) ctx_solve_mlp_tc(con
       const float scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
       const bool keep = scaled < 1.0f;
       const float inv = 1.0f / scaled;
-      float factor = 0.9f * powf(inv, 0.2f);
+      float factor = 0.9f * __powf(inv, 0.2f);
       factor = fminf(fmaxf(factor, keep ? 1.0f : 0.2f), 10.0f);
       float dt_next = dt * factor;
       if (scaled != scaled) dt_next = scaled;
