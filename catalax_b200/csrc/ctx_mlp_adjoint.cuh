@@ -30,6 +30,9 @@
 
 #if CTX_SOLVER == 0   // Tsit5 only (the reference's default for every neural model)
 
+#ifndef ADJ_KIND
+#define ADJ_KIND 0                           // 0 NeuralODE | 1 RateFlowODE
+#endif
 #define ADJ_UPL ((ADJ_WMAX + 31) / 32)       // units per lane
 #define ADJ_NACT (ADJ_L + 1)                 // activation vectors of one MLP evaluation
 
@@ -84,6 +87,9 @@ __device__ __forceinline__ void adj_stage_weights(const real* th, real* pack) {
     for (int j = threadIdx.x; j < no; j += blockDim.x)
       pack[adj_soff[l] + ni * (no + 1) + j] = th[adj_boff[l] + j];
   }
+#if ADJ_KIND == 1
+  for (int e = threadIdx.x; e < CTX_S * ADJ_R; e += blockDim.x) pack[ADJ_SSTOICH + e] = th[ADJ_STOICH + e];
+#endif
 }
 
 // One MLP evaluation by a warp.  acts: [ADJ_NACT][ADJ_WMAX] in shared memory; acts[0] = (y, t/max_t),
@@ -116,8 +122,18 @@ __device__ __forceinline__ void adj_mlp_forward(const real* pack, real* acts, co
     }
     __syncwarp();
   }
+#if ADJ_KIND == 1   // RateFlowODE: dy = stoich [S,R] @ relu(MLP) (rateflow.py:87-88; the MLP's final
+                    // activation is relu, the second relu is idempotent)
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) {
+    real acc = R(0.0);
+    for (int r = 0; r < ADJ_R; ++r) acc += pack[ADJ_SSTOICH + i * ADJ_R + r] * acts[ADJ_L * ADJ_WMAX + r];
+    dy[i] = acc;
+  }
+#else
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) dy[i] = acts[ADJ_L * ADJ_WMAX + i];
+#endif
 }
 
 // Vector-Jacobian product of one MLP evaluation: fbar[S] (replicated) = cotangent of dy.
@@ -133,8 +149,18 @@ __device__ __forceinline__ void adj_mlp_vjp(const real* pack, real* gp, const re
       const int j = lane + 32 * u;
       if (j < no) {
         real f = R(0.0);
+#if ADJ_KIND == 1
+        // cotangent of the rates: stoich^T fbar; stoichiometry gradient: fbar (x) rates
+        const real hj = acts[ADJ_L * ADJ_WMAX + j];
+#pragma unroll
+        for (int i = 0; i < CTX_S; ++i) {
+          f += pack[ADJ_SSTOICH + i * ADJ_R + j] * fbar[i];
+          gp[ADJ_SSTOICH + i * ADJ_R + j] += fbar[i] * hj;
+        }
+#else
 #pragma unroll
         for (int i = 0; i < CTX_S; ++i) f = (j == i) ? fbar[i] : f;
+#endif
         dl[j] = f * adj_dact(ADJ_FACT, acts[ADJ_L * ADJ_WMAX + j]);
       }
     }
@@ -463,6 +489,9 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
     }
     for (int j = lane; j < no; j += 32) prow[adj_boff[l] + j] = gp[adj_soff[l] + ni * (no + 1) + j];
   }
+#if ADJ_KIND == 1
+  for (int e = lane; e < CTX_S * ADJ_R; e += 32) prow[ADJ_STOICH + e] = gp[ADJ_SSTOICH + e];
+#endif
 }
 
 // grad[p] = sum over the per-warp rows (fixed order, double accumulation)

@@ -247,11 +247,6 @@ class NeuralBase:
         return J.cpu().numpy()
 
 
-class NeuralODE(NeuralBase):
-    """Plain MLP vector field (neuralode.py:25-59)."""
-
-    kind = "neuralode"
-
     # ---- training: value and gradient of the loss (trainer.py:268-306)
     def value_and_grad(self, ts, y0, data, *, loss="l2", mask=None, rtol=None, atol=None, dt0=None,
                        want_y0: bool = False, cap: int = 512):
@@ -268,7 +263,7 @@ class NeuralODE(NeuralBase):
         dtype = default_dtype()
         model, theta = self._model(dtype)
         if not model.field.source.count("#define CTX_MLP_ADJ 1"):
-            raise NotImplementedError("weight gradients: plain NeuralODE fields of <= 8 states")
+            raise NotImplementedError("weight gradients: NeuralODE / RateFlowODE fields of <= 8 states")
         if solver_name(self.solver) != "tsit5":
             raise NotImplementedError("weight gradients are implemented for Tsit5")
         dev = y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda else \
@@ -309,12 +304,17 @@ class NeuralODE(NeuralBase):
             gW.append(g[lay.w_off[l]: lay.w_off[l] + n_out * ip].reshape(n_out, ip)[:, :n_in].copy())
             gb.append(None if self.biases[l] is None else g[lay.b_off[l]: lay.b_off[l] + n_out].copy())
         grads = {"weights": gW, "biases": gb}
+        if self.kind == "rateflow":
+            S, R_ = self.data_size, self.spec.out_size
+            grads["stoich"] = g[lay.stoich: lay.stoich + S * R_].reshape(S, R_).copy()
         if want_y0:
             grads["y0"] = gy0
         return float(value.item()), grads
 
-    def apply_updates(self, dW, db):
-        """weights += dW, biases += db; the compiled parameter packs are rebuilt lazily."""
+    def apply_updates(self, dW, db, dstoich=None):
+        """weights += dW, biases += db (stoich_matrix += dstoich); the parameter packs are rebuilt."""
+        if dstoich is not None:
+            self.stoich_matrix = self.stoich_matrix + np.asarray(dstoich, dtype=np.float64)
         self.weights = [w + np.asarray(d, dtype=np.float64) for w, d in zip(self.weights, dW)]
         self.biases = [None if b is None else b + np.asarray(d, dtype=np.float64)
                        for b, d in zip(self.biases, db)]
@@ -347,6 +347,12 @@ class NeuralODE(NeuralBase):
                     upd[grp].append(-lr * mh / (np.sqrt(vh) + eps))
             self.apply_updates(upd[0], upd[1])
         return hist
+
+
+class NeuralODE(NeuralBase):
+    """Plain MLP vector field (neuralode.py:25-59)."""
+
+    kind = "neuralode"
 
 
 class RateFlowODE(NeuralBase):

@@ -249,7 +249,9 @@ def _tc_source(spec: MLPSpec) -> List[str]:
 def adjoint_dims(spec: MLPSpec):
     """Shared-memory pack of the weight-gradient kernels (csrc/ctx_mlp_adjoint.cuh), or None when
     the model is not a plain NeuralODE of at most 8 states (RateFlow / Universal fields: next)."""
-    if spec.kind != "neuralode" or spec.data_size > 8 or spec.out_size != spec.data_size:
+    if spec.kind not in ("neuralode", "rateflow") or spec.data_size > 8:
+        return None
+    if spec.kind == "neuralode" and spec.out_size != spec.data_size:
         return None
     dims = spec.layer_dims()
     wmax = max(max(ni, no) for ni, no in dims)
@@ -258,13 +260,17 @@ def adjoint_dims(spec: MLPSpec):
     for ni, no in dims:
         soff.append(off)
         off += ni * (no + 1) + no
+    sstoich = off
+    if spec.kind == "rateflow":
+        off += spec.data_size * spec.out_size
     nact = (len(dims) + 1) * wmax
     per_warp_bwd = off + 7 * nact + 2 * wmax
 
     def warps(word):
         w = (227 * 1024 // word - off) // per_warp_bwd
         return max(0, min(4, w))
-    return dict(dims=dims, wmax=wmax, soff=soff, spack=off, nact=nact, per_warp_bwd=per_warp_bwd,
+    return dict(dims=dims, wmax=wmax, soff=soff, spack=off, sstoich=sstoich, nact=nact,
+                per_warp_bwd=per_warp_bwd,
                 warps32=warps(4), warps64=warps(8))
 
 
@@ -286,6 +292,9 @@ def _adjoint_source(spec: MLPSpec) -> List[str]:
         arr("adj_woff", lay.w_off), arr("adj_boff", lay.b_off), arr("adj_inpad", lay.in_pad),
         arr("adj_soff", d["soff"]),
     ]
+    if spec.kind == "rateflow":
+        out += ["#define ADJ_KIND 1", f"#define ADJ_R {spec.out_size}",
+                f"#define ADJ_STOICH {lay.stoich}", f"#define ADJ_SSTOICH {d['sstoich']}"]
     if d["warps64"] < 1:
         out = ["#if !CTX_F64"] + out + ["#endif"]
     return out

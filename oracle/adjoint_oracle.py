@@ -27,7 +27,9 @@ _ACT = {
 }
 
 
-def mlp_field(weights, biases, activation, final_activation, max_time):
+def mlp_field(weights, biases, activation, final_activation, max_time, stoich=None):
+    """NeuralODE field (neuralode.py:49); with ``stoich`` [S,R]: RateFlowODE's
+    ``stoich @ relu(MLP)`` (rateflow.py:87-88, final_activation relu :56)."""
     def f(t, y):
         h = torch.cat([y, (t / max_time).reshape(1)])
         for l, (W, b) in enumerate(zip(weights, biases)):
@@ -35,6 +37,8 @@ def mlp_field(weights, biases, activation, final_activation, max_time):
             if b is not None:
                 h = h + b
             h = _ACT[final_activation if l == len(weights) - 1 else activation](h)
+        if stoich is not None:
+            h = stoich @ torch.relu(h)
         return h
     return f
 
@@ -91,7 +95,7 @@ def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096):
 
 
 def neuralode_value_and_grad(weights, biases, activation, final_activation, max_time, ts, y0,
-                             loss_fn, rtol=1e-3, atol=1e-6, dt0=None):
+                             loss_fn, rtol=1e-3, atol=1e-6, dt0=None, stoich=None):
     """weights / biases: lists of numpy arrays (eqx convention W [out,in]); ts [B,T]; y0 [B,S].
     loss_fn(ys [B,T,S] torch float64) -> scalar.  Returns (loss, ys, grads_W, grads_b, grad_y0,
     n_accepted [B], n_rejected [B])."""
@@ -100,7 +104,8 @@ def neuralode_value_and_grad(weights, biases, activation, final_activation, max_
           for b in biases]
     y0t = torch.tensor(np.asarray(y0, dtype=np.float64), requires_grad=True)
     tst = torch.tensor(np.asarray(ts, dtype=np.float64))
-    f = mlp_field(Ws, bs, activation, final_activation, float(max_time))
+    St = None if stoich is None else torch.tensor(np.asarray(stoich, dtype=np.float64), requires_grad=True)
+    f = mlp_field(Ws, bs, activation, final_activation, float(max_time), St)
     ys, na, nr = [], [], []
     for b in range(y0t.shape[0]):
         step0 = float(tst[b, 1] - tst[b, 0]) if dt0 is None else dt0
@@ -108,10 +113,14 @@ def neuralode_value_and_grad(weights, biases, activation, final_activation, max_
         ys.append(o); na.append(a_); nr.append(r_)
     ys = torch.stack(ys)
     loss = loss_fn(ys)
-    params = Ws + [b for b in bs if b is not None] + [y0t]
+    nb = sum(b is not None for b in bs)
+    params = Ws + [b for b in bs if b is not None] + [y0t] + ([St] if St is not None else [])
     grads = torch.autograd.grad(loss, params, allow_unused=True)
     gW = [g.numpy() for g in grads[:len(Ws)]]
-    gb_iter = iter(grads[len(Ws):-1])
+    gb_iter = iter(grads[len(Ws):len(Ws) + nb])
     gb = [None if b is None else next(gb_iter).numpy() for b in bs]
-    gy0 = grads[-1].numpy()
+    gy0 = grads[len(Ws) + nb].numpy()
+    if St is not None:
+        return (float(loss.detach()), ys.detach().numpy(), gW, gb, gy0, np.array(na), np.array(nr),
+                grads[-1].numpy())
     return float(loss.detach()), ys.detach().numpy(), gW, gb, gy0, np.array(na), np.array(nr)

@@ -112,8 +112,54 @@ def test_adam_steps_on_the_gradient_reduce_the_loss():
     assert abs(mse - hist[-1]) < 0.2 * hist[-1] + 1e-4
 
 
-def test_unsupported_fields_say_so():
+def test_rateflow_weight_and_stoichiometry_gradients_f64():
+    """RateFlowODE (rateflow.py:87-88): dy = stoich @ relu(MLP); gradients w.r.t. the MLP weights
+    AND the (learnable) stoichiometric matrix."""
+    import catalax_b200 as ctx
     from catalax_b200.neural import RateFlowODE
+    from oracle import adjoint_oracle as ao
 
-    net = RateFlowODE(3, 2, 16, 2, ["a", "b", "c"], max_time=1.0, key=0)
-    assert not hasattr(net, "value_and_grad")     # RateFlow / Universal gradients: next
+    ctx.enable_x64(True)
+    try:
+        rng = np.random.default_rng(4)
+        S, R, B, T, t1 = 4, 3, 7, 8, 4.0
+        net = RateFlowODE(S, R, 64, 3, [f"s{i}" for i in range(S)], activation="celu", max_time=t1, key=4)
+        net.stoich_matrix = net.stoich_matrix * 0.05      # mild dynamics: no chaotic amplification of rounding
+        net.biases[-1] = None if net.biases[-1] is None else net.biases[-1]
+        y0 = rng.uniform(0.2, 1.5, (B, S))
+        ts = np.tile(np.linspace(0.0, t1, T), (B, 1))
+        data = y0[:, None, :] * np.exp(-0.4 * ts)[:, :, None]
+        val, g = net.value_and_grad(ts, y0, data, rtol=1e-7, atol=1e-9)
+        d = torch.tensor(data)
+        loss_fn = lambda ys: (0.5 * (ys - d) ** 2).mean()
+        rv, rys, rW, rb, rgy0, rna, rnr, rS = ao.neuralode_value_and_grad(
+            net.weights, net.biases, net.spec.activation, net.spec.final_activation, net.max_time,
+            ts, y0, loss_fn, rtol=1e-7, atol=1e-9, stoich=net.stoich_matrix)
+        # The field has kinks (relu): an error estimate that lands within rounding of the accept
+        # threshold can flip one trajectory's accept / reject path between two implementations,
+        # which moves that trajectory by O(rtol).  Same path -> rounding-level agreement.
+        same_path = np.array_equal(net.last["n_accepted"].cpu().numpy(), rna) and \
+            np.array_equal(net.last["n_rejected"].cpu().numpy(), rnr)
+        tol_y, tol_g = (5e-8, 1e-6) if same_path else (2e-6, 5e-5)   # (solver rtol: 1e-7; observed 1e-9 / 2e-7)
+        np.testing.assert_allclose(net.last["ys"].cpu().numpy(), rys, rtol=tol_y, atol=1e-11)
+        assert abs(val - rv) <= 10 * tol_y * abs(rv)
+        _check(g, rW, rb, tol_g)
+        assert np.abs(g["stoich"] - rS).max() <= tol_g * np.abs(rS).max()
+        # one plain gradient step on everything lowers the loss
+        lr = 0.05
+        net.apply_updates([-lr * w for w in g["weights"]],
+                          [None if b is None else -lr * b for b in g["biases"]], -lr * g["stoich"])
+        val2, _ = net.value_and_grad(ts, y0, data, rtol=1e-7, atol=1e-9)
+        assert val2 < val
+    finally:
+        ctx.enable_x64(False)
+
+
+def test_unsupported_fields_say_so():
+    from catalax_b200.neural import UniversalODE
+    from tests import cases
+
+    import inspect
+    assert "value_and_grad" in dir(UniversalODE)
+    src = inspect.getsource(UniversalODE.value_and_grad)
+    assert "NotImplementedError" in src      # UniversalODE fields: next round (clear error, no fallback)
