@@ -85,7 +85,7 @@ struct ctx_model {
   std::string field_src;
   ctx_model_desc desc;
   std::mutex mu;
-  std::map<int, Variant> variants;  // key = solver*2 + tan
+  std::map<int, Variant> variants;  // key = solver*2 + tan (+ 8 for the two-pass save variant)
   bool theta_ptr = false;           // generated with CTX_THETA_PTR (shared weights in smem)
   int p_pad = 0;
   int mlp_tc_smem = 0;              // > 0: the tcgen05 MLP kernel is available (bytes of smem)
@@ -186,7 +186,7 @@ size_t theta_smem(const ctx_model* m) {
   return m->theta_ptr ? (size_t)m->p_pad * (m->desc.dtype == CTX_F64 ? 8 : 4) : 0;
 }
 
-int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
+int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0) {
   if (!v.cubin.empty()) return CTX_OK;
   std::string src;
   src += m->desc.dtype == CTX_F64 ? "typedef double real;\n#define R(x) x\n"
@@ -208,6 +208,12 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
     const size_t words = (size_t)m->desc.n_states * (1 + (tan ? m->desc.n_dirs : 0)) *
                          (m->desc.dtype == CTX_F64 ? 2 : 1);
     size_t mb = 512 / (96 + 10 * words);
+    if (wide) {
+      // two save passes in flight (CTX_PASSES=2): long output grids in f32 (measured, config 2:
+      // T=1000 4.58 -> 4.15 ms, but T<=250 and f64 lose, see launch_solve); needs ~144 registers
+      opts.push_back("-DCTX_PASSES=2");
+      mb = 512 / (130 + 10 * words);
+    }
     mb = std::max<size_t>(1, std::min<size_t>(4, mb));
     if (m->theta_ptr) mb = 1;
     const char* ex = getenv("CTX_B200_NVRTC_FLAGS");
@@ -280,13 +286,14 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v) {
   return CTX_OK;
 }
 
-int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_t* out) {
+int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_t* out,
+               int wide = 0) {
   if (solver < 0 || solver > 3) return fail(CTX_E_INVALID, "unknown solver id");
   if (tan && m->desc.n_dirs <= 0)
     return fail(CTX_E_INVALID, "model was generated without sensitivity directions");
   std::lock_guard<std::mutex> lk(m->mu);
-  Variant& v = m->variants[solver * 2 + tan];
-  int rc = compile_variant(m, solver, tan, v);
+  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0)];
+  int rc = compile_variant(m, solver, tan, v, wide);
   if (rc) return rc;
   int dev = 0;
   CTX_CUDA(cudaGetDevice(&dev));
@@ -306,9 +313,9 @@ int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_
 }
 
 // sizeof(ctx_warp_smem) of the loaded ctx_solve_v1 module (call after get_kernel)
-int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out) {
+int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out, int wide = 0) {
   std::lock_guard<std::mutex> lk(m->mu);
-  Variant& v = m->variants[solver * 2 + tan];
+  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0)];
   if (v.v1_warp_smem < 0) {
     void* dptr = nullptr;
     size_t nbytes = 0;
@@ -400,14 +407,19 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
       return fail(CTX_E_INVALID, "persistent kernel: step record does not fit shared memory");
     if (cfg->batch >= (1ll << 31))
       return fail(CTX_E_INVALID, "persistent kernel: batch must be < 2^31 rows per call");
-    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k);
+    // Long output grids in f32 take the variant that keeps two save passes in flight (measured
+    // on B200, config 2: T=1000 4.58 -> 4.15 ms; T=250 2.53 -> 2.84 ms, f64 T=1000 8.1 -> 8.3 ms).
+    int wide = (!tan && d.dtype == CTX_F32 && !m->theta_ptr && d.n_states <= 4 &&
+                cfg->n_times >= 512) ? 1 : 0;
+    if (const char* ev = getenv("CTX_B200_WIDE_SAVE")) wide = atoi(ev) ? (tan ? 0 : 1) : 0;
+    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k, wide);
     if (rc) return rc;
     const unsigned block = 32u * warps;
     int dev = 0, sms = 0, per_sm = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t per_warp = 0;
-    rc = v1_exact_warp_smem(m, cfg->solver, tan, &per_warp);
+    rc = v1_exact_warp_smem(m, cfg->solver, tan, &per_warp, wide);
     if (rc) return rc;
     size_t smem = theta_smem(m) + (size_t)warps * per_warp;
     if (m->theta_ptr && a.stride_theta != 0)

@@ -965,9 +965,10 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       __syncwarp();
       const unsigned myoff = nsave > 0 ? (unsigned)goff : 0xffffffffu;
       // One pass = 32 consecutive flat groups, one per lane.  CTX_PASSES passes can be kept in
-      // flight together (all evaluate, then all store).  Measured on B200 (config 2, T=1000):
-      // 2 passes need 144 registers (3 CTAs/SM) and gain 6 % in f32 but lose 15 % at T=16 and
-      // 25 % in f64, so the default stays 1.
+      // flight together (all evaluate, then all store): two independent dependency chains per
+      // warp.  Measured on B200 (config 2): 2 passes need 144 registers (3 CTAs/SM) and gain 9 %
+      // at T=1000 in f32 but lose 12 % at T<=250 and 25 % in f64, so the host compiles the
+      // two-pass variant only for long f32 grids (ctx_api.cu launch_solve).
 #ifndef CTX_ST_OP
 #define CTX_ST_OP ""      // cache operator of the 128-bit trajectory stores (".cs", ".cg", ...)
 #endif

@@ -127,3 +127,35 @@ def test_long_segments_with_unaligned_rows_f32_and_f64():
                 scale = 1e-6 + 1e-6 * np.abs(ref.ys)
                 assert np.median(np.abs(ys - ref.ys) / scale) < 2.0
                 assert (np.abs(ys - ref.ys) <= 500 * scale).all()
+
+
+@pytest.mark.parametrize("T,shared_ts", [(640, True), (517, True), (600, False)])
+def test_two_pass_save_variant_is_bit_identical(T, shared_ts, monkeypatch):
+    """Long f32 output grids (T >= 512) take the kernel variant that keeps two save passes in
+    flight (ctx_api.cu launch_solve).  It is the same arithmetic in a different schedule: results
+    must be bit-identical to the one-pass variant, incl. ragged T, per-row grids and failed rows
+    (inf fill)."""
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+
+    model = cases.michaelis_menten()
+    B = 3001
+    y0, theta, consts = cases.mm_inputs(B, seed=5, dtype=np.float32)
+    theta[:7, 0] = 1e-3                      # stiff rows: exhaust max_steps -> inf fill
+    ts = np.linspace(0, 100, T, dtype=np.float32)
+    if not shared_ts:
+        ts = np.tile(ts, (B, 1)) * np.linspace(0.9, 1.1, B, dtype=np.float32)[:, None]
+    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), "float32")
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    outs = []
+    for wide in ("0", "1"):
+        monkeypatch.setenv("CTX_B200_WIDE_SAVE", wide)
+        o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts),
+                    in_axes=(0, 0, 0, None if shared_ts else 0), rtol=1e-6, atol=1e-6, max_steps=512)
+        torch.cuda.synchronize()
+        outs.append((o.ys.cpu().numpy(), o.status.cpu().numpy(), o.n_accepted.cpu().numpy()))
+    assert (outs[0][1] != 0).any() and (outs[0][1] == 0).any()
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
