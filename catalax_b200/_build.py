@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cu = [str(p) for p in sorted(CSRC.glob("*.cu"))]
     cmd = [NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
            *cu, str(gen / "ctx_integrator_embed.cpp"), str(gen / "ctx_mlp_tc_embed.cpp"),
-           str(gen / "ctx_mlp_adjoint_embed.cpp"), "-o", str(LIB), "-lnvrtc",
+           str(gen / "ctx_mlp_adjoint_embed.cpp"), "-o", str(LIB), "-ldl",
            "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -7,6 +7,7 @@
 #include "../../include/ctx_b200.h"
 
 #include <cuda_runtime_api.h>
+#include <dlfcn.h>
 #include <nvrtc.h>
 
 #include <algorithm>
@@ -182,6 +183,68 @@ int v1_warps(const ctx_model_desc& d, int solver, int tan, size_t fixed = 0) {
   return (int)warps;
 }
 
+// NVRTC is loaded explicitly, by path, into a private namespace: the process usually holds
+// another libnvrtc.so.12 already (PyTorch bundles the one of ITS CUDA release, 12.8 here), and a
+// link-time dependency would bind to whichever copy was loaded first.  The kernels use PTX of
+// the toolkit this library was built with (256-bit st.global.v8.f32 needs PTX ISA 8.8 = CUDA 12.9),
+// so the toolkit's own NVRTC is preferred; with an older NVRTC those paths are compiled out.
+struct NvrtcApi {
+  void* handle = nullptr;
+  nvrtcResult (*Version)(int*, int*) = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*,
+                               const char* const*) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  const char* (*GetErrorString)(nvrtcResult) = nullptr;
+  int major = 0, minor = 0;
+  std::string path;
+};
+
+const NvrtcApi* nvrtc_api() {
+  static NvrtcApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    std::vector<std::string> cand;
+    if (const char* e = getenv("CTX_B200_NVRTC")) cand.push_back(e);
+    cand.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+    cand.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+    cand.push_back("libnvrtc.so.12");
+    cand.push_back("libnvrtc.so");
+    for (const auto& c : cand) {
+      void* h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (!h) continue;
+      NvrtcApi a;
+      a.handle = h;
+      a.path = c;
+#define CTX_SYM(field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name))
+      CTX_SYM(Version, "nvrtcVersion");
+      CTX_SYM(CreateProgram, "nvrtcCreateProgram");
+      CTX_SYM(CompileProgram, "nvrtcCompileProgram");
+      CTX_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+      CTX_SYM(GetProgramLog, "nvrtcGetProgramLog");
+      CTX_SYM(DestroyProgram, "nvrtcDestroyProgram");
+      CTX_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+      CTX_SYM(GetCUBIN, "nvrtcGetCUBIN");
+      CTX_SYM(GetErrorString, "nvrtcGetErrorString");
+#undef CTX_SYM
+      if (!a.Version || !a.CreateProgram || !a.CompileProgram || !a.GetProgramLogSize ||
+          !a.GetProgramLog || !a.DestroyProgram || !a.GetCUBINSize || !a.GetCUBIN ||
+          !a.GetErrorString) {
+        dlclose(h);
+        continue;
+      }
+      a.Version(&a.major, &a.minor);
+      api = a;
+      break;
+    }
+  });
+  return api.handle ? &api : nullptr;
+}
+
 size_t theta_smem(const ctx_model* m) {
   return m->theta_ptr ? (size_t)m->p_pad * (m->desc.dtype == CTX_F64 ? 8 : 4) : 0;
 }
@@ -231,8 +294,13 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0)
   std::string keysrc = src + "\x01" + ctx_integrator_src + "\x01" + ctx_mlp_tc_src + "\x01" +
                        ctx_mlp_adjoint_src;
   for (auto& o : opts) keysrc += "\x02" + o;
-  int nv_major = 0, nv_minor = 0;
-  nvrtcVersion(&nv_major, &nv_minor);
+  const NvrtcApi* nv = nvrtc_api();
+  if (!nv) return fail(CTX_E_NVRTC, "libnvrtc.so.12 not found (set CTX_B200_NVRTC to its path)");
+  const int nv_major = nv->major, nv_minor = nv->minor;
+  if (nv_major < 12 || (nv_major == 12 && nv_minor < 9)) {
+    opts.push_back("-DCTX_ST256=0");   // 256-bit vector stores need PTX ISA 8.8 (CUDA 12.9)
+    keysrc += "\x02-DCTX_ST256=0";
+  }
   keysrc += "\x03" + std::to_string(nv_major) + "." + std::to_string(nv_minor);
   char name[64];
   snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)fnv1a(keysrc),
@@ -256,24 +324,24 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0)
   nvrtcProgram prog;
   const char* hdr_src[] = {ctx_integrator_src, ctx_mlp_tc_src, ctx_mlp_adjoint_src};
   const char* hdr_name[] = {"ctx_integrator.cuh", "ctx_mlp_tc.cuh", "ctx_mlp_adjoint.cuh"};
-  nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "ctx_model.cu", 3, hdr_src, hdr_name);
-  if (r != NVRTC_SUCCESS) return fail(CTX_E_NVRTC, nvrtcGetErrorString(r));
+  nvrtcResult r = nv->CreateProgram(&prog, src.c_str(), "ctx_model.cu", 3, hdr_src, hdr_name);
+  if (r != NVRTC_SUCCESS) return fail(CTX_E_NVRTC, nv->GetErrorString(r));
   std::vector<const char*> copts;
   for (auto& o : opts) copts.push_back(o.c_str());
-  r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+  r = nv->CompileProgram(prog, (int)copts.size(), copts.data());
   if (r != NVRTC_SUCCESS) {
     size_t ln = 0;
-    nvrtcGetProgramLogSize(prog, &ln);
+    nv->GetProgramLogSize(prog, &ln);
     std::string log(ln, '\0');
-    nvrtcGetProgramLog(prog, log.data());
-    nvrtcDestroyProgram(&prog);
-    return fail(CTX_E_NVRTC, std::string("nvrtc: ") + nvrtcGetErrorString(r) + "\n" + log);
+    nv->GetProgramLog(prog, log.data());
+    nv->DestroyProgram(&prog);
+    return fail(CTX_E_NVRTC, std::string("nvrtc (") + nv->path + "): " + nv->GetErrorString(r) + "\n" + log);
   }
   size_t n = 0;
-  nvrtcGetCUBINSize(prog, &n);
+  nv->GetCUBINSize(prog, &n);
   v.cubin.resize(n);
-  nvrtcGetCUBIN(prog, v.cubin.data());
-  nvrtcDestroyProgram(&prog);
+  nv->GetCUBIN(prog, v.cubin.data());
+  nv->DestroyProgram(&prog);
   if (use_disk) {
     mkdirs(dir);
     std::string tmp = path + "." + std::to_string((long)getpid()) + ".tmp";

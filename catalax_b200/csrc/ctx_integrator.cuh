@@ -446,6 +446,9 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #ifndef CTX_PASSES
 #define CTX_PASSES 1      // save passes kept in flight together (see the save loop)
 #endif
+#ifndef CTX_ST256
+#define CTX_ST256 1       // full-sector (256-bit) stores of complete groups, see the save loop
+#endif
 #ifndef CTX_BULK
 // 1: complete groups leave through shared memory + one cp.async.bulk (TMA) per run of groups of
 // one trajectory.  Measured on B200 (config 2, T=1000): 4.68 ms vs 4.44 ms (f32), 9.5 vs 8.1 ms
@@ -1095,6 +1098,53 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
             if (o[0] != R(-12345.678)) continue;
 #endif
             if (p0 + 4 <= rr.r.i1) {
+#if CTX_ST256 && !CTX_BULK
+              // Full-sector stores.  A group is 16*S (f32) / 32*S (f64) bytes; with 128-bit stores
+              // and lanes 16*S bytes apart every store instruction writes HALF of 32 different
+              // sectors, i.e. every sector travels from L1 to L2 twice -- and that path moves one
+              // sector per clock per SM: measured, it (not DRAM, not the math) bounds the save
+              // path.  sm_100 has 256-bit stores: f64 and even S write whole sectors directly; for
+              // odd S the groups of even / odd index q start on / in the middle of a sector, so
+              // lanes shift their 256-bit stores by one 16-byte piece according to the parity of
+              // q, and the left-over pieces of two neighbouring lanes (last piece of the even
+              // group, first of the odd one) share a sector AND an instruction: coalesced.
+              if ((rr.r.row_lo & 31u) == 0u) {
+#if CTX_F64
+#pragma unroll
+                for (int j = 0; j < CTX_S; ++j)
+                  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                               "d"(o[4 * j]), "d"(o[4 * j + 1]), "d"(o[4 * j + 2]), "d"(o[4 * j + 3])
+                               : "memory");
+#elif (CTX_S % 2) == 0
+#pragma unroll
+                for (int j = 0; j < CTX_S / 2; ++j)
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j),
+                               "f"(o[8 * j]), "f"(o[8 * j + 1]), "f"(o[8 * j + 2]), "f"(o[8 * j + 3]),
+                               "f"(o[8 * j + 4]), "f"(o[8 * j + 5]), "f"(o[8 * j + 6]), "f"(o[8 * j + 7])
+                               : "memory");
+#else
+                const bool par = ((p0 >> 2) & 1) != 0;   // odd S: the group starts mid-sector
+#pragma unroll
+                for (int j = 0; j < (CTX_S - 1) / 2; ++j) {
+                  real v8[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v8[e] = par ? o[8 * j + 4 + e] : o[8 * j + e];
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(
+                                   dst + 8 * j + (par ? 4 : 0)),
+                               "f"(v8[0]), "f"(v8[1]), "f"(v8[2]), "f"(v8[3]), "f"(v8[4]), "f"(v8[5]),
+                               "f"(v8[6]), "f"(v8[7]) : "memory");
+                }
+                {
+                  real v4[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v4[e] = par ? o[e] : o[4 * (CTX_S - 1) + e];
+                  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                   dst + (par ? 0 : 4 * (CTX_S - 1))),
+                               "f"(v4[0]), "f"(v4[1]), "f"(v4[2]), "f"(v4[3]) : "memory");
+                }
+#endif
+              } else
+#endif
               if ((rr.r.row_lo & 15u) == 0u) {   // p0 * S reals = a multiple of 16 bytes
 #if CTX_BULK
                 // stage the group; lanes are 4*S reals apart (conflict-free 128-bit stores)
