@@ -86,7 +86,7 @@ struct ctx_model {
   std::string field_src;
   ctx_model_desc desc;
   std::mutex mu;
-  std::map<int, Variant> variants;  // key = solver*2 + tan (+ 8 for the two-pass save variant)
+  std::map<int, Variant> variants;  // key = solver*2 + tan (+ 8 for the 8-point-group save variant)
   bool theta_ptr = false;           // generated with CTX_THETA_PTR (shared weights in smem)
   int p_pad = 0;
   int mlp_tc_smem = 0;              // > 0: the tcgen05 MLP kernel is available (bytes of smem)
@@ -164,7 +164,7 @@ size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan, bool theta_ptr
   const size_t q_in = 2 * qw * 32 * w;
   if (!tan) {   // ctx_rec records (16-byte aligned) + one pending group per lane
     const size_t rec = (((2 + (deg + 1) * N) * w + 7 * 4) + 15) / 16 * 16;
-    return q_in + 32 * rec + 32 * 4 * S * w + 2 * 32 * 4 * S * w + 64;   // + bulk-store staging
+    return q_in + 32 * rec + 32 * 8 * S * w + 64;   // (pending groups of up to 8 points)
   }
   const size_t rec = 2 + (deg + 1) * N;
   return q_in + 32 * rec * w + 3 * 32 * 8 + 32 * S * w + 32 * (N - S) * w + 64;
@@ -272,10 +272,10 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0)
                          (m->desc.dtype == CTX_F64 ? 2 : 1);
     size_t mb = 512 / (96 + 10 * words);
     if (wide) {
-      // two save passes in flight (CTX_PASSES=2): long output grids in f32 (measured, config 2:
-      // T=1000 4.58 -> 4.15 ms, but T<=250 and f64 lose, see launch_solve); needs ~144 registers
-      opts.push_back("-DCTX_PASSES=2");
-      mb = 512 / (130 + 10 * words);
+      // 8 requested times per lane and pass instead of 4 (CTX_GP=8): long output grids in f32
+      // (measured, config 2: T=1000 4.19 -> 3.73 ms; T<=250 and f64 lose, see launch_solve).
+      // 128 registers for the 3-state model: still 4 CTAs/SM.
+      opts.push_back("-DCTX_GP=8");
     }
     mb = std::max<size_t>(1, std::min<size_t>(4, mb));
     if (m->theta_ptr) mb = 1;
@@ -475,10 +475,12 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
       return fail(CTX_E_INVALID, "persistent kernel: step record does not fit shared memory");
     if (cfg->batch >= (1ll << 31))
       return fail(CTX_E_INVALID, "persistent kernel: batch must be < 2^31 rows per call");
-    // Long output grids in f32 take the variant that keeps two save passes in flight (measured
-    // on B200, config 2: T=1000 4.58 -> 4.15 ms; T=250 2.53 -> 2.84 ms, f64 T=1000 8.1 -> 8.3 ms).
+    // Long output grids in f32 take the variant whose lanes evaluate 8 requested times per pass
+    // (half the segment look-ups / record loads per point, two independent Horner groups, whole
+    // 96-byte = 3-sector stores).  Measured on B200, config 2: T=1000 4.19 -> 3.73 ms, but
+    // T=250 2.68 -> 3.03 ms (more partial groups per segment) and f64 T=1000 6.1 -> 7.6 ms.
     int wide = (!tan && d.dtype == CTX_F32 && !m->theta_ptr && d.n_states <= 4 &&
-                cfg->n_times >= 512) ? 1 : 0;
+                cfg->n_times >= 768) ? 1 : 0;
     if (const char* ev = getenv("CTX_B200_WIDE_SAVE")) wide = atoi(ev) ? (tan ? 0 : 1) : 0;
     int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k, wide);
     if (rc) return rc;
@@ -493,7 +495,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     if (m->theta_ptr && a.stride_theta != 0)
       return fail(CTX_E_INVALID, "a weight-array model takes shared parameters (in_axes[1] = None)");
     // a time grid shared by all trajectories is staged in shared memory (<= 32 KB)
-    const size_t ts_bytes = (((size_t)cfg->n_times + 3) & ~(size_t)3) * sizeof(real);
+    const size_t ts_bytes = (((size_t)cfg->n_times + 7) & ~(size_t)7) * sizeof(real);
     if (a.stride_ts == 0 && ts_bytes <= 32 * 1024 && smem + ts_bytes <= 200 * 1024 &&
         !getenv("CTX_B200_NO_TS_SMEM")) {
       a.ts_smem = 1;

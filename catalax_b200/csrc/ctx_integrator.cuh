@@ -446,6 +446,10 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #ifndef CTX_PASSES
 #define CTX_PASSES 1      // save passes kept in flight together (see the save loop)
 #endif
+#ifndef CTX_GP
+#define CTX_GP 4          // requested times per group (4 or 8): the unit of work of one lane in a pass
+#endif
+#define CTX_GSH (CTX_GP == 8 ? 3 : 2)
 #ifndef CTX_ST256
 #define CTX_ST256 1       // full-sector (256-bit) stores of complete groups, see the save loop
 #endif
@@ -593,7 +597,7 @@ union ctx_rec_u {
   uint4 q[CTX_REC_Q];
   __device__ __forceinline__ ctx_rec_u() {}
 };
-#define CTX_PEND_Q ((int)(4 * CTX_S * sizeof(real) / 16))   // 16-byte chunks of one group
+#define CTX_PEND_Q ((int)(CTX_GP * CTX_S * sizeof(real) / 16))   // 16-byte chunks of one group
 #endif
 
 struct ctx_warp_smem {
@@ -700,7 +704,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
     real* ts_sm = reinterpret_cast<real*>(sm_cur);
     ts_sa = (unsigned)__cvta_generic_to_shared(ts_sm);
     asm volatile("mov.u32 %0, %0;" : "+r"(ts_sa));   // opaque: keep it in a register
-    const int Tpad = (T + 3) & ~3;
+    const int Tpad = (T + CTX_GP - 1) & ~(CTX_GP - 1);
     for (int i = threadIdx.x; i < Tpad; i += blockDim.x) ts_sm[i] = a.ts[min(i, T - 1)];
     sm_cur += (size_t)Tpad * sizeof(real);
     ts_base = ts_sm;
@@ -921,8 +925,8 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
     // 16-byte stores (scalar stores remain for unaligned rows and a ragged last group).
     const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
     if (nz) {
-      const int gq0 = idx >> 2;
-      const int ng = nsave > 0 ? ((idx + nsave + 3) >> 2) - gq0 : 0;
+      const int gq0 = idx >> CTX_GSH;
+      const int ng = nsave > 0 ? ((idx + nsave + CTX_GP - 1) >> CTX_GSH) - gq0 : 0;
       int incl = ng;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -967,17 +971,17 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       }
       __syncwarp();
       const unsigned myoff = nsave > 0 ? (unsigned)goff : 0xffffffffu;
-      // One pass = 32 consecutive flat groups, one per lane.  CTX_PASSES passes can be kept in
-      // flight together (all evaluate, then all store): two independent dependency chains per
-      // warp.  Measured on B200 (config 2): 2 passes need 144 registers (3 CTAs/SM) and gain 9 %
-      // at T=1000 in f32 but lose 12 % at T<=250 and 25 % in f64, so the host compiles the
-      // two-pass variant only for long f32 grids (ctx_api.cu launch_solve).
+      // One pass = 32 consecutive flat groups, one per lane.  Two ways to give a warp more
+      // independent work per pass were measured on B200 (config 2, f32): CTX_PASSES=2 passes in
+      // flight (144 registers, T=1000 -7 %, T=16 +15 %, f64 +25 %) and CTX_GP=8 requested times
+      // per group (128 registers, T=1000 -11 %, T=250 +13 %, f64 +25 %).  The host compiles the
+      // CTX_GP=8 variant for long f32 grids only (ctx_api.cu launch_solve).
 #ifndef CTX_ST_OP
 #define CTX_ST_OP ""      // cache operator of the 128-bit trajectory stores (".cs", ".cg", ...)
 #endif
       struct pass_t {
         ctx_rec_u rr;
-        real o[4 * CTX_S];
+        real o[CTX_GP * CTX_S];
         int s_have, p0;
         bool act;
       } ps[CTX_PASSES];
@@ -1028,29 +1032,32 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #pragma unroll
             for (int j = 0; j < CTX_REC_Q; ++j) rr.q[j] = srcq[j];
           }
-          const int p0 = (rr.r.gf + g) << 2;
+          const int p0 = (rr.r.gf + g) << CTX_GSH;
           q.p0 = p0;
           real* o = q.o;
           if (act) {
-            real tq[4];
-            if (TSM) {   // padded to a multiple of 4 and 16-byte aligned
+            real tq[CTX_GP];
+            if (TSM) {   // padded to a multiple of CTX_GP and 16-byte aligned
+#pragma unroll
+              for (int h = 0; h < CTX_GP / 4; ++h) {
 #if CTX_F64
-              asm("ld.shared.v2.f64 {%0, %1}, [%2];"
-                  : "=d"(tq[0]), "=d"(tq[1]) : "r"(ts_sa + 8u * (unsigned)p0));
-              asm("ld.shared.v2.f64 {%0, %1}, [%2];"
-                  : "=d"(tq[2]), "=d"(tq[3]) : "r"(ts_sa + 8u * (unsigned)p0 + 16u));
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tq[4 * h]), "=d"(tq[4 * h + 1])
+                    : "r"(ts_sa + 8u * (unsigned)p0 + 32u * h));
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tq[4 * h + 2]), "=d"(tq[4 * h + 3])
+                    : "r"(ts_sa + 8u * (unsigned)p0 + 32u * h + 16u));
 #else
-              asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                  : "=f"(tq[0]), "=f"(tq[1]), "=f"(tq[2]), "=f"(tq[3])
-                  : "r"(ts_sa + 4u * (unsigned)p0));
+                asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                    : "=f"(tq[4 * h]), "=f"(tq[4 * h + 1]), "=f"(tq[4 * h + 2]), "=f"(tq[4 * h + 3])
+                    : "r"(ts_sa + 4u * (unsigned)p0 + 16u * h));
 #endif
+              }
             } else {
               const real* r_ts = ts_base + (size_t)rr.r.ri * a.stride_ts;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) tq[u] = (p0 + u < rr.r.i1) ? r_ts[p0 + u] : rr.r.v[0];
+              for (int u = 0; u < CTX_GP; ++u) tq[u] = (p0 + u < rr.r.i1) ? r_ts[p0 + u] : rr.r.v[0];
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < CTX_GP; ++u) {
               const real th_ = (tq[u] - rr.r.v[0]) * rr.r.v[1];
 #pragma unroll
               for (int i = 0; i < CTX_S; ++i) {
@@ -1065,11 +1072,11 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
               }
             }
             if (p0 < rr.r.i0) {   // points of this group that earlier steps evaluated
-              union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
+              union { uint4 q[CTX_PEND_Q]; real v[CTX_GP * CTX_S]; } pd;
 #pragma unroll
               for (int j = 0; j < CTX_PEND_Q; ++j) pd.q[j] = w.pend[rr.r.owner][j];
 #pragma unroll
-              for (int u = 0; u < 3; ++u)
+              for (int u = 0; u < CTX_GP - 1; ++u)
                 if (p0 + u < rr.r.i0) {
 #pragma unroll
                   for (int i = 0; i < CTX_S; ++i) o[u * CTX_S + i] = pd.v[u * CTX_S + i];
@@ -1097,7 +1104,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #ifdef CTX_DBG_NOSTORE   // developer experiment: everything but the global stores
             if (o[0] != R(-12345.678)) continue;
 #endif
-            if (p0 + 4 <= rr.r.i1) {
+            if (p0 + CTX_GP <= rr.r.i1) {
 #if CTX_ST256 && !CTX_BULK
               // Full-sector stores.  A group is 16*S (f32) / 32*S (f64) bytes; with 128-bit stores
               // and lanes 16*S bytes apart every store instruction writes HALF of 32 different
@@ -1111,19 +1118,19 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
               if ((rr.r.row_lo & 31u) == 0u) {
 #if CTX_F64
 #pragma unroll
-                for (int j = 0; j < CTX_S; ++j)
+                for (int j = 0; j < CTX_GP * CTX_S / 4; ++j)
                   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
                                "d"(o[4 * j]), "d"(o[4 * j + 1]), "d"(o[4 * j + 2]), "d"(o[4 * j + 3])
                                : "memory");
-#elif (CTX_S % 2) == 0
+#elif (CTX_GP * CTX_S) % 8 == 0
 #pragma unroll
-                for (int j = 0; j < CTX_S / 2; ++j)
+                for (int j = 0; j < CTX_GP * CTX_S / 8; ++j)
                   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j),
                                "f"(o[8 * j]), "f"(o[8 * j + 1]), "f"(o[8 * j + 2]), "f"(o[8 * j + 3]),
                                "f"(o[8 * j + 4]), "f"(o[8 * j + 5]), "f"(o[8 * j + 6]), "f"(o[8 * j + 7])
                                : "memory");
 #else
-                const bool par = ((p0 >> 2) & 1) != 0;   // odd S: the group starts mid-sector
+                const bool par = ((p0 >> 2) & 1) != 0;   // odd S, 4-point groups: starts mid-sector
 #pragma unroll
                 for (int j = 0; j < (CTX_S - 1) / 2; ++j) {
                   real v8[8];
@@ -1148,39 +1155,39 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
               if ((rr.r.row_lo & 15u) == 0u) {   // p0 * S reals = a multiple of 16 bytes
 #if CTX_BULK
                 // stage the group; lanes are 4*S reals apart (conflict-free 128-bit stores)
-                union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } sg;
+                union { uint4 q[CTX_PEND_Q]; real v[CTX_GP * CTX_S]; } sg;
 #pragma unroll
-                for (int j = 0; j < 4 * CTX_S; ++j) sg.v[j] = o[j];
+                for (int j = 0; j < CTX_GP * CTX_S; ++j) sg.v[j] = o[j];
 #pragma unroll
                 for (int j = 0; j < CTX_PEND_Q; ++j) w.stg[(stg_round & 1u) * CTX_PASSES + k][lane][j] = sg.q[j];
                 ok[k] = true;
 #elif CTX_F64
 #pragma unroll
-                for (int j = 0; j < 2 * CTX_S; ++j)
+                for (int j = 0; j < CTX_GP * CTX_S / 2; ++j)
                   asm volatile("st.global" CTX_ST_OP ".v2.f64 [%0], {%1, %2};" ::"l"(dst + 2 * j), "d"(o[2 * j]),
                                "d"(o[2 * j + 1]) : "memory");
 #else
 #pragma unroll
-                for (int j = 0; j < CTX_S; ++j)   // st.global: the address was rebuilt from integers
+                for (int j = 0; j < CTX_GP * CTX_S / 4; ++j)   // st.global: the address was rebuilt from integers
                   asm volatile("st.global" CTX_ST_OP ".v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
                                "f"(o[4 * j]), "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
                                : "memory");
 #endif
               } else {
 #pragma unroll
-                for (int j = 0; j < 4 * CTX_S; ++j) dst[j] = o[j];
+                for (int j = 0; j < CTX_GP * CTX_S; ++j) dst[j] = o[j];
               }
             } else if (rr.r.i1 == T) {   // ragged last group of the trajectory
 #pragma unroll
-              for (int u = 0; u < 3; ++u)
+              for (int u = 0; u < CTX_GP - 1; ++u)
                 if (p0 + u < T) {
 #pragma unroll
                   for (int i = 0; i < CTX_S; ++i) dst[u * CTX_S + i] = o[u * CTX_S + i];
                 }
             } else {                      // incomplete: park it for the step that completes it
-              union { uint4 q[CTX_PEND_Q]; real v[4 * CTX_S]; } pd;
+              union { uint4 q[CTX_PEND_Q]; real v[CTX_GP * CTX_S]; } pd;
 #pragma unroll
-              for (int j = 0; j < 4 * CTX_S; ++j) pd.v[j] = o[j];
+              for (int j = 0; j < CTX_GP * CTX_S; ++j) pd.v[j] = o[j];
 #pragma unroll
               for (int j = 0; j < CTX_PEND_Q; ++j) w.pend[rr.r.owner][j] = pd.q[j];
             }
@@ -1206,7 +1213,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
             const unsigned src = (unsigned)__cvta_generic_to_shared(
                 &w.stg[(stg_round & 1u) * CTX_PASSES + k][lane][0]);
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                         "r"(src), "r"(len * (int)(4 * CTX_S * sizeof(real))) : "memory");
+                         "r"(src), "r"(len * (int)(CTX_GP * CTX_S * sizeof(real))) : "memory");
           }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");

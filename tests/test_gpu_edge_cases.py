@@ -129,12 +129,12 @@ def test_long_segments_with_unaligned_rows_f32_and_f64():
                 assert (np.abs(ys - ref.ys) <= 500 * scale).all()
 
 
-@pytest.mark.parametrize("T,shared_ts", [(640, True), (517, True), (600, False)])
-def test_two_pass_save_variant_is_bit_identical(T, shared_ts, monkeypatch):
-    """Long f32 output grids (T >= 512) take the kernel variant that keeps two save passes in
-    flight (ctx_api.cu launch_solve).  It is the same arithmetic in a different schedule: results
-    must be bit-identical to the one-pass variant, incl. ragged T, per-row grids and failed rows
-    (inf fill)."""
+@pytest.mark.parametrize("T,shared_ts", [(640, True), (517, True), (600, False), (1001, True)])
+def test_wide_save_variant_is_bit_identical(T, shared_ts, monkeypatch):
+    """Long f32 output grids (T >= 512) take the kernel variant whose lanes evaluate 8 requested
+    times per pass instead of 4 (ctx_api.cu launch_solve).  It is the same arithmetic in a
+    different schedule: results must be bit-identical to the 4-point variant, incl. ragged T,
+    per-row grids and failed rows (inf fill)."""
     from catalax_b200 import engine
     from catalax_b200.tools import codegen as cg
 
