@@ -159,3 +159,55 @@ def test_wide_save_variant_is_bit_identical(T, shared_ts, monkeypatch):
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
     np.testing.assert_array_equal(outs[0][2], outs[1][2])
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
+
+
+@pytest.mark.parametrize("S", [1, 2, 4, 5])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_store_paths_agree_bitwise_for_every_state_count(S, dtype, monkeypatch):
+    """The save path picks its store instructions from S and the dtype (256-bit whole-sector
+    stores, parity-shifted for odd S in f32; 8-point groups for long f32 grids).  Whatever the
+    path, the VALUES are the same arithmetic: compare with a build restricted to 4-point groups
+    and 128-bit stores, on a short ragged grid and on a long one, with one constant state."""
+    import sympy as sp
+
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+
+    states = [f"x{i}" for i in range(S)]
+    params = [f"k{i}" for i in range(S)]
+    odes = {}
+    for i in range(S):
+        e = -sp.Symbol(params[i]) * sp.Symbol(states[i])
+        if i > 0:
+            e = e + sp.Float(0.5) * sp.Symbol(states[i - 1])
+        odes[states[i]] = e
+    if S >= 4:
+        odes[states[S - 1]] = sp.Integer(0)          # a constant state (CTX_CONST_MASK)
+    model = (states, params, [], odes, [])
+    rng = np.random.default_rng(S)
+    B = 777
+    y0 = rng.uniform(0.5, 2.0, (B, S)).astype(dtype)
+    theta = rng.uniform(0.05, 1.0, (B, S)).astype(dtype)
+    consts = np.zeros((B, 0), dtype)
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    for T in (37, 1001):
+        ts = np.linspace(0, 20, T).astype(dtype)
+        res = []
+        for flags, wide in (("", None), ("-DCTX_ST256=0 -DCTX_GP=4", "0")):
+            monkeypatch.setenv("CTX_B200_NVRTC_FLAGS", flags)
+            if wide is None:
+                monkeypatch.delenv("CTX_B200_WIDE_SAVE", raising=False)
+            else:
+                monkeypatch.setenv("CTX_B200_WIDE_SAVE", wide)
+            m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), np.dtype(dtype).name)
+            o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), in_axes=(0, 0, 0, None), rtol=1e-6,
+                        atol=1e-6, kernel=2)
+            torch.cuda.synchronize()
+            assert (o.status == 0).all()
+            res.append(o.ys.cpu().numpy())
+        np.testing.assert_array_equal(res[0], res[1])
+        # ... and they are the solution: x0(t) = x0(0) exp(-k0 t)
+        want = y0[:, None, 0] * np.exp(-theta[:, None, 0].astype(np.float64) * ts[None, :].astype(np.float64))
+        tol = 2e-4 if dtype == np.float32 else 2e-5
+        assert np.abs(res[0][:, :, 0] - want).max() <= tol
