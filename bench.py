@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nuts", action="store_true")
+    ap.add_argument("--no-other", action="store_true")
     ap.add_argument("--nuts-chains", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -194,7 +195,7 @@ def nuts_inputs(chains, M, T, dt, seed):
     return c(y0s), c(theta), np.zeros((M, 0), dtype=dt), c(ts), c(data), c(sigma)
 
 
-def run_nuts_leg(a, model_field, dev, rank, world, dist):
+def run_nuts_leg(a, model_field, dev, rank, world, dist, fma_peak=None):
     """Chain-sharded (no collective): every rank evaluates its own `nuts_chains` chains over all
     64 series.  value = chain-level (log-density, gradient) evaluations per second, all ranks."""
     import torch
@@ -244,7 +245,7 @@ def run_nuts_leg(a, model_field, dev, rank, world, dist):
         flops_step = 6 * F + 56 * N + 8 * S + 11
         flops_point = 40 + 14 * N + 25 * S
         flops = steps * flops_step + CH * M * T * flops_point
-        peak = engine.measure_fma_peak(np.dtype(dt).name)
+        peak = fma_peak or engine.measure_fma_peak(np.dtype(dt).name)
         achieved = flops / (ms / n_iter * 1e-3) / 1e12
         roof = {"bound": "fp32" if a.dtype == "f32" else "fp64", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak,
@@ -294,6 +295,101 @@ def run_nuts_leg(a, model_field, dev, rank, world, dist):
             "failed_series": fails, "all_finite": finite}
 
 
+# ----------------------------------------------------------------------------- other configs
+def run_other_configs(a, model, sets, dev, rank, world, dist, fma_peak=None):
+    """Short device-timed legs for the other BASELINE configs (rank 0's GPU only, reported beside
+    the headline, never part of `value`): configs[1] in the integrator-bound regime (T=16),
+    configs[2] (32-state mass-action network, warp-per-trajectory kernel) and configs[4]
+    (NeuralODE field 5-64-64-64-4 on the tcgen05 tensor cores)."""
+    import torch
+
+    from catalax_b200 import engine
+    from catalax_b200.neural import NeuralODE
+    from catalax_b200.tools import codegen as cg
+    from tests import cases
+
+    if rank != 0:
+        return None
+    dt = np_dtype(a)
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+
+    def timed(fn, n=5):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, out
+
+    res = {}
+    # configs[1], T=16: the output is negligible, the integrator is the bound
+    y0, th, c = sets[0]
+    ts16 = torch.linspace(0, 100, 16, dtype=tdt, device=dev)
+    out16 = torch.empty((y0.shape[0], 16, 3), dtype=tdt, device=dev)
+    ms, o = timed(lambda: model.solve(y0, th, c, ts16, solver="tsit5", in_axes=(0, 0, 0, None),
+                                      rtol=1e-6, atol=1e-6, dt0=0.1, max_steps=4096, out=out16))
+    steps = int((o.n_accepted.sum(dtype=torch.int64) + o.n_rejected.sum(dtype=torch.int64)).item())
+    fl = steps * (6 * 6 + 64 * 3 + 11) / (ms * 1e-3) / 1e12
+    res["config2_T16"] = {"ms": ms, "steps_per_s": steps / (ms * 1e-3), "rows": int(y0.shape[0]),
+                          "roofline": {"bound": a.dtype.replace("f", "fp"), "achieved": fl,
+                                       "unit": "TFLOP/s", "flops_per_step": 6 * 6 + 64 * 3 + 11}}
+    # configs[2]: 32 states / 64 reactions, 262144 rows, T=32 on [0, 10]
+    B3 = 262144
+    f3 = cg.generate_field(cases.field_spec(cases.mass_action_network(32)))
+    m3 = engine.CompiledModel(f3, np.dtype(dt).name)
+    rng = np.random.default_rng(1)
+    y3 = torch.as_tensor(rng.uniform(0.1, 2.0, (B3, 32)).astype(dt), device=dev)
+    k3 = torch.as_tensor(np.exp(rng.uniform(np.log(0.01), np.log(1.0), (B3, 64))).astype(dt), device=dev)
+    c3 = torch.empty((B3, 0), dtype=tdt, device=dev)
+    ts3 = torch.linspace(0, 10, 32, dtype=tdt, device=dev)
+    out3 = torch.empty((B3, 32, 32), dtype=tdt, device=dev)    # (preallocated: no allocator traffic
+    ms, o = timed(lambda: m3.solve(y3, k3, c3, ts3, in_axes=(0, 0, 0, None), rtol=1e-6, atol=1e-6,
+                                   out=out3))                   #  inside the timed region)
+    steps = int((o.n_accepted.sum(dtype=torch.int64) + o.n_rejected.sum(dtype=torch.int64)).item())
+    fps = 6 * f3.flops_rhs + 64 * 32 + 11
+    fl = steps * fps / (ms * 1e-3) / 1e12
+    res["config3_mass_action_32x64"] = {
+        "ms": ms, "steps_per_s": steps / (ms * 1e-3), "rows": B3, "kernel": "ctx_solve_w (warp per trajectory)",
+        "failed_rows": int((o.status != 0).sum().item()),
+        "roofline": {"bound": a.dtype.replace("f", "fp"), "achieved": fl, "unit": "TFLOP/s",
+                     "flops_per_step": fps}}
+    # configs[4]: NeuralODE 5-64-64-64-4 (tanh), 524288 rows, T=16 on [0, 10], rtol 1e-3 (f32 only:
+    # the tensor-core form; f64 runs the FFMA form)
+    if a.dtype == "f32":
+        B5 = 1 << 19
+        net = NeuralODE(4, 64, 3, ["a", "b", "c", "d"], activation="tanh", max_time=10.0, key=3)
+        y5 = torch.as_tensor(np.random.default_rng(3).uniform(0, 2, (B5, 4)).astype(np.float32), device=dev)
+        ts5 = torch.linspace(0, 10, 16, dtype=torch.float32, device=dev)
+        ms, _ = timed(lambda: net.predict_arrays(ts5, y5), n=3)
+        o = net.last
+        steps = int((o.n_accepted.sum(dtype=torch.int64) + o.n_rejected.sum(dtype=torch.int64)).item())
+        mlp_flops = steps * 6 * 17536            # 6 stage evaluations per step attempt, 8768 MAC each
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1384.0)) / 2.0   # tf32 dense = bf16 / 2
+        ach = 3.0 * mlp_flops / (ms * 1e-3) / 1e12   # 3xTF32 split: three MMAs per useful product
+        res["config5_neuralode_5x64x64x64x4"] = {
+            "ms": ms, "steps_per_s": steps / (ms * 1e-3), "rows": B5,
+            "kernel": "ctx_solve_mlp_tc (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
+            "useful_mlp_tflops": mlp_flops / (ms * 1e-3) / 1e12,
+            "failed_rows": int((o.status != 0).sum().item()),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                         "frac": ach / tpeak,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32)"}}
+    peak = fma_peak or engine.measure_fma_peak(np.dtype(dt).name)
+    for key in ("config2_T16", "config3_mass_action_32x64"):
+        r = res[key]["roofline"]
+        r["peak"] = peak
+        r["frac"] = r["achieved"] / peak
+        r["peak_source"] = "ctx_measure_fma_peak (FMA loop measured on this GPU)"
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_b200(a):
     import torch
@@ -321,6 +417,9 @@ def run_b200(a):
     B, T, S, P = a.rows, a.T, 3, 2
     field = cg.generate_field(cases.field_spec(cases.michaelis_menten()))
     model = engine.CompiledModel(field, np.dtype(dt).name)
+    # FMA peak (denominator of the compute rooflines of the side legs) first: the micro-benchmark
+    # loads the GPU heavily, nothing timed may run in its wake (input generation + warm-up follow)
+    fma_peak = engine.measure_fma_peak(np.dtype(dt).name) if rank == 0 else None
 
     # rows are sharded by rank: every rank draws its own seeds (no data-path collective)
     sets = []
@@ -426,7 +525,15 @@ def run_b200(a):
     # ---- second headline metric: NUTS log-density + gradient evaluations / s (configs[3])
     nuts = None
     if not a.no_nuts:
-        nuts = run_nuts_leg(a, model_field=None, dev=dev, rank=rank, world=world, dist=dist)
+        nuts = run_nuts_leg(a, model_field=None, dev=dev, rank=rank, world=world, dist=dist,
+                            fma_peak=fma_peak)
+
+    other = None
+    if not a.no_other and world == 1:
+        try:
+            other = run_other_configs(a, model, sets, dev, rank, world, dist, fma_peak=fma_peak)
+        except Exception as exc:       # never lose the headline line to a side leg
+            other = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -469,6 +576,8 @@ def run_b200(a):
         line["e2e"] = e2e
     if nuts:
         line["nuts"] = nuts
+    if other:
+        line["other_configs"] = other
     if not a.no_cpu_baseline and world == 1:
         rows = B                       # the whole batch once: ~1.5 s on 16 cores (~20 core-seconds)
         v, sec, steps, threads = cpu_oracle_run(a, rows)

@@ -3,7 +3,7 @@
 # per dominant kernel).  Everything lands in gpurun_out/.
 set -u
 TAG=${1:-r1}
-ARGS="--steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-nuts"
+ARGS="--steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-nuts --no-other"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/${TAG}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
