@@ -1023,17 +1023,18 @@ int ctx_mlp_adjoint_forward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void
                                (cudaStream_t)stream);
 }
 
-int ctx_mlp_adjoint_backward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void* theta,
-                             const void* ts, const void* gys, int32_t* status, void* grad_theta,
-                             void* grad_y0, void* workspace, size_t ws_bytes, void* stream) {
+int ctx_mlp_adjoint_backward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void* y0,
+                             const void* theta, const void* ts, const void* gys, int32_t* status,
+                             void* grad_theta, void* grad_y0, void* workspace, size_t ws_bytes,
+                             void* stream) {
   if (!m || !cfg || !gys || !grad_theta || !status) return fail(CTX_E_INVALID, "null argument");
   if (ctx_device_count() <= 0)
     return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
   if (m->desc.dtype == CTX_F64)
-    return launch_adjoint<double>(m, cfg, true, nullptr, theta, ts, nullptr, gys, status, nullptr,
+    return launch_adjoint<double>(m, cfg, true, y0, theta, ts, nullptr, gys, status, nullptr,
                                   nullptr, grad_theta, grad_y0, workspace, ws_bytes,
                                   (cudaStream_t)stream);
-  return launch_adjoint<float>(m, cfg, true, nullptr, theta, ts, nullptr, gys, status, nullptr,
+  return launch_adjoint<float>(m, cfg, true, y0, theta, ts, nullptr, gys, status, nullptr,
                                nullptr, grad_theta, grad_y0, workspace, ws_bytes,
                                (cudaStream_t)stream);
 }

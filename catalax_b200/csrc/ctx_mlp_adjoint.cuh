@@ -90,13 +90,19 @@ __device__ __forceinline__ void adj_stage_weights(const real* th, real* pack) {
 #if ADJ_KIND == 1
   for (int e = threadIdx.x; e < CTX_S * ADJ_R; e += blockDim.x) pack[ADJ_SSTOICH + e] = th[ADJ_STOICH + e];
 #endif
+#if ADJ_KIND == 2
+  for (int e = threadIdx.x; e < CTX_S * CTX_S; e += blockDim.x) pack[ADJ_SGATE + e] = th[ADJ_GATE + e];
+  for (int e = threadIdx.x; e < CTX_S; e += blockDim.x) pack[ADJ_SALPHA + e] = th[ADJ_ALPHA + e];
+  for (int e = threadIdx.x; e < ADJ_PM; e += blockDim.x) pack[ADJ_SMECH + e] = th[ADJ_MECH + e];
+#endif
 }
 
 // One MLP evaluation by a warp.  acts: [ADJ_NACT][ADJ_WMAX] in shared memory; acts[0] = (y, t/max_t),
 // acts[l+1] = act_l(W_l acts[l] + b_l).  dy (replicated in all lanes) = acts[ADJ_L][0..S).
 __device__ __forceinline__ void adj_mlp_forward(const real* pack, real* acts, const real t,
                                                 const real* y, const real inv_max_t, real* dy,
-                                                const int lane) {
+                                                const int lane, const real* yinit) {
+  (void)yinit;
   {
     real v = t * inv_max_t;
 #pragma unroll
@@ -130,6 +136,20 @@ __device__ __forceinline__ void adj_mlp_forward(const real* pack, real* acts, co
     for (int r = 0; r < ADJ_R; ++r) acc += pack[ADJ_SSTOICH + i * ADJ_R + r] * acts[ADJ_L * ADJ_WMAX + r];
     dy[i] = acc;
   }
+#elif ADJ_KIND == 2   // UniversalODE (universalode.py:84-101):
+                      // dy = mech(t, y, theta_m) + softplus(alpha) * sigmoid(10 G y) * MLP(t, y)
+  {
+    real m[CTX_S];
+    adj_mech(t, y, pack + ADJ_SMECH, yinit, m);
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) {
+      real z = R(0.0);
+#pragma unroll
+      for (int j = 0; j < CTX_S; ++j) z += pack[ADJ_SGATE + i * CTX_S + j] * y[j];
+      const real g = R(1.0) / (R(1.0) + exp(-(R(10.0) * z)));
+      dy[i] = m[i] + pack[ADJ_SALPHA + i] * g * acts[ADJ_L * ADJ_WMAX + i];
+    }
+  }
 #else
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) dy[i] = acts[ADJ_L * ADJ_WMAX + i];
@@ -140,7 +160,47 @@ __device__ __forceinline__ void adj_mlp_forward(const real* pack, real* acts, co
 // Accumulates the weight / bias gradient into the warp's private pack `gp`; returns the cotangent
 // of the input state in ybar[S] (replicated).  dl: [2][ADJ_WMAX] scratch in shared memory.
 __device__ __forceinline__ void adj_mlp_vjp(const real* pack, real* gp, const real* acts,
-                                            real* dl, const real* fbar, real* ybar, const int lane) {
+                                            real* dl, const real* fbar_in, real* ybar, const int lane,
+                                            const real t, const real* yinit) {
+  (void)t; (void)yinit;
+#if ADJ_KIND == 2
+  // gate / alpha / mechanistic part (replicated in all lanes; lane 0 accumulates the gradients):
+  //   f = mech + a * g * o,  g = sigmoid(10 G y):  obar = fbar a g  (-> through the MLP below),
+  //   abar = fbar g o,  zbar = 10 fbar a o g (1 - g),  Gbar = zbar (x) y,  ybar += G^T zbar + mech^T fbar
+  real fbar[CTX_S], yex[CTX_S], Ys[CTX_S];
+  {
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) { Ys[i] = acts[i]; yex[i] = R(0.0); }
+    real thb[ADJ_PM > 0 ? ADJ_PM : 1];
+#pragma unroll
+    for (int q = 0; q < ADJ_PM; ++q) thb[q] = R(0.0);
+    adj_mech_vjp(t, Ys, pack + ADJ_SMECH, yinit, fbar_in, yex, thb);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < ADJ_PM; ++q) gp[ADJ_SMECH + q] += thb[q];
+    }
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) {
+      real z = R(0.0);
+#pragma unroll
+      for (int j = 0; j < CTX_S; ++j) z += pack[ADJ_SGATE + i * CTX_S + j] * Ys[j];
+      const real g = R(1.0) / (R(1.0) + exp(-(R(10.0) * z)));
+      const real a_ = pack[ADJ_SALPHA + i];
+      const real o_ = acts[ADJ_L * ADJ_WMAX + i];
+      fbar[i] = fbar_in[i] * a_ * g;
+      const real zb = R(10.0) * fbar_in[i] * a_ * o_ * g * (R(1.0) - g);
+      if (lane == 0) {
+        gp[ADJ_SALPHA + i] += fbar_in[i] * g * o_;
+#pragma unroll
+        for (int j = 0; j < CTX_S; ++j) gp[ADJ_SGATE + i * CTX_S + j] += zb * Ys[j];
+      }
+#pragma unroll
+      for (int j = 0; j < CTX_S; ++j) yex[j] += pack[ADJ_SGATE + i * CTX_S + j] * zb;
+    }
+  }
+#else
+  const real* fbar = fbar_in;
+#endif
   // delta' of the output layer
   {
     const int no = adj_nout[ADJ_L - 1];
@@ -199,6 +259,10 @@ __device__ __forceinline__ void adj_mlp_vjp(const real* pack, real* gp, const re
   }
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) ybar[i] = cur[i];
+#if ADJ_KIND == 2
+#pragma unroll
+  for (int i = 0; i < CTX_S; ++i) ybar[i] += yex[i];
+#endif
   __syncwarp();
 }
 
@@ -231,7 +295,8 @@ __device__ const real adj_C[7] = {R(0.0), C2, C3, C4, C5, R(1.0), R(1.0)};
 __device__ __forceinline__ void adj_stages(const real* pack, real* acts_all, const real t,
                                            const real dt, const real* y, const real inv_max_t,
                                            real (*f)[CTX_S], real* y1, const int lane,
-                                           const bool have_f1, const int act_stride) {
+                                           const bool have_f1, const int act_stride,
+                                           const real* yinit) {
   real Y[CTX_S];
 #pragma unroll
   for (int i = 0; i < 7; ++i) {   // (fully unrolled: static indices keep f in registers)
@@ -247,7 +312,8 @@ __device__ __forceinline__ void adj_stages(const real* pack, real* acts_all, con
       for (int s = 0; s < CTX_S; ++s) y1[s] = Y[s];
     }
     if (i == 0 && have_f1) continue;   // FSAL: f[0] carried over from the previous step
-    adj_mlp_forward(pack, acts_all + i * act_stride, t + adj_C[i] * dt, Y, inv_max_t, f[i], lane);
+    adj_mlp_forward(pack, acts_all + i * act_stride, t + adj_C[i] * dt, Y, inv_max_t, f[i], lane,
+                    yinit);
   }
 }
 
@@ -272,11 +338,15 @@ ctx_mlp_adj_forward(const ctx_adj_args a) {
     real* out = a.ys + (size_t)b * T * CTX_S;
     real* ckr = a.ck_real + (size_t)b * a.cap * (2 + CTX_S);
     int* cki = a.ck_int + (size_t)b * a.cap * 2;
-    real y[CTX_S], ynew[CTX_S], f[7][CTX_S];
+    real y[CTX_S], ynew[CTX_S], f[7][CTX_S], yinit[CTX_S];
 #pragma unroll
-    for (int i = 0; i < CTX_S; ++i) y[i] = a.y0[(size_t)b * CTX_S + i];
+    for (int i = 0; i < CTX_S; ++i) yinit[i] = y[i] = a.y0[(size_t)b * CTX_S + i];
     const real t_end = ts[T - 1];
+#ifdef ADJ_T0_ZERO
+    real tprev = R(0.0);                      // universalode.py:133: t0 = 0.0
+#else
     real tprev = ts[0];                       // neuralode.py:52: t0 = ts[0]
+#endif
     // dt0 <= 0: the reference's default dt0 = ts[1] - ts[0] of THIS trajectory (neuralode.py:44-47)
     const real dt0 = (a.dt0 > R(0.0) || T < 2) ? a.dt0 : ts[1] - ts[0];
     real tnext = fmin(tprev + dt0, t_end);
@@ -289,7 +359,7 @@ ctx_mlp_adj_forward(const ctx_adj_args a) {
     for (int n = 0; tprev < t_end; ++n) {
       if (n >= a.max_steps) { status = CTX_ST_MAX; break; }
       const real dt = tnext - tprev;
-      adj_stages(pack, acts, tprev, dt, y, inv_max_t, f, ynew, lane, have_f1, 0);
+      adj_stages(pack, acts, tprev, dt, y, inv_max_t, f, ynew, lane, have_f1, 0, yinit);
       // error estimate / controller: same arithmetic as ctx_scaled_error + the I-controller
       bool has_nan = false;
 #pragma unroll
@@ -400,9 +470,12 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
     const real* ckr = a.ck_real + (size_t)b * a.cap * (2 + CTX_S);
     const int* cki = a.ck_int + (size_t)b * a.cap * 2;
     const int nsteps = a.n_steps[b];
-    real lam[CTX_S], carry[CTX_S];
+    real lam[CTX_S], carry[CTX_S], yinit[CTX_S];
 #pragma unroll
-    for (int i = 0; i < CTX_S; ++i) { lam[i] = R(0.0); carry[i] = R(0.0); }
+    for (int i = 0; i < CTX_S; ++i) {
+      lam[i] = R(0.0); carry[i] = R(0.0);
+      yinit[i] = a.y0 ? a.y0[(size_t)b * CTX_S + i] : R(0.0);
+    }
     if (a.status[b] == 0 && nsteps == 0) {
       // t0 == t1: ys[q] = y0 for every q
       for (int q = 0; q < T; ++q)
@@ -416,7 +489,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
       real y[CTX_S], y1[CTX_S], f[7][CTX_S], fb[7][CTX_S], yb[CTX_S];
 #pragma unroll
       for (int i = 0; i < CTX_S; ++i) y[i] = ckr[n * (2 + CTX_S) + 2 + i];
-      adj_stages(pack, acts, t, dt, y, inv_max_t, f, y1, lane, false, ADJ_NACT * ADJ_WMAX);
+      adj_stages(pack, acts, t, dt, y, inv_max_t, f, y1, lane, false, ADJ_NACT * ADJ_WMAX, yinit);
 #pragma unroll
       for (int k = 0; k < 7; ++k)
 #pragma unroll
@@ -438,7 +511,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
       }
       // stage 7: f_7 = MLP(t + dt, y1), y1 = y + dt sum_j A7j f_j
       real Yb[CTX_S];
-      adj_mlp_vjp(pack, gp, acts + 6 * (ADJ_NACT * ADJ_WMAX), dl, fb[6], Yb, lane);
+      adj_mlp_vjp(pack, gp, acts + 6 * (ADJ_NACT * ADJ_WMAX), dl, fb[6], Yb, lane, t + dt, yinit);
 #pragma unroll
       for (int i = 0; i < CTX_S; ++i) {
         const real tot = lam[i] + Yb[i];
@@ -449,7 +522,8 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
       // stages 6..2
 #pragma unroll
       for (int k = 5; k >= 1; --k) {
-        adj_mlp_vjp(pack, gp, acts + k * (ADJ_NACT * ADJ_WMAX), dl, fb[k], Yb, lane);
+        adj_mlp_vjp(pack, gp, acts + k * (ADJ_NACT * ADJ_WMAX), dl, fb[k], Yb, lane,
+                    t + adj_C[k] * dt, yinit);
 #pragma unroll
         for (int i = 0; i < CTX_S; ++i) {
           yb[i] += Yb[i];
@@ -462,7 +536,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
 #pragma unroll
         for (int i = 0; i < CTX_S; ++i) carry[i] = fb[0][i];
       } else {
-        adj_mlp_vjp(pack, gp, acts, dl, fb[0], Yb, lane);
+        adj_mlp_vjp(pack, gp, acts, dl, fb[0], Yb, lane, t, yinit);
 #pragma unroll
         for (int i = 0; i < CTX_S; ++i) yb[i] += Yb[i];
       }
@@ -491,6 +565,11 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
   }
 #if ADJ_KIND == 1
   for (int e = lane; e < CTX_S * ADJ_R; e += 32) prow[ADJ_STOICH + e] = gp[ADJ_SSTOICH + e];
+#endif
+#if ADJ_KIND == 2   // (d/d alpha is w.r.t. softplus(alpha_residual), the value the pack carries)
+  for (int e = lane; e < CTX_S * CTX_S; e += 32) prow[ADJ_GATE + e] = gp[ADJ_SGATE + e];
+  for (int e = lane; e < CTX_S; e += 32) prow[ADJ_ALPHA + e] = gp[ADJ_SALPHA + e];
+  for (int e = lane; e < ADJ_PM; e += 32) prow[ADJ_MECH + e] = gp[ADJ_SMECH + e];
 #endif
 }
 

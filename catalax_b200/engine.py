@@ -101,7 +101,7 @@ def lib() -> C.CDLL:
     L.ctx_mlp_adjoint_forward.restype = C.c_int
     L.ctx_mlp_adjoint_forward.argtypes = [vp, C.POINTER(ctx_adjoint_cfg)] + [vp] * 8 + [C.c_size_t, vp]
     L.ctx_mlp_adjoint_backward.restype = C.c_int
-    L.ctx_mlp_adjoint_backward.argtypes = [vp, C.POINTER(ctx_adjoint_cfg)] + [vp] * 7 + [C.c_size_t, vp]
+    L.ctx_mlp_adjoint_backward.argtypes = [vp, C.POINTER(ctx_adjoint_cfg)] + [vp] * 8 + [C.c_size_t, vp]
     L.ctx_solve_host.restype = C.c_int
     L.ctx_solve_host.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -395,7 +395,7 @@ class CompiledModel:
                                                  p(counts[0]), p(counts[1]), p(counts[2]), p(ws),
                                                  wsb, C.c_void_p(stream)))
         return dict(cfg=cfg, ws=ws, wsb=wsb, ys=ys, status=counts[0], n_accepted=counts[1],
-                    n_rejected=counts[2], theta=theta, ts=ts)
+                    n_rejected=counts[2], theta=theta, ts=ts, y0=y0)
 
     def adjoint_backward(self, ctx, gys, want_y0: bool = False):
         """d loss / d theta [P] (and d loss / d y0 [B,S]) from gys = d loss / d ys [B,T,S]."""
@@ -410,8 +410,9 @@ class CompiledModel:
             gy0 = torch.empty((ys.shape[0], ys.shape[2]), dtype=ys.dtype, device=ys.device) \
                 if want_y0 else None
             stream = torch.cuda.current_stream(ys.device).cuda_stream
-            _check(lib().ctx_mlp_adjoint_backward(self._h, C.byref(ctx["cfg"]), p(ctx["theta"]),
-                                                  p(ctx["ts"]), p(gys), p(ctx["status"]), p(g), p(gy0),
+            _check(lib().ctx_mlp_adjoint_backward(self._h, C.byref(ctx["cfg"]), p(ctx["y0"]),
+                                                  p(ctx["theta"]), p(ctx["ts"]), p(gys),
+                                                  p(ctx["status"]), p(g), p(gy0),
                                                   p(ctx["ws"]), ctx["wsb"], C.c_void_p(stream)))
         return (g, gy0) if want_y0 else g
 

@@ -263,7 +263,8 @@ class NeuralBase:
         dtype = default_dtype()
         model, theta = self._model(dtype)
         if not model.field.source.count("#define CTX_MLP_ADJ 1"):
-            raise NotImplementedError("weight gradients: NeuralODE / RateFlowODE fields of <= 8 states")
+            raise NotImplementedError("weight gradients: neural fields of <= 8 states whose network "
+                                      "fits shared memory")
         if solver_name(self.solver) != "tsit5":
             raise NotImplementedError("weight gradients are implemented for Tsit5")
         dev = y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda else \
@@ -307,14 +308,26 @@ class NeuralBase:
         if self.kind == "rateflow":
             S, R_ = self.data_size, self.spec.out_size
             grads["stoich"] = g[lay.stoich: lay.stoich + S * R_].reshape(S, R_).copy()
+        if self.kind == "universalode":
+            S = self.data_size
+            grads["gate_matrix"] = g[lay.gate: lay.gate + S * S].reshape(S, S).copy()
+            # the kernel differentiates w.r.t. softplus(alpha_residual); softplus' = sigmoid
+            grads["alpha_residual"] = g[lay.alpha: lay.alpha + S] / (1.0 + np.exp(-self.alpha_residual))
+            grads["parameters"] = g[lay.mech: lay.mech + len(self.parameters)].copy()
         if want_y0:
             grads["y0"] = gy0
         return float(value.item()), grads
 
-    def apply_updates(self, dW, db, dstoich=None):
-        """weights += dW, biases += db (stoich_matrix += dstoich); the parameter packs are rebuilt."""
+    def apply_updates(self, dW, db, dstoich=None, dgate=None, dalpha=None, dparameters=None):
+        """weights += dW, biases += db (and the class-specific leaves); the packs are rebuilt."""
         if dstoich is not None:
             self.stoich_matrix = self.stoich_matrix + np.asarray(dstoich, dtype=np.float64)
+        if dgate is not None:
+            self.gate_matrix = self.gate_matrix + np.asarray(dgate, dtype=np.float64)
+        if dalpha is not None:
+            self.alpha_residual = self.alpha_residual + np.asarray(dalpha, dtype=np.float64)
+        if dparameters is not None:
+            self.parameters = self.parameters + np.asarray(dparameters, dtype=np.float64)
         self.weights = [w + np.asarray(d, dtype=np.float64) for w, d in zip(self.weights, dW)]
         self.biases = [None if b is None else b + np.asarray(d, dtype=np.float64)
                        for b, d in zip(self.biases, db)]

@@ -249,9 +249,9 @@ def _tc_source(spec: MLPSpec) -> List[str]:
 def adjoint_dims(spec: MLPSpec):
     """Shared-memory pack of the weight-gradient kernels (csrc/ctx_mlp_adjoint.cuh), or None when
     the model is not a plain NeuralODE of at most 8 states (RateFlow / Universal fields: next)."""
-    if spec.kind not in ("neuralode", "rateflow") or spec.data_size > 8:
+    if spec.kind not in ("neuralode", "rateflow", "universalode") or spec.data_size > 8:
         return None
-    if spec.kind == "neuralode" and spec.out_size != spec.data_size:
+    if spec.kind != "rateflow" and spec.out_size != spec.data_size:
         return None
     dims = spec.layer_dims()
     wmax = max(max(ni, no) for ni, no in dims)
@@ -263,15 +263,69 @@ def adjoint_dims(spec: MLPSpec):
     sstoich = off
     if spec.kind == "rateflow":
         off += spec.data_size * spec.out_size
+    sgate = salpha = smech = off
+    if spec.kind == "universalode":
+        S_ = spec.data_size
+        sgate = off; off += S_ * S_
+        salpha = off; off += S_
+        smech = off; off += len(spec.mech.parameters)
     nact = (len(dims) + 1) * wmax
     per_warp_bwd = off + 7 * nact + 2 * wmax
 
     def warps(word):
         w = (227 * 1024 // word - off) // per_warp_bwd
         return max(0, min(4, w))
-    return dict(dims=dims, wmax=wmax, soff=soff, spack=off, sstoich=sstoich, nact=nact,
+    return dict(dims=dims, wmax=wmax, soff=soff, spack=off, sstoich=sstoich, sgate=sgate,
+                salpha=salpha, smech=smech, nact=nact,
                 per_warp_bwd=per_warp_bwd,
                 warps32=warps(4), warps64=warps(8))
+
+
+def _adjoint_mech_source(spec: MLPSpec, lay: MLPLayout, d) -> List[str]:
+    """UniversalODE (universalode.py:84-101): the mechanistic field and its vector-Jacobian
+    products w.r.t. the states and the mechanistic parameters, generated from the sympy model."""
+    S = spec.data_size
+    mech = spec.mech
+    used = set().union(*[e.free_symbols for e in mech.total_exprs()])
+    if any(sp.Symbol(cn) in used for cn in mech.constants):
+        raise ValueError("UniversalODE: the mechanistic model must not use constants")
+    names = {cg.T_SYM: "t"}
+    y_syms, p_syms = [], []
+    for i, s_ in enumerate(mech.states):
+        names[sp.Symbol(s_)] = f"y[{i}]"
+        names[sp.Symbol(f"{s_}_init")] = f"y0[{i}]"
+        y_syms.append(sp.Symbol(s_))
+    for i, p_ in enumerate(mech.parameters):
+        names[sp.Symbol(p_)] = f"thm[{i}]"
+        p_syms.append(sp.Symbol(p_))
+    exprs = [sp.sympify(e) for e in mech.total_exprs()]
+    fwd, _ = cg._emit_block([(f"m[{i}]", e) for i, e in enumerate(exprs)], names, "u")
+    fb = [sp.Symbol(f"ctx_fb{i}") for i in range(S)]
+    vnames = dict(names)
+    for i, b in enumerate(fb):
+        vnames[b] = f"fbar[{i}]"
+    outs = []
+    for j, ys in enumerate(y_syms):
+        outs.append((f"const real yb{j}", sum(fb[i] * sp.diff(exprs[i], ys) for i in range(S))))
+    for p_i, ps in enumerate(p_syms):
+        outs.append((f"const real tb{p_i}", sum(fb[i] * sp.diff(exprs[i], ps) for i in range(S))))
+    vjp, _ = cg._emit_block(outs, vnames, "v")
+    P_m = len(mech.parameters)
+    return [
+        "#define ADJ_KIND 2", "#define ADJ_T0_ZERO 1", f"#define ADJ_PM {P_m}",
+        f"#define ADJ_GATE {lay.gate}", f"#define ADJ_ALPHA {lay.alpha}", f"#define ADJ_MECH {lay.mech}",
+        f"#define ADJ_SGATE {d['sgate']}", f"#define ADJ_SALPHA {d['salpha']}",
+        f"#define ADJ_SMECH {d['smech']}",
+        "__device__ __forceinline__ void adj_mech(const real t, const real* y, const real* thm,",
+        "                                         const real* y0, real* m) {",
+        "  (void)t; (void)y; (void)thm; (void)y0;", *fwd, "}",
+        "__device__ __forceinline__ void adj_mech_vjp(const real t, const real* y, const real* thm,",
+        "                                             const real* y0, const real* fbar, real* ybar,",
+        "                                             real* thbar) {",
+        "  (void)t; (void)y; (void)thm; (void)y0; (void)fbar; (void)thbar;", *vjp,
+        *[f"  ybar[{j}] += yb{j};" for j in range(S)],
+        *[f"  thbar[{p_i}] += tb{p_i};" for p_i in range(P_m)], "}",
+    ]
 
 
 def _adjoint_source(spec: MLPSpec) -> List[str]:
@@ -295,6 +349,8 @@ def _adjoint_source(spec: MLPSpec) -> List[str]:
     if spec.kind == "rateflow":
         out += ["#define ADJ_KIND 1", f"#define ADJ_R {spec.out_size}",
                 f"#define ADJ_STOICH {lay.stoich}", f"#define ADJ_SSTOICH {d['sstoich']}"]
+    if spec.kind == "universalode":
+        out += _adjoint_mech_source(spec, lay, d)
     if d["warps64"] < 1:
         out = ["#if !CTX_F64"] + out + ["#endif"]
     return out

@@ -170,7 +170,9 @@ int ctx_rate_loglik_grad(ctx_model* m, int32_t likelihood, int64_t n_chains, int
 /* ---- NeuralODE training: value and gradient w.r.t. the MLP weights ---------------------------
  * Replaces eqx.filter_value_and_grad of the training loss -- catalax/neural/trainer.py:268-306
  * (y_pred = vmap(model)(ti, y0i); loss(y_pred, yi)) through diffrax's discretise-then-optimise
- * adjoint of neuralode.py:38-59 (Tsit5, t0 = ts[0], SaveAt(ts)).  Two calls around the caller's
+ * adjoint of neuralode.py:38-59 / rateflow.py:100-121 (Tsit5, t0 = ts[0], SaveAt(ts)) and
+ * universalode.py:118-141 (t0 = 0; grad_theta then also carries d/d gate_matrix,
+ * d/d softplus(alpha_residual) and d/d mechanistic parameters at their offsets in theta).  Two calls around the caller's
  * loss: forward integrates, writes ys [B,T,S] and records every accepted step in the workspace;
  * backward takes gys = d loss / d ys [B,T,S] and the SAME workspace and returns
  * grad_theta [n_params] (flat parameter layout of the model) and optionally grad_y0 [B,S].
@@ -190,9 +192,10 @@ int ctx_mlp_adjoint_forward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void
                             const void* theta, const void* ts, void* ys, int32_t* status,
                             int32_t* n_accepted, int32_t* n_rejected, void* workspace,
                             size_t ws_bytes, void* stream);
-int ctx_mlp_adjoint_backward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void* theta,
-                             const void* ts, const void* gys, int32_t* status, void* grad_theta,
-                             void* grad_y0, void* workspace, size_t ws_bytes, void* stream);
+int ctx_mlp_adjoint_backward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void* y0,
+                             const void* theta, const void* ts, const void* gys, int32_t* status,
+                             void* grad_theta, void* grad_y0, void* workspace, size_t ws_bytes,
+                             void* stream);
 
 /* ---- host-buffer convenience (the call a reference-side ctypes binding would make) --------
  * Same as ctx_solve but every array is a HOST pointer; device staging, the H2D / D2H copies

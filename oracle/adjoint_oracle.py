@@ -27,9 +27,31 @@ _ACT = {
 }
 
 
-def mlp_field(weights, biases, activation, final_activation, max_time, stoich=None):
+def sympy_field_torch(states, parameters, exprs):
+    """The mechanistic stack (catalax/tools/stack.py:159-173) as a torch function
+    ``mech(t, y [S], theta [P], y0 [S]) -> [S]`` (sympy.lambdify with torch functions)."""
+    import sympy as sp
+
+    args = [sp.Symbol("t")] + [sp.Symbol(s) for s in states] + [sp.Symbol(p) for p in parameters] \
+        + [sp.Symbol(f"{s}_init") for s in states]
+    mods = [{"exp": torch.exp, "log": torch.log, "sqrt": torch.sqrt, "tanh": torch.tanh,
+             "sin": torch.sin, "cos": torch.cos, "Abs": torch.abs}, "math"]
+    funs = [sp.lambdify(args, sp.sympify(e), modules=mods) for e in exprs]
+
+    def mech(t, y, theta, y0):
+        vals = [t] + [y[i] for i in range(len(states))] + [theta[i] for i in range(len(parameters))] \
+            + [y0[i] for i in range(len(states))]
+        out = [fn(*vals) for fn in funs]
+        return torch.stack([o if torch.is_tensor(o) else torch.tensor(float(o), dtype=torch.float64)
+                            for o in out])
+    return mech
+
+
+def mlp_field(weights, biases, activation, final_activation, max_time, stoich=None, uode=None):
     """NeuralODE field (neuralode.py:49); with ``stoich`` [S,R]: RateFlowODE's
-    ``stoich @ relu(MLP)`` (rateflow.py:87-88, final_activation relu :56)."""
+    ``stoich @ relu(MLP)`` (rateflow.py:87-88, final_activation relu :56); with
+    ``uode = (mech, theta_m, alpha_residual, gate_matrix, y0)``: UniversalODE's
+    ``mech + softplus(alpha) * sigmoid(10 G y) * MLP`` (universalode.py:84-101)."""
     def f(t, y):
         h = torch.cat([y, (t / max_time).reshape(1)])
         for l, (W, b) in enumerate(zip(weights, biases)):
@@ -39,15 +61,20 @@ def mlp_field(weights, biases, activation, final_activation, max_time, stoich=No
             h = _ACT[final_activation if l == len(weights) - 1 else activation](h)
         if stoich is not None:
             h = stoich @ torch.relu(h)
+        if uode is not None:
+            mech, theta_m, alpha, gate, y_init = uode
+            h = mech(t, y, theta_m, y_init) + torch.nn.functional.softplus(alpha) \
+                * torch.sigmoid(10.0 * (gate @ y)) * h
         return h
     return f
 
 
-def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096):
-    """One trajectory: ts [T] (float64 tensor), y0 [S] -> ys [T,S] (differentiable), n_acc, n_rej."""
+def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096, t0=None):
+    """One trajectory: ts [T] (float64 tensor), y0 [S] -> ys [T,S] (differentiable), n_acc, n_rej.
+    t0 = ts[0] (neuralode.py:52) unless given (universalode.py:133: 0.0)."""
     T = ts.shape[0]
     t_end = float(ts[-1])
-    tprev = float(ts[0])
+    tprev = float(ts[0]) if t0 is None else float(t0)
     tnext = min(tprev + dt0, t_end)
     y = y0
     out = [None] * T
@@ -124,3 +151,38 @@ def neuralode_value_and_grad(weights, biases, activation, final_activation, max_
         return (float(loss.detach()), ys.detach().numpy(), gW, gb, gy0, np.array(na), np.array(nr),
                 grads[-1].numpy())
     return float(loss.detach()), ys.detach().numpy(), gW, gb, gy0, np.array(na), np.array(nr)
+
+
+def uode_value_and_grad(weights, biases, activation, final_activation, max_time, ts, y0, loss_fn,
+                        mech_states, mech_parameters, mech_exprs, theta_m, alpha_residual,
+                        gate_matrix, rtol=1e-3, atol=1e-6, dt0=None):
+    """UniversalODE (universalode.py:84-141): t0 = 0, field = mech + softplus(alpha) *
+    sigmoid(10 G y) * MLP.  Returns (loss, ys, grads_W, grads_b, grad_theta_m, grad_alpha,
+    grad_gate, n_accepted, n_rejected)."""
+    Ws = [torch.tensor(np.asarray(W, dtype=np.float64), requires_grad=True) for W in weights]
+    bs = [None if b is None else torch.tensor(np.asarray(b, dtype=np.float64), requires_grad=True)
+          for b in biases]
+    th = torch.tensor(np.asarray(theta_m, dtype=np.float64), requires_grad=True)
+    al = torch.tensor(np.asarray(alpha_residual, dtype=np.float64), requires_grad=True)
+    G = torch.tensor(np.asarray(gate_matrix, dtype=np.float64), requires_grad=True)
+    y0t = torch.tensor(np.asarray(y0, dtype=np.float64))
+    tst = torch.tensor(np.asarray(ts, dtype=np.float64))
+    mech = sympy_field_torch(mech_states, mech_parameters, mech_exprs)
+    ys, na, nr = [], [], []
+    for b in range(y0t.shape[0]):
+        f = mlp_field(Ws, bs, activation, final_activation, float(max_time),
+                      uode=(mech, th, al, G, y0t[b]))
+        step0 = float(tst[b, 1] - tst[b, 0]) if dt0 is None else dt0
+        o, a_, r_ = solve_one(f, tst[b], y0t[b], rtol, atol, step0, max_steps=100000, t0=0.0)
+        ys.append(o); na.append(a_); nr.append(r_)
+    ys = torch.stack(ys)
+    loss = loss_fn(ys)
+    nb = sum(b is not None for b in bs)
+    params = Ws + [b for b in bs if b is not None] + [th, al, G]
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    gW = [g.numpy() for g in grads[:len(Ws)]]
+    gb_iter = iter(grads[len(Ws):len(Ws) + nb])
+    gb = [None if b is None else next(gb_iter).numpy() for b in bs]
+    z = lambda g, like: np.zeros_like(like.detach().numpy()) if g is None else g.numpy()
+    return (float(loss.detach()), ys.detach().numpy(), gW, gb, z(grads[-3], th), z(grads[-2], al),
+            z(grads[-1], G), np.array(na), np.array(nr))

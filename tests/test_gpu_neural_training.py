@@ -155,11 +155,44 @@ def test_rateflow_weight_and_stoichiometry_gradients_f64():
         ctx.enable_x64(False)
 
 
-def test_unsupported_fields_say_so():
+def test_universalode_gradients_f64():
+    """UniversalODE (universalode.py:84-141): mech + softplus(alpha) * sigmoid(10 G y) * MLP,
+    t0 = 0; gradients w.r.t. the MLP weights, the gate matrix, alpha_residual and the mechanistic
+    parameters (all of them inexact-array leaves the reference's optimiser updates)."""
+    import catalax_b200 as ctx
     from catalax_b200.neural import UniversalODE
-    from tests import cases
+    from oracle import adjoint_oracle as ao
 
-    import inspect
-    assert "value_and_grad" in dir(UniversalODE)
-    src = inspect.getsource(UniversalODE.value_and_grad)
-    assert "NotImplementedError" in src      # UniversalODE fields: next round (clear error, no fallback)
+    ctx.enable_x64(True)
+    try:
+        model = ctx.Model(name="decay2")
+        model.add_state(a="a", b="b")
+        model.add_ode("a", "-k1 * a / (K + a)")
+        model.add_ode("b", "k1 * a / (K + a) - k2 * b + 0.01 * a_init")
+        model.parameters.k1.value, model.parameters.k2.value, model.parameters.K.value = 0.8, 0.3, 1.5
+        rng = np.random.default_rng(9)
+        B, T, t1 = 6, 9, 3.0
+        net = UniversalODE(2, 32, 2, model, activation="celu", max_time=t1, key=9,
+                           gate_matrix=0.3 * rng.normal(size=(2, 2)),
+                           alpha_residual=0.2 * rng.normal(size=2))
+        net.weights[-1] = net.weights[-1] * 0.3
+        y0 = rng.uniform(0.5, 2.0, (B, 2))
+        ts = np.tile(np.linspace(0.2, t1, T), (B, 1))           # first save after t0 = 0
+        data = y0[:, None, :] * np.exp(-0.5 * ts)[:, :, None]
+        val, g = net.value_and_grad(ts, y0, data, rtol=1e-7, atol=1e-9)
+        d = torch.tensor(data)
+        loss_fn = lambda ys: (0.5 * (ys - d) ** 2).mean()
+        mech = net.spec.mech
+        rv, rys, rW, rb, gth, gal, gG, rna, rnr = ao.uode_value_and_grad(
+            net.weights, net.biases, net.spec.activation, net.spec.final_activation, net.max_time,
+            ts, y0, loss_fn, mech.states, mech.parameters, mech.total_exprs(), net.parameters,
+            net.alpha_residual, net.gate_matrix, rtol=1e-7, atol=1e-9)
+        assert np.array_equal(net.last["n_accepted"].cpu().numpy(), rna)
+        assert np.array_equal(net.last["n_rejected"].cpu().numpy(), rnr)
+        np.testing.assert_allclose(net.last["ys"].cpu().numpy(), rys, rtol=1e-9, atol=1e-11)
+        assert abs(val - rv) <= 1e-10 * abs(rv)
+        _check(g, rW, rb, 1e-7)
+        for name, ref in (("parameters", gth), ("alpha_residual", gal), ("gate_matrix", gG)):
+            assert np.abs(g[name] - ref).max() <= 1e-7 * np.abs(ref).max(), (name, g[name], ref)
+    finally:
+        ctx.enable_x64(False)
