@@ -1603,7 +1603,9 @@ ctx_loglik_v1(const ctx_loglik_args a) {
 // added to the owning trajectory's accumulators (shared memory) by the last lane of every
 // segment, sequentially in time order starting from the accumulator's value: the summation order
 // of a trajectory is independent of which lanes evaluated it, so results are reproducible.
-#define CTX_LL_RW (2 + CTX_NCOEF + CTX_S)   // tp, 1/dt, coefficients [power][component], sigma
+// tp, 1/dt, coefficients [power][component], then per observable 1/|sigma|, 1/sigma, log|sigma|
+// (the chain's scale enters every term only through these: computed once by the publisher)
+#define CTX_LL_RW (2 + CTX_NCOEF + 3 * CTX_S)
 struct ctx_ll_warp_smem {
   real rec[CTX_LL_RW][32];   // one column per publishing lane of this iteration
   real acc[CTX_KP][32];      // accumulators of the trajectory each lane integrates
@@ -1738,7 +1740,12 @@ ctx_loglik_v2(const ctx_loglik_args a) {
 #pragma unroll
         for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
 #pragma unroll
-        for (int i = 0; i < CTX_S; ++i) w.rec[2 + CTX_NCOEF + i][s] = sg[i];
+        for (int i = 0; i < CTX_S; ++i) {
+          const real sa_ = fabs(sg[i]);
+          w.rec[2 + CTX_NCOEF + 3 * i][s] = R(1.0) / sa_;
+          w.rec[2 + CTX_NCOEF + 3 * i + 1][s] = R(1.0) / sg[i];
+          w.rec[2 + CTX_NCOEF + 3 * i + 2][s] = log(sa_);
+        }
         w.pt0[s] = m * T + idx - off;
         w.off[s] = off;
         w.cnt[s] = nsave;
@@ -1784,25 +1791,29 @@ ctx_loglik_v2(const ctx_loglik_args a) {
             const real x = drow[o];
             const bool use = mrow ? (mrow[o] != 0) : (fabs(x) < CTX_INF);
             if (use) {
-              const real sgo = w.rec[2 + CTX_NCOEF + o][s];
-              const real sd = fabs(sgo);
-              const real z = (x - out[o]) / sd;
-              real lp, dl_dloc, dl_ds;
+              const real inv_sd = w.rec[2 + CTX_NCOEF + 3 * o][s];       // 1 / |sigma|
+              const real inv_sg = w.rec[2 + CTX_NCOEF + 3 * o + 1][s];   // 1 / sigma (sign of d|s|/ds)
+              const real log_sd = w.rec[2 + CTX_NCOEF + 3 * o + 2][s];
+              const real z = (x - out[o]) * inv_sd;
+              real lp, dl_dloc, dl_ds;   // dl_ds: d lp / d sigma (sign included)
               if (a.likelihood == 0) {
-                lp = R(-0.5) * z * z - log(sd) - R(0.9189385332046727418);
-                dl_dloc = z / sd;
-                dl_ds = (z * z - R(1.0)) / sd;
+                lp = R(-0.5) * z * z - log_sd - R(0.9189385332046727418);
+                dl_dloc = z * inv_sd;
+                dl_ds = (z * z - R(1.0)) * inv_sg;
               } else {
+                // one expm1 serves both log(1 + exp(-2|z|)) and tanh(|z|) = -em1 / (2 + em1)
                 const real az = fabs(z);
-                lp = R(-0.4515827052894548647) - log(sd) - (az + ctx_log1p_exp_neg2a(az));
-                const real tz = tanh(z);
-                dl_dloc = tz / sd;
-                dl_ds = (z * tz - R(1.0)) / sd;
+                const real em1 = expm1(R(-2.0) * az);
+                lp = R(-0.4515827052894548647) - log_sd - (az + log1p(R(1.0) + em1));
+                const real ta = -em1 / (R(2.0) + em1);
+                const real tz = z < R(0.0) ? -ta : ta;
+                dl_dloc = tz * inv_sd;
+                dl_ds = (z * tz - R(1.0)) * inv_sg;
               }
               cv[0] += lp;
 #pragma unroll
               for (int d = 0; d < CTX_D_THETA; ++d) cv[1 + d] += dl_dloc * out[CTX_S + d * CTX_S + o];
-              cv[1 + CTX_D_THETA + o] += dl_ds * (sgo < R(0.0) ? R(-1.0) : R(1.0));
+              cv[1 + CTX_D_THETA + o] += dl_ds;
 #pragma unroll
               for (int d = 0; d < CTX_D_Y0; ++d)
                 cv[1 + CTX_D_THETA + CTX_S + d] += dl_dloc * out[CTX_S + (CTX_D_THETA + d) * CTX_S + o];
