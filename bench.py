@@ -178,16 +178,23 @@ def nuts_inputs(chains, M, T, dt, seed):
     theta* + noise; per-chain theta ~ theta* LogN(0, 0.2), sigma ~ LogN(log 0.5, 0.3).
     theta* = (K_m=40, k_cat=0.3): with the README values the discrete tangents of the reference
     algorithm blow up after substrate depletion (tests/test_gpu_parity_loglik.py)."""
-    from oracle import c_oracle
+    import torch
+
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
     from tests import cases
 
     rng = np.random.default_rng(seed)
-    m = cases.michaelis_menten()
     y0s = np.stack([rng.uniform(5, 20, M), np.zeros(M), rng.uniform(50, 300, M)], axis=1)
     ts = np.tile(np.linspace(0, 100, T), (M, 1))
     theta_star = np.array([40.0, 0.3])
-    clean = c_oracle.COracle(*m[:4], m[4], dtype=np.float64).solve(
-        y0s, theta_star, np.zeros((M, 0)), ts, rtol=1e-8, atol=1e-8).ys
+    # noise-free trajectories at theta*: the engine itself in x64 at a tight tolerance (the oracle
+    # is test infrastructure and stays out of the GPU arm)
+    gen = engine.CompiledModel(cg.generate_field(cases.field_spec(cases.michaelis_menten())), "float64")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tt64 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev)
+    clean = gen.solve(tt64(y0s), tt64(theta_star), tt64(np.zeros((M, 0))), tt64(ts),
+                      in_axes=(0, None, 0, 0), rtol=1e-8, atol=1e-8).ys.cpu().numpy()
     data = clean + rng.normal(size=clean.shape) * (0.05 * np.abs(clean) + 1e-3)
     theta = theta_star * np.exp(rng.normal(0, 0.2, (chains, 2)))
     sigma = np.exp(rng.normal(np.log(0.5), 0.3, (chains, 3)))
