@@ -569,8 +569,8 @@ def run_b200(a):
         "config": {"workload": workload_name(a), "rows_total": B * world, "saved_points": T,
                    "l2": f"outputs {B*T*S*w/1e9:.1f} GB/step >> 126 MB L2; inputs rotate over "
                          f"{N_INPUT_SETS} sets",
-                   "kernel": "ctx_solve_v1 (persistent refill + cooperative dense output, 8-point groups, "
-                             "256-bit stores)",
+                   "kernel": "ctx_solve_v2 (producer warps step with lane refill, consumer warps evaluate "
+                             "the dense output: 8-point groups, 256-bit stores)",
                    "failed_rows": total_fails, "steps_per_row": total_steps / (B * world * a.steps)},
         "gpu_launches": launches, "clocks": clocks,
         "saved_points_per_s": B * world * T * a.steps / (ms_max * 1e-3),

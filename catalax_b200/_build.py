@@ -46,10 +46,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     _embed(CSRC / "ctx_integrator.cuh", gen / "ctx_integrator_embed.cpp", "ctx_integrator_src")
     _embed(CSRC / "ctx_mlp_tc.cuh", gen / "ctx_mlp_tc_embed.cpp", "ctx_mlp_tc_src")
     _embed(CSRC / "ctx_mlp_adjoint.cuh", gen / "ctx_mlp_adjoint_embed.cpp", "ctx_mlp_adjoint_src")
+    _embed(CSRC / "ctx_solve_v2.cuh", gen / "ctx_solve_v2_embed.cpp", "ctx_solve_v2_src")
     cu = [str(p) for p in sorted(CSRC.glob("*.cu"))]
     cmd = [NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
            *cu, str(gen / "ctx_integrator_embed.cpp"), str(gen / "ctx_mlp_tc_embed.cpp"),
-           str(gen / "ctx_mlp_adjoint_embed.cpp"), "-o", str(LIB), "-ldl",
+           str(gen / "ctx_mlp_adjoint_embed.cpp"), str(gen / "ctx_solve_v2_embed.cpp"), "-o", str(LIB), "-ldl",
            "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -25,6 +25,7 @@
 extern const char ctx_integrator_src[];  // generated from ctx_integrator.cuh (embed step)
 extern const char ctx_mlp_tc_src[];      // generated from ctx_mlp_tc.cuh
 extern const char ctx_mlp_adjoint_src[]; // generated from ctx_mlp_adjoint.cuh
+extern const char ctx_solve_v2_src[];    // generated from ctx_solve_v2.cuh
 
 namespace {
 
@@ -292,7 +293,7 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0)
     }
   }
   std::string keysrc = src + "\x01" + ctx_integrator_src + "\x01" + ctx_mlp_tc_src + "\x01" +
-                       ctx_mlp_adjoint_src;
+                       ctx_mlp_adjoint_src + "\x01" + ctx_solve_v2_src;
   for (auto& o : opts) keysrc += "\x02" + o;
   const NvrtcApi* nv = nvrtc_api();
   if (!nv) return fail(CTX_E_NVRTC, "libnvrtc.so.12 not found (set CTX_B200_NVRTC to its path)");
@@ -322,9 +323,10 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0)
     }
   }
   nvrtcProgram prog;
-  const char* hdr_src[] = {ctx_integrator_src, ctx_mlp_tc_src, ctx_mlp_adjoint_src};
-  const char* hdr_name[] = {"ctx_integrator.cuh", "ctx_mlp_tc.cuh", "ctx_mlp_adjoint.cuh"};
-  nvrtcResult r = nv->CreateProgram(&prog, src.c_str(), "ctx_model.cu", 3, hdr_src, hdr_name);
+  const char* hdr_src[] = {ctx_integrator_src, ctx_mlp_tc_src, ctx_mlp_adjoint_src, ctx_solve_v2_src};
+  const char* hdr_name[] = {"ctx_integrator.cuh", "ctx_mlp_tc.cuh", "ctx_mlp_adjoint.cuh",
+                            "ctx_solve_v2.cuh"};
+  nvrtcResult r = nv->CreateProgram(&prog, src.c_str(), "ctx_model.cu", 4, hdr_src, hdr_name);
   if (r != NVRTC_SUCCESS) return fail(CTX_E_NVRTC, nv->GetErrorString(r));
   std::vector<const char*> copts;
   for (auto& o : opts) copts.push_back(o.c_str());
@@ -467,6 +469,14 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     // ... and a warp per trajectory (lane = state) beats both once the generated field has a
     // lane-parallel form (config 3, 32 states: 2.4x over the static kernel).
     if (kernel == 1 && m->warp_warps > 0 && !tan) kernel = 4;
+    // Long shared f32 output grids: the warp-specialised form (producer warps step, consumer
+    // warps evaluate and store; ctx_solve_v2.cuh) -- bit-identical, measured 3.55 vs 3.72 ms on
+    // config 2 at T=1000; it loses when stepping dominates (T=16: 1.87 vs 1.73 ms) and in f64
+    // (80 registers per thread), so it is selected only where the output dominates.
+    if (kernel == 2 && !tan && !m->theta_ptr && d.dtype == CTX_F32 && d.n_states <= 4 &&
+        cfg->solver <= CTX_DOPRI5 && a.stride_ts == 0 && cfg->n_times >= 768 &&
+        cfg->batch >= 65536 && cfg->max_steps <= 65536 && !getenv("CTX_B200_NO_V2"))
+      kernel = 5;
   }
   cudaKernel_t k;
   void* params[] = {&a};
@@ -516,6 +526,49 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
                               stream));
+    g_launches++;
+  } else if (kernel == 5) {
+    // warp-specialised persistent kernel (ctx_solve_v2.cuh): producers step, consumers save
+    if (tan || m->theta_ptr || cfg->solver > CTX_DOPRI5)
+      return fail(CTX_E_INVALID, "warp-specialised kernel: symbolic models, Tsit5 / Dopri5, no tangents");
+    if (a.stride_ts != 0)
+      return fail(CTX_E_INVALID, "warp-specialised kernel: the time grid must be shared (in_axes[3] = None)");
+    if (cfg->batch >= (1ll << 31))
+      return fail(CTX_E_INVALID, "persistent kernel: batch must be < 2^31 rows per call");
+    int wide = (d.dtype == CTX_F32 && d.n_states <= 4 && cfg->n_times >= 768) ? 1 : 0;
+    if (const char* ev = getenv("CTX_B200_WIDE_SAVE")) wide = atoi(ev) ? 1 : 0;
+    int rc = get_kernel(m, cfg->solver, 0, "ctx_solve_v2", &k, wide);
+    if (rc) return rc;
+    unsigned info[3] = {0, 0, 0};   // sizeof(v2_prod_smem), producer warps, consumer warps per CTA
+    {
+      std::lock_guard<std::mutex> lk(m->mu);
+      Variant& v = m->variants[cfg->solver * 2 + (wide ? 8 : 0)];
+      void* dptr = nullptr;
+      size_t nbytes = 0;
+      CTX_CUDA(cudaLibraryGetGlobal(&dptr, &nbytes, v.lib, "ctx_v2_info"));
+      CTX_CUDA(cudaMemcpy(info, dptr, sizeof(info), cudaMemcpyDeviceToHost));
+    }
+    const unsigned np = info[1], nc = info[2];
+    const size_t ts_bytes = ((((size_t)cfg->n_times + 7) & ~(size_t)7) * sizeof(real) + 15) & ~(size_t)15;
+    const size_t smem = ts_bytes + (size_t)np * info[0];
+    if (smem > 227 * 1024)
+      return fail(CTX_E_INVALID, "warp-specialised kernel: time grid + step-record ring exceed shared memory");
+    int dev = 0, sms = 0, per_sm = 0;
+    CTX_CUDA(cudaGetDevice(&dev));
+    CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > 48 * 1024)
+      CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    const unsigned block = (np + nc) * 32;
+    CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long grid = (unsigned long long)sms * per_sm;
+    const unsigned long long want = (cfg->batch + 32ull * np - 1) / (32ull * np);
+    if (grid > want) grid = want;
+    a.q_div = (int)std::min<unsigned long long>(1u << 30, 4ull * grid * np);
+    a.ts_smem = 1;
+    CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem, stream));
     g_launches++;
   } else if (kernel == 3) {
     // K3: tcgen05 MLP tiles (ctx_mlp_tc.cuh); theta = [aux | UMMA weight pack]

@@ -661,27 +661,33 @@ __device__ __forceinline__ int ctx_upper_bound(const real* ts, const unsigned sa
 }
 
 // issue the operand copies of the batch [base, base + q_batch) into queue buffer `buf`
-__device__ __forceinline__ void ctx_queue_fetch(const ctx_solve_args& a, ctx_warp_smem& w,
-                                                const int buf, const unsigned long long base,
-                                                const int count, const int lane) {
+__device__ __forceinline__ void ctx_queue_fetch_q(const ctx_solve_args& a, real (*q_in)[CTX_QW][32],
+                                                  const int buf, const unsigned long long base,
+                                                  const int count, const int lane) {
   const unsigned long long u = base + (unsigned long long)lane;
   if (lane < count && u < (unsigned long long)a.B) {
     CTX_ROWS((long long)u, ro, ri);
     (void)ro;
     int k = 0;
 #pragma unroll
-    for (int i = 0; i < CTX_S; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.y0 + (size_t)ri * a.stride_y0 + i);
+    for (int i = 0; i < CTX_S; ++i) ctx_cp_async(&q_in[buf][k++][lane], a.y0 + (size_t)ri * a.stride_y0 + i);
 #if !CTX_THETA_PTR
 #pragma unroll
-    for (int i = 0; i < CTX_P; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.theta + (size_t)ro * a.stride_theta + i);
+    for (int i = 0; i < CTX_P; ++i) ctx_cp_async(&q_in[buf][k++][lane], a.theta + (size_t)ro * a.stride_theta + i);
 #endif
 #pragma unroll
-    for (int i = 0; i < CTX_C; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.consts + (size_t)ri * a.stride_consts + i);
+    for (int i = 0; i < CTX_C; ++i) ctx_cp_async(&q_in[buf][k++][lane], a.consts + (size_t)ri * a.stride_consts + i);
     const real* tr = a.ts + (size_t)ri * a.stride_ts;
-    ctx_cp_async(&w.q_in[buf][k++][lane], tr);
-    ctx_cp_async(&w.q_in[buf][k++][lane], tr + (a.T - 1));
+    ctx_cp_async(&q_in[buf][k++][lane], tr);
+    ctx_cp_async(&q_in[buf][k++][lane], tr + (a.T - 1));
   }
   CTX_CP_COMMIT();
+}
+
+__device__ __forceinline__ void ctx_queue_fetch(const ctx_solve_args& a, ctx_warp_smem& w,
+                                                const int buf, const unsigned long long base,
+                                                const int count, const int lane) {
+  ctx_queue_fetch_q(a, w.q_in, buf, base, count, lane);
 }
 
 // TSM: the time grid is shared by all trajectories and staged in shared memory (ts_sm).
@@ -1378,6 +1384,11 @@ ctx_solve_v1(const ctx_solve_args a) {
 
 // bytes of dynamic shared memory one warp of ctx_solve_v1 needs (read by the host at load time)
 extern "C" __device__ const unsigned ctx_v1_warp_smem_bytes = sizeof(ctx_warp_smem);
+
+#if !CTX_TAN && !CTX_THETA_PTR && CTX_QUEUE && (CTX_SOLVER == 0 || CTX_SOLVER == 1)
+#define CTX_HAVE_V2 1
+#include "ctx_solve_v2.cuh"
+#endif
 
 #endif  // CTX_NO_V1
 

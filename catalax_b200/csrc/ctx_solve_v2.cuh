@@ -1,0 +1,517 @@
+// ctx_solve_v2.cuh -- warp-specialised form of the persistent solve kernel (included by
+// ctx_integrator.cuh for non-tangent builds).
+//
+// Same computation as ctx_solve_v1 (catalax/tools/simulation.py:259-273 under vmap :346-355), same
+// records, same group / pending-merge logic, bit-identical results -- but the two phases of v1
+// run on DIFFERENT warps:
+//   * producer warps (warpgroup 0, V2_PREG registers after setmaxnreg.inc) integrate: lane =
+//     trajectory, refill from the cp.async input queue, one step attempt per iteration.  After an
+//     iteration in which any lane accepted a step that covers requested times they write the
+//     step records into a slot of a shared-memory ring and go on stepping;
+//   * consumer warps (warpgroups 1-2, V2_CREG registers after setmaxnreg.dec) evaluate the dense
+//     output and store: every producer feeds two consumers, one per half-warp of trajectories
+//     (so the pending-group buffers of a trajectory are touched by one consumer only); a
+//     consumer deals the flattened groups of its half of a slot out to its 32 lanes exactly as v1.
+// In v1 every warp needs the registers of both phases (113-128), 16 warps/SM, and a trajectory
+// waits while its warp evaluates the saves of its 31 neighbours.  Here: 8 producer + 16 consumer
+// warps per SM (2 CTAs x 384 threads, 80 registers per thread at launch), stepping and saving
+// overlap, and the irregular stepping never sits between two store passes.
+// Hand-off: per slot one mbarrier "full" (producer lane 0 arrives, release) and one "empty"
+// (lane 0 of both consumers arrive); the ring holds V2_SLOTS iterations.
+#pragma once
+
+#ifndef V2_BACKOFF
+#define V2_BACKOFF 100
+#endif
+#ifndef V2_SETMAXNREG
+#define V2_SETMAXNREG 0
+#endif
+#ifndef V2_PREG
+#define V2_PREG 112
+#endif
+#ifndef V2_CREG
+#define V2_CREG 64
+#endif
+#ifndef V2_NP
+#define V2_NP 6           // producer warps per CTA
+#endif
+#ifndef V2_CPP
+#define V2_CPP 1          // consumers per producer: 1 (whole warp of trajectories) | 2 (half-warps)
+#endif
+#define V2_NC (V2_NP * V2_CPP)
+#define V2_HL (32 / V2_CPP)   // producer lanes served by one consumer
+#ifndef V2_SLOTS
+#define V2_SLOTS 4
+#endif
+
+struct alignas(16) v2_rec {
+  real v[2 + CTX_NPACK];   // tp, 1/dt, polynomial coefficients (packed layout, ctx_pidx)
+  int i0, i1;              // [first, last) requested-time index covered by the step
+  int gf;                  // (first group of the segment) - (its offset in the half's flat list)
+  int owner;               // publishing lane (index of the trajectory's pending-point buffer)
+  unsigned row_lo, row_hi; // address of the trajectory's output row ys[b, 0, 0]
+  int ri;                  // row of its time grid (unused: the grid is shared)
+  int goff;                // offset of the segment in its half's flat group list
+};
+#define V2_REC_Q ((int)(sizeof(v2_rec) / 16))
+union v2_rec_u {
+  v2_rec r;
+  uint4 q[V2_REC_Q];
+  __device__ __forceinline__ v2_rec_u() {}
+};
+
+struct alignas(16) v2_slot {
+  v2_rec rec[32];          // [half * V2_HL + s]: compacted per consumer's share of the lanes
+  int nseg[2], gtotal[2];  // per half: records, flat groups
+  int done, pad[3];        // 1: the producer has retired its last trajectory
+};
+
+struct alignas(16) v2_prod_smem {
+  real q_in[2][CTX_QW][32];              // input queue of the producer
+  v2_slot slot[V2_SLOTS];
+  uint4 pend[32][CTX_PEND_Q];            // per producer lane: the group its trajectory has not completed
+  unsigned long long full[V2_SLOTS], empty[V2_SLOTS];   // mbarriers
+};
+
+__device__ __forceinline__ void v2_mbar_init(const unsigned addr, const int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_arrive(const unsigned addr) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_wait(const unsigned addr, const unsigned parity) {
+  unsigned ok = 0;
+  int spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok) {
+      if (++spins > (1 << 24)) __trap();   // a lost hand-off must not hang the GPU
+#if V2_BACKOFF
+      __nanosleep(V2_BACKOFF);             // leave the issue slots to the warps that have work
+#endif
+    }
+  } while (!ok);
+}
+
+// ------------------------------------------------------------------------------- producer
+__device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_smem& w,
+                                            const real* ts_sm, const unsigned ts_sa) {
+  const int lane = threadIdx.x & 31;
+  const int half = lane / V2_HL;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned half_mask = V2_CPP == 1 ? CTX_FULL : (half ? 0xffff0000u : 0x0000ffffu);
+  const int T = a.T;
+
+  long long b = -1;
+  int phase = 0;
+  real y[CTX_N], ynew[CTX_N], y0[CTX_S];
+#if !CTX_THETA_PTR
+  real th[CTX_P > 0 ? CTX_P : 1];
+#endif
+  real c[CTX_C > 0 ? CTX_C : 1];
+  real K[CTX_NST][CTX_N];
+  real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
+  int idx = 0, nacc = 0, nrej = 0, status = 0;
+  int ri_row = 0;
+  unsigned pub = 0;   // slots published so far
+
+  const unsigned long long Bq = (unsigned long long)a.B;
+  const unsigned long long qdiv = (unsigned long long)a.q_div;
+#define V2_CLAIM(done) ((int)min(32ull, max(1ull, (Bq > (done) ? Bq - (done) : 0ull) / qdiv)))
+  unsigned long long qb_cur = 0, qb_nxt = 0, qb_pend = 0;
+  int qn_cur = V2_CLAIM(0ull), qn_nxt = qn_cur, qn_pend = qn_cur;
+  int q_cur = 0, q_pos = 0;
+  bool q_empty = false;
+  {
+    if (lane == 0) qb_cur = atomicAdd(a.work_counter, (unsigned long long)(2 * qn_cur));
+    qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
+    qb_nxt = qb_cur + qn_cur;
+    ctx_queue_fetch_q(a, w.q_in, 0, qb_cur, qn_cur, lane);
+    ctx_queue_fetch_q(a, w.q_in, 1, qb_nxt, qn_nxt, lane);
+    qn_pend = V2_CLAIM(qb_nxt + qn_nxt);
+    if (lane == 0) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);
+    CTX_CP_WAIT(1);
+    __syncwarp();
+    q_empty = qb_cur >= Bq;
+  }
+
+  while (true) {
+    // ------------------------------------------------------------- refill free lanes
+    const unsigned need = __ballot_sync(CTX_FULL, b < 0);
+    if (need && !q_empty) {
+      const int nval = (int)min((unsigned long long)qn_cur, Bq - qb_cur);
+      const int take = min(__popc(need), nval - q_pos);
+      const int rank = __popc(need & lt_mask);
+      if (b < 0 && rank < take) {
+        const int e = q_pos + rank;
+        b = (long long)qb_cur + e;
+        CTX_ROWS(b, ro, ri);
+        (void)ro;
+        ri_row = (int)ri;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = w.q_in[q_cur][k++][e];
+#if !CTX_THETA_PTR
+#pragma unroll
+        for (int i = 0; i < CTX_P; ++i) th[i] = w.q_in[q_cur][k++][e];
+#endif
+#pragma unroll
+        for (int i = 0; i < CTX_C; ++i) c[i] = w.q_in[q_cur][k++][e];
+        const real t_first = w.q_in[q_cur][k++][e];
+        t_end = w.q_in[q_cur][k++][e];
+        tprev = a.t0_from_ts ? t_first : R(0.0);
+        tnext = fmin(tprev + a.dt0, t_end);
+        idx = 0; nacc = 0; nrej = 0; status = 0;
+        phase = (tprev < t_end) ? 0 : 1;
+        ctx_field(tprev, y, th, c, y0, K[0]);
+      }
+      q_pos += take;
+      if (q_pos >= nval) {
+        CTX_CP_WAIT(0);
+        __syncwarp();
+        const unsigned long long nbase = __shfl_sync(CTX_FULL, qb_pend, 0);
+        ctx_queue_fetch_q(a, w.q_in, q_cur, nbase, qn_pend, lane);
+        qb_cur = qb_nxt; qn_cur = qn_nxt;
+        qb_nxt = nbase; qn_nxt = qn_pend;
+        qn_pend = V2_CLAIM(nbase + qn_nxt);
+        if (lane == 0 && nbase < Bq) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);
+        q_cur ^= 1; q_pos = 0;
+        q_empty = qb_cur >= Bq;
+      }
+    }
+    if (__ballot_sync(CTX_FULL, b >= 0) == 0u) {
+      if (q_empty) break;
+      continue;
+    }
+
+    // ------------------------------------------------------------- one step attempt
+    const bool stepping = (b >= 0) && phase == 0;
+    int nsave = 0;
+    bool accepted = false, retire = false;
+    real rec_tp = R(0.0), rec_dt = R(0.0);
+    if (stepping) {
+      const real dt = tnext - tprev;
+      ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
+      bool keep = true;
+      real dt_next = a.dt0;
+#if CTX_ADAPTIVE
+      const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
+      keep = scaled < R(1.0);
+      const real inv = R(1.0) / scaled;
+      real factor = R(0.9) * ctx_pow02(inv);
+      factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
+      dt_next = dt * factor;
+      if (scaled != scaled) dt_next = scaled;
+#endif
+      rec_tp = tprev; rec_dt = dt;
+      real tp_new = tprev;
+      if (keep) {
+        if (!(tnext < t_end)) nsave = T - idx;
+        else nsave = ctx_upper_bound<true>(ts_sm, ts_sa, idx, T, tnext, t_end) - idx;
+        tp_new = tnext;
+        accepted = true;
+        ++nacc;
+      } else {
+        ++nrej;
+      }
+      tp_new = fmin(tp_new, t_end);
+      real tn = tp_new + dt_next;
+      if (tn > t_end - CTX_TOL_END) tn = keep ? t_end : tp_new + R(0.5) * (t_end - tp_new);
+      const bool done = !(tp_new < t_end);
+      if (!done) {
+        if (!(fabs(tn) < CTX_INF)) status = CTX_ST_BAD;
+        else if (nacc + nrej >= a.max_steps) status = CTX_ST_MAX;
+      }
+      retire = done;
+      tprev = tp_new; tnext = tn;
+      phase = (status != 0) ? 1 : 0;
+    }
+    const bool filling = (b >= 0) && !stepping;
+    if (filling) { nsave = T - idx; retire = true; }
+
+    // ------------------------------------------------------------- publish the step records
+    const unsigned nz = __ballot_sync(CTX_FULL, nsave > 0);
+    if (nz) {
+      const int gq0 = idx >> CTX_GSH;
+      const int ng = nsave > 0 ? ((idx + nsave + CTX_GP - 1) >> CTX_GSH) - gq0 : 0;
+      int incl = ng;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(CTX_FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int tot0 = V2_CPP == 1 ? 0 : __shfl_sync(CTX_FULL, incl, 15);
+      const int tot = __shfl_sync(CTX_FULL, incl, 31);
+      const int goff = incl - ng - (half ? tot0 : 0);
+      const int sl = (int)(pub % V2_SLOTS);
+      const unsigned use = pub / V2_SLOTS;
+      if (use > 0) v2_mbar_wait((unsigned)__cvta_generic_to_shared(&w.empty[sl]), (use - 1u) & 1u);
+      v2_slot& S = w.slot[sl];
+      if (nsave > 0) {
+        const int s = __popc(nz & lt_mask & half_mask);
+        v2_rec_u u;
+        if (filling) {
+          const bool fill_inf = status != 0;
+#pragma unroll
+          for (int i = 0; i < CTX_N; ++i) u.r.v[2 + ctx_pidx(0, i)] = fill_inf ? CTX_INF : y[i];
+#pragma unroll
+          for (int i = CTX_N; i < CTX_NPACK; ++i) u.r.v[2 + i] = R(0.0);
+          u.r.v[0] = R(0.0);
+          u.r.v[1] = R(0.0);
+        } else {
+          ctx_dense_coefs_packed(rec_dt, y, ynew, K, u.r.v + 2);
+          u.r.v[0] = rec_tp;
+          u.r.v[1] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+        }
+        u.r.i0 = idx;
+        u.r.i1 = idx + nsave;
+        u.r.gf = gq0 - goff;
+        u.r.owner = lane;
+        const unsigned long long rowp =
+            reinterpret_cast<unsigned long long>(a.ys + (size_t)b * (size_t)T * CTX_S);
+        u.r.row_lo = (unsigned)rowp;
+        u.r.row_hi = (unsigned)(rowp >> 32);
+        u.r.ri = ri_row;
+        u.r.goff = goff;
+        uint4* dstq = reinterpret_cast<uint4*>(&S.rec[half * V2_HL + s]);
+#pragma unroll
+        for (int k = 0; k < V2_REC_Q; ++k) dstq[k] = u.q[k];
+      }
+      if (lane == 0) {
+        if (V2_CPP == 1) {
+          S.nseg[0] = __popc(nz);
+          S.gtotal[0] = tot;
+        } else {
+          S.nseg[0] = __popc(nz & 0xffffu);
+          S.nseg[1] = __popc(nz >> 16);
+          S.gtotal[0] = tot0;
+          S.gtotal[1] = tot - tot0;
+        }
+        S.done = 0;
+      }
+      __syncwarp();
+      if (lane == 0) v2_mbar_arrive((unsigned)__cvta_generic_to_shared(&w.full[sl]));
+      ++pub;
+    }
+
+    // ------------------------------------------------------------- advance / retire
+    if (accepted) {
+      idx += nsave;
+#pragma unroll
+      for (int i = 0; i < CTX_N; ++i) y[i] = ynew[i];
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1
+#pragma unroll
+      for (int i = 0; i < CTX_N; ++i) K[0][i] = K[6][i];
+#else
+      ctx_field(tprev, y, th, c, y0, K[0]);
+#endif
+    }
+    if ((retire && phase == 0) || filling) {
+      a.status[b] = status;
+      a.n_accepted[b] = nacc;
+      a.n_rejected[b] = nrej;
+      b = -1;
+      phase = 0;
+    }
+  }
+  // final slot: tell the consumers to leave
+  {
+    const int sl = (int)(pub % V2_SLOTS);
+    const unsigned use = pub / V2_SLOTS;
+    if (use > 0) v2_mbar_wait((unsigned)__cvta_generic_to_shared(&w.empty[sl]), (use - 1u) & 1u);
+    if (lane == 0) {
+      v2_slot& S = w.slot[sl];
+      S.nseg[0] = S.nseg[1] = 0;
+      S.gtotal[0] = S.gtotal[1] = 0;
+      S.done = 1;
+    }
+    __syncwarp();
+    if (lane == 0) v2_mbar_arrive((unsigned)__cvta_generic_to_shared(&w.full[sl]));
+  }
+#undef V2_CLAIM
+}
+
+// ------------------------------------------------------------------------------- consumer
+__device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_smem& w, const int half,
+                                            const unsigned ts_sa) {
+  const int lane = threadIdx.x & 31;
+  const unsigned le_mask = CTX_FULL >> (31 - lane);
+  const int T = a.T;
+  unsigned cons = 0;
+  while (true) {
+    const int sl = (int)(cons % V2_SLOTS);
+    const unsigned use = cons / V2_SLOTS;
+    v2_mbar_wait((unsigned)__cvta_generic_to_shared(&w.full[sl]), use & 1u);
+    v2_slot& S = w.slot[sl];
+    const int done = S.done;
+    const int nseg = S.nseg[half];
+    const int gtotal = S.gtotal[half];
+    if (gtotal > 0) {
+      const v2_rec* recs = &S.rec[half * V2_HL];
+      const unsigned myoff = lane < nseg ? (unsigned)recs[lane].goff : 0xffffffffu;
+      int seg_base = 0, s_have = -1;
+      v2_rec_u rr;
+      rr.r.i0 = 0; rr.r.i1 = 0; rr.r.gf = 0; rr.r.owner = 0; rr.r.row_lo = 0; rr.r.row_hi = 0;
+      unsigned bits = __reduce_or_sync(CTX_FULL, myoff < 32u ? (1u << myoff) : 0u);
+      for (int g0 = 0; g0 < gtotal; g0 += 32) {
+        const unsigned bits_cur = bits;
+        if (g0 + 32 < gtotal) {
+          const unsigned dn = myoff - (unsigned)(g0 + 32);
+          bits = __reduce_or_sync(CTX_FULL, dn < 32u ? (1u << dn) : 0u);
+        }
+        const int s = seg_base + __popc(bits_cur & le_mask) - 1;
+        seg_base += __popc(bits_cur);
+        const int g = g0 + lane;
+        const bool act = g < gtotal;
+        if (act && s != s_have) {
+          s_have = s;
+          const uint4* srcq = reinterpret_cast<const uint4*>(&recs[s]);
+#pragma unroll
+          for (int j = 0; j < V2_REC_Q; ++j) rr.q[j] = srcq[j];
+        }
+        const int p0 = (rr.r.gf + g) << CTX_GSH;
+        real o[CTX_GP * CTX_S];
+        if (act) {
+          real tq[CTX_GP];
+#pragma unroll
+          for (int h = 0; h < CTX_GP / 4; ++h) {
+#if CTX_F64
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tq[4 * h]), "=d"(tq[4 * h + 1])
+                : "r"(ts_sa + 8u * (unsigned)p0 + 32u * h));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tq[4 * h + 2]), "=d"(tq[4 * h + 3])
+                : "r"(ts_sa + 8u * (unsigned)p0 + 32u * h + 16u));
+#else
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                : "=f"(tq[4 * h]), "=f"(tq[4 * h + 1]), "=f"(tq[4 * h + 2]), "=f"(tq[4 * h + 3])
+                : "r"(ts_sa + 4u * (unsigned)p0 + 16u * h));
+#endif
+          }
+#pragma unroll
+          for (int u = 0; u < CTX_GP; ++u) {
+            const real th_ = (tq[u] - rr.r.v[0]) * rr.r.v[1];
+#pragma unroll
+            for (int i = 0; i < CTX_S; ++i) {
+              if (ctx_is_const(i)) {
+                o[u * CTX_S + i] = rr.r.v[2 + ctx_pidx(0, i)];
+              } else {
+                real v = rr.r.v[2 + ctx_pidx(CTX_DEG, i)];
+#pragma unroll
+                for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + rr.r.v[2 + ctx_pidx(mm, i)];
+                o[u * CTX_S + i] = v;
+              }
+            }
+          }
+          if (p0 < rr.r.i0) {   // points of this group that earlier steps evaluated
+            union { uint4 q[CTX_PEND_Q]; real v[CTX_GP * CTX_S]; } pd;
+#pragma unroll
+            for (int j = 0; j < CTX_PEND_Q; ++j) pd.q[j] = w.pend[rr.r.owner][j];
+#pragma unroll
+            for (int u = 0; u < CTX_GP - 1; ++u)
+              if (p0 + u < rr.r.i0) {
+#pragma unroll
+                for (int i = 0; i < CTX_S; ++i) o[u * CTX_S + i] = pd.v[u * CTX_S + i];
+              }
+          }
+        }
+        __syncwarp();   // every read of a pending buffer precedes the writes below
+        if (act) {
+          real* dst = reinterpret_cast<real*>(((unsigned long long)rr.r.row_hi << 32) |
+                                              (unsigned long long)rr.r.row_lo) + p0 * CTX_S;
+          if (p0 + CTX_GP <= rr.r.i1) {
+            if ((rr.r.row_lo & 31u) == 0u) {   // whole-sector stores (see ctx_solve_v1)
+#if CTX_F64
+#pragma unroll
+              for (int j = 0; j < CTX_GP * CTX_S / 4; ++j)
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                             "d"(o[4 * j]), "d"(o[4 * j + 1]), "d"(o[4 * j + 2]), "d"(o[4 * j + 3])
+                             : "memory");
+#elif (CTX_GP * CTX_S) % 8 == 0
+#pragma unroll
+              for (int j = 0; j < CTX_GP * CTX_S / 8; ++j)
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j),
+                             "f"(o[8 * j]), "f"(o[8 * j + 1]), "f"(o[8 * j + 2]), "f"(o[8 * j + 3]),
+                             "f"(o[8 * j + 4]), "f"(o[8 * j + 5]), "f"(o[8 * j + 6]), "f"(o[8 * j + 7])
+                             : "memory");
+#else
+              const bool par = ((p0 >> 2) & 1) != 0;
+#pragma unroll
+              for (int j = 0; j < (CTX_S - 1) / 2; ++j) {
+                real v8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v8[e] = par ? o[8 * j + 4 + e] : o[8 * j + e];
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(
+                                 dst + 8 * j + (par ? 4 : 0)),
+                             "f"(v8[0]), "f"(v8[1]), "f"(v8[2]), "f"(v8[3]), "f"(v8[4]), "f"(v8[5]),
+                             "f"(v8[6]), "f"(v8[7]) : "memory");
+              }
+              {
+                real v4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v4[e] = par ? o[e] : o[4 * (CTX_S - 1) + e];
+                asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                 dst + (par ? 0 : 4 * (CTX_S - 1))),
+                             "f"(v4[0]), "f"(v4[1]), "f"(v4[2]), "f"(v4[3]) : "memory");
+              }
+#endif
+            } else {
+#pragma unroll
+              for (int j = 0; j < CTX_GP * CTX_S; ++j) dst[j] = o[j];
+            }
+          } else if (rr.r.i1 == T) {   // ragged last group of the trajectory
+#pragma unroll
+            for (int u = 0; u < CTX_GP - 1; ++u)
+              if (p0 + u < T) {
+#pragma unroll
+                for (int i = 0; i < CTX_S; ++i) dst[u * CTX_S + i] = o[u * CTX_S + i];
+              }
+          } else {                      // incomplete: park it for the step that completes it
+            union { uint4 q[CTX_PEND_Q]; real v[CTX_GP * CTX_S]; } pd;
+#pragma unroll
+            for (int j = 0; j < CTX_GP * CTX_S; ++j) pd.v[j] = o[j];
+#pragma unroll
+            for (int j = 0; j < CTX_PEND_Q; ++j) w.pend[rr.r.owner][j] = pd.q[j];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) v2_mbar_arrive((unsigned)__cvta_generic_to_shared(&w.empty[sl]));
+    ++cons;
+    if (done) break;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__((V2_NP + V2_NC) * 32, 2)
+ctx_solve_v2(const ctx_solve_args a) {
+  // dynamic smem: [shared time grid, padded to a multiple of CTX_GP reals][V2_NP * v2_prod_smem]
+  extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];
+  const int T = a.T;
+  real* ts_sm = reinterpret_cast<real*>(ctx_dyn_smem);
+  unsigned ts_sa = (unsigned)__cvta_generic_to_shared(ts_sm);
+  asm volatile("mov.u32 %0, %0;" : "+r"(ts_sa));
+  const int Tpad = (T + 7) & ~7;
+  for (int i = threadIdx.x; i < Tpad; i += blockDim.x) ts_sm[i] = a.ts[min(i, T - 1)];
+  v2_prod_smem* P = reinterpret_cast<v2_prod_smem*>(ctx_dyn_smem + (((size_t)Tpad * sizeof(real) + 15) & ~(size_t)15));
+  if (threadIdx.x < V2_NP) {
+    for (int s = 0; s < V2_SLOTS; ++s) {
+      v2_mbar_init((unsigned)__cvta_generic_to_shared(&P[threadIdx.x].full[s]), 1);
+      v2_mbar_init((unsigned)__cvta_generic_to_shared(&P[threadIdx.x].empty[s]), V2_CPP);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  if (warp < V2_NP) {
+#if V2_SETMAXNREG   // (needs warpgroup-aligned roles; ptxas 12.9 keeps both roles within the launch count)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V2_PREG));
+#endif
+    v2_producer(a, P[warp], ts_sm, ts_sa);
+  } else {
+#if V2_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_CREG));
+#endif
+    v2_consumer(a, P[(warp - V2_NP) / V2_CPP], (warp - V2_NP) % V2_CPP, ts_sa);
+  }
+}
+
+extern "C" __device__ const unsigned ctx_v2_info[3] = {(unsigned)sizeof(v2_prod_smem), V2_NP, V2_NC};

@@ -9,7 +9,7 @@ python bench.py $ARGS > gpurun_out/${TAG}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py $ARGS > gpurun_out/${TAG}_ncu_launches.log 2>&1
 python bench.py $ARGS > gpurun_out/${TAG}_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:ctx_solve_v1 -s 12 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:ctx_solve_v[12] -s 12 -c 1 \
     -o gpurun_out/${TAG}_solve_full python bench.py $ARGS > gpurun_out/${TAG}_ncu_full.log 2>&1
 python scripts/dev_bench_nuts.py f32 > gpurun_out/${TAG}_nuts_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:ctx_loglik_v2 -s 2 -c 1 \

@@ -77,6 +77,7 @@ def full(rep_name, kernel, label):
 
 
 launches()
-full("solve_full", "ctx_solve_v1", "bench.py f32 T=1000 B=2^20 (Michaelis-Menten, config 2)")
+full("solve_full", "ctx_solve_v2" if tag >= "r1n" else "ctx_solve_v1",
+     "bench.py f32 T=1000 B=2^20 (Michaelis-Menten, config 2)")
 full("loglik_full", "ctx_loglik_v2" if tag >= "r1i" else "ctx_loglik_v1", "config 4: 16384 chains x 64 series x 20 points, f32, SoftLaplace")
 full("mlp_tc_full", "ctx_solve_mlp_tc", "config 5 (B=262144): NeuralODE 5-64-64-64-4 tanh, f32, tcgen05")

@@ -211,3 +211,49 @@ def test_store_paths_agree_bitwise_for_every_state_count(S, dtype, monkeypatch):
         want = y0[:, None, 0] * np.exp(-theta[:, None, 0].astype(np.float64) * ts[None, :].astype(np.float64))
         tol = 2e-4 if dtype == np.float32 else 2e-5
         assert np.abs(res[0][:, :, 0] - want).max() <= tol
+
+
+@pytest.mark.parametrize("S,solver,B,T", [(3, "tsit5", 3001, 37), (3, "tsit5", 70000, 1001),
+                                          (1, "dopri5", 517, 800), (2, "tsit5", 40, 5),
+                                          (4, "dopri5", 9000, 300)])
+def test_warp_specialised_kernel_is_bit_identical_to_the_persistent_kernel(S, solver, B, T):
+    """ctx_solve_v2 (producer warps step, consumer warps evaluate + store, mbarrier ring) is the
+    same arithmetic as ctx_solve_v1 on different warps: same bits, same status / step counts --
+    for batches smaller than the grid, ragged T, failed rows (inf fill), constant states."""
+    import sympy as sp
+
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+
+    if S == 3:
+        model = cases.michaelis_menten()
+        y0, theta, consts = cases.mm_inputs(B, seed=5, dtype=np.float32)
+        theta[:7, 0] = 1e-3                  # stiff rows -> max_steps -> inf fill
+        t1 = 100.0
+    else:
+        states = [f"x{i}" for i in range(S)]
+        params = [f"k{i}" for i in range(S)]
+        odes = {states[i]: -sp.Symbol(params[i]) * sp.Symbol(states[i])
+                + (sp.Float(0.5) * sp.Symbol(states[i - 1]) if i else 0) for i in range(S)}
+        if S == 4:
+            odes[states[3]] = sp.Integer(0)
+        model = (states, params, [], odes, [])
+        rng = np.random.default_rng(S)
+        y0 = rng.uniform(0.5, 2.0, (B, S)).astype(np.float32)
+        theta = rng.uniform(0.05, 1.0, (B, S)).astype(np.float32)
+        consts = np.zeros((B, 0), np.float32)
+        t1 = 20.0
+    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), "float32")
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    ts = np.linspace(0, t1, T).astype(np.float32)
+    outs = []
+    for kernel in (2, 5):
+        o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), in_axes=(0, 0, 0, None), solver=solver,
+                    rtol=1e-6, atol=1e-6, max_steps=512, kernel=kernel)
+        torch.cuda.synchronize()
+        outs.append([x.cpu().numpy() for x in (o.ys, o.status, o.n_accepted, o.n_rejected)])
+    for a_, b_ in zip(*outs):
+        np.testing.assert_array_equal(a_, b_)
+    if S == 3:
+        assert (outs[0][1] != 0).any()
