@@ -426,7 +426,8 @@ def run_b200(a):
     model = engine.CompiledModel(field, np.dtype(dt).name)
     # FMA peak (denominator of the compute rooflines of the side legs) first: the micro-benchmark
     # loads the GPU heavily, nothing timed may run in its wake (input generation + warm-up follow)
-    fma_peak = engine.measure_fma_peak(np.dtype(dt).name) if rank == 0 else None
+    need_peak = rank == 0 and not (a.no_nuts and (a.no_other or world > 1))
+    fma_peak = engine.measure_fma_peak(np.dtype(dt).name) if need_peak else None
 
     # rows are sharded by rank: every rank draws its own seeds (no data-path collective)
     sets = []
