@@ -475,6 +475,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     // (80 registers per thread), so it is selected only where the output dominates.
     if (kernel == 2 && !tan && !m->theta_ptr && d.dtype == CTX_F32 && d.n_states <= 4 &&
         cfg->solver <= CTX_DOPRI5 && a.stride_ts == 0 && cfg->n_times >= 768 &&
+        cfg->n_times <= 8192 /* the grid is staged in shared memory */ &&
         cfg->batch >= 65536 && cfg->max_steps <= 65536 && !getenv("CTX_B200_NO_V2"))
       kernel = 5;
   }
