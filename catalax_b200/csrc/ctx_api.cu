@@ -459,6 +459,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.dt0 = (real)cfg->dt0;
 
   int kernel = cfg->kernel;
+  bool auto_v2 = false;
   const int warps = v1_warps(m->desc, cfg->solver, tan, theta_smem(m));
   if (kernel == 0) {
     // The persistent kernel wins while a trajectory's state fits registers (measured: S=3 f32
@@ -476,12 +477,66 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     if (kernel == 2 && !tan && !m->theta_ptr && d.dtype == CTX_F32 && d.n_states <= 4 &&
         cfg->solver <= CTX_DOPRI5 && a.stride_ts == 0 && cfg->n_times >= 768 &&
         cfg->n_times <= 8192 /* the grid is staged in shared memory */ &&
-        cfg->batch >= 65536 && cfg->max_steps <= 65536 && !getenv("CTX_B200_NO_V2"))
+        cfg->batch >= 65536 && cfg->max_steps <= 65536 && !getenv("CTX_B200_NO_V2")) {
       kernel = 5;
+      auto_v2 = true;
+    }
   }
   cudaKernel_t k;
   void* params[] = {&a};
-  if (kernel == 2) {
+  bool launched = false;
+  if (kernel == 5) {
+    // warp-specialised persistent kernel (ctx_solve_v2.cuh): producers step, consumers save
+    if (tan || m->theta_ptr || cfg->solver > CTX_DOPRI5)
+      return fail(CTX_E_INVALID, "warp-specialised kernel: symbolic models, Tsit5 / Dopri5, no tangents");
+    if (a.stride_ts != 0)
+      return fail(CTX_E_INVALID, "warp-specialised kernel: the time grid must be shared (in_axes[3] = None)");
+    if (cfg->batch >= (1ll << 31))
+      return fail(CTX_E_INVALID, "persistent kernel: batch must be < 2^31 rows per call");
+    int wide = (d.dtype == CTX_F32 && d.n_states <= 4 && cfg->n_times >= 768) ? 1 : 0;
+    if (const char* ev = getenv("CTX_B200_WIDE_SAVE")) wide = atoi(ev) ? 1 : 0;
+    int rc = get_kernel(m, cfg->solver, 0, "ctx_solve_v2", &k, wide);
+    if (rc) return rc;
+    unsigned info[3] = {0, 0, 0};   // sizeof(v2_prod_smem), producer warps, consumer warps per CTA
+    {
+      std::lock_guard<std::mutex> lk(m->mu);
+      Variant& v = m->variants[cfg->solver * 2 + (wide ? 8 : 0)];
+      void* dptr = nullptr;
+      size_t nbytes = 0;
+      CTX_CUDA(cudaLibraryGetGlobal(&dptr, &nbytes, v.lib, "ctx_v2_info"));
+      CTX_CUDA(cudaMemcpy(info, dptr, sizeof(info), cudaMemcpyDeviceToHost));
+    }
+    const unsigned np = info[1], nc = info[2];
+    const size_t ts_bytes = ((((size_t)cfg->n_times + 7) & ~(size_t)7) * sizeof(real) + 15) & ~(size_t)15;
+    const size_t smem = ts_bytes + (size_t)np * info[0];
+    if (smem > 227 * 1024) {
+      if (!auto_v2)
+        return fail(CTX_E_INVALID, "warp-specialised kernel: time grid + step-record ring exceed shared memory");
+      kernel = 2;   // selected automatically but it does not fit: the persistent kernel takes over
+    } else {
+    int dev = 0, sms = 0, per_sm = 0;
+    CTX_CUDA(cudaGetDevice(&dev));
+    CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > 48 * 1024)
+      CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    const unsigned block = (np + nc) * 32;
+    CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long grid = (unsigned long long)sms * per_sm;
+    const unsigned long long want = (cfg->batch + 32ull * np - 1) / (32ull * np);
+    if (grid > want) grid = want;
+    a.q_div = (int)std::min<unsigned long long>(1u << 30, 4ull * grid * np);
+    a.ts_smem = 1;
+    CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem, stream));
+    g_launches++;
+    launched = true;
+    }
+  }
+  if (launched) {
+    // done
+  } else if (kernel == 2) {
     if (warps <= 0)
       return fail(CTX_E_INVALID, "persistent kernel: step record does not fit shared memory");
     if (cfg->batch >= (1ll << 31))
@@ -527,49 +582,6 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
                               stream));
-    g_launches++;
-  } else if (kernel == 5) {
-    // warp-specialised persistent kernel (ctx_solve_v2.cuh): producers step, consumers save
-    if (tan || m->theta_ptr || cfg->solver > CTX_DOPRI5)
-      return fail(CTX_E_INVALID, "warp-specialised kernel: symbolic models, Tsit5 / Dopri5, no tangents");
-    if (a.stride_ts != 0)
-      return fail(CTX_E_INVALID, "warp-specialised kernel: the time grid must be shared (in_axes[3] = None)");
-    if (cfg->batch >= (1ll << 31))
-      return fail(CTX_E_INVALID, "persistent kernel: batch must be < 2^31 rows per call");
-    int wide = (d.dtype == CTX_F32 && d.n_states <= 4 && cfg->n_times >= 768) ? 1 : 0;
-    if (const char* ev = getenv("CTX_B200_WIDE_SAVE")) wide = atoi(ev) ? 1 : 0;
-    int rc = get_kernel(m, cfg->solver, 0, "ctx_solve_v2", &k, wide);
-    if (rc) return rc;
-    unsigned info[3] = {0, 0, 0};   // sizeof(v2_prod_smem), producer warps, consumer warps per CTA
-    {
-      std::lock_guard<std::mutex> lk(m->mu);
-      Variant& v = m->variants[cfg->solver * 2 + (wide ? 8 : 0)];
-      void* dptr = nullptr;
-      size_t nbytes = 0;
-      CTX_CUDA(cudaLibraryGetGlobal(&dptr, &nbytes, v.lib, "ctx_v2_info"));
-      CTX_CUDA(cudaMemcpy(info, dptr, sizeof(info), cudaMemcpyDeviceToHost));
-    }
-    const unsigned np = info[1], nc = info[2];
-    const size_t ts_bytes = ((((size_t)cfg->n_times + 7) & ~(size_t)7) * sizeof(real) + 15) & ~(size_t)15;
-    const size_t smem = ts_bytes + (size_t)np * info[0];
-    if (smem > 227 * 1024)
-      return fail(CTX_E_INVALID, "warp-specialised kernel: time grid + step-record ring exceed shared memory");
-    int dev = 0, sms = 0, per_sm = 0;
-    CTX_CUDA(cudaGetDevice(&dev));
-    CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (smem > 48 * 1024)
-      CTX_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    const unsigned block = (np + nc) * 32;
-    CTX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, (int)block, smem));
-    if (per_sm < 1) per_sm = 1;
-    unsigned long long grid = (unsigned long long)sms * per_sm;
-    const unsigned long long want = (cfg->batch + 32ull * np - 1) / (32ull * np);
-    if (grid > want) grid = want;
-    a.q_div = (int)std::min<unsigned long long>(1u << 30, 4ull * grid * np);
-    a.ts_smem = 1;
-    CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
-    CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem, stream));
     g_launches++;
   } else if (kernel == 3) {
     // K3: tcgen05 MLP tiles (ctx_mlp_tc.cuh); theta = [aux | UMMA weight pack]
