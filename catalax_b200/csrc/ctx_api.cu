@@ -471,11 +471,12 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     // lane-parallel form (config 3, 32 states: 2.4x over the static kernel).
     if (kernel == 1 && m->warp_warps > 0 && !tan) kernel = 4;
     // Long shared f32 output grids: the warp-specialised form (producer warps step, consumer
-    // warps evaluate and store; ctx_solve_v2.cuh) -- bit-identical, measured 3.55 vs 3.72 ms on
-    // config 2 at T=1000; it loses when stepping dominates (T=16: 1.87 vs 1.73 ms) and in f64
-    // (80 registers per thread), so it is selected only where the output dominates.
+    // warps evaluate and store; ctx_solve_v2.cuh) -- bit-identical; measured on config 2 (v1 / v2
+    // ms): T=128 2.12 / 2.13, 250 2.64 / 2.66, 384 2.70 / 2.51, 512 3.01 / 2.68, 1000 3.74 / 3.51,
+    // 2000 5.71 / 5.42; it loses when stepping dominates (T=16: 1.73 / 1.87) and in f64 (80
+    // registers per thread), so it is selected only where the output dominates.
     if (kernel == 2 && !tan && !m->theta_ptr && d.dtype == CTX_F32 && d.n_states <= 4 &&
-        cfg->solver <= CTX_DOPRI5 && a.stride_ts == 0 && cfg->n_times >= 768 &&
+        cfg->solver <= CTX_DOPRI5 && a.stride_ts == 0 && cfg->n_times >= 320 &&
         cfg->n_times <= 8192 /* the grid is staged in shared memory */ &&
         cfg->batch >= 65536 && cfg->max_steps <= 65536 && !getenv("CTX_B200_NO_V2")) {
       kernel = 5;
