@@ -32,8 +32,21 @@
 #ifndef V2_CREG
 #define V2_CREG 64
 #endif
+// Measured on B200 (config 2, T=1000): f32 6 + 6 warps, 2 CTAs/SM (80 registers): 3.51 ms (v1 3.72);
+// f64 8 + 8 warps, 1 CTA/SM (128 registers): 5.76 ms (v1 6.1); f64 at 80 registers spills (7.6 ms).
 #ifndef V2_NP
-#define V2_NP 6           // producer warps per CTA
+#if CTX_F64
+#define V2_NP 8           // producer warps per CTA
+#else
+#define V2_NP 6
+#endif
+#endif
+#ifndef V2_MIN_BLOCKS
+#if CTX_F64
+#define V2_MIN_BLOCKS 1
+#else
+#define V2_MIN_BLOCKS 2
+#endif
 #endif
 #ifndef V2_CPP
 #define V2_CPP 1          // consumers per producer: 1 (whole warp of trajectories) | 2 (half-warps)
@@ -482,7 +495,7 @@ __device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_sme
   }
 }
 
-extern "C" __global__ void __launch_bounds__((V2_NP + V2_NC) * 32, 2)
+extern "C" __global__ void __launch_bounds__((V2_NP + V2_NC) * 32, V2_MIN_BLOCKS)
 ctx_solve_v2(const ctx_solve_args a) {
   // dynamic smem: [shared time grid, padded to a multiple of CTX_GP reals][V2_NP * v2_prod_smem]
   extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];

@@ -213,10 +213,11 @@ def test_store_paths_agree_bitwise_for_every_state_count(S, dtype, monkeypatch):
         assert np.abs(res[0][:, :, 0] - want).max() <= tol
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("S,solver,B,T", [(3, "tsit5", 3001, 37), (3, "tsit5", 70000, 1001),
                                           (1, "dopri5", 517, 800), (2, "tsit5", 40, 5),
                                           (4, "dopri5", 9000, 300)])
-def test_warp_specialised_kernel_is_bit_identical_to_the_persistent_kernel(S, solver, B, T):
+def test_warp_specialised_kernel_is_bit_identical_to_the_persistent_kernel(S, solver, B, T, dtype):
     """ctx_solve_v2 (producer warps step, consumer warps evaluate + store, mbarrier ring) is the
     same arithmetic as ctx_solve_v1 on different warps: same bits, same status / step counts --
     for batches smaller than the grid, ragged T, failed rows (inf fill), constant states."""
@@ -227,7 +228,7 @@ def test_warp_specialised_kernel_is_bit_identical_to_the_persistent_kernel(S, so
 
     if S == 3:
         model = cases.michaelis_menten()
-        y0, theta, consts = cases.mm_inputs(B, seed=5, dtype=np.float32)
+        y0, theta, consts = cases.mm_inputs(B, seed=5, dtype=dtype)
         theta[:7, 0] = 1e-3                  # stiff rows -> max_steps -> inf fill
         t1 = 100.0
     else:
@@ -239,18 +240,24 @@ def test_warp_specialised_kernel_is_bit_identical_to_the_persistent_kernel(S, so
             odes[states[3]] = sp.Integer(0)
         model = (states, params, [], odes, [])
         rng = np.random.default_rng(S)
-        y0 = rng.uniform(0.5, 2.0, (B, S)).astype(np.float32)
-        theta = rng.uniform(0.05, 1.0, (B, S)).astype(np.float32)
-        consts = np.zeros((B, 0), np.float32)
+        y0 = rng.uniform(0.5, 2.0, (B, S)).astype(dtype)
+        theta = rng.uniform(0.05, 1.0, (B, S)).astype(dtype)
+        consts = np.zeros((B, 0), dtype)
         t1 = 20.0
-    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), "float32")
+    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), np.dtype(dtype).name)
     dev = torch.device("cuda:0")
     tt = lambda a: torch.as_tensor(a, device=dev)
-    ts = np.linspace(0, t1, T).astype(np.float32)
+    ts = np.linspace(0, t1, T).astype(dtype)
     outs = []
     for kernel in (2, 5):
-        o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), in_axes=(0, 0, 0, None), solver=solver,
-                    rtol=1e-6, atol=1e-6, max_steps=512, kernel=kernel)
+        try:
+            o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), in_axes=(0, 0, 0, None), solver=solver,
+                        rtol=1e-6, atol=1e-6, max_steps=512, kernel=kernel)
+        except engine.EngineError as exc:
+            # an explicit request that does not fit shared memory is an error (the automatic
+            # selection falls back to the persistent kernel instead)
+            assert kernel == 5 and "shared memory" in str(exc)
+            pytest.skip("step-record ring of this model does not fit shared memory")
         torch.cuda.synchronize()
         outs.append([x.cpu().numpy() for x in (o.ys, o.status, o.n_accepted, o.n_rejected)])
     for a_, b_ in zip(*outs):
