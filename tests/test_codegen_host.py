@@ -136,3 +136,86 @@ def test_lane_parallel_form_is_automatic_only_for_large_structured_models():
     assert not odd.warp_form
     with pytest.raises(cg.UnsupportedExpression):
         cg.generate_field(cg.FieldSpec(states, ["k"], [], odes, []), warp_form=True)
+
+
+def test_constant_state_mask_and_adjoint_layout():
+    """Host-side pieces of the save path / adjoint kernels: states with dy/dt == 0 are flagged
+    (CTX_CONST_MASK), the shared-memory pack of the adjoint kernels fits 227 KB."""
+    import sympy as sp
+
+    from catalax_b200.neural import NeuralODE, RateFlowODE
+    from catalax_b200.tools import codegen as cg, codegen_mlp as cm
+    from tests import cases
+
+    f = cg.generate_field(cases.field_spec(cases.michaelis_menten()))
+    assert "#define CTX_CONST_MASK 0x1u" in f.source          # E (state 0 of [E, P, S]) is constant
+    x, k = sp.symbols("x k")
+    g = cg.generate_field(cg.FieldSpec(["x", "z"], ["k"], [], {"x": -k * x, "z": k * x - k * x}, []))
+    assert "#define CTX_CONST_MASK 0x2u" in g.source          # z: identically zero after expansion
+    for net in (NeuralODE(4, 64, 3, list("abcd"), activation="tanh", max_time=1.0, key=0),
+                RateFlowODE(4, 3, 64, 3, list("abcd"), max_time=1.0, key=0)):
+        d = cm.adjoint_dims(net.spec)
+        assert d is not None and d["warps32"] >= 1 and d["warps64"] >= 1
+        assert (d["spack"] + d["warps32"] * d["per_warp_bwd"]) * 4 <= 227 * 1024
+        assert (d["spack"] + max(1, d["warps64"]) * d["per_warp_bwd"]) * 8 <= 227 * 1024
+    big = NeuralODE(4, 256, 3, list("abcd"), max_time=1.0, key=0)   # 256-wide: does not fit
+    src = cm.generate_mlp_field(big.spec).source
+    assert "CTX_MLP_ADJ" not in src
+
+
+def test_generated_mechanistic_vjp_matches_finite_differences():
+    """UniversalODE adjoint (universalode.py:84-101): the generated adj_mech / adj_mech_vjp,
+    compiled as host C++, against central differences."""
+    import ctypes as C
+    import hashlib
+    import subprocess
+    import tempfile
+    from pathlib import Path
+
+    import catalax_b200 as ctx
+    from catalax_b200.neural import UniversalODE
+    from catalax_b200.tools import codegen_mlp as cm
+
+    model = ctx.Model(name="m")
+    model.add_state(a="a", b="b")
+    model.add_ode("a", "-k1 * a / (K + a) + 0.1 * exp(-t) * b")
+    model.add_ode("b", "k1 * a / (K + a) - k2 * b * b + 0.01 * a_init")
+    for n, v in (("k1", 0.8), ("k2", 0.3), ("K", 1.5)):
+        model.parameters[n].value = v
+    net = UniversalODE(2, 16, 1, model, max_time=1.0, key=0)
+    lines = cm._adjoint_mech_source(net.spec, cm.layout_of(net.spec), cm.adjoint_dims(net.spec))
+    body = "\n".join(l for l in lines if not l.startswith("#define"))
+    src = ("#include <cmath>\ntypedef double real;\n#define R(x) x\n#define __device__\n"
+           "#define __forceinline__ inline\nusing std::exp; using std::log; using std::sqrt;\n" + body +
+           "\nextern \"C\" void f(double t, const double* y, const double* th, const double* y0, double* m)"
+           " { adj_mech(t, y, th, y0, m); }\n"
+           "extern \"C\" void v(double t, const double* y, const double* th, const double* y0,"
+           " const double* fb, double* yb, double* tb) { adj_mech_vjp(t, y, th, y0, fb, yb, tb); }\n")
+    d = Path(tempfile.gettempdir()) / "ctx_hostfield"
+    d.mkdir(exist_ok=True)
+    so = d / f"mech_{hashlib.sha1(src.encode()).hexdigest()[:12]}.so"
+    if not so.exists():
+        (d / (so.stem + ".cpp")).write_text(src)
+        subprocess.run(["g++", "-O1", "-shared", "-fPIC", str(d / (so.stem + ".cpp")), "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    lib.f.argtypes = [C.c_double] + [C.POINTER(C.c_double)] * 4
+    lib.v.argtypes = [C.c_double] + [C.POINTER(C.c_double)] * 6
+    rng = np.random.default_rng(0)
+    t, y, y0 = 0.7, rng.uniform(0.5, 2, 2), rng.uniform(0.5, 2, 2)
+    th = np.asarray(net.parameters, dtype=np.float64).copy()
+    fb = rng.normal(size=2)
+
+    def mech(yy, tt):
+        m = np.zeros(2)
+        lib.f(t, P(np.ascontiguousarray(yy)), P(np.ascontiguousarray(tt)), P(y0), P(m))
+        return m
+
+    yb, tb = np.zeros(2), np.zeros(len(th))
+    lib.v(t, P(y), P(th), P(y0), P(fb), P(yb), P(tb))
+    for j in range(2):
+        e = np.zeros(2); e[j] = 1e-6
+        np.testing.assert_allclose(yb[j], fb @ (mech(y + e, th) - mech(y - e, th)) / 2e-6, rtol=1e-6, atol=1e-9)
+    for p in range(len(th)):
+        e = np.zeros(len(th)); e[p] = 1e-6
+        np.testing.assert_allclose(tb[p], fb @ (mech(y, th + e) - mech(y, th - e)) / 2e-6, rtol=1e-6, atol=1e-9)
