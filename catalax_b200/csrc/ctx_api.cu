@@ -476,7 +476,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     // 2000 5.71 / 5.42; it loses when stepping dominates (T=16: 1.73 / 1.87) and in f64 (80
     // registers per thread), so it is selected only where the output dominates.
     // (f64: 8 + 8 warps in one CTA per SM, T=1000 6.1 -> 5.76 ms; selected for long grids only)
-    if (kernel == 2 && !tan && !m->theta_ptr && d.n_states <= 4 &&
+    if (kernel == 2 && !tan && !m->theta_ptr && d.n_states <= 4 && a.inner == 0 &&
         cfg->solver <= CTX_DOPRI5 && a.stride_ts == 0 &&
         cfg->n_times >= (d.dtype == CTX_F32 ? 320 : 768) &&
         cfg->n_times <= 8192 /* the grid is staged in shared memory */ &&
