@@ -417,18 +417,6 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        # one process per GPU: run on the CPUs next to that GPU, so that the pinned host buffers of
-        # the e2e leg are allocated on its NUMA node (8 ranks x 12.6 GB D2H per step otherwise
-        # cross the socket interconnect).  N=1 keeps all cores: the CPU baseline uses them.
-        try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(
-                int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local])
-                if os.environ.get("CUDA_VISIBLE_DEVICES") else local))
-        except Exception:
-            pass
 
     dt = np_dtype(a)
     tdt = torch.float32 if a.dtype == "f32" else torch.float64
