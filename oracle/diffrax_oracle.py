@@ -73,7 +73,7 @@ def _bcast(a, B, dtype):
 
 def solve(rhs, y0, theta, consts, ts, *, solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,
           max_steps=4096, dtype=np.float64, n_err=None, init_aug=None,
-          record_steps=False, forced_steps=None, t0_from_ts=False):
+          record_steps=False, forced_steps=None, t0_from_ts=False, factor_override=None):
     """Integrate a batch of trajectories the way the reference does.
 
     rhs(t[B], Y[B,N], theta[B,P], consts[B,C], y0[B,S]) -> dY[B,N]  (vectorised over B).
@@ -82,6 +82,10 @@ def solve(rhs, y0, theta, consts, ts, *, solver="tsit5", rtol=1e-5, atol=1e-5, d
     init_aug : optional [B, N-S] initial values of the augmented components (tangents).
     forced_steps : optional list (per lane) of accepted (tprev, tnext) pairs to replay
         instead of running the controller (used to verify tangents by finite differences).
+    factor_override : optional [B, K] array; a finite entry [b, n] replaces the controller's
+        step-size factor after loop iteration n of lane b (NaN = computed factor).  Used by
+        ``tests/test_reference_croissant.py`` to stand in for the step factors that are pure
+        f32 rounding noise in the reference's own run.
     """
     dtype = np.dtype(dtype)
     R = dtype.type
@@ -207,6 +211,12 @@ def solve(rhs, y0, theta, consts, ts, *, solver="tsit5", rtol=1e-5, atol=1e-5, d
                 factor = safety * np.power(inv, expo)
                 lo = np.where(keep, R(1.0), fmin)
                 factor = np.minimum(np.maximum(factor, lo), fmax).astype(dtype)
+                if factor_override is not None:
+                    n_it = nsteps[act]
+                    inside = n_it < factor_override.shape[1]
+                    forced = factor_override[act, np.minimum(n_it, factor_override.shape[1] - 1)]
+                    use = inside & np.isfinite(forced)
+                    factor = np.where(use, forced, factor).astype(dtype)
                 new_dt = (dt * factor).astype(dtype)
             else:
                 keep = np.ones(act.size, dtype=bool)

@@ -1,0 +1,103 @@
+"""The CUDA path against OUTPUTS OF THE REFERENCE ITSELF (see tests/test_reference_pins.py for
+what the two artefacts are and how the oracle is pinned on them).  Everything goes through the
+drop-in facade: ``Model.simulate`` (f32, default config) and ``BayesianModel.log_density``."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import catalax_b200 as ctx
+from oracle import jax_prng
+from tests.test_reference_pins import (HMC_SUMMARY, KM_GRID, SIG_GRID, THETA_TRUE, VM_GRID,
+                                       check_against_hmc_notebook, closed_form,
+                                       fingerprint_cosine, posterior_moments)
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+GOLD = Path(__file__).parent / "golden" / "croissant_menten.npz"
+
+
+def _menten_model():
+    # examples/GenerateData.ipynb cell 3 / examples/HMC.ipynb cell 3
+    model = ctx.Model(name="Simple menten model")
+    model.add_state("s1")
+    model.add_ode("s1", "- (v_max * s1) / ( K_m + s1)")
+    model.parameters["v_max"].value = 7.0
+    model.parameters["K_m"].value = 100.0
+    return model
+
+
+def test_simulate_f32_lands_on_the_reference_trajectories():
+    """GenerateData.ipynb cells 4-5 through the facade on the GPU, f32, default config.  The
+    reference's 120 outputs carry their discretisation error (100x f32 rounding) as a fingerprint
+    of the accepted steps; the CUDA result must carry the same one wherever the rounding-noise
+    factor after the step [0.1, 1.1] falls alike (numpy f32 oracle: 40 % of the series above
+    0.9 cosine, median 0.86; any other solver / tolerance / dt0: <= 16 %, <= 0.65)."""
+    g = np.load(GOLD)
+    data, times = g["data"].astype(np.float64), g["times"]
+    ctx.enable_x64(False)
+    model = _menten_model()
+    dataset = ctx.Dataset.from_model(model)
+    for s0 in g["data"][:, 0]:
+        dataset.add_initial(s1=float(s0))
+    _, result = model.simulate(dataset=dataset, config=ctx.SimulationConfig(t0=0, t1=100),
+                               saveat=times, return_array=True)
+    ys = np.asarray(result.cpu() if hasattr(result, "cpu") else result, dtype=np.float64)[:, :, 0]
+    assert ys.shape == data.shape and np.isfinite(ys).all()
+    truth = closed_form(times.astype(np.float64)[None, :], data[:, :1], THETA_TRUE[1], THETA_TRUE[0])
+    # same accuracy class as the reference's own run ...
+    rms, rms_ref = np.sqrt(((ys - truth) ** 2).mean()), np.sqrt(((data - truth) ** 2).mean())
+    assert 0.4 < rms / rms_ref < 2.5, (rms, rms_ref)
+    assert np.abs(ys - data).max() < 6e-2          # 2 x the reference's own worst error
+    # ... and the same error vectors
+    cos = fingerprint_cosine(ys, data, truth)
+    print(f"fingerprint: frac(cos>0.9)={(cos > 0.9).mean():.3f} median={np.median(cos):.3f} "
+          f"rms/rms_ref={rms / rms_ref:.3f}")
+    assert (cos > 0.9).mean() > 0.25, (cos > 0.9).mean()
+    assert np.median(cos) > 0.7, np.median(cos)
+
+
+def test_log_density_reproduces_the_posterior_of_the_hmc_notebook():
+    """HMC.ipynb cells 3-6: priors Uniform(1e-6, 200) / Uniform(1e-6, 1e3), yerrs=2.0, default
+    SoftLaplace likelihood and HalfNormal(yerrs) noise prior; the log joint evaluated by the CUDA
+    likelihood kernel on a (K_m, v_max, sigma) grid of 94 136 chains x 120 series and integrated
+    must give the posterior mean / sd the reference's NUTS run printed, to 3 MCSE."""
+    from catalax_b200.mcmc import BayesianModel, priors
+
+    g = np.load(GOLD)
+    M, T = g["data"].shape
+    observed = jax_prng.augment_multiplicative(g["data"], 5e-2, seed=0).astype(np.float64)
+    ctx.enable_x64(True)
+    try:
+        model = _menten_model()
+        model.parameters["v_max"].prior = priors.Uniform(low=1e-6, high=200.0)
+        model.parameters["K_m"].prior = priors.Uniform(low=1e-6, high=1e3)
+        assert model.get_parameter_order() == ["K_m", "v_max"]
+        ds = ctx.Dataset.from_jax_arrays(["s1"], observed[:, :, None],
+                                         np.tile(g["times"].astype(np.float64), (M, 1)),
+                                         g["data"][:, :1].astype(np.float64))
+        bm = BayesianModel(model, ds, yerrs=2.0)
+        assert bm.likelihood == "softlaplace"
+        KM, VM, SG = np.meshgrid(KM_GRID, VM_GRID, SIG_GRID, indexing="ij")
+        dev = torch.device("cuda:0")
+        theta = torch.as_tensor(np.stack([KM.ravel(), VM.ravel()], 1), device=dev)
+        sigma = torch.as_tensor(SG.reshape(-1, 1), device=dev)
+        logp, g_th, g_sg = bm.log_density(theta, sigma)
+        torch.cuda.synchronize()
+        logp = logp.cpu().numpy().reshape(KM_GRID.size * VM_GRID.size, SIG_GRID.size)
+        assert np.isfinite(logp).all()
+        th_grid = np.stack([KM[:, :, 0].ravel(), VM[:, :, 0].ravel()], 1)
+        moments, edge = posterior_moments(logp, th_grid, SIG_GRID)
+        print("posterior (CUDA log-density):", {k: (round(m, 4), round(s, 4)) for k, (m, s) in moments.items()},
+              "reference:", HMC_SUMMARY)
+        assert edge < 1e-3, edge
+        check_against_hmc_notebook(moments)
+        # the gradient is the derivative of the pinned density: central differences along the
+        # K_m axis of the grid (spacing 0.3) at the grid's interior, relative to the gradient scale
+        lp3 = logp.reshape(KM_GRID.size, VM_GRID.size, SIG_GRID.size)
+        gk = g_th[:, 0].cpu().numpy().reshape(lp3.shape)
+        fd = (lp3[2:] - lp3[:-2]) / (KM_GRID[2] - KM_GRID[0])
+        assert np.abs(fd - gk[1:-1]).max() < 5e-3 * np.abs(gk).max()   # oracle: 3e-4
+    finally:
+        ctx.enable_x64(False)

@@ -1,0 +1,209 @@
+"""Pin the oracle against OUTPUTS OF THE REFERENCE ITSELF that ship inside /root/reference.  CPU.
+
+Two artefacts of real reference runs exist besides the test fixtures:
+
+1. ``examples/datasets/croissant_dataset.zip`` -- 120 trajectories written by
+   ``examples/GenerateData.ipynb``: ``Model.simulate`` with the DEFAULT config (Tsit5,
+   rtol=atol=1e-5, dt0=0.1, f32) of ``ds1/dt = -v_max s1/(K_m+s1)``, ``K_m=100, v_max=7``, 20
+   points on [0, 100] (``tests/golden/croissant_menten.npz``, made by
+   ``tests/golden/make_croissant_golden.py``).  At this tolerance the discretisation error
+   (up to 2e-2 absolute, inside steps of 40 time units) is 100x the f32 rounding, so
+   ``reference - closed form`` is a fingerprint of diffrax's accepted steps and of the Tsit5
+   dense interpolant -- the step-sequence-level evidence the reference's own asserts
+   (<= 1e-3 against closed forms) cannot give.
+
+   One caveat is physical, not an implementation detail: the step [0.1, 1.1] has a true error
+   estimate of ~1e-9 relative, i.e. its f32 value is rounding noise, and the controller turns
+   that noise into the next step length (factor anywhere in ~[4, 10]).  No second implementation
+   (not even XLA on another CPU) reproduces that number.  The test therefore treats that ONE
+   factor per series as a nuisance parameter (``factor_override``), fitted on the 20 points.
+
+2. ``examples/HMC.ipynb`` cell 6 prints the posterior summary of a real numpyro NUTS run
+   (1000 draws) on that data set after ``augment(seed=0, sigma=5e-2, multiplicative=True)``:
+   ``K_m 102.868 +- 1.043, sigma 2.138 +- 0.041, v_max 7.087 +- 0.035`` with MCSEs
+   0.048 / 0.002 / 0.002.  Posterior moments are functionals of the log-density, so integrating
+   the ORACLE's log-density on a grid must reproduce them to Monte-Carlo error.  The notebook
+   predates the ``sigma_y`` error models: its single ``sigma`` site is the "historical default"
+   HalfNormal(yerrs) (``catalax/mcmc/error.py`` HalfNormal docstring) with SoftLaplace likelihood.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+from scipy.special import lambertw
+
+from oracle import diffrax_oracle as do, jax_prng, loglik_oracle as lo, symbolic as sy
+from oracle.c_oracle import COracle
+
+GOLD = Path(__file__).parent / "golden" / "croissant_menten.npz"
+MENTEN = (["s1"], ["K_m", "v_max"], [], {"s1": "-(v_max * s1) / (K_m + s1)"}, [])
+THETA_TRUE = np.array([100.0, 7.0])
+
+# examples/HMC.ipynb cell 6 (results.summary()): mean, sd, mcse_mean, mcse_sd
+HMC_SUMMARY = {"K_m": (102.868, 1.043, 0.048, 0.034),
+               "sigma": (2.138, 0.041, 0.002, 0.001),
+               "v_max": (7.087, 0.035, 0.002, 0.001)}
+
+
+def _golden():
+    g = np.load(GOLD)
+    return g["data"].astype(np.float64), g["times"].astype(np.float64)
+
+
+def closed_form(t, s0, v, k):
+    return k * np.real(lambertw(s0 / k * np.exp((s0 - v * t) / k)))
+
+
+# ----------------------------------------------------------------------------- jax PRNG KATs
+def test_threefry_and_jax_random_known_answers():
+    # Random123 kat_vectors: threefry2x32_20, zero counter, zero key
+    a, b = jax_prng.threefry2x32(0, 0, [0], [0])
+    assert (int(a[0]), int(b[0])) == (0x6B200159, 0x99BA4EFE)
+    # values printed by jax's documentation for key(0) / key(42): partitionable layout (jax >= 0.5)
+    assert abs(float(jax_prng.uniform(0, 1)[0]) - 0.947667) < 1e-6
+    assert abs(float(jax_prng.normal(0, 1)[0]) - 1.6226422) < 2e-6
+    assert abs(float(jax_prng.normal(42, 1)[0]) + 0.028304616) < 1e-6
+    # ... and the legacy layout (jax < 0.5)
+    assert abs(float(jax_prng.uniform(0, 1, partitionable=False)[0]) - 0.41845703) < 1e-7
+    assert abs(float(jax_prng.normal(0, 1, partitionable=False)[0]) + 0.20584226) < 1e-6
+    assert abs(float(jax_prng.normal(42, 1, partitionable=False)[0]) + 0.18471177) < 1e-6
+
+
+# ------------------------------------------------------------- 1. the reference's trajectories
+def _fit_noise_factor(rhs, data, times, truth, dtype, n_grid=161, **kw):
+    """Best ||oracle(f2) - reference|| / ||reference - closed form|| per series over the factor
+    that follows loop iteration 1 (the step [0.1, 1.1])."""
+    M = data.shape[0]
+    grid = np.linspace(2.0, 10.0, n_grid)
+    G = grid.size
+    fo = np.full((M * G, 2), np.nan)
+    fo[:, 1] = np.tile(grid, M)
+    cfg = {**dict(rtol=1e-5, atol=1e-5, dt0=0.1), **kw}
+    r = do.solve(rhs, np.repeat(data[:, :1], G, axis=0).astype(dtype), THETA_TRUE.astype(dtype),
+                 np.zeros((0,), dtype), times.astype(dtype), dtype=dtype, factor_override=fo, **cfg)
+    assert (r.status == 0).all()
+    ys = r.ys[:, :, 0].astype(np.float64).reshape(M, G, -1)
+    nref = np.linalg.norm(data - truth, axis=1)
+    return (np.linalg.norm(ys - data[:, None, :], axis=2) / nref[:, None]).min(axis=1)
+
+
+def test_oracle_reproduces_the_discretisation_error_of_the_reference_trajectories():
+    data, times = _golden()
+    assert data.shape == (120, 20)
+    truth = closed_form(times[None, :], data[:, :1], THETA_TRUE[1], THETA_TRUE[0])
+    eref = data - truth
+    # the fingerprint is there: errors far above f32 rounding (ulp(300) = 3e-5)
+    assert np.abs(eref).max() > 2e-2 and np.median(np.linalg.norm(eref, axis=1)) > 3e-4
+    rhs, *_ = sy.make_rhs(*MENTEN[:4], MENTEN[4])
+
+    ratio = _fit_noise_factor(rhs, data, times, truth, np.float32)
+    # the oracle explains ~90 % of the reference's error vector in nearly every series
+    # (floor: f32 rounding of both results ~ 0.05-0.1 of the typical error norm)
+    assert np.median(ratio) < 0.15, np.median(ratio)
+    assert (ratio < 0.25).mean() > 0.85, (ratio < 0.25).mean()
+    assert ratio.max() < 0.7, ratio.max()
+
+    # discriminating power: the same fit with another solver, or the tolerance off by 2x,
+    # leaves most of the error unexplained
+    # (measured: correct config median 0.105, 96 % of the series below 0.25;
+    #  Dopri5 0.51 / 0 %, rtol x2 0.52 / 30 %, rtol / 2 0.39 / 23 %)
+    for kw, floor in ((dict(solver="dopri5"), 0.4), (dict(rtol=2e-5, atol=2e-5), 0.4),
+                      (dict(rtol=5e-6, atol=5e-6), 0.3)):
+        wrong = _fit_noise_factor(rhs, data[::2], times, truth[::2], np.float32, n_grid=81, **kw)
+        assert np.median(wrong) > floor, (kw, np.median(wrong))
+        assert (wrong < 0.25).mean() < 0.5, (kw, (wrong < 0.25).mean())
+
+
+def test_unfitted_f32_oracle_matches_the_reference_pattern_in_distribution():
+    """Without any fitted factor the f32 oracle still lands on the reference's error vector for
+    a large fraction of the series (where the rounding-noise factor happens to fall alike); the
+    same statistic is asserted for the CUDA kernel in tests/test_gpu_reference_pins.py.
+    Other configurations: <= 0.16 / <= 0.65 (measured: Dopri5 0.02 / 0.43, rtol 2e-5 0.15 / 0.65,
+    rtol 5e-6 0.16 / 0.61, dt0 0.05 0.10 / 0.41, f64 arithmetic 0.08 / 0.01)."""
+    data, times = _golden()
+    truth = closed_form(times[None, :], data[:, :1], THETA_TRUE[1], THETA_TRUE[0])
+    rhs, *_ = sy.make_rhs(*MENTEN[:4], MENTEN[4])
+    f32 = np.float32
+    r = do.solve(rhs, data[:, :1].astype(f32), THETA_TRUE.astype(f32), np.zeros((0,), f32),
+                 times.astype(f32), rtol=1e-5, atol=1e-5, dt0=0.1, dtype=f32)
+    cos = fingerprint_cosine(r.ys[:, :, 0].astype(np.float64), data, truth)
+    assert (cos > 0.9).mean() > 0.3, (cos > 0.9).mean()
+    assert np.median(cos) > 0.75, np.median(cos)
+
+
+def fingerprint_cosine(ys, data, truth):
+    e, eref = ys - truth, data - truth
+    return (e * eref).sum(1) / (np.linalg.norm(e, axis=1) * np.linalg.norm(eref, axis=1) + 1e-300)
+
+
+# ------------------------------------------------- 2. the reference's published NUTS posterior
+KM_GRID = np.linspace(97.0, 109.0, 41)
+VM_GRID = np.linspace(6.88, 7.30, 41)
+SIG_GRID = np.linspace(1.9, 2.45, 56)
+
+
+def posterior_moments(logp, theta, sig):
+    """Moments of exp(logp [G, n_sigma]) on the tensor grid theta [G, 2] x sig."""
+    w = np.exp(logp - logp.max())
+    w /= w.sum()
+    wt, ws = w.sum(1), w.sum(0)
+    out = {}
+    for name, x, wx in (("K_m", theta[:, 0], wt), ("v_max", theta[:, 1], wt), ("sigma", sig, ws)):
+        m = (wx * x).sum()
+        out[name] = (m, np.sqrt((wx * (x - m) ** 2).sum()))
+    n = KM_GRID.size
+    edge = max(wt.reshape(n, -1).sum(1)[[0, -1]].max(), wt.reshape(n, -1).sum(0)[[0, -1]].max(),
+               ws[[0, -1]].max())
+    return out, edge
+
+
+def check_against_hmc_notebook(moments):
+    for name, (mean, sd, mcse_mean, mcse_sd) in HMC_SUMMARY.items():
+        got_mean, got_sd = moments[name]
+        # 3 Monte-Carlo standard errors + the 3-decimal rounding of the printed table
+        assert abs(got_mean - mean) < 3 * mcse_mean + 5e-4, (name, got_mean, mean)
+        assert abs(got_sd - sd) < 3 * mcse_sd + 5e-4, (name, got_sd, sd)
+
+
+def _theta_grid():
+    KM, VM = np.meshgrid(KM_GRID, VM_GRID, indexing="ij")
+    return np.stack([KM.ravel(), VM.ravel()], 1)
+
+
+def _oracle_logp(sim, observed, likelihood, sig=SIG_GRID):
+    """log joint on the grid: oracle likelihood terms + HalfNormal(yerrs=2) on sigma (uniform
+    priors on K_m / v_max are constant inside their support)."""
+    logp = np.empty((sim.shape[0], sig.size))
+    for j, s in enumerate(sig):
+        lp, _, _ = lo.logpdf_terms(observed[None, :], sim, s, likelihood)
+        logp[:, j] = lp.sum(1) - 0.5 * (s / 2.0) ** 2
+    return logp
+
+
+def test_oracle_log_density_reproduces_the_posterior_of_the_hmc_notebook():
+    data, times = _golden()
+    M, T = data.shape
+    theta = _theta_grid()
+    G = theta.shape[0]
+    # HMC.run -> SimulationConfig defaults rtol=atol=1e-5, dt0=0.1 (mcmc.py:73-79); f64 oracle:
+    # the solver error (1e-5 relative) is far below sigma ~ 2
+    orc = COracle(*MENTEN[:4], MENTEN[4], dtype=np.float64)
+    r = orc.solve(np.tile(data[:, :1], (G, 1)), np.repeat(theta, M, axis=0), np.zeros((G * M, 0)),
+                  times, rtol=1e-5, atol=1e-5, dt0=0.1)
+    assert (r.status == 0).all()
+    sim = r.ys[:, :, 0].reshape(G, M * T)
+
+    observed = jax_prng.augment_multiplicative(data, 5e-2, seed=0).astype(np.float64).ravel()
+    moments, edge = posterior_moments(_oracle_logp(sim, observed, "softlaplace"), theta, SIG_GRID)
+    assert edge < 1e-3, edge                      # the grid holds the whole posterior
+    check_against_hmc_notebook(moments)
+
+    # discriminating power: the other likelihood, or the legacy PRNG layout (another noise
+    # vector), are many standard errors away
+    for lik, part in (("normal", True), ("softlaplace", False)):
+        obs = jax_prng.augment_multiplicative(data, 5e-2, seed=0, partitionable=part)
+        sig = np.linspace(1.9, 6.0, 56) if lik == "normal" else SIG_GRID
+        wrong, _ = posterior_moments(_oracle_logp(sim, obs.astype(np.float64).ravel(), lik, sig),
+                                     theta, sig)
+        with pytest.raises(AssertionError):
+            check_against_hmc_notebook(wrong)
