@@ -235,9 +235,19 @@ class BayesianModel:
     # ------------------------------------------------------------------ log joint
     def log_density(self, theta, sigma):
         """theta [CH,P], sigma [CH,S] (torch, on the GPU) ->
-        (logp [CH], dlogp/dtheta [CH,P], dlogp/dsigma [CH,S])."""
+        (logp [CH], dlogp/dtheta [CH,P], dlogp/dsigma [CH,S]).
+
+        With a ``shared=True`` error model the sampled site is ONE scalar broadcast over the
+        observables (error.py:56-60, 88-91): ``sigma`` is then [CH,1], its prior counts once and
+        the returned gradient is [CH,1] (the sum of the per-observable partials)."""
         import torch
 
+        shared = bool(getattr(self.error_model, "shared", False))
+        if shared:
+            if sigma.shape[-1] != 1:
+                raise ValueError("a shared error model samples one scalar: sigma must be [CH, 1]")
+            site = sigma
+            sigma = site.expand(-1, self.field.S).contiguous()
         block = self.log_likelihood(theta, sigma)
         P = self.field.P
         logp = block[:, 0].clone()
@@ -247,6 +257,9 @@ class BayesianModel:
             logp += prior.log_prob(theta[:, j])
             g_theta[:, j] += prior.grad(theta[:, j])
         hint = torch.as_tensor(self.yerrs, dtype=sigma.dtype, device=sigma.device)
+        if shared:
+            g_sigma = g_sigma.sum(-1, keepdim=True)
+            sigma, hint = site, hint.mean().reshape(1)
         if self.error_model.sampled:
             logp += self.error_model.log_prob(sigma, hint.expand_as(sigma))
             g_sigma += self.error_model.grad(sigma, hint.expand_as(sigma))

@@ -101,3 +101,38 @@ def test_log_density_reproduces_the_posterior_of_the_hmc_notebook():
         assert np.abs(fd - gk[1:-1]).max() < 5e-3 * np.abs(gk).max()   # oracle: 3e-4
     finally:
         ctx.enable_x64(False)
+
+
+def test_masked_three_state_log_density_reproduces_the_inhomogeneous_data_notebook():
+    """InhomogeneousData.ipynb cells 2-5 (three-state inactivation model from the EnzymeML
+    document, last measurement cut and NaN-padded, one noise scalar shared by the three
+    observables): the CUDA likelihood kernel on 2.3 M (K_M, k_cat, k_inact, sigma) chains x 3
+    ragged series, integrated, against the summary the reference's 4-chain NUTS run printed."""
+    from catalax_b200.mcmc import BayesianModel, error
+    from tests.test_reference_pins import (INACT_GRIDS, INACT_SUMMARY, check_against_inactivation_notebook,
+                                           inactivation_model_and_dataset, inactivation_moments)
+
+    ctx.enable_x64(True)
+    try:
+        model, padded, _ = inactivation_model_and_dataset()
+        bm = BayesianModel(model, padded, yerrs=2.0, error_model=error.HalfNormal(shared=True))
+        mesh = np.meshgrid(*INACT_GRIDS, indexing="ij")
+        dev = torch.device("cuda:0")
+        theta = torch.as_tensor(np.stack([m.ravel() for m in mesh[:3]], 1), device=dev)
+        sigma = torch.as_tensor(mesh[3].reshape(-1, 1), device=dev)
+        logp, g_th, g_sg = bm.log_density(theta, sigma)
+        torch.cuda.synchronize()
+        assert g_sg.shape == (theta.shape[0], 1) and torch.isfinite(logp).all()
+        moments, edge = inactivation_moments(logp.cpu().numpy())
+        print("posterior (CUDA log-density):", {k: (round(m, 5), round(s, 5)) for k, (m, s) in moments.items()},
+              "reference:", INACT_SUMMARY)
+        assert edge < 1e-3, edge
+        check_against_inactivation_notebook(moments)
+        # d logp / d sigma of the shared site = central differences along the sigma axis
+        shape = tuple(g.size for g in INACT_GRIDS)
+        lp4 = logp.cpu().numpy().reshape(shape)
+        gs = g_sg[:, 0].cpu().numpy().reshape(shape)
+        fd = (lp4[..., 2:] - lp4[..., :-2]) / (INACT_GRIDS[3][2] - INACT_GRIDS[3][0])
+        assert np.abs(fd - gs[..., 1:-1]).max() < 1e-2 * np.abs(gs).max()
+    finally:
+        ctx.enable_x64(False)

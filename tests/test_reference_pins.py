@@ -207,3 +207,116 @@ def test_oracle_log_density_reproduces_the_posterior_of_the_hmc_notebook():
                                      theta, sig)
         with pytest.raises(AssertionError):
             check_against_hmc_notebook(wrong)
+
+
+# --------------------- 3. a second published posterior: ragged, NaN-masked, three observables
+# examples/InhomogeneousData.ipynb cell 5 (4 chains x 1000 draws): mean, sd, mcse_mean, mcse_sd.
+# Columns the table prints as 0.000 are bounded by the 3-decimal rounding (5e-4).
+INACT_SUMMARY = {"K_M": (187.057, 5.462, 0.088, 0.062),
+                 "k_cat": (1.098, 0.013, 5e-4, 5e-4),
+                 "k_inact": (0.004, 0.000, 5e-4, 5e-4),
+                 "sigma": (1.005, 0.082, 0.001, 0.001)}
+INACT_GRIDS = (np.linspace(162.0, 220.0, 59), np.linspace(1.045, 1.155, 31),
+               np.linspace(0.0030, 0.0054, 31), np.linspace(0.72, 1.42, 41))
+INACT_GOLD = Path(__file__).parent / "golden" / "enzymeml_inactivation.npz"
+
+
+def inactivation_model_and_dataset():
+    """``ctx.from_enzymeml`` + cell 2 + ``dataset.pad()`` of the notebook, from the arrays of the
+    EnzymeML document: three ODEs (Michaelis-Menten with first-order enzyme inactivation), three
+    measurements of 19 points, the last one cut to 9 and NaN-padded back to 19."""
+    import catalax_b200 as ctx
+    from catalax_b200.dataset.measurement import Measurement
+    from catalax_b200.mcmc import priors
+
+    g = np.load(INACT_GOLD)
+    states = [str(s) for s in g["states"]]
+    model = ctx.Model(name="inactivation")
+    model.add_state(**{s: s for s in states})
+    for s, eq in zip(states, g["odes"]):
+        model.add_ode(s, str(eq))
+    model.parameters.k_cat.prior = priors.Uniform(low=0.1, high=2)
+    model.parameters.K_M.prior = priors.Uniform(low=100, high=500)
+    model.parameters.k_inact.prior = priors.Uniform(low=0.0001, high=0.01)
+    assert model.get_parameter_order() == ["K_M", "k_cat", "k_inact"]
+    dataset = ctx.Dataset.from_model(model)
+    for i in range(g["data"].shape[0]):
+        n = 19 if i < 2 else 9                          # species.data[:-10] of the last measurement
+        dataset.add_measurement(Measurement(
+            initial_conditions={s: float(g["y0"][i, j]) for j, s in enumerate(states)},
+            data={s: g["data"][i, :n, j] for j, s in enumerate(states)}, time=g["times"][i, :n]))
+    padded = dataset.pad()
+    assert [len(m.time) for m in padded.measurements] == [19, 19, 19]
+    return model, padded, states
+
+
+def inactivation_moments(logp):
+    """Moments of exp(logp) on the tensor grid INACT_GRIDS (C order)."""
+    shape = tuple(g.size for g in INACT_GRIDS)
+    w = np.exp(logp.reshape(shape) - logp.max())
+    w /= w.sum()
+    out, edge = {}, 0.0
+    for ax, name in enumerate(("K_M", "k_cat", "k_inact", "sigma")):
+        wx = w.sum(tuple(a for a in range(4) if a != ax))
+        m = (wx * INACT_GRIDS[ax]).sum()
+        out[name] = (m, np.sqrt((wx * (INACT_GRIDS[ax] - m) ** 2).sum()))
+        edge = max(edge, wx[0], wx[-1])
+    return out, edge
+
+
+def check_against_inactivation_notebook(moments):
+    for name, (mean, sd, mcse_mean, mcse_sd) in INACT_SUMMARY.items():
+        got_mean, got_sd = moments[name]
+        assert abs(got_mean - mean) < 3 * mcse_mean + 5e-4, (name, got_mean, mean)
+        assert abs(got_sd - sd) < 3 * mcse_sd + 5e-4, (name, got_sd, sd)
+
+
+def test_masked_three_state_posterior_of_the_inhomogeneous_data_notebook():
+    """Host side of the log-density entry point (Dataset.pad, NaN mask, priors, the shared scalar
+    noise site of the notebook's Catalax version) through ``BayesianModel.log_density``; the CUDA
+    likelihood block is replaced by the oracle here (no GPU) and is the real kernel in
+    tests/test_gpu_reference_pins.py."""
+    import torch
+
+    import catalax_b200 as ctx
+    from catalax_b200.mcmc import BayesianModel, error
+
+    ctx.enable_x64(True)
+    try:
+        model, padded, states = inactivation_model_and_dataset()
+        bm = BayesianModel(model, padded, yerrs=2.0, error_model=error.HalfNormal(shared=True),
+                           shard="none")
+        data, times, y0s, consts = bm._arrays
+        assert bm.mask.sum() == 3 * (19 + 19 + 9) and times[2, -1] == 90.0   # pad: 81, 82, ... 90
+        odes = {s: str(model.odes[s].equation) for s in states}
+        orc = COracle(states, ["K_M", "k_cat", "k_inact"], [], odes, dtype=np.float64)
+
+        def oracle_block(theta, sigma):
+            th, sg = theta.numpy(), sigma.numpy()
+            G = th.shape[0]
+            r = orc.solve(np.tile(y0s, (G, 1)), np.repeat(th, 3, axis=0), np.zeros((3 * G, 0)),
+                          np.tile(times, (G, 1)), rtol=1e-5, atol=1e-5, dt0=0.1)
+            assert (r.status == 0).all()
+            ok = bm.mask.ravel()
+            sim, obs = r.ys.reshape(G, -1)[:, ok], data.ravel()[ok]
+            out = np.zeros((G, 1 + 3 + 3))
+            lp, _, _ = lo.logpdf_terms(obs[None, :], sim, sg[:, :1], "softlaplace")
+            out[:, 0] = lp.sum(1)
+            return torch.as_tensor(out)
+
+        bm._local_loglik = oracle_block
+        mesh = np.meshgrid(*INACT_GRIDS[:3], indexing="ij")
+        theta = np.stack([m.ravel() for m in mesh], 1)
+        logp = np.empty((theta.shape[0], INACT_GRIDS[3].size))
+        for j, s in enumerate(INACT_GRIDS[3]):
+            lp, _, g_sg = bm.log_density(torch.as_tensor(theta), torch.full((theta.shape[0], 1), s,
+                                                                            dtype=torch.float64))
+            assert g_sg.shape == (theta.shape[0], 1)
+            logp[:, j] = lp.numpy()
+        moments, edge = inactivation_moments(logp)
+        assert edge < 1e-3, edge
+        check_against_inactivation_notebook(moments)
+        with pytest.raises(ValueError):                 # the shared site is one scalar
+            bm.log_density(torch.as_tensor(theta[:2]), torch.ones((2, 3), dtype=torch.float64))
+    finally:
+        ctx.enable_x64(False)
