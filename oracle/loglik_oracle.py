@@ -12,9 +12,12 @@ and numpyro 0.19's distributions (un-vendored dependency, ``pyproject.toml:17``)
 ``SoftLaplace.log_prob = log(2/pi) - log s - logaddexp(z, -z)``, ``z = (x-loc)/s``.
 The gradient is what ``jax.value_and_grad`` of that log-density gives: the chain rule through
 the discrete tangents of the solve (``diffrax_oracle.solve`` with ``n_err``), ``d/dsigma``
-through ``s = sqrt(sigma^2)``.  PARITY UNPINNED against numpyro itself (the reference asserts
-no log-density or gradient value anywhere); pinned against finite differences of
-the frozen-step oracle and closed-form sensitivities in tests/.
+through ``s = sqrt(sigma^2)``.  PARITY: numpyro cannot be run here and the reference asserts no
+log-density value in its tests; the DENSITY is pinned through the posterior
+summaries two real NUTS runs of the reference printed (``examples/HMC.ipynb``,
+``examples/InhomogeneousData.ipynb``; ``tests/test_reference_pins.py``), the GRADIENT against
+finite differences of the frozen-step oracle and closed-form sensitivities (unpinned against
+``jax.grad`` itself).
 """
 from __future__ import annotations
 
