@@ -96,6 +96,20 @@ def surrogate_rate_jacobian(surrogate, states_flat, times_flat):
     return J
 
 
+def per_species_scale_hint(yerrs, n_obs: int) -> np.ndarray:
+    """``yerrs`` -> default noise scale per observable, shape (n_obs,) (mcmc.py:316-329): the mean
+    over every leading axis when the last axis lines up with the observables (a scalar gives the
+    same value for every species, a full ``[M, T, n_obs]`` array its per-species means), else the
+    global mean broadcast across species."""
+    arr = np.asarray(yerrs, dtype=np.float64)
+    if arr.ndim >= 1 and arr.shape[-1] == n_obs:
+        return arr.reshape(-1, n_obs).mean(axis=0)
+    return np.full(n_obs, arr.mean())
+
+
+_per_species_scale_hint = per_species_scale_hint        # the reference's (private) name
+
+
 class BayesianModel:
     """Batched log-density of the posterior the reference samples with NUTS (mcmc.py:332-491).
 
@@ -140,7 +154,7 @@ class BayesianModel:
         self._series = slice(lo, hi)
         self._arrays = tuple(np.asarray(a, dtype=self.dtype)[lo:hi] for a in (data, times, y0s, constants))
         self.mask = np.isfinite(self._arrays[0])                       # mcmc.py:566
-        self.yerrs = np.broadcast_to(np.asarray(yerrs, dtype=np.float64), data.shape[-1:]).copy()
+        self.yerrs = per_species_scale_hint(yerrs, data.shape[-1])
         self.mode = "surrogate" if (surrogate is not None or surrogate_arrays is not None) else "integrated"
         self._surr = None
         if self.mode == "surrogate":

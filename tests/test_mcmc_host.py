@@ -173,3 +173,101 @@ def test_surrogate_rate_jacobian_by_central_differences_and_series_slicing():
     with pytest.raises(NotImplementedError):
         BayesianModel(model, arrays=(data, times, data[:, 0, :], np.zeros((M, 0))), shard="none",
                       surrogate_arrays=(rates, jac, None), estimate_initials=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference's tests/unit/test_error_model.py, against the facade: how ``yerrs`` becomes the
+# per-observable default scale and how each error model turns it into its prior.  The reference
+# inspects the numpyro distribution handed to ``sample``; here the prior's log-density is compared
+# with scipy's for the scale the reference asserts.
+HINT = np.array([0.1, 1.0, 5.0])
+N_OBS = 3
+
+
+def test_scale_hint_from_yerrs():
+    from catalax_b200.mcmc.mcmc import per_species_scale_hint
+
+    np.testing.assert_allclose(per_species_scale_hint(0.5, N_OBS), np.full(N_OBS, 0.5))       # :39-44
+    np.testing.assert_allclose(per_species_scale_hint(HINT, N_OBS), HINT)                     # :46-49
+    full = np.stack([np.full((4, N_OBS), 0.2), np.full((4, N_OBS), 0.4)]) * np.array([1.0, 2.0, 3.0])
+    np.testing.assert_allclose(per_species_scale_hint(full, N_OBS),                           # :51-64
+                               full.reshape(-1, N_OBS).mean(axis=0))
+    odd = np.array([0.1, 0.2, 0.3, 0.4, 0.5])                                                 # :66-71
+    np.testing.assert_allclose(per_species_scale_hint(odd, N_OBS), np.full(N_OBS, odd.mean()))
+
+
+def _log_prior(em, sigma, hint=HINT):
+    s = torch.as_tensor(np.atleast_2d(sigma), dtype=torch.float64)
+    h = torch.as_tensor(np.ascontiguousarray(hint), dtype=torch.float64)
+    if getattr(em, "shared", False):
+        h = h.mean().reshape(1)
+    return em.log_prob(s, h.expand_as(s)).item()
+
+
+def test_error_model_scale_is_per_species_or_shared_or_explicit():
+    from scipy import stats
+
+    sig = np.array([0.07, 0.8, 3.0])
+    # :102-125 per-species scale / median / rate, one entry per observable
+    assert abs(_log_prior(error.HalfNormal(), sig) - stats.halfnorm(scale=HINT).logpdf(sig).sum()) < 1e-12
+    assert abs(_log_prior(error.LogNormal(sigma=0.7), sig)
+               - stats.lognorm(s=0.7, scale=HINT).logpdf(sig).sum()) < 1e-12
+    assert abs(_log_prior(error.Gamma(concentration=2.0), sig)
+               - stats.gamma(a=2.0, scale=HINT / 2.0).logpdf(sig).sum()) < 1e-12
+    # distinct hints give distinct scales: swapping two hints changes the density
+    assert abs(_log_prior(error.HalfNormal(), sig) - _log_prior(error.HalfNormal(), sig, HINT[::-1])) > 1.0
+    # :131-143 shared=True: ONE scalar site whose scale is the mean of the hint
+    s1 = np.array([0.9])
+    assert abs(_log_prior(error.HalfNormal(shared=True), s1)
+               - stats.halfnorm(scale=HINT.mean()).logpdf(0.9)) < 1e-12
+    assert abs(_log_prior(error.LogNormal(shared=True), s1)
+               - stats.lognorm(s=0.7, scale=HINT.mean()).logpdf(0.9)) < 1e-12
+    # :147-159 an explicit scale / rate ignores the hint
+    assert abs(_log_prior(error.HalfNormal(scale=0.3), sig) - stats.halfnorm(scale=0.3).logpdf(sig).sum()) < 1e-12
+    assert abs(_log_prior(error.Gamma(concentration=2.0, rate=4.0), sig)
+               - stats.gamma(a=2.0, scale=0.25).logpdf(sig).sum()) < 1e-12
+
+
+def test_bayesian_model_uses_the_per_species_hint_and_the_shared_scalar_site():
+    """mcmc.py:464-465 (scale hint from yerrs) and integration/test_mcmc.py:241-256 / 258-293
+    (shared collapses to a scalar; per-species yerrs arrays) through ``log_density`` with a
+    zero likelihood block standing in for the kernel."""
+    import catalax_b200 as ctx
+    from catalax_b200.mcmc import BayesianModel
+    from scipy import stats
+
+    ctx.enable_x64(True)
+    try:
+        model = ctx.Model(name="two")
+        model.add_state(a="a", b="b")
+        model.add_ode("a", "-k * a"); model.add_ode("b", "k * a")
+        model.parameters.k.prior = priors.Uniform(0.1, 2.0)
+        M, T = 2, 4
+        arrays = (np.ones((M, T, 2)), np.tile(np.arange(T, dtype=float), (M, 1)), np.ones((M, 2)),
+                  np.zeros((M, 0)))
+        theta = torch.full((3, 1), 0.5, dtype=torch.float64)
+        zero = lambda th, sg: torch.zeros((th.shape[0], 1 + 1 + 2), dtype=torch.float64)
+        log_k = -math.log(1.9)
+
+        bm = BayesianModel(model, arrays=arrays, yerrs=np.array([0.2, 3.0]), shard="none")
+        bm._local_loglik = zero
+        np.testing.assert_allclose(bm.yerrs, [0.2, 3.0])
+        sg = torch.tensor([[0.1, 2.0]] * 3, dtype=torch.float64)
+        lp, _, g_sg = bm.log_density(theta, sg)
+        want = stats.halfnorm(scale=[0.2, 3.0]).logpdf([0.1, 2.0]).sum() + log_k
+        np.testing.assert_allclose(lp.numpy(), want, rtol=1e-13)
+        np.testing.assert_allclose(g_sg.numpy(), np.tile([-0.1 / 0.04, -2.0 / 9.0], (3, 1)), rtol=1e-13)
+
+        full = np.broadcast_to(np.array([0.2, 3.0]), (M, T, 2)) * np.linspace(0.5, 1.5, T)[None, :, None]
+        assert np.allclose(BayesianModel(model, arrays=arrays, yerrs=full, shard="none").yerrs, [0.2, 3.0])
+
+        sh = BayesianModel(model, arrays=arrays, yerrs=np.array([0.2, 3.0]), shard="none",
+                           error_model=error.HalfNormal(shared=True))
+        sh._local_loglik = lambda th, sg: torch.cat([torch.zeros((th.shape[0], 2), dtype=torch.float64),
+                                                     sg * 10.0], dim=1)     # d/dsigma_j = 10 sigma_j
+        lp, _, g_sg = sh.log_density(theta, torch.full((3, 1), 0.7, dtype=torch.float64))
+        np.testing.assert_allclose(lp.numpy(), stats.halfnorm(scale=1.6).logpdf(0.7) + log_k, rtol=1e-13)
+        assert g_sg.shape == (3, 1)                       # sum of the two partials + the prior's
+        np.testing.assert_allclose(g_sg.numpy(), 2 * 7.0 - 0.7 / 1.6 ** 2, rtol=1e-13)
+    finally:
+        ctx.enable_x64(False)
