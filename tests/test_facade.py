@@ -151,3 +151,59 @@ def test_reference_model_json_loads():
 
     f = cg.generate_field(spec)
     assert f.S == 4 and f.P == 10 and f.C == 1 and f.uses_t
+
+
+# The reference's tests/unit/model/test_reaction.py (scheme strings -> reactants / products) and
+# tests/unit/model/test_stoich.py (matrix layout), case by case against the facade.
+SCHEMES = [
+    ("A + B -> C", [(1.0, "A"), (1.0, "B")], [(1.0, "C")]),
+    ("A + B <-> C", [(1.0, "A"), (1.0, "B")], [(1.0, "C")]),
+    ("2 A + 3 B -> 4 C", [(2.0, "A"), (3.0, "B")], [(4.0, "C")]),
+    ("1.5 A + 2.5 B -> 3.0 C", [(1.5, "A"), (2.5, "B")], [(3.0, "C")]),
+    ("reactant_1 + reactant_2 -> product_1", [(1.0, "reactant_1"), (1.0, "reactant_2")], [(1.0, "product_1")]),
+    ("H2 + O2 -> H2O", [(1.0, "H2"), (1.0, "O2")], [(1.0, "H2O")]),
+    ("2 H2 + O2 -> 2 H2O", [(2.0, "H2"), (1.0, "O2")], [(2.0, "H2O")]),
+    ("A -> B -> C", [(1.0, "A")], [(1.0, "B")]),                    # first arrow splits, rest ignored
+    ("  A  +  B  ->  C  ", [(1.0, "A"), (1.0, "B")], [(1.0, "C")]),
+    ("A -> B + C + D", [(1.0, "A")], [(1.0, "B"), (1.0, "C"), (1.0, "D")]),
+    ("A <===> B", [(1.0, "A")], [(1.0, "B")]),
+    ("1 A + 2.5 B + 3 C -> 4.5 D", [(1.0, "A"), (2.5, "B"), (3.0, "C")], [(4.5, "D")]),
+]
+
+
+@pytest.mark.parametrize("schema,reactants,products", SCHEMES)
+def test_scheme_cases_of_the_reference(schema, reactants, products):
+    r = Reaction.from_scheme(symbol="r", schema=schema, equation="k*A", reversible="<" in schema)
+    assert [(e.stoichiometry, e.state) for e in r.reactants] == reactants
+    assert [(e.stoichiometry, e.state) for e in r.products] == products
+    assert r.reversible is ("<" in schema) and r.symbol == "r"
+
+
+@pytest.mark.parametrize("schema,message", [
+    ("-> A", "Reaction must have at least one reactant and one product"),
+    ("A ->", "Reaction must have at least one reactant and one product"),
+    ("A + B", "No supported arrow pattern found"),
+    ("A + @invalid -> B", "Could not parse term"),
+    ("0 A + 1 B -> C", "Stoichiometries must be positive and not zero"),
+])
+def test_scheme_errors_of_the_reference(schema, message):
+    with pytest.raises(ValueError, match=message):
+        Reaction.from_scheme(symbol="r", schema=schema, equation="k", reversible=False)
+
+
+def test_stoichiometry_matrix_layout():
+    """test_stoich.py: rows = species in the given order, columns = reactions in sorted-symbol
+    order (stoich.py:47-59), overlapping species accumulate, absent species give zero rows."""
+    from catalax_b200.model.stoich import derive_stoich_matrix
+
+    mk = lambda sym, lhs, rhs: Reaction.from_scheme(symbol=sym, schema=f"{lhs} -> {rhs}", equation="k",
+                                                    reversible=False)
+    np.testing.assert_array_equal(derive_stoich_matrix([mk("r1", "A", "B")], ["A", "B"]), [[-1.0], [1.0]])
+    two = [mk("r1", "2 A + B", "C"), mk("r2", "C", "D + E")]
+    np.testing.assert_array_equal(derive_stoich_matrix(two, ["A", "B", "C", "D", "E"]),
+                                  [[-2, 0], [-1, 0], [1, -1], [0, 1], [0, 1]])
+    # reaction ordering: columns follow the sorted symbols whatever the list order
+    np.testing.assert_array_equal(derive_stoich_matrix(two[::-1], ["A", "B", "C", "D", "E"]),
+                                  [[-2, 0], [-1, 0], [1, -1], [0, 1], [0, 1]])
+    np.testing.assert_array_equal(derive_stoich_matrix([mk("r1", "A", "B")], ["A", "B", "X"]),
+                                  [[-1.0], [1.0], [0.0]])
