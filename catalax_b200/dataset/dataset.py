@@ -101,13 +101,32 @@ class Dataset:
         return SimulationConfig(t0=t0, t1=t1, nsteps=nsteps)
 
     def pad(self) -> "Dataset":
-        """Pad every measurement to the longest one: time continues last+1, last+2, ...,
-        data is NaN (dataset.py:256-330)."""
-        tmax = max(len(m.time) for m in self.measurements)
-        out = Dataset(states=self.states, id=self.id, name=self.name)
+        """A copy with uniform array lengths (dataset.py:256-330): the maximum length is the longest
+        ``time`` array (measurements without time are ignored for it); every measurement gets a
+        ``data`` entry for every state of the dataset -- right-padded with NaN, all-NaN when the
+        state has no data; ``time`` continues monotonically (last+1, last+2, ...; 0, 1, ... when it
+        is empty) and stays ``None`` when it was ``None``.  The original is left untouched."""
+        max_len = max((len(m.time) for m in self.measurements if m.time is not None), default=0)
         for m in self.measurements:
-            n = tmax - len(m.time)
-            time = np.concatenate([m.time, m.time[-1] + np.arange(1, n + 1, dtype=m.time.dtype)])
-            data = {s: np.concatenate([v, np.full(n, np.nan, dtype=v.dtype)]) for s, v in m.data.items()}
-            out.measurements.append(Measurement(m.initial_conditions, data, time, id=m.id))
+            missing = sorted(set(self.states) - set(m.initial_conditions))
+            if missing:
+                raise ValueError(f"Measurement {m.id} missing definition of initial condition "
+                                 f"for states: {missing}")
+        out = Dataset(states=list(self.states), id=self.id, name=self.name)
+        dt = default_dtype()
+        for m in self.measurements:
+            time = m.time
+            if time is not None and len(time) < max_len:
+                start = time[-1] + 1.0 if len(time) else 0.0
+                time = np.concatenate([time, start + np.arange(max_len - len(time), dtype=dt)])
+            data = {k: v for k, v in m.data.items() if k not in self.states}
+            for s in self.states:
+                v = m.data.get(s)
+                if v is None:
+                    data[s] = np.full(max_len, np.nan, dtype=dt)
+                else:
+                    data[s] = np.concatenate([v, np.full(max(max_len - len(v), 0), np.nan, dtype=dt)])
+            padded = Measurement(dict(m.initial_conditions), None, time, id=m.id, name=m.name)
+            padded.data = data                       # lengths need not match a ``None`` time
+            out.measurements.append(padded)
         return out

@@ -207,3 +207,65 @@ def test_stoichiometry_matrix_layout():
                                   [[-2, 0], [-1, 0], [1, -1], [0, 1], [0, 1]])
     np.testing.assert_array_equal(derive_stoich_matrix([mk("r1", "A", "B")], ["A", "B", "X"]),
                                   [[-1.0], [1.0], [0.0]])
+
+
+# The reference's tests/unit/dataset/test_dataset.py (Dataset.pad: the ragged-input path that
+# feeds the NaN-masked likelihood), case by case.
+def _meas(id, time, inits, data):
+    from catalax_b200.dataset.measurement import Measurement
+
+    return Measurement(id=id, time=time, initial_conditions=inits, data=data)
+
+
+def test_pad_leaves_equal_lengths_alone_and_copies():
+    ds = ctx.Dataset(states=["s1", "s2"], id="test_pad")
+    ds.add_measurement(_meas("m1", [0, 1, 2], {"s1": 1.0, "s2": 2.0}, {"s1": [1.0, 1.1, 1.2], "s2": [2.0, 2.1, 2.2]}))
+    ds.add_measurement(_meas("m2", [0, 1, 2], {"s1": 3.0, "s2": 4.0}, {"s1": [3.0, 3.1, 3.2], "s2": [4.0, 4.1, 4.2]}))
+    padded = ds.pad()
+    assert padded is not ds and len(padded.measurements) == 2
+    for a, b in zip(padded.measurements, ds.measurements):
+        assert a is not b and a.id == b.id
+        for s in ("s1", "s2"):
+            np.testing.assert_allclose(a.data[s], b.data[s])
+        np.testing.assert_allclose(a.time, b.time)
+
+
+def test_pad_missing_state_and_ragged_lengths():
+    ds = ctx.Dataset(states=["s1", "s2"], id="test_pad")
+    ds.add_measurement(_meas("m1", [0, 1, 2, 3], {"s1": 1.0, "s2": 2.0},
+                             {"s1": [1.0, 1.1, 1.2, 1.3], "s2": [2.0, 2.1, 2.2, 2.3]}))
+    ds.add_measurement(_meas("m2", [0, 1], {"s1": 3.0, "s2": 4.0}, {"s1": [3.0, 3.1]}))   # no s2 data
+    ds.add_measurement(_meas("m3", [0, 1, 2], {"s1": 5.0, "s2": 6.0}, {"s1": [5.0, 5.1, 5.2], "s2": [6.0, 6.1, 6.2]}))
+    padded = ds.pad()
+    m1, m2, m3 = padded.measurements
+    assert not np.isnan(m1.data["s1"]).any() and not np.isnan(m1.data["s2"]).any()
+    np.testing.assert_allclose(m2.data["s1"][:2], [3.0, 3.1])
+    assert np.isnan(m2.data["s1"][2:]).all() and len(m2.data["s1"]) == 4
+    assert np.isnan(m2.data["s2"]).all() and len(m2.data["s2"]) == 4          # added as NaN array
+    np.testing.assert_allclose(m2.time, [0, 1, 2, 3])                          # continues with +1
+    np.testing.assert_allclose(m3.data["s2"][:3], [6.0, 6.1, 6.2])
+    assert np.isnan(m3.data["s2"][3:]).all() and m3.time.tolist() == [0, 1, 2, 3]
+    # the original is untouched
+    assert "s2" not in ds.measurements[1].data and len(ds.measurements[1].data["s1"]) == 2
+    assert len(ds.measurements[2].time) == 3
+    # ... and the padded arrays are what the masked likelihood consumes
+    data, times, y0s = padded.to_jax_arrays(["s1", "s2"], inits_to_array=True)
+    assert data.shape == (3, 4, 2) and times.shape == (3, 4) and y0s.shape == (3, 2)
+    assert np.isfinite(data).sum() == 8 + 2 + 6
+
+
+def test_pad_measurement_with_initial_conditions_only():
+    ds = ctx.Dataset(states=["s1", "s2"], id="test_pad")
+    ds.add_measurement(_meas("m1", [0, 1, 2], {"s1": 1.0, "s2": 2.0}, {"s1": [1.0, 1.1, 1.2], "s2": [2.0, 2.1, 2.2]}))
+    ds.add_measurement(_meas("m2", None, {"s1": 3.0, "s2": 4.0}, {}))
+    m1, m2 = ds.pad().measurements
+    assert len(m1.data["s1"]) == 3 and len(m1.data["s2"]) == 3
+    assert len(m2.data["s1"]) == 3 and np.isnan(m2.data["s1"]).all() and np.isnan(m2.data["s2"]).all()
+    assert m2.time is None
+
+
+def test_pad_needs_initial_conditions_for_every_state():
+    ds = ctx.Dataset(states=["s1", "s2"], id="test_pad")
+    ds.measurements.append(_meas("m1", [0, 1], {"s1": 1.0}, {"s1": [1.0, 1.1]}))
+    with pytest.raises(ValueError, match="missing definition of initial condition"):
+        ds.pad()
