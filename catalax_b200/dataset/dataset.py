@@ -100,6 +100,18 @@ class Dataset:
         t1 = np.array([m.time[-1] for m in self.measurements], dtype=default_dtype())
         return SimulationConfig(t0=t0, t1=t1, nsteps=nsteps)
 
+    def augment(self, n_augmentations: int, sigma: float = 0.5, seed: int = 42, append: bool = True,
+                multiplicative: bool = False) -> "Dataset":
+        """Noise-augmented copies of every measurement (dataset.py:1201-1250): augmentation ``i``
+        uses ``seed + i`` for ALL measurements; ``append`` keeps the originals in front."""
+        out = Dataset(states=list(self.states), id=self.id, name=self.name)
+        if append:
+            out.measurements = list(self.measurements)
+        for i in range(n_augmentations):
+            for m in self.measurements:
+                out.measurements.append(m.augment(sigma=sigma, seed=seed + i, multiplicative=multiplicative))
+        return out
+
     def pad(self) -> "Dataset":
         """A copy with uniform array lengths (dataset.py:256-330): the maximum length is the longest
         ``time`` array (measurements without time are ignored for it); every measurement gets a

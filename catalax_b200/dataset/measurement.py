@@ -45,5 +45,19 @@ class Measurement:
                  if inits_to_array else self.initial_conditions)
         return data, time, inits
 
+    def augment(self, sigma: float, seed: int, multiplicative: bool = False) -> "Measurement":
+        """A copy with Gaussian noise on every state's data (measurement.py:759-817): the noise
+        vector is ``jax.random.normal(PRNGKey(seed), x.shape)`` -- the same key for every state,
+        as in the reference -- applied as ``x * (noise * sigma + 1)`` or ``x + noise * sigma``.
+        Initial conditions and time are kept; the copy gets a new id."""
+        from . import jaxrandom
+
+        data = {}
+        for state, x in self.data.items():
+            noise = jaxrandom.normal(int(seed), x.shape[0], x.dtype)
+            scale = x.dtype.type(sigma)
+            data[state] = x * (noise * scale + x.dtype.type(1.0)) if multiplicative else x + noise * scale
+        return Measurement(dict(self.initial_conditions), data, self.time, id=str(uuid.uuid4()))
+
     def to_y0_array(self, state_order: List[str]) -> np.ndarray:
         return np.array([self.initial_conditions[s] for s in state_order], dtype=default_dtype())

@@ -269,3 +269,30 @@ def test_pad_needs_initial_conditions_for_every_state():
     ds.measurements.append(_meas("m1", [0, 1], {"s1": 1.0}, {"s1": [1.0, 1.1]}))
     with pytest.raises(ValueError, match="missing definition of initial condition"):
         ds.pad()
+
+
+def test_augment_draws_the_reference_noise():
+    """Dataset.augment / Measurement.augment (dataset.py:1201-1250, measurement.py:759-817): the
+    noise is jax.random.normal(PRNGKey(seed + i)) -- bitwise the oracle's restatement, which is
+    pinned by known answers and by the HMC.ipynb posterior (tests/test_reference_pins.py)."""
+    from oracle import jax_prng
+
+    ctx.enable_x64(False)
+    ds = ctx.Dataset(states=["s1", "s2"], id="aug")
+    t = np.arange(20, dtype=np.float32)
+    ds.add_measurement(_meas("m1", t, {"s1": 100.0, "s2": 1.0}, {"s1": 100.0 - 3 * t, "s2": 1.0 + t}))
+    ds.add_measurement(_meas("m2", t, {"s1": 50.0, "s2": 2.0}, {"s1": 50.0 - t, "s2": 2.0 + t}))
+    mult = ds.augment(n_augmentations=1, seed=0, sigma=5e-2, append=False, multiplicative=True)   # HMC.ipynb cell 4
+    assert len(mult.measurements) == 2 and mult.measurements[0].id != "m1"
+    z = jax_prng.normal(0, 20)
+    for a, b in zip(mult.measurements, ds.measurements):
+        assert a.initial_conditions == b.initial_conditions and np.array_equal(a.time, b.time)
+        for s in ("s1", "s2"):                      # the same noise vector for every state and series
+            np.testing.assert_array_equal(a.data[s], b.data[s] * (z * np.float32(5e-2) + np.float32(1.0)))
+    add = ds.augment(n_augmentations=3, sigma=0.01)                          # NeuralODE.ipynb cell 4
+    assert len(add.measurements) == 2 + 3 * 2 and add.measurements[0] is ds.measurements[0]
+    for i in range(3):
+        zi = jax_prng.normal(42 + i, 20)
+        np.testing.assert_array_equal(add.measurements[2 + 2 * i + 1].data["s2"],
+                                      ds.measurements[1].data["s2"] + zi * np.float32(0.01))
+    assert float(jax_prng.normal(0, 1)[0]) == pytest.approx(1.6226422, abs=2e-6)

@@ -67,16 +67,20 @@ def test_log_density_reproduces_the_posterior_of_the_hmc_notebook():
 
     g = np.load(GOLD)
     M, T = g["data"].shape
-    observed = jax_prng.augment_multiplicative(g["data"], 5e-2, seed=0).astype(np.float64)
+    # cell 4: the f32 data set, augmented through the facade exactly as the notebook does
+    ctx.enable_x64(False)
+    raw = ctx.Dataset.from_jax_arrays(["s1"], g["data"][:, :, None], np.tile(g["times"], (M, 1)),
+                                      g["data"][:, :1])
+    ds = raw.augment(n_augmentations=1, seed=0, sigma=5e-2, append=False, multiplicative=True)
+    observed = np.stack([m.data["s1"] for m in ds.measurements])
+    assert observed.dtype == np.float32
+    np.testing.assert_array_equal(observed, jax_prng.augment_multiplicative(g["data"], 5e-2, seed=0))
     ctx.enable_x64(True)
     try:
         model = _menten_model()
         model.parameters["v_max"].prior = priors.Uniform(low=1e-6, high=200.0)
         model.parameters["K_m"].prior = priors.Uniform(low=1e-6, high=1e3)
         assert model.get_parameter_order() == ["K_m", "v_max"]
-        ds = ctx.Dataset.from_jax_arrays(["s1"], observed[:, :, None],
-                                         np.tile(g["times"].astype(np.float64), (M, 1)),
-                                         g["data"][:, :1].astype(np.float64))
         bm = BayesianModel(model, ds, yerrs=2.0)
         assert bm.likelihood == "softlaplace"
         KM, VM, SG = np.meshgrid(KM_GRID, VM_GRID, SIG_GRID, indexing="ij")
