@@ -563,6 +563,14 @@ def run_b200(a):
             traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # informational: a pure write stream (memset of the same 12.6 GB) measured on this pool's B200s
+    write_only = None
+    wo = ROOT / "profiles" / "r1q_write_only_bw.json"
+    if wo.exists():
+        try:
+            write_only = json.loads(wo.read_text())["memset_12.6GB"]["GBps"]
+        except Exception:
+            write_only = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "warmup_done": n_warm, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
@@ -578,7 +586,8 @@ def run_b200(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                     "algorithmic_bytes_per_launch": algo_bytes},
+                     "algorithmic_bytes_per_launch": algo_bytes,
+                     "write_only_peak_gbs": write_only},
     }
     if e2e:
         line["e2e"] = e2e
