@@ -129,6 +129,12 @@ def test_unfitted_f32_oracle_matches_the_reference_pattern_in_distribution():
     cos = fingerprint_cosine(r.ys[:, :, 0].astype(np.float64), data, truth)
     assert (cos > 0.9).mean() > 0.3, (cos > 0.9).mean()
     assert np.median(cos) > 0.75, np.median(cos)
+    # the C / OpenMP port that bench.py times as the CPU baseline (its own rounding: 40 %, 0.83)
+    orc = COracle(*MENTEN[:4], MENTEN[4], dtype=f32)
+    rc = orc.solve(data[:, :1], np.tile(THETA_TRUE, (data.shape[0], 1)), np.zeros((data.shape[0], 0)),
+                   times, rtol=1e-5, atol=1e-5, dt0=0.1)
+    cos_c = fingerprint_cosine(rc.ys[:, :, 0].astype(np.float64), data, truth)
+    assert (cos_c > 0.9).mean() > 0.3 and np.median(cos_c) > 0.75, ((cos_c > 0.9).mean(), np.median(cos_c))
 
 
 def fingerprint_cosine(ys, data, truth):
