@@ -360,7 +360,11 @@ __device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_sme
     const int done = S.done;
     const int nseg = S.nseg[half];
     const int gtotal = S.gtotal[half];
+#ifdef V2_DBG_NOCONSUME   // developer ablation: hand-off only, nothing evaluated or stored
+    if (false) {
+#else
     if (gtotal > 0) {
+#endif
       const v2_rec* recs = &S.rec[half * V2_HL];
       const unsigned myoff = lane < nseg ? (unsigned)recs[lane].goff : 0xffffffffu;
       int seg_base = 0, s_have = -1;
@@ -431,6 +435,14 @@ __device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_sme
         if (act) {
           real* dst = reinterpret_cast<real*>(((unsigned long long)rr.r.row_hi << 32) |
                                               (unsigned long long)rr.r.row_lo) + p0 * CTX_S;
+#ifdef V2_DBG_NOSTORE     // developer ablation: everything but the global stores of full groups
+          if (p0 + CTX_GP <= rr.r.i1) {
+            real acc = R(0.0);
+#pragma unroll
+            for (int j = 0; j < CTX_GP * CTX_S; ++j) acc += o[j];
+            if (acc == R(-1.2345e30)) dst[0] = acc;   // keeps the evaluation alive
+          } else
+#endif
           if (p0 + CTX_GP <= rr.r.i1) {
             if ((rr.r.row_lo & 31u) == 0u) {   // whole-sector stores (see ctx_solve_v1)
 #if CTX_F64
