@@ -36,10 +36,26 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+_MARK = b"CTXB200-SOURCE-STAMP:"
+
+
+def lib_stamp(path: Path = LIB):
+    """Source hash baked into a built library (`ctx_build_stamp()`), read from the file itself:
+    the library, not a side file that git can update behind its back, says what it was built
+    from.  None when the file is missing or carries no stamp."""
+    try:
+        data = path.read_bytes()
+    except OSError:
+        return None
+    i = data.find(_MARK)
+    if i < 0:
+        return None
+    return data[i + len(_MARK): i + len(_MARK) + 64].decode("ascii", "replace")
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    stamp_file = HERE / "csrc" / ".build_stamp"
     stamp = _stamp()
-    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+    if not force and lib_stamp() == stamp:
         return LIB
     gen = CSRC / "_gen"
     gen.mkdir(exist_ok=True)
@@ -49,14 +65,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     _embed(CSRC / "ctx_solve_v2.cuh", gen / "ctx_solve_v2_embed.cpp", "ctx_solve_v2_src")
     cu = [str(p) for p in sorted(CSRC.glob("*.cu"))]
     cmd = [NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+           f'-DCTX_BUILD_STAMP="{stamp}"',
            *cu, str(gen / "ctx_integrator_embed.cpp"), str(gen / "ctx_mlp_tc_embed.cpp"),
            str(gen / "ctx_mlp_adjoint_embed.cpp"), str(gen / "ctx_solve_v2_embed.cpp"), "-o", str(LIB), "-ldl",
            "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
+    tmp = LIB.with_suffix(".so.tmp")
+    cmd[cmd.index(str(LIB))] = str(tmp)
     subprocess.run(cmd, check=True, cwd=str(CSRC))
-    stamp_file.write_text(stamp)
+    os.replace(tmp, LIB)
+    assert lib_stamp() == stamp, "built library does not carry the source stamp"
     return LIB
 
 

@@ -93,9 +93,16 @@ struct ctx_model {
   int mlp_tc_smem = 0;              // > 0: the tcgen05 MLP kernel is available (bytes of smem)
   bool has_adjoint = false;         // weight-gradient kernels were generated (ctx_mlp_adjoint.cuh)
   int warp_warps = 0;               // > 0: lane-parallel form present (ctx_solve_w), warps per CTA
-  // host-call staging (ctx_solve_host)
+  // host-call staging (ctx_solve_host / ctx_loglik_grad_host): device buffers, two private
+  // non-blocking streams and the events of the double-buffered pipeline.  `host_mu` is held for
+  // the whole call, so concurrent host-buffer calls on ONE model serialise (device-pointer entry
+  // points stay lock-free and stream-ordered).
+  std::mutex host_mu;
   void* stage = nullptr;
   size_t stage_bytes = 0;
+  int stage_device = -1;
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_solved[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -930,6 +937,12 @@ void ctx_model_free(ctx_model* m) {
   for (auto& kv : m->variants)
     if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
   if (m->stage) cudaFree(m->stage);
+  for (int i = 0; i < 2; ++i) {
+    if (m->ev_solved[i]) cudaEventDestroy(m->ev_solved[i]);
+    if (m->ev_copied[i]) cudaEventDestroy(m->ev_copied[i]);
+  }
+  if (m->s_compute) cudaStreamDestroy(m->s_compute);
+  if (m->s_copy) cudaStreamDestroy(m->s_copy);
   delete m;
 }
 
@@ -1108,6 +1121,58 @@ int ctx_mlp_adjoint_backward(ctx_model* m, const ctx_adjoint_cfg* cfg, const voi
                                (cudaStream_t)stream);
 }
 
+// (re)allocate the staging area and the private streams of the host-buffer entry points;
+// call with m->host_mu held
+static int host_stage(ctx_model* m, size_t total) {
+  int dev = 0;
+  CTX_CUDA(cudaGetDevice(&dev));
+  if (m->stage_device != dev) {
+    // first call, or the caller switched devices: everything below belongs to one device
+    if (m->stage) cudaFree(m->stage);
+    m->stage = nullptr;
+    m->stage_bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+      if (m->ev_solved[i]) cudaEventDestroy(m->ev_solved[i]);
+      if (m->ev_copied[i]) cudaEventDestroy(m->ev_copied[i]);
+      m->ev_solved[i] = m->ev_copied[i] = nullptr;
+    }
+    if (m->s_compute) cudaStreamDestroy(m->s_compute);
+    if (m->s_copy) cudaStreamDestroy(m->s_copy);
+    m->s_compute = m->s_copy = nullptr;
+    CTX_CUDA(cudaStreamCreateWithFlags(&m->s_compute, cudaStreamNonBlocking));
+    CTX_CUDA(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CTX_CUDA(cudaEventCreateWithFlags(&m->ev_solved[i], cudaEventDisableTiming));
+      CTX_CUDA(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+    }
+    m->stage_device = dev;
+  }
+  if (m->stage_bytes < total) {
+    if (m->stage) cudaFree(m->stage);
+    m->stage = nullptr;
+    m->stage_bytes = 0;
+    CTX_CUDA(cudaMalloc(&m->stage, total));
+    m->stage_bytes = total;
+  }
+  return CTX_OK;
+}
+
+// Rows per chunk of the host-buffer solve: ~512 MB of trajectory output per chunk, never fewer
+// than 65536 rows (the warp-specialised kernel's threshold), a multiple of 4096; the whole batch
+// when it is smaller than two chunks.  CTX_B200_HOST_CHUNK_ROWS overrides (0 = one chunk).
+static size_t host_chunk_rows(size_t B, size_t row_bytes) {
+  if (const char* e = getenv("CTX_B200_HOST_CHUNK_ROWS")) {
+    const long long v = atoll(e);
+    if (v <= 0) return B;
+    return std::min<size_t>(B, (size_t)v);
+  }
+  size_t rows = (512ull << 20) / std::max<size_t>(row_bytes, 1);
+  rows = std::max<size_t>(rows, 65536);
+  rows = (rows + 4095) / 4096 * 4096;
+  if (2 * rows > B) return B;
+  return rows;
+}
+
 int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
                    const void* consts, const void* ts, void* ys, int32_t* status, int32_t* nacc,
                    int32_t* nrej) {
@@ -1115,51 +1180,136 @@ int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
   if (ctx_device_count() <= 0)
     return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
   if (cfg->inner > 0) return fail(CTX_E_INVALID, "ctx_solve_host: two-level batches take device buffers (ctx_solve)");
+  if (cfg->batch <= 0) return CTX_OK;
+  if (cfg->n_times <= 0) return fail(CTX_E_INVALID, "n_times must be >= 1");
+  if (!y0 || !ts || !ys) return fail(CTX_E_INVALID, "null y0 / ts / ys");
   const ctx_model_desc& d = m->desc;
   const size_t w = d.dtype == CTX_F64 ? 8 : 4;
-  const size_t B = (size_t)cfg->batch, T = (size_t)cfg->n_times;
-  auto rows = [&](int ax) { return cfg->in_axes[ax] == 0 ? B : (size_t)1; };
+  const size_t B = (size_t)cfg->batch, T = (size_t)cfg->n_times, S = (size_t)d.n_states;
+  const size_t row_out = T * S * w;
+  const size_t R = host_chunk_rows(B, row_out);          // rows per chunk
+  const size_t n_chunks = (B + R - 1) / R;
+  const size_t n_buf = n_chunks > 1 ? 2 : 1;
+  auto rows = [&](int ax, size_t n) { return cfg->in_axes[ax] == 0 ? n : (size_t)1; };
   auto al = [](size_t n) { return (n + 255) / 256 * 256; };
-  const size_t n_y0 = al(rows(0) * d.n_states * w), n_th = al(rows(1) * d.n_params * w),
-               n_c = al(rows(2) * d.n_consts * w), n_ts = al(rows(3) * T * w),
-               n_ys = al(B * T * d.n_states * w), n_i = al(B * 4);
-  const size_t n_ws = al(ctx_workspace_bytes(m, cfg));
-  const size_t total = n_y0 + n_th + n_c + n_ts + n_ys + 3 * n_i + n_ws;
-  {
-    std::lock_guard<std::mutex> lk(m->mu);
-    if (m->stage_bytes < total) {
-      if (m->stage) cudaFree(m->stage);
-      m->stage = nullptr;
-      m->stage_bytes = 0;
-      CTX_CUDA(cudaMalloc(&m->stage, total));
-      m->stage_bytes = total;
-    }
+  ctx_solve_cfg ccfg = *cfg;
+  ccfg.batch = (int64_t)R;
+  // per buffer: inputs of one chunk, its outputs, counters, workspace
+  const size_t n_y0 = al(rows(0, R) * S * w), n_th = al(rows(1, R) * d.n_params * w),
+               n_c = al(rows(2, R) * d.n_consts * w), n_ts = al(rows(3, R) * T * w),
+               n_ys = al(R * row_out), n_i = al(R * 4);
+  const size_t n_ws = al(ctx_workspace_bytes(m, &ccfg));
+  const size_t per_buf = n_y0 + n_th + n_c + n_ts + n_ys + 3 * n_i + n_ws;
+  std::lock_guard<std::mutex> lk(m->host_mu);
+  int rc = host_stage(m, per_buf * n_buf);
+  if (rc) return rc;
+  cudaStream_t sc = m->s_compute, sd = m->s_copy;
+  // Pipeline: chunk k is solved on the compute stream into buffer k % 2 while the copy stream
+  // drains chunk k - 1 to the host; a buffer is reused once the copy of chunk k - 2 has finished.
+  for (size_t k = 0; k < n_chunks; ++k) {
+    const size_t r0 = k * R, nr = std::min(R, B - r0);
+    const int bi = (int)(k % n_buf);
+    char* p = (char*)m->stage + per_buf * bi;
+    char* dy0 = p; p += n_y0;
+    char* dth = p; p += n_th;
+    char* dc = p; p += n_c;
+    char* dts = p; p += n_ts;
+    char* dys = p; p += n_ys;
+    int32_t* dst = (int32_t*)p; p += n_i;
+    int32_t* dna = (int32_t*)p; p += n_i;
+    int32_t* dnr = (int32_t*)p; p += n_i;
+    char* dws = p;
+    if (k >= n_buf) CTX_CUDA(cudaStreamWaitEvent(sc, m->ev_copied[bi], 0));
+    auto off = [&](const void* base, int ax, size_t width) {
+      return (const char*)base + (cfg->in_axes[ax] == 0 ? r0 * width * w : 0);
+    };
+    CTX_CUDA(cudaMemcpyAsync(dy0, off(y0, 0, S), rows(0, nr) * S * w, cudaMemcpyHostToDevice, sc));
+    if (d.n_params)
+      CTX_CUDA(cudaMemcpyAsync(dth, off(theta, 1, d.n_params), rows(1, nr) * d.n_params * w,
+                               cudaMemcpyHostToDevice, sc));
+    if (d.n_consts)
+      CTX_CUDA(cudaMemcpyAsync(dc, off(consts, 2, d.n_consts), rows(2, nr) * d.n_consts * w,
+                               cudaMemcpyHostToDevice, sc));
+    if (cfg->in_axes[3] == 0 || k < n_buf)    // a shared grid is staged once per buffer
+      CTX_CUDA(cudaMemcpyAsync(dts, off(ts, 3, T), rows(3, nr) * T * w, cudaMemcpyHostToDevice, sc));
+    ccfg.batch = (int64_t)nr;
+    rc = ctx_solve(m, &ccfg, dy0, dth, dc, dts, dys, dst, dna, dnr, dws, n_ws, sc);
+    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sd); return rc; }
+    CTX_CUDA(cudaEventRecord(m->ev_solved[bi], sc));
+    CTX_CUDA(cudaStreamWaitEvent(sd, m->ev_solved[bi], 0));
+    CTX_CUDA(cudaMemcpyAsync((char*)ys + r0 * row_out, dys, nr * row_out, cudaMemcpyDeviceToHost, sd));
+    if (status) CTX_CUDA(cudaMemcpyAsync(status + r0, dst, nr * 4, cudaMemcpyDeviceToHost, sd));
+    if (nacc) CTX_CUDA(cudaMemcpyAsync(nacc + r0, dna, nr * 4, cudaMemcpyDeviceToHost, sd));
+    if (nrej) CTX_CUDA(cudaMemcpyAsync(nrej + r0, dnr, nr * 4, cudaMemcpyDeviceToHost, sd));
+    CTX_CUDA(cudaEventRecord(m->ev_copied[bi], sd));
   }
+  CTX_CUDA(cudaStreamSynchronize(sc));
+  CTX_CUDA(cudaStreamSynchronize(sd));
+  return CTX_OK;
+}
+
+int ctx_loglik_grad_host(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s,
+                         const void* theta, const void* consts, const void* ts, const void* data,
+                         const uint8_t* mask, const void* sigma, void* out, void* partial,
+                         int32_t* status) {
+  if (!m || !cfg || !out) return fail(CTX_E_INVALID, "null argument");
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  if (cfg->n_chains <= 0 || cfg->n_series <= 0) return CTX_OK;
+  if (cfg->n_times <= 0) return fail(CTX_E_INVALID, "n_times must be >= 1");
+  const ctx_model_desc& d = m->desc;
+  const size_t w = d.dtype == CTX_F64 ? 8 : 4;
+  const size_t CH = (size_t)cfg->n_chains, M = (size_t)cfg->n_series, T = (size_t)cfg->n_times,
+               S = (size_t)d.n_states, P = (size_t)d.n_params, Cn = (size_t)d.n_consts;
+  const size_t KR = 1 + (size_t)d.n_theta_dirs + S;
+  const size_t KP = KR + (size_t)(d.n_dirs - d.n_theta_dirs);
+  auto al = [](size_t n) { return (n + 255) / 256 * 256; };
+  const size_t n_y0 = al(M * S * w), n_th = al(CH * P * w), n_c = al(M * Cn * w),
+               n_ts = al(M * T * w), n_d = al(M * T * S * w), n_m = al(M * T * S),
+               n_sg = al(CH * S * w), n_out = al(CH * KR * w), n_part = al(CH * M * KP * w),
+               n_st = al(CH * M * 4), n_ws = al(ctx_loglik_workspace_bytes(m, cfg));
+  const size_t total = n_y0 + n_th + n_c + n_ts + n_d + n_m + n_sg + n_out + n_part + n_st + n_ws;
+  std::lock_guard<std::mutex> lk(m->host_mu);
+  int rc = host_stage(m, total);
+  if (rc) return rc;
+  cudaStream_t s = m->s_compute;
   char* p = (char*)m->stage;
   char* dy0 = p; p += n_y0;
   char* dth = p; p += n_th;
   char* dc = p; p += n_c;
   char* dts = p; p += n_ts;
-  char* dys = p; p += n_ys;
-  int32_t* dst = (int32_t*)p; p += n_i;
-  int32_t* dna = (int32_t*)p; p += n_i;
-  int32_t* dnr = (int32_t*)p; p += n_i;
+  char* dd = p; p += n_d;
+  uint8_t* dm = (uint8_t*)p; p += n_m;
+  char* dsg = p; p += n_sg;
+  char* dout = p; p += n_out;
+  char* dpart = p; p += n_part;
+  int32_t* dst = (int32_t*)p; p += n_st;
   char* dws = p;
-  cudaStream_t s = 0;
-  CTX_CUDA(cudaMemcpyAsync(dy0, y0, rows(0) * d.n_states * w, cudaMemcpyHostToDevice, s));
-  if (d.n_params)
-    CTX_CUDA(cudaMemcpyAsync(dth, theta, rows(1) * d.n_params * w, cudaMemcpyHostToDevice, s));
-  if (d.n_consts)
-    CTX_CUDA(cudaMemcpyAsync(dc, consts, rows(2) * d.n_consts * w, cudaMemcpyHostToDevice, s));
-  CTX_CUDA(cudaMemcpyAsync(dts, ts, rows(3) * T * w, cudaMemcpyHostToDevice, s));
-  int rc = ctx_solve(m, cfg, dy0, dth, dc, dts, dys, dst, dna, dnr, dws, n_ws, s);
-  if (rc) return rc;
-  CTX_CUDA(cudaMemcpyAsync(ys, dys, B * T * d.n_states * w, cudaMemcpyDeviceToHost, s));
-  if (status) CTX_CUDA(cudaMemcpyAsync(status, dst, B * 4, cudaMemcpyDeviceToHost, s));
-  if (nacc) CTX_CUDA(cudaMemcpyAsync(nacc, dna, B * 4, cudaMemcpyDeviceToHost, s));
-  if (nrej) CTX_CUDA(cudaMemcpyAsync(nrej, dnr, B * 4, cudaMemcpyDeviceToHost, s));
+  CTX_CUDA(cudaMemcpyAsync(dy0, y0s, M * S * w, cudaMemcpyHostToDevice, s));
+  CTX_CUDA(cudaMemcpyAsync(dth, theta, CH * P * w, cudaMemcpyHostToDevice, s));
+  if (Cn) CTX_CUDA(cudaMemcpyAsync(dc, consts, M * Cn * w, cudaMemcpyHostToDevice, s));
+  CTX_CUDA(cudaMemcpyAsync(dts, ts, M * T * w, cudaMemcpyHostToDevice, s));
+  CTX_CUDA(cudaMemcpyAsync(dd, data, M * T * S * w, cudaMemcpyHostToDevice, s));
+  if (mask) CTX_CUDA(cudaMemcpyAsync(dm, mask, M * T * S, cudaMemcpyHostToDevice, s));
+  CTX_CUDA(cudaMemcpyAsync(dsg, sigma, CH * S * w, cudaMemcpyHostToDevice, s));
+  rc = ctx_loglik_grad(m, cfg, dy0, dth, dc, dts, dd, mask ? dm : nullptr, dsg, dout, dpart, dst,
+                       dws, n_ws, s);
+  if (rc) { cudaStreamSynchronize(s); return rc; }
+  CTX_CUDA(cudaMemcpyAsync(out, dout, CH * KR * w, cudaMemcpyDeviceToHost, s));
+  if (partial) CTX_CUDA(cudaMemcpyAsync(partial, dpart, CH * M * KP * w, cudaMemcpyDeviceToHost, s));
+  if (status) CTX_CUDA(cudaMemcpyAsync(status, dst, CH * M * 4, cudaMemcpyDeviceToHost, s));
   CTX_CUDA(cudaStreamSynchronize(s));
   return CTX_OK;
+}
+
+#ifndef CTX_BUILD_STAMP
+#define CTX_BUILD_STAMP "unstamped"
+#endif
+// hash of the sources this library was built from (catalax_b200/_build.py compares it with the
+// tree at load time, so a stale library next to newer sources is rebuilt or refused)
+const char* ctx_build_stamp(void) {
+  static const char marked[] = "CTXB200-SOURCE-STAMP:" CTX_BUILD_STAMP;
+  return marked + sizeof("CTXB200-SOURCE-STAMP:") - 1;
 }
 
 }  // extern "C"

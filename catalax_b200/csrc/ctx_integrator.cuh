@@ -68,8 +68,11 @@ struct ctx_solve_args {
   int inner;       // M > 0: b = d*M + m, theta row d, y0 / consts / ts row m (predictive.py:150-154)
   int q_div;       // persistent kernels: a warp claims clamp(remaining / q_div, 1, 32) trajectories
   int ts_smem;     // 1: the shared time grid (stride_ts == 0) is staged in shared memory
-  real rtol, atol, dt0;
+  real rtol, atol, dt0;   // dt0 <= 0: every trajectory takes ts[1] - ts[0] of ITS time row, the
+                          // reference's default `dt0 or ts[1] - ts[0]` under vmap (neuralode.py:44-47)
 };
+// first step size of a trajectory whose requested times are `row` (T of them)
+#define CTX_ROW_DT0(row, T) (((a.dt0 > R(0.0)) || (T) < 2) ? a.dt0 : ((row)[1] - (row)[0]))
 
 // operand rows of trajectory b: `ro` for the parameters, `ri` for y0 / constants / times
 #define CTX_ROWS(b, ro, ri)                                              \
@@ -343,7 +346,8 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
   const int T = a.T;
   const real t_end = ts[T - 1];
   real tprev = a.t0_from_ts ? ts[0] : R(0.0);
-  real tnext = fmin(tprev + a.dt0, t_end);
+  const real dt0_r = CTX_ROW_DT0(ts, T);
+  real tnext = fmin(tprev + dt0_r, t_end);
   int idx = 0, nacc = 0, nrej = 0, status = 0;
 
   if (!(tprev < t_end)) {  // t0 == t1: every requested time is t0
@@ -356,7 +360,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
     const real dt = tnext - tprev;
     ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
     bool keep = true;
-    real dt_next = a.dt0;
+    real dt_next = dt0_r;
 #if CTX_ADAPTIVE
     const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
     keep = scaled < R(1.0);
@@ -736,6 +740,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
   real K[CTX_NST][CTX_N];
   real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
   int idx = 0, nacc = 0, nrej = 0, status = 0;
+  real dt0_l = a.dt0;         // first step size of this trajectory (the step size of Euler / Heun)
   const real* tsr = ts_base;
   long long ts_row = 0;       // element offset of this trajectory's time row
   int ri_row = 0;             // row of its y0 / constants / time grid
@@ -800,7 +805,8 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #endif
         tsr = ts_base + ts_row;
         tprev = a.t0_from_ts ? t_first : R(0.0);
-        tnext = fmin(tprev + a.dt0, t_end);
+        dt0_l = CTX_ROW_DT0(tsr, T);
+        tnext = fmin(tprev + dt0_l, t_end);
         idx = 0; nacc = 0; nrej = 0; status = 0;
         phase = (tprev < t_end) ? 0 : 1;  // t0 == t1: emit y0 for every requested time
         ctx_field(tprev, y, th, c, y0, K[0]);
@@ -856,7 +862,8 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
           tsr = ts_base + ts_row;
           t_end = tsr[T - 1];
           tprev = a.t0_from_ts ? tsr[0] : R(0.0);
-          tnext = fmin(tprev + a.dt0, t_end);
+          dt0_l = CTX_ROW_DT0(tsr, T);
+          tnext = fmin(tprev + dt0_l, t_end);
           idx = 0; nacc = 0; nrej = 0; status = 0;
           phase = (tprev < t_end) ? 0 : 1;
           ctx_field(tprev, y, th, c, y0, K[0]);
@@ -878,7 +885,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       const real dt = tnext - tprev;
       ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
       bool keep = true;
-      real dt_next = a.dt0;
+      real dt_next = dt0_l;
 #if CTX_ADAPTIVE
       const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
       keep = scaled < R(1.0);
@@ -2132,7 +2139,8 @@ ctx_solve_w(const ctx_solve_args a) {
     real* out = a.ys + (size_t)b * T * CTX_S;
     const real t_end = ts[T - 1];
     real tprev = a.t0_from_ts ? ts[0] : R(0.0);
-    real tnext = fmin(tprev + a.dt0, t_end);
+    const real dt0_r = CTX_ROW_DT0(ts, T);
+    real tnext = fmin(tprev + dt0_r, t_end);
     int idx = 0, nacc = 0, nrej = 0, status = 0;
 
     if (!(tprev < t_end)) {   // t0 == t1: every requested time is t0
@@ -2184,7 +2192,7 @@ ctx_solve_w(const ctx_solve_args a) {
       for (int u = 0; u < CTXW_NSS; ++u) ynew[u] = y[u] + dt * (R(0.5) * K[0][u] + R(0.5) * K[1][u]);
 #endif
       bool keep = true;
-      real dt_next = a.dt0;
+      real dt_next = dt0_r;
 #if CTX_ADAPTIVE
       {
         bool my_nan = false;

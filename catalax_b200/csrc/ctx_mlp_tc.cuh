@@ -326,7 +326,7 @@ extern "C" __global__ void __launch_bounds__(TC_THREADS, 1) ctx_solve_mlp_tc(con
           tsr = a.ts + (size_t)ri * a.stride_ts;
           t_end = tsr[Tn - 1];
           tprev = a.t0_from_ts ? tsr[0] : 0.0f;
-          tnext = fminf(tprev + a.dt0, t_end);
+          tnext = fminf(tprev + CTX_ROW_DT0(tsr, Tn), t_end);
           idx = 0; nacc = 0; nrej = 0;
           if (!(tprev < t_end)) {                    // t0 == t1: every requested time is t0
             for (; idx < Tn; ++idx)

@@ -174,7 +174,7 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
         const real t_first = w.q_in[q_cur][k++][e];
         t_end = w.q_in[q_cur][k++][e];
         tprev = a.t0_from_ts ? t_first : R(0.0);
-        tnext = fmin(tprev + a.dt0, t_end);
+        tnext = fmin(tprev + CTX_ROW_DT0(ts_sm, T), t_end);   // (v2: the grid is shared)
         idx = 0; nacc = 0; nrej = 0; status = 0;
         phase = (tprev < t_end) ? 0 : 1;
         ctx_field(tprev, y, th, c, y0, K[0]);
@@ -444,6 +444,7 @@ __device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_sme
           } else
 #endif
           if (p0 + CTX_GP <= rr.r.i1) {
+#if CTX_ST256   // (0 when the loaded NVRTC predates PTX ISA 8.8: 128-bit stores below, as v1)
             if ((rr.r.row_lo & 31u) == 0u) {   // whole-sector stores (see ctx_solve_v1)
 #if CTX_F64
 #pragma unroll
@@ -478,6 +479,21 @@ __device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_sme
                                  dst + (par ? 0 : 4 * (CTX_S - 1))),
                              "f"(v4[0]), "f"(v4[1]), "f"(v4[2]), "f"(v4[3]) : "memory");
               }
+#endif
+            } else
+#endif  // CTX_ST256
+            if ((rr.r.row_lo & 15u) == 0u) {
+#if CTX_F64
+#pragma unroll
+              for (int j = 0; j < CTX_GP * CTX_S / 2; ++j)
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst + 2 * j), "d"(o[2 * j]),
+                             "d"(o[2 * j + 1]) : "memory");
+#else
+#pragma unroll
+              for (int j = 0; j < CTX_GP * CTX_S / 4; ++j)
+                asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                             "f"(o[4 * j]), "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                             : "memory");
 #endif
             } else {
 #pragma unroll

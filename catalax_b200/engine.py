@@ -48,11 +48,26 @@ class ctx_adjoint_cfg(C.Structure):
                 ("atol", C.c_double), ("dt0", C.c_double)]
 
 
+class ctx_xla_solve_desc(C.Structure):
+    """Opaque bytes of the ctx_xla_solve / ctx_xla_solve_sens custom calls (include/ctx_b200.h)."""
+    _fields_ = [("abi", C.c_int32), ("reserved", C.c_int32), ("model", C.c_uint64),
+                ("ws_bytes", C.c_uint64), ("cfg", ctx_solve_cfg)]
+
+
 class ctx_loglik_cfg(C.Structure):
     _fields_ = [("solver", C.c_int32), ("likelihood", C.c_int32), ("n_chains", C.c_int64),
                 ("n_series", C.c_int32), ("n_times", C.c_int32), ("max_steps", C.c_int32),
                 ("kernel", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("dt0", C.c_double)]
+
+
+class ctx_xla_loglik_desc(C.Structure):
+    """Opaque bytes of the ctx_xla_loglik_grad custom call."""
+    _fields_ = [("abi", C.c_int32), ("has_mask", C.c_int32), ("model", C.c_uint64),
+                ("ws_bytes", C.c_uint64), ("cfg", ctx_loglik_cfg)]
+
+
+ABI_VERSION = 3
 
 
 def lib() -> C.CDLL:
@@ -64,6 +79,19 @@ def lib() -> C.CDLL:
         raise EngineError(
             f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "-- catalax_b200 has no CPU fallback")
+    # The library carries the hash of the sources it was built from.  A library that is older
+    # than the tree (e.g. after `git pull`) would run new Python / code generation against stale
+    # kernels and stale embedded NVRTC sources: rebuild it when a compiler is here, refuse it
+    # otherwise.  CTX_B200_SKIP_STAMP_CHECK=1 loads it regardless (developer override).
+    from . import _build
+
+    if not os.environ.get("CTX_B200_SKIP_STAMP_CHECK") and _build.lib_stamp() != _build._stamp():
+        if os.path.exists(_build.NVCC):
+            _build.build()
+        else:
+            raise EngineError(
+                f"{_LIB_PATH} was built from other sources than this tree (stamp "
+                f"{_build.lib_stamp()!r}) and nvcc is not available to rebuild it")
     L = C.CDLL(str(_LIB_PATH))
     vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
     L.ctx_abi_version.restype = C.c_int
@@ -104,6 +132,18 @@ def lib() -> C.CDLL:
     L.ctx_mlp_adjoint_backward.argtypes = [vp, C.POINTER(ctx_adjoint_cfg)] + [vp] * 8 + [C.c_size_t, vp]
     L.ctx_solve_host.restype = C.c_int
     L.ctx_solve_host.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ctx_loglik_grad_host.restype = C.c_int
+    L.ctx_loglik_grad_host.argtypes = [vp, C.POINTER(ctx_loglik_cfg)] + [vp] * 10
+    L.ctx_build_stamp.restype = C.c_char_p
+    for name in ("ctx_xla_solve", "ctx_xla_solve_sens", "ctx_xla_loglik_grad"):
+        fn = getattr(L, name)
+        fn.restype = None
+        fn.argtypes = [vp, C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.ctx_xla_desc_bytes.restype = C.c_size_t
+    L.ctx_xla_desc_bytes.argtypes = [C.c_int32]
+    L.ctx_xla_last_status.restype = C.c_int
+    L.ctx_xla_last_error.restype = C.c_size_t
+    L.ctx_xla_last_error.argtypes = [C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
@@ -117,6 +157,16 @@ def last_error() -> str:
 def _check(rc: int) -> None:
     if rc != 0:
         raise EngineError(f"ctx error {rc}: {last_error()}")
+
+
+def xla_check() -> None:
+    """Raise if an XLA custom-call entry point failed since the last check (that ABI has no
+    status channel: failures are parked in a process-wide slot)."""
+    rc = int(lib().ctx_xla_last_status())
+    if rc != 0:
+        buf = C.create_string_buffer(1 << 16)
+        lib().ctx_xla_last_error(buf, len(buf))
+        raise EngineError(f"ctx error {rc}: {buf.value.decode(errors='replace')}")
 
 
 def device_count() -> int:
@@ -213,6 +263,13 @@ class CompiledModel:
             if in_axes[1] != 0 or in_axes[0] != 0:
                 raise ValueError("two-level batch needs batched y0 and parameters")
             B = theta.shape[0] * int(inner)
+            # y0 / constants / times are indexed by the series m < inner: anything shorter would
+            # be read out of bounds on the device
+            for name, arr, ax in (("y0", y0, in_axes[0]), ("consts", consts, in_axes[2]),
+                                  ("ts", ts, in_axes[3])):
+                if ax == 0 and arr.shape[0] != int(inner):
+                    raise ValueError(f"two-level batch: {name} must have inner={int(inner)} rows, "
+                                     f"got {arr.shape[0]}")
         else:
             Bs = [a.shape[0] for a, ax in ((y0, in_axes[0]), (theta, in_axes[1]),
                                            (consts, in_axes[2]), (ts, in_axes[3])) if ax == 0]
@@ -226,6 +283,11 @@ class CompiledModel:
         cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
                             max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel,
                             t0_from_ts=t0_from_ts, inner=inner)
+        if out is not None:
+            if (tuple(out.shape) != (B, T, S) or out.dtype != tdt or out.device != dev
+                    or not out.is_contiguous()):
+                raise ValueError(f"out must be a contiguous {tdt} tensor of shape {(B, T, S)} on {dev}, "
+                                 f"got {tuple(out.shape)} {out.dtype} on {out.device}")
         with torch.cuda.device(dev):
             ys = out if out is not None else torch.empty((B, T, S), dtype=tdt, device=dev)
             status = torch.empty(B, dtype=torch.int32, device=dev)
@@ -259,6 +321,16 @@ class CompiledModel:
         T = ts.shape[-1]
         cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
                             max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel)
+        if any(b != B for b in Bs):
+            raise ValueError(f"inconsistent batch sizes {Bs}")
+        for name, arr, ax, width in (("y0", y0, in_axes[0], S), ("theta", theta, in_axes[1], P),
+                                     ("consts", consts, in_axes[2], Cn), ("ts", ts, in_axes[3], T)):
+            if arr.ndim != (2 if ax == 0 else 1) or arr.shape[-1] != width:
+                raise ValueError(f"{name}: expected last dim {width} and "
+                                 f"{2 if ax == 0 else 1} dims, got {arr.shape}")
+        if out is not None and (out.shape != (B, T, S) or out.dtype != dt
+                                or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError(f"out must be a C-contiguous {dt} array of shape {(B, T, S)}")
         ys = out if out is not None else np.empty((B, T, S), dtype=dt)
         status = np.empty(B, dtype=np.int32); nacc = np.empty(B, dtype=np.int32)
         nrej = np.empty(B, dtype=np.int32)
@@ -266,6 +338,118 @@ class CompiledModel:
         _check(lib().ctx_solve_host(self._h, C.byref(cfg), vp(y0), vp(theta), vp(consts), vp(ts),
                                     vp(ys), vp(status), vp(nacc), vp(nrej)))
         return SolveOutput(ys, status, nacc, nrej)
+
+    def solve_xla(self, y0, theta, consts, ts, *, solver="tsit5", in_axes=(0, None, 0, None),
+                  rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096, tangents=False, kernel=0,
+                  t0_from_ts=False, inner=0):
+        """The same solve through the XLA custom-call entry point (ctx_xla_solve[_sens]): a
+        `void* buffers[]` of operands then results and the packed descriptor as opaque bytes --
+        exactly what XLA's GPU runtime passes (include/ctx_b200.h)."""
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = y0.device
+        if dev.type != "cuda":
+            raise EngineError("solve_xla() needs CUDA tensors: catalax_b200 has no CPU fallback")
+        S, D = self.field.S, self.field.D
+        f = lambda x: x.to(device=dev, dtype=tdt).contiguous()
+        y0, theta, consts, ts = f(y0), f(theta), f(consts), f(ts)
+        if inner:
+            B = theta.shape[0] * int(inner)
+        else:
+            Bs = [a.shape[0] for a, ax in ((y0, in_axes[0]), (theta, in_axes[1]),
+                                           (consts, in_axes[2]), (ts, in_axes[3])) if ax == 0]
+            B = Bs[0] if Bs else 1
+        T = ts.shape[-1]
+        d = ctx_xla_solve_desc()
+        d.abi, d.model = ABI_VERSION, self._h.value
+        d.cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T,
+                              max_steps=max_steps, rtol=rtol, atol=atol, dt0=dt0, kernel=kernel,
+                              t0_from_ts=t0_from_ts, inner=inner)
+        d.ws_bytes = int(lib().ctx_workspace_bytes(self._h, C.byref(d.cfg)))
+        with torch.cuda.device(dev):
+            ys = torch.empty((B, T, S), dtype=tdt, device=dev)
+            sens = torch.empty((B, T, S, D), dtype=tdt, device=dev) if tangents else None
+            cnt = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(3)]
+            ws = torch.empty(max(int(d.ws_bytes), 1), dtype=torch.uint8, device=dev)
+            bufs = [y0, theta, consts, ts, ys] + ([sens] if tangents else []) + cnt + [ws]
+            arr = (C.c_void_p * len(bufs))(*[b.data_ptr() if b.numel() else 0 for b in bufs])
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            opaque = bytes(d)
+            fn = lib().ctx_xla_solve_sens if tangents else lib().ctx_xla_solve
+            fn(C.c_void_p(stream), arr, opaque, len(opaque))
+        xla_check()
+        return SolveOutput(ys, cnt[0], cnt[1], cnt[2], sens)
+
+    def loglik_grad_xla(self, y0s, theta, consts, ts, data, sigma, *, mask=None,
+                        likelihood="softlaplace", solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,
+                        max_steps=4096, kernel=0):
+        """loglik_grad through the XLA custom-call entry point (ctx_xla_loglik_grad)."""
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = theta.device
+        S, P, D = self.field.S, self.field.P, self.field.D
+        f = lambda x: x.to(device=dev, dtype=tdt).contiguous()
+        y0s, theta, consts, ts, data, sigma = map(f, (y0s, theta, consts, ts, data, sigma))
+        M, T = ts.shape
+        CH = theta.shape[0]
+        d = ctx_xla_loglik_desc()
+        d.abi, d.model, d.has_mask = ABI_VERSION, self._h.value, int(mask is not None)
+        d.cfg.solver, d.cfg.likelihood = SOLVER_IDS[solver], LIKELIHOOD_IDS[likelihood]
+        d.cfg.n_chains, d.cfg.n_series, d.cfg.n_times, d.cfg.max_steps = CH, M, T, int(max_steps)
+        d.cfg.rtol, d.cfg.atol, d.cfg.dt0, d.cfg.kernel = float(rtol), float(atol), float(dt0), int(kernel)
+        d.ws_bytes = int(lib().ctx_loglik_workspace_bytes(self._h, C.byref(d.cfg)))
+        with torch.cuda.device(dev):
+            mk = (mask.to(device=dev, dtype=torch.uint8).contiguous() if mask is not None
+                  else torch.zeros(1, dtype=torch.uint8, device=dev))   # XLA has no null operands
+            out = torch.empty((CH, 1 + P + S), dtype=tdt, device=dev)
+            partial = torch.empty((CH * M, 1 + P + S + (D - P)), dtype=tdt, device=dev)
+            status = torch.empty(CH * M, dtype=torch.int32, device=dev)
+            ws = torch.empty(max(int(d.ws_bytes), 1), dtype=torch.uint8, device=dev)
+            bufs = [y0s, theta, consts, ts, data, mk, sigma, out, partial, status, ws]
+            arr = (C.c_void_p * len(bufs))(*[b.data_ptr() if b.numel() else 0 for b in bufs])
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            opaque = bytes(d)
+            lib().ctx_xla_loglik_grad(C.c_void_p(stream), arr, opaque, len(opaque))
+        xla_check()
+        return out, partial, status
+
+    def loglik_grad_host(self, y0s, theta, consts, ts, data, sigma, *, mask=None,
+                         likelihood="softlaplace", solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,
+                         max_steps=4096, kernel=0, out=None, want_partial=False):
+        """Host-buffer log-likelihood + gradient (ctx_loglik_grad_host): numpy in, numpy out; the
+        H2D copies of every operand and the D2H copy of `out` happen inside the call."""
+        dt = self.dtype
+        S, P, Cn, D = self.field.S, self.field.P, self.field.C, self.field.D
+        if self.field.n_theta_dirs != P:
+            raise EngineError("model must be generated with sens_theta=True")
+        g = lambda x: np.ascontiguousarray(x, dtype=dt)
+        y0s, theta, consts, ts, data, sigma = map(g, (y0s, theta, consts, ts, data, sigma))
+        M, T = ts.shape
+        CH = theta.shape[0]
+        if (y0s.shape != (M, S) or theta.shape != (CH, P) or data.shape != (M, T, S)
+                or sigma.shape != (CH, S) or consts.shape != (M, Cn)):
+            raise ValueError("loglik_grad_host: inconsistent operand shapes")
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if mask.shape != (M, T, S):
+                raise ValueError("mask must be [M,T,S]")
+        cfg = ctx_loglik_cfg()
+        cfg.solver, cfg.likelihood = SOLVER_IDS[solver], LIKELIHOOD_IDS[likelihood]
+        cfg.n_chains, cfg.n_series, cfg.n_times, cfg.max_steps = CH, M, T, int(max_steps)
+        cfg.rtol, cfg.atol, cfg.dt0, cfg.kernel = float(rtol), float(atol), float(dt0), int(kernel)
+        if out is None:
+            out = np.empty((CH, 1 + P + S), dtype=dt)
+        elif out.shape != (CH, 1 + P + S) or out.dtype != dt or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a C-contiguous {dt} array of shape {(CH, 1 + P + S)}")
+        partial = np.empty((CH * M, 1 + P + S + (D - P)), dtype=dt) if want_partial else None
+        status = np.empty(CH * M, dtype=np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if (a is not None and a.size) else C.c_void_p(0)
+        _check(lib().ctx_loglik_grad_host(self._h, C.byref(cfg), vp(y0s), vp(theta), vp(consts),
+                                          vp(ts), vp(data), vp(mask), vp(sigma), vp(out),
+                                          vp(partial), vp(status)))
+        return out, partial, status
 
     def loglik_grad(self, y0s, theta, consts, ts, data, sigma, *, mask=None,
                     likelihood="softlaplace", solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,

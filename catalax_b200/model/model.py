@@ -363,6 +363,21 @@ class Model:
         result = self._run_simulation(y0, parameters, constants, saveat)
         return self._format_simulation_results(result, saveat, return_array, y0, constants)
 
+    def predict(self, dataset: Dataset, config: Optional[SimulationConfig] = None,
+                n_steps: int = 100, use_times: bool = False, hdi=None) -> Dataset:
+        """Convenience wrapper around ``simulate`` (model.py:569-603): the configuration comes from
+        the dataset when none is given; ``use_times`` solves on the dataset's own time points."""
+        if config is None:
+            config = dataset.to_config(nsteps=n_steps)
+        if use_times:
+            config.nsteps = None
+            _, times, _ = dataset.to_jax_arrays(self.get_state_order())
+        else:
+            times = None
+        if config.nsteps != n_steps and not use_times:
+            config.nsteps = n_steps
+        return self.simulate(dataset, config, saveat=times, use_hdi=hdi)
+
     def _initialize_simulation_data(self, dataset: Dataset):
         return (dataset.to_y0_matrix(state_order=self.get_state_order()),
                 dataset.to_y0_matrix(state_order=self.get_constants_order()))
@@ -476,6 +491,45 @@ class Model:
                     setattr(q, k, p[k])
             q.prior = p.get("prior")
         return m
+
+    def to_dict(self) -> Dict:
+        """Serializable dictionary in the reference's model-JSON schema (model.py:1265-1292;
+        ``from_dict`` reads it back).  None-valued attributes are left out (``exclude_none``);
+        reactions are written too (the reference's ``to_dict`` drops them)."""
+        def clean(d):
+            return {k: v for k, v in d.items() if v is not None}
+
+        res = {
+            "name": self.name,
+            "states": [clean({"name": s.name, "symbol": str(s.symbol)}) for s in self.states.values()],
+            "constants": [clean({"name": c.name, "symbol": str(c.symbol)}) for c in self.constants.values()],
+            "odes": [{"equation": str(o.equation), "observable": bool(o.observable), "state": k}
+                     for k, o in self.odes.items()],
+            "parameters": [clean({"name": q.name, "symbol": str(q.symbol), "value": q.value,
+                                  "constant": bool(q.constant), "initial_value": q.initial_value,
+                                  "lower_bound": q.lower_bound, "upper_bound": q.upper_bound})
+                           for q in self.parameters.values()],
+            "assignments": [{"symbol": a.symbol, "equation": str(a.equation)}
+                            for a in self.assignments.values()],
+            "reactions": [{"symbol": r.symbol, "equation": str(r.equation),
+                           "reversible": bool(r.reversible),
+                           "reactants": [{"state": e.state, "stoichiometry": e.stoichiometry} for e in r.reactants],
+                           "products": [{"state": e.state, "stoichiometry": e.stoichiometry} for e in r.products]}
+                          for r in self.reactions.values()],
+        }
+        for key in ("constants", "assignments", "reactions"):
+            if not res[key]:
+                res.pop(key)
+        return res
+
+    def save(self, path: str, name: Optional[str] = None) -> str:
+        """Write the model JSON (model.py:1214-1230)."""
+        import os
+
+        fname = os.path.join(str(path), f"{(name or self.name).replace(' ', '_')}.json")
+        with open(fname, "w") as f:
+            json.dump(self.to_dict(), f, indent=2, default=str)
+        return fname
 
     @classmethod
     def load(cls, path) -> "Model":

@@ -1,3 +1,3 @@
-from .neuralbase import NeuralBase, NeuralODE, RateFlowODE, UniversalODE
+from .neuralbase import NeuralBase, NeuralODE, RateFlowODE, RBFLayer, UniversalODE
 
-__all__ = ["NeuralBase", "NeuralODE", "RateFlowODE", "UniversalODE"]
+__all__ = ["NeuralBase", "NeuralODE", "RateFlowODE", "UniversalODE", "RBFLayer"]

@@ -3,8 +3,8 @@
 Mirror of the forward (predict / rates) surface of ``catalax/neural``:
 ``NeuralBase.__call__`` / ``predict`` (neuralbase.py:134-143, 252-317), ``rates`` (:319-327),
 the per-class solve calls (neuralode.py:38-59, rateflow.py:100-121, universalode.py:118-141) and
-the controller defaults (neuralbase.py:623-645: rtol=1e-3, atol=1e-6).  Training (optax loop,
-back-propagation through the solver, penalties) and the .eqx serialisation are out of scope.
+the controller defaults (neuralbase.py:623-645: rtol=1e-3, atol=1e-6), the ``.eqx`` checkpoint
+format of all three classes (neuralbase.py:481-571) and the training gradient (trainer.py:268-306).
 
 Weights follow equinox's convention (``Linear(x) = W @ x + b``, ``W: [out, in]``); they are given
 explicitly or drawn from ``numpy.random.default_rng(seed)`` with ``N(0, 1/fan_in)``.
@@ -30,15 +30,33 @@ def _act_name(a) -> str:
     return name
 
 
+class RBFLayer:
+    """Stand-in for ``catalax.neural.RBFLayer(gamma)`` (rbf.py:10-39) as an ``activation=``
+    argument: every hidden activation becomes ``exp(-gamma * sum_j (x_i - mu_j)^2)`` with learned
+    centres ``mu`` [width] per hidden layer (mlp.py:86-118)."""
+
+    def __init__(self, gamma: float, width_size: Optional[int] = None, *, key=None):
+        self.gamma = float(gamma)
+
+
 class NeuralBase:
     kind = "neuralode"
+    default_activation = "tanh"      # neuralbase.py:79 (jax.nn.tanh)
 
     def __init__(self, data_size: int, width_size: int, depth: int, state_order: List[str],
                  observable_indices: Optional[List[int]] = None, solver=Tsit5,
-                 activation="softplus", final_activation=None, use_final_bias: bool = False,
+                 activation="tanh", final_activation=None, use_final_bias: bool = False,
                  out_size: Optional[int] = None, max_time: float = 1.0, *, key=0,
                  weights: Optional[Sequence[np.ndarray]] = None,
-                 biases: Optional[Sequence[Optional[np.ndarray]]] = None, mech=None):
+                 biases: Optional[Sequence[Optional[np.ndarray]]] = None, mech=None,
+                 rbf_mu: Optional[Sequence[np.ndarray]] = None, **hyper):
+        # activation=RBFLayer(gamma) replaces every hidden activation by a radial-basis layer with
+        # its own centres mu [width] (mlp.py:86-118, rbf.py:14-39)
+        rbf = isinstance(activation, RBFLayer)
+        self.rbf_gamma = float(activation.gamma) if rbf else None
+        if rbf:
+            activation = "identity"
+        self.hyperparams = dict(hyper)     # extra constructor kwargs travel in the checkpoint header
         self.data_size, self.width_size, self.depth = data_size, width_size, depth
         self.state_order = list(state_order)
         self.observable_indices = list(observable_indices) if observable_indices is not None \
@@ -49,7 +67,7 @@ class NeuralBase:
                                depth=depth, out_size=out_size or data_size,
                                activation=_act_name(activation),
                                final_activation=_act_name(final_activation),
-                               use_final_bias=use_final_bias, mech=mech)
+                               use_final_bias=use_final_bias, mech=mech, rbf=rbf)
         rng = np.random.default_rng(key)
         dims = self.spec.layer_dims()
         if weights is None:
@@ -60,12 +78,22 @@ class NeuralBase:
                 biases[-1] = None
         self.weights = [np.asarray(w, dtype=np.float64) for w in weights]
         self.biases = [None if b is None else np.asarray(b, dtype=np.float64) for b in biases]
+        self.rbf_mu = None
+        if rbf:     # rbf.py:27: centres ~ U(0, 1), one vector per hidden layer
+            self.rbf_mu = [np.asarray(m, dtype=np.float64) for m in rbf_mu] if rbf_mu is not None \
+                else [rng.uniform(0.0, 1.0, (width_size,)) for _ in range(depth)]
         self._compiled = {}
         self._rng = rng
 
     # ------------------------------------------------------------------ engine plumbing
     def _extra(self):
         return {}
+
+    def _pack_extra(self):
+        e = dict(self._extra())
+        if self.spec.rbf:
+            e.update(rbf_mu=self.rbf_mu, rbf_gamma=self.rbf_gamma)
+        return e
 
     def _t0_from_ts(self) -> bool:
         return True     # neuralode.py:52 / rateflow.py:114: t0 = ts[0]
@@ -80,7 +108,7 @@ class NeuralBase:
         if key not in self._compiled:
             field = cm.generate_mlp_field(self.spec)
             theta = cm.pack_parameters(self.spec, self.weights, self.biases, self.max_time,
-                                       np.dtype(dtype), **self._extra())
+                                       np.dtype(dtype), **self._pack_extra())
             self._compiled[key] = (engine.CompiledModel(field, key), theta)
         return self._compiled[key]
 
@@ -95,51 +123,169 @@ class NeuralBase:
         return self._compiled["tc"]
 
     # ------------------------------------------------------------------ reference checkpoints
-    @classmethod
-    def from_eqx(cls, path, **overrides):
-        """Load a model saved by the reference's ``save_to_eqx`` (neuralbase.py:481-571).
-
-        File layout (equinox ``tree_serialise_leaves``): one JSON line with the constructor
-        hyper-parameters, then every array leaf as consecutive ``numpy.save`` blobs in pytree
-        order -- for the MLP classes: ``W_0, b_0, W_1, b_1, ..., W_last[, b_last]`` followed by
-        the scalar ``max_time`` and static fields (ignored).  Plain NeuralODE checkpoints are
-        supported; RateFlow / Universal checkpoints carry extra leaves and raise."""
+    # File layout written by the reference's ``save_to_eqx`` (neuralbase.py:530-571): one JSON
+    # line ``{"hyperparameters": {...}}`` (the constructor arguments), then
+    # ``eqx.tree_serialise_leaves``: every leaf of the module pytree that is an array or a Python
+    # / numpy scalar as consecutive ``numpy.save`` blobs, in field order --
+    #   func.mlp.layers: W_0, b_0, [mu_0, gamma_0 (rbf)], ..., W_last[, b_last]; func.max_time;
+    #   observable_indices (ints); hyperparams (numeric leaves, keys sorted); then the subclass
+    #   fields: RateFlowODE stoich_matrix [S,R], reaction_size, mass_constraint [n_c,S] | absent
+    #   (rateflow.py:19-27); UniversalODE parameters [P], alpha_residual [S], gate_matrix [S,S]
+    #   (universalode.py:20-26; its ``model`` dict and ``use_gate`` are static).
+    # Strings, None and static fields are not leaves.  Verified on the checkpoint the reference
+    # ships (examples/trained/menten_trained.eqx: 5 arrays, max_time, then 7 scalar leaves).
+    @staticmethod
+    def _read_eqx(path):
         import json
 
         with open(path, "rb") as f:
             header = json.loads(f.readline().decode())
-            hp = dict(header["hyperparameters"])
             leaves = []
             while True:
                 try:
                     leaves.append(np.load(f, allow_pickle=False))
                 except (EOFError, ValueError):
                     break
-        if cls.kind != "neuralode" or hp.get("rbf"):
-            raise NotImplementedError("only plain NeuralODE .eqx checkpoints are supported")
+        return dict(header["hyperparameters"]), leaves
+
+    @staticmethod
+    def _mlp_from_leaves(path, hp, leaves):
         S, W, depth = int(hp["data_size"]), int(hp["width_size"]), int(hp["depth"])
         out = int(hp["out_size"]) if hp.get("out_size") else S
+        rbf = bool(hp.get("rbf"))
         dims = [S + 1] + [W] * depth + [out]
-        weights, biases, k = [], [], 0
+        weights, biases, mus, gammas, k = [], [], [], [], 0
         for l, (i, o) in enumerate(zip(dims[:-1], dims[1:])):
             Wm = leaves[k]; k += 1
             if Wm.shape != (o, i):
                 raise ValueError(f"{path}: layer {l} weight has shape {Wm.shape}, expected {(o, i)}")
             weights.append(Wm)
-            has_bias = l < depth or bool(hp.get("use_final_bias"))
-            if has_bias:
+            if l < depth or bool(hp.get("use_final_bias")):
                 biases.append(leaves[k]); k += 1
             else:
                 biases.append(None)
+            if rbf and l < depth:
+                mu = leaves[k]; k += 1
+                if mu.shape != (W,):
+                    raise ValueError(f"{path}: RBF centres of layer {l} have shape {mu.shape}")
+                mus.append(mu)
+                gammas.append(float(leaves[k])); k += 1
         max_time = float(leaves[k]) if k < len(leaves) and leaves[k].shape == () else 1.0
-        kw = dict(data_size=S, width_size=W, depth=depth, state_order=hp["state_order"],
-                  observable_indices=hp.get("observable_indices"),
-                  activation=hp.get("activation", "softplus"),
-                  final_activation=hp.get("final_activation"),
-                  use_final_bias=bool(hp.get("use_final_bias")), out_size=hp.get("out_size"),
+        k += 1
+        return weights, biases, mus, gammas, max_time, k
+
+    @classmethod
+    def from_eqx(cls, path, **overrides):
+        """Load a model saved by the reference's ``save_to_eqx`` (neuralbase.py:481-571):
+        NeuralODE (also with RBF hidden layers), RateFlowODE and UniversalODE checkpoints."""
+        hp, leaves = cls._read_eqx(path)
+        weights, biases, mus, gammas, max_time, k = cls._mlp_from_leaves(path, hp, leaves)
+        S = int(hp["data_size"])
+        rest = [a for a in leaves[k:] if a.ndim > 0]      # the scalar leaves repeat the header
+        if mus and len(set(gammas)) > 1:
+            raise NotImplementedError("RBF layers with different gammas")
+        # neuralbase.py:508-518: a header without the key falls back to the class default
+        activation = RBFLayer(gammas[0]) if mus else hp.get("activation", cls.default_activation)
+        kw = dict(data_size=S, width_size=int(hp["width_size"]), depth=int(hp["depth"]),
+                  observable_indices=hp.get("observable_indices", [0]),
+                  activation=activation, use_final_bias=bool(hp.get("use_final_bias")),
                   max_time=max_time, weights=weights, biases=biases)
+        if mus:
+            kw["rbf_mu"] = mus
+        if cls.kind == "neuralode":
+            kw.update(state_order=hp["state_order"], final_activation=hp.get("final_activation"),
+                      out_size=hp.get("out_size"))
+        elif cls.kind == "rateflow":
+            R_ = int(hp.get("reaction_size") or hp["out_size"])
+            sm = next((a for a in rest if a.shape == (S, R_)), None)
+            if sm is None:
+                raise ValueError(f"{path}: no stoichiometric matrix of shape {(S, R_)} among the leaves")
+            after = rest[next(i for i, a in enumerate(rest) if a is sm) + 1:]
+            mc = next((a for a in after if a.ndim == 2 and a.shape[1] == S), None)
+            kw.update(state_order=hp["state_order"], reaction_size=R_, stoich_matrix=sm,
+                      learn_stoich=bool(hp.get("learn_stoich", True)), mass_constraint=mc)
+        else:   # universalode: the mechanistic model travels in the header (universalode.py:63)
+            from ..model import Model
+
+            md = hp.get("model")
+            if md is None:
+                raise ValueError(f"{path}: UniversalODE checkpoint without a model in its header")
+            if isinstance(md, str):
+                import json
+
+                md = json.loads(md)
+            model = Model.from_dict(md)
+            if len(rest) < 3 or rest[-1].shape != (S, S) or rest[-2].shape != (S,):
+                raise ValueError(f"{path}: expected parameters, alpha_residual [S], gate_matrix [S,S] "
+                                 "as the last array leaves")
+            kw.update(model=model, final_activation=hp.get("final_activation") or "identity",
+                      gate_matrix=rest[-1], alpha_residual=rest[-2], parameters=rest[-3])
         kw.update(overrides)
         return cls(**kw)
+
+    def _header(self):
+        hp = {"data_size": self.data_size, "width_size": self.width_size, "depth": self.depth,
+              "out_size": None if self.kind != "rateflow" else self.spec.out_size,
+              "rbf": bool(self.spec.rbf), "use_final_bias": bool(self.spec.use_final_bias),
+              "observable_indices": list(self.observable_indices),
+              "state_order": list(self.state_order), **self.hyperparams}
+        if not self.spec.rbf:
+            hp["activation"] = self.spec.activation
+        hp["final_activation"] = self.spec.final_activation
+        return hp
+
+    def _own_leaves(self):
+        return []
+
+    def save_to_eqx(self, path, name: str, **kwargs):
+        """Write the reference's checkpoint format (neuralbase.py:530-571) so that
+        ``catalax.neural.<Class>.from_eqx`` (and ours) can load the model."""
+        import json
+        import os
+
+        if name.endswith(".eqx"):
+            name = name[: -len(".eqx")]
+        filename = os.path.join(str(path), name + ".eqx")
+        hp = self._header()
+        f32 = lambda a: np.asarray(a, dtype=np.float32)
+        leaves = []
+        for l, (W, b) in enumerate(zip(self.weights, self.biases)):
+            leaves.append(f32(W))
+            if b is not None:
+                leaves.append(f32(b))
+            if self.spec.rbf and l < self.depth:
+                leaves += [f32(self.rbf_mu[l]), np.asarray(self.rbf_gamma, dtype=np.float32)]
+        leaves.append(np.asarray(self.max_time, dtype=np.float32))
+        leaves += [np.asarray(int(i)) for i in self.observable_indices]
+
+        def numeric_leaves(o):      # jax flattens dicts with sorted keys; str / None are no leaves
+            if isinstance(o, dict):
+                return [x for key in sorted(o) for x in numeric_leaves(o[key])]
+            if isinstance(o, (list, tuple)):
+                return [x for v in o for x in numeric_leaves(v)]
+            if isinstance(o, (bool, int, float, np.generic)):
+                return [np.asarray(o)]
+            return []
+        leaves += numeric_leaves(hp)
+        leaves += self._own_leaves()
+        with open(filename, "wb") as f:
+            f.write((json.dumps({"hyperparameters": hp, **kwargs}, default=str) + "\n").encode())
+            for a in leaves:
+                np.save(f, a, allow_pickle=False)
+        return filename
+
+    @classmethod
+    def from_model(cls, model, width_size: int, depth: int, seed: int = 0,
+                   use_final_bias: bool = False, final_activation="identity", solver=Tsit5,
+                   activation="tanh", **kwargs):
+        """neuralbase.py:392-431: sizes and state order come from a ``Model``."""
+        modeled = len(model.odes) > 0 or len(model.reactions) > 0
+        state_order = model.get_state_order(modeled=modeled)
+        return cls(data_size=len(state_order), width_size=width_size, depth=depth,
+                   state_order=state_order,
+                   observable_indices=model.get_state_order(as_indices=True, modeled=modeled),
+                   solver=solver, activation=activation, final_activation=final_activation,
+                   use_final_bias=use_final_bias, key=seed, **kwargs)
 
     def get_weights_and_biases(self):
         return [a for pair in zip(self.weights, self.biases) for a in pair if a is not None]
@@ -162,9 +308,10 @@ class NeuralBase:
         ts_t, y0_t = tt(ts).to(dev), tt(y0s).to(dev)
         if y0_t.dim() == 1:
             y0_t = y0_t[None]
-        if dt0 is None:     # dt0 or ts[1] - ts[0]
-            first = ts_t if ts_t.dim() == 1 else ts_t[0]
-            dt0 = float((first[1] - first[0]).item())
+        if dt0 is None:
+            # `dt0 or ts[1] - ts[0]` under vmap (neuralode.py:44-47): every trajectory takes the
+            # spacing of ITS time row -- dt0 = 0 asks the kernel for exactly that
+            dt0 = 0.0
         sname = solver_name(solver or self.solver)
         if kernel == 0:     # auto: tensor cores (kernel 3) when eligible, else CUDA cores (2)
             kernel = 3 if (self.tensor_core_eligible(dtype) and sname in ("tsit5", "dopri5")) else 2
@@ -337,7 +484,8 @@ class NeuralBase:
             else:
                 model, _ = self._compiled[key]
                 self._compiled[key] = (model, cm.pack_parameters(
-                    self.spec, self.weights, self.biases, self.max_time, np.dtype(key), **self._extra()))
+                    self.spec, self.weights, self.biases, self.max_time, np.dtype(key),
+                    **self._pack_extra()))
 
     def train(self, ts, y0, data, *, steps: int = 100, lr: float = 1e-3, loss="l2", **kw):
         """Minimal Adam loop over ``value_and_grad`` (the role of trainer.py:173-253's optax loop;
@@ -381,15 +529,38 @@ class RateFlowODE(NeuralBase):
         super().__init__(data_size=data_size, width_size=width_size, depth=depth,
                          state_order=state_order, observable_indices=observable_indices,
                          solver=solver, activation=activation, final_activation="relu",
-                         use_final_bias=use_final_bias, out_size=reaction_size, key=key, **kw)
+                         use_final_bias=use_final_bias, out_size=reaction_size, key=key,
+                         reaction_size=reaction_size, learn_stoich=learn_stoich, **kw)
         self.reaction_size = reaction_size
         self.learn_stoich = learn_stoich
+        if mass_constraint is not None:     # rateflow.py:62-75
+            mass_constraint = np.asarray(mass_constraint, dtype=np.float64)
+            assert mass_constraint.ndim == 2 and mass_constraint.shape[1] == len(state_order), (
+                "Mass constraint must be a matrix of shape (n_constraints, n_state). Given shape: "
+                f"{mass_constraint.shape}")
         self.mass_constraint = mass_constraint
         self.stoich_matrix = (self._rng.normal(size=(data_size, reaction_size))
                               if stoich_matrix is None else np.asarray(stoich_matrix, dtype=np.float64))
 
+    default_activation = "celu"      # rateflow.py:38
+
     def _extra(self):
         return {"stoich_matrix": self.stoich_matrix}
+
+    def _own_leaves(self):           # rateflow.py:19-27: stoich_matrix, reaction_size, mass_constraint
+        out = [np.asarray(self.stoich_matrix, dtype=np.float32), np.asarray(int(self.reaction_size))]
+        if self.mass_constraint is not None:
+            out.append(np.asarray(self.mass_constraint, dtype=np.float32))
+        return out
+
+    @classmethod
+    def from_model(cls, model, width_size: int, depth: int, reaction_size: int, seed: int = 0,
+                   use_final_bias: bool = False, solver=Tsit5, activation="celu", **kwargs):
+        state_order = model.get_state_order(modeled=len(model.odes) > 0 or len(model.reactions) > 0)
+        return cls(data_size=len(state_order), reaction_size=reaction_size, width_size=width_size,
+                   depth=depth, state_order=state_order,
+                   observable_indices=list(range(len(state_order))), solver=solver,
+                   activation=activation, use_final_bias=use_final_bias, key=seed, **kwargs)
 
 
 class UniversalODE(NeuralBase):
@@ -400,16 +571,27 @@ class UniversalODE(NeuralBase):
     def __init__(self, data_size: int, width_size: int, depth: int, model,
                  observable_indices: Optional[List[int]] = None, solver=Tsit5,
                  use_final_bias: bool = False, activation="celu", final_activation="identity",
-                 use_gate: bool = True, *, key=0, gate_matrix=None, alpha_residual=None, **kw):
+                 use_gate: bool = True, *, key=0, gate_matrix=None, alpha_residual=None,
+                 parameters=None, **kw):
+        if isinstance(model, str):    # universalode.py:47-50
+            import json
+
+            model = json.loads(model)
+        if isinstance(model, dict):
+            from ..model import Model
+
+            model = Model.from_dict(model)
         resolved = model._replace_assignments()
         state_order = model.get_state_order()
         super().__init__(data_size=data_size, width_size=width_size, depth=depth,
                          state_order=state_order, observable_indices=observable_indices,
                          solver=solver, activation=activation, final_activation=final_activation,
                          use_final_bias=use_final_bias, key=key,
-                         mech=resolved.sim_input.field_spec(), **kw)
+                         mech=resolved.sim_input.field_spec(), model=model.to_dict(), **kw)
         self.use_gate = True          # effectively always True in the reference (universalode.py:65-68)
-        self.parameters = np.asarray(resolved._get_parameters(), dtype=np.float64)
+        self.model = model
+        self.parameters = np.asarray(resolved._get_parameters() if parameters is None else parameters,
+                                     dtype=np.float64)
         S = len(state_order)
         self.alpha_residual = (0.05 * self._rng.normal(size=(S,)) if alpha_residual is None
                                else np.asarray(alpha_residual, dtype=np.float64))
@@ -419,6 +601,23 @@ class UniversalODE(NeuralBase):
     def _extra(self):
         return {"gate_matrix": self.gate_matrix, "alpha_residual": self.alpha_residual,
                 "mech_parameters": self.parameters}
+
+    default_activation = "celu"      # universalode.py:38
+
+    def _own_leaves(self):           # universalode.py:20-26: parameters, alpha_residual, gate_matrix
+        f32 = lambda a: np.asarray(a, dtype=np.float32)
+        return [f32(self.parameters), f32(self.alpha_residual), f32(self.gate_matrix)]
+
+    @classmethod
+    def from_model(cls, model, width_size: int, depth: int, seed: int = 0,
+                   use_final_bias: bool = False, final_activation="identity", solver=Tsit5,
+                   activation="celu", **kwargs):
+        """universalode.py:188-: sizes come from the mechanistic ``Model``."""
+        n = len(model.get_state_order())
+        return cls(data_size=n, width_size=width_size, depth=depth, model=model,
+                   observable_indices=list(range(n)), solver=solver, activation=activation,
+                   final_activation=final_activation, use_final_bias=use_final_bias, key=seed,
+                   **kwargs)
 
     def _t0_from_ts(self) -> bool:
         return False    # universalode.py:133: t0 = 0.0

@@ -53,6 +53,7 @@ class MLPSpec:
     final_activation: str = "identity"
     use_final_bias: bool = False
     mech: Optional[cg.FieldSpec] = None      # universalode: mechanistic model (assignments inlined)
+    rbf: bool = False                        # hidden activation = RBFLayer (mlp.py:86-118, rbf.py:32-39)
 
     def layer_dims(self) -> List[Tuple[int, int]]:
         dims = [self.data_size + 1] + [self.width_size] * self.depth + [self.out_size]
@@ -67,6 +68,7 @@ class MLPLayout:
     b_off: List[int] = field(default_factory=list)
     in_pad: List[int] = field(default_factory=list)
     inv_max_time: int = 0
+    rbf_off: List[int] = field(default_factory=list)   # per hidden layer: (g*W, 2g*sum mu, g*sum mu^2, 0)
     stoich: int = -1
     gate: int = -1
     alpha: int = -1
@@ -83,6 +85,9 @@ def layout_of(spec: MLPSpec) -> MLPLayout:
         lay.w_off.append(off); off += n_out * ip
         lay.b_off.append(off); off += _pad4(n_out)
     lay.inv_max_time = off; off += 4
+    if spec.rbf:
+        for _ in range(spec.depth):
+            lay.rbf_off.append(off); off += 4
     S = spec.data_size
     if spec.kind == "rateflow":
         lay.stoich = off; off += _pad4(S * spec.out_size)
@@ -96,7 +101,7 @@ def layout_of(spec: MLPSpec) -> MLPLayout:
 
 def pack_parameters(spec: MLPSpec, weights: Sequence[np.ndarray], biases: Sequence[Optional[np.ndarray]],
                     max_time: float, dtype, stoich_matrix=None, gate_matrix=None, alpha_residual=None,
-                    mech_parameters=None) -> np.ndarray:
+                    mech_parameters=None, rbf_mu=None, rbf_gamma=None) -> np.ndarray:
     """Flatten eqx-convention weights (W [out, in], b [out]) into the kernel's layout."""
     lay = layout_of(spec)
     out = np.zeros(lay.size, dtype=np.float64)
@@ -109,6 +114,13 @@ def pack_parameters(spec: MLPSpec, weights: Sequence[np.ndarray], biases: Sequen
         if b is not None:
             out[lay.b_off[l]: lay.b_off[l] + n_out] = np.asarray(b, dtype=np.float64)
     out[lay.inv_max_time] = 1.0 / float(max_time)
+    if spec.rbf:
+        # RBFLayer.__call__ (rbf.py:32-39) on a vector x [W] with centres mu [W]:
+        #   out_i = exp(-gamma * sum_j (x_i - mu_j)^2) = exp(-(gamma W x_i^2 - 2 gamma sum(mu) x_i + gamma sum(mu^2)))
+        for l in range(spec.depth):
+            mu = np.asarray(rbf_mu[l], dtype=np.float64)
+            g = float(rbf_gamma[l] if np.ndim(rbf_gamma) else rbf_gamma)
+            out[lay.rbf_off[l]: lay.rbf_off[l] + 3] = (g * mu.size, 2.0 * g * mu.sum(), g * (mu * mu).sum())
     S = spec.data_size
     if spec.kind == "rateflow":
         sm = np.asarray(stoich_matrix, dtype=np.float64)
@@ -132,6 +144,8 @@ def tc_dims(spec: MLPSpec):
     W = spec.width_size
     if W % 32 or W > 64 or spec.depth < 1 or spec.data_size + 1 > 8 or spec.out_size > 16:
         return None
+    if spec.rbf:
+        return None     # radial-basis hidden layers run the CUDA-core form
     in_pad, out_pad = 8, 16
     layers = [(in_pad if l == 0 else W, out_pad if l == spec.depth else W) for l in range(spec.depth + 1)]
     wpack = sum(2 * k * n for k, n in layers)
@@ -249,7 +263,7 @@ def _tc_source(spec: MLPSpec) -> List[str]:
 def adjoint_dims(spec: MLPSpec):
     """Shared-memory pack of the weight-gradient kernels (csrc/ctx_mlp_adjoint.cuh), or None when
     the model is not a plain NeuralODE of at most 8 states (RateFlow / Universal fields: next)."""
-    if spec.kind not in ("neuralode", "rateflow", "universalode") or spec.data_size > 8:
+    if spec.kind not in ("neuralode", "rateflow", "universalode") or spec.data_size > 8 or spec.rbf:
         return None
     if spec.kind != "rateflow" and spec.out_size != spec.data_size:
         return None
@@ -407,7 +421,9 @@ def generate_mlp_field(spec: MLPSpec) -> cg.GeneratedField:
             f"        acc += w4[0] * x{l}[k]; acc += w4[1] * x{l}[k + 1];",
             f"        acc += w4[2] * x{l}[k + 2]; acc += w4[3] * x{l}[k + 3];",
             "      }",
-            f"      h{l + 1}[j] = " + ACTIVATIONS[act].format(x="acc") + ";",
+            f"      h{l + 1}[j] = " + (
+                f"exp(-((th[{lay.rbf_off[l]}] * acc - th[{lay.rbf_off[l] + 1}]) * acc + th[{lay.rbf_off[l] + 2}]))"
+                if (spec.rbf and not last) else ACTIVATIONS[act].format(x="acc")) + ";",
         ]
         if n_out % JB == 0 and n_out > JB:
             src += ["#pragma unroll 1", f"  for (int j0 = 0; j0 < {n_out}; j0 += {JB}) {{",

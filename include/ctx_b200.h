@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CTX_ABI_VERSION 2
+#define CTX_ABI_VERSION 3
 
 enum { CTX_F32 = 0, CTX_F64 = 1 };
 /* solver ids: simconfig.py:16 (`solver: Any = Tsit5`), simulation.py:23-26 (non-adaptive list) */
@@ -204,6 +204,50 @@ int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
                    const void* consts, const void* ts, void* ys, int32_t* status,
                    int32_t* n_accepted, int32_t* n_rejected);
 
+/* Same for ctx_loglik_grad: every array is a HOST pointer (partial / status may be NULL); one
+ * NUTS leapfrog evaluation through this call moves theta [CH,P] + sigma [CH,S] (+ the constant
+ * data block) to the device and out [CH, 1+D_theta+S] back.  Replaces the host-side round trip
+ * of numpyro's potential_fn around mcmc.py:405-491. */
+int ctx_loglik_grad_host(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s,
+                         const void* theta, const void* consts, const void* ts, const void* data,
+                         const uint8_t* mask, const void* sigma, void* out, void* partial,
+                         int32_t* status);
+
+/* ---- XLA GPU custom-call shims (legacy "API_VERSION_ORIGINAL" ABI: no XLA/jaxlib header) -----
+ * The reference calls its seam (simulation.py:160-196) from inside jit-compiled programs
+ * (model.py:699, mcmc.py:448 under numpyro's jitted potential).  These entry points let XLA call
+ * the kernels on ITS stream with ITS buffers: `buffers` = operands in order, then results in
+ * order (the workspace is declared as the last result); `opaque` = one of the packed descriptors
+ * below, byte-copied.  `stream` is a cudaStream_t.  Python registration: INTEGRATION.md section 3.
+ *   ctx_xla_solve        operands y0, theta, consts, ts
+ *                        results  ys, status, n_accepted, n_rejected, workspace
+ *   ctx_xla_solve_sens   operands y0, theta, consts, ts
+ *                        results  ys, sens, status, n_accepted, n_rejected, workspace
+ *   ctx_xla_loglik_grad  operands y0s, theta, consts, ts, data, mask(uint8), sigma
+ *                        results  out, partial, status, workspace
+ * The ABI has no status channel: a failing call stores its code / message in a process-wide
+ * slot; ctx_xla_last_status() returns and clears it (0 = no failure since the last query). */
+typedef struct ctx_xla_solve_desc {
+  int32_t abi;        /* CTX_ABI_VERSION */
+  int32_t reserved;
+  uint64_t model;     /* ctx_model* of this process */
+  uint64_t ws_bytes;  /* size of the workspace result = ctx_workspace_bytes(model, &cfg) */
+  ctx_solve_cfg cfg;
+} ctx_xla_solve_desc;
+typedef struct ctx_xla_loglik_desc {
+  int32_t abi;
+  int32_t has_mask;   /* 0: the mask operand is a dummy, use isfinite(data) (mcmc.py:566) */
+  uint64_t model;
+  uint64_t ws_bytes;  /* ctx_loglik_workspace_bytes(model, &cfg) */
+  ctx_loglik_cfg cfg;
+} ctx_xla_loglik_desc;
+void ctx_xla_solve(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void ctx_xla_solve_sens(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void ctx_xla_loglik_grad(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+size_t ctx_xla_desc_bytes(int32_t which); /* 0: ctx_xla_solve_desc, 1: ctx_xla_loglik_desc */
+int ctx_xla_last_status(void);
+size_t ctx_xla_last_error(char* buf, size_t n);
+
 /* ---- diagnostics ------------------------------------------------------------------------ */
 int ctx_abi_version(void);
 int ctx_device_count(void); /* 0 when no GPU is visible; never throws */
@@ -213,6 +257,8 @@ size_t ctx_last_error(char* buf, size_t n);
 int ctx_measure_fma_peak(int32_t dtype, double* tflops);
 /* number of kernel launches this library has issued in this process (bench "gpu_launches") */
 int64_t ctx_launch_count(void);
+/* hash of the sources this library was built from (checked against the tree at load time) */
+const char* ctx_build_stamp(void);
 
 #ifdef __cplusplus
 }

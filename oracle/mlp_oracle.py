@@ -20,23 +20,37 @@ ACT = {
 }
 
 
-def mlp_forward(x, weights, biases, activation, final_activation):
-    """x [B, in] -> [B, out]; W [out, in]."""
+def rbf_layer(x, mu, gamma):
+    """``RBFLayer.__call__`` (catalax/neural/rbf.py:32-39) applied to each row of x [B, W] with
+    centres mu [W]: ``diff = x[:, None] - mu[None, :]``, ``exp(-gamma * sum(diff**2, -1))`` --
+    unit i sees the distances of ITS pre-activation to all W centres."""
+    diff = x[:, :, None] - np.asarray(mu, dtype=x.dtype)[None, None, :]
+    return np.exp(-x.dtype.type(gamma) * np.sum(np.square(diff), axis=-1))
+
+
+def mlp_forward(x, weights, biases, activation, final_activation, rbf_mu=None, rbf_gamma=None):
+    """x [B, in] -> [B, out]; W [out, in].  ``rbf_mu`` (one centre vector per hidden layer): the
+    hidden activations are RBF layers and ``activation`` is the identity (mlp.py:86-118)."""
     h = x
     for l, (W, b) in enumerate(zip(weights, biases)):
         h = h @ W.T.astype(h.dtype)
         if b is not None:
             h = h + b.astype(h.dtype)
-        h = ACT[final_activation if l == len(weights) - 1 else activation](h)
+        last = l == len(weights) - 1
+        if rbf_mu is not None and not last:
+            h = rbf_layer(h, rbf_mu[l], rbf_gamma)
+        else:
+            h = ACT[final_activation if last else activation](h)
     return h
 
 
 def make_rhs(kind, weights, biases, activation, final_activation, max_time, stoich_matrix=None,
-             gate_matrix=None, alpha_residual=None, mech_rhs=None, mech_parameters=None):
+             gate_matrix=None, alpha_residual=None, mech_rhs=None, mech_parameters=None,
+             rbf_mu=None, rbf_gamma=None):
     def rhs(t, Y, theta, consts, y0):
         dt = Y.dtype
         x = np.concatenate([Y, (t / dt.type(max_time))[:, None]], axis=1)
-        out = mlp_forward(x, weights, biases, activation, final_activation)
+        out = mlp_forward(x, weights, biases, activation, final_activation, rbf_mu, rbf_gamma)
         if kind == "neuralode":
             return out
         if kind == "rateflow":
