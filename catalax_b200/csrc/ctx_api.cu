@@ -30,6 +30,7 @@ extern const char ctx_solve_v2_src[];    // generated from ctx_solve_v2.cuh
 namespace {
 
 thread_local std::string g_err;
+thread_local const char* g_last_kernel = "";   // name of the solve kernel this thread launched last
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const std::string& msg) {
@@ -541,6 +542,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem, stream));
     g_launches++;
+    g_last_kernel = "ctx_solve_v2";
     launched = true;
     }
   }
@@ -593,6 +595,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
                               stream));
     g_launches++;
+    g_last_kernel = "ctx_solve_v1";
   } else if (kernel == 3) {
     // K3: tcgen05 MLP tiles (ctx_mlp_tc.cuh); theta = [aux | UMMA weight pack]
     if (m->mlp_tc_smem <= 0 || m->desc.dtype != CTX_F32 || tan || cfg->solver > CTX_DOPRI5)
@@ -612,6 +615,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(512), params,
                               (size_t)m->mlp_tc_smem, stream));
     g_launches++;
+    g_last_kernel = "ctx_solve_mlp_tc";
   } else if (kernel == 4) {
     // K1w: one warp per trajectory, persistent warps (ctx_integrator.cuh ctx_solve_w)
     if (m->warp_warps <= 0 || tan)
@@ -631,6 +635,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
     g_launches++;
+    g_last_kernel = "ctx_solve_w";
   } else if (kernel == 1) {
     if (m->theta_ptr && warps > 0)
       return fail(CTX_E_INVALID, "weight-array models run the persistent kernel (kernel 0 or 2)");
@@ -641,6 +646,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     const unsigned long long grid = (cfg->batch + block - 1) / block;
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, 0, stream));
     g_launches++;
+    g_last_kernel = "ctx_solve_v0";
   } else {
     return fail(CTX_E_INVALID, "unknown kernel id");
   }
@@ -901,6 +907,8 @@ size_t ctx_last_error(char* buf, size_t n) {
 }
 
 int64_t ctx_launch_count(void) { return g_launches.load(); }
+
+const char* ctx_last_solve_kernel(void) { return g_last_kernel; }
 
 int ctx_model_compile(const char* field_src, const ctx_model_desc* desc, ctx_model** out) {
   if (!field_src || !desc || !out) return fail(CTX_E_INVALID, "null argument");

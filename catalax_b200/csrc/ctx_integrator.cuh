@@ -252,6 +252,19 @@ __device__ __forceinline__ real ctx_scaled_error(const real dt, const real* y, c
 }
 #endif
 
+// Test hook (never defined in shipped builds): the step-size factor that follows loop iteration
+// CTX_DBG_FACTOR_STEP is taken from constant CTX_DBG_FACTOR_CONST of the trajectory when that
+// constant is positive.  In f32 the error estimate of the reference's first steps is rounding
+// noise, so the factor the reference itself drew there is a nuisance parameter of every pin
+// against reference OUTPUTS (tests/test_gpu_reference_pins.py fits it per trajectory, exactly as
+// oracle.diffrax_oracle.solve(factor_override=...) does on the CPU).
+#ifdef CTX_DBG_FACTOR_CONST
+#define CTX_DBG_FACTOR(n_it, c, factor)                                                       \
+  if ((n_it) == CTX_DBG_FACTOR_STEP && (c)[CTX_DBG_FACTOR_CONST] > R(0.0)) (factor) = (c)[CTX_DBG_FACTOR_CONST]
+#else
+#define CTX_DBG_FACTOR(n_it, c, factor)
+#endif
+
 // ------------------------------------------------------------------ dense output
 // Evaluate the solver's interpolant of the accepted step [tp, tp+dt] at time tq.
 __device__ __forceinline__ void ctx_dense(const real tq, const real tp, const real tn,
@@ -368,6 +381,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
     real factor = R(0.9) * ctx_pow02(inv);
     factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
     if (factor != factor) factor = inv;  // clip(NaN) stays NaN in the reference
+    CTX_DBG_FACTOR(n, c, factor);
     dt_next = dt * factor;
 #endif
     if (keep) {
@@ -892,6 +906,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       const real inv = R(1.0) / scaled;
       real factor = R(0.9) * ctx_pow02(inv);
       factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
+      CTX_DBG_FACTOR(nacc + nrej, c, factor);
       dt_next = dt * factor;
       if (scaled != scaled) dt_next = scaled;  // NaN error norm poisons the step size
 #endif

@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
     L.ctx_loglik_grad_host.restype = C.c_int
     L.ctx_loglik_grad_host.argtypes = [vp, C.POINTER(ctx_loglik_cfg)] + [vp] * 10
     L.ctx_build_stamp.restype = C.c_char_p
+    L.ctx_last_solve_kernel.restype = C.c_char_p
     for name in ("ctx_xla_solve", "ctx_xla_solve_sens", "ctx_xla_loglik_grad"):
         fn = getattr(L, name)
         fn.restype = None
@@ -182,6 +183,11 @@ def measure_fma_peak(dtype: str = "float32") -> float:
 
 def launch_count() -> int:
     return int(lib().ctx_launch_count())
+
+
+def last_solve_kernel() -> str:
+    """Kernel the last solve of this thread launched (what ``kernel=0`` resolved to)."""
+    return lib().ctx_last_solve_kernel().decode()
 
 
 @dataclass

@@ -257,6 +257,9 @@ size_t ctx_last_error(char* buf, size_t n);
 int ctx_measure_fma_peak(int32_t dtype, double* tflops);
 /* number of kernel launches this library has issued in this process (bench "gpu_launches") */
 int64_t ctx_launch_count(void);
+/* name of the kernel the last ctx_solve / ctx_solve_sens call of THIS thread launched
+ * ("ctx_solve_v0|v1|v2|w|mlp_tc"): lets tests assert which form `kernel = 0` selected */
+const char* ctx_last_solve_kernel(void);
 /* hash of the sources this library was built from (checked against the tree at load time) */
 const char* ctx_build_stamp(void);
 

@@ -81,6 +81,42 @@ def loglik_grad(model, y0s, theta, consts, ts, data, sigma, *, mask=None,
     return out, gy0, status
 
 
+def loglik_grad_c(model, y0s, theta, consts, ts, data, sigma, *, mask=None,
+                  likelihood="softlaplace", dtype=np.float64, n_threads=None, oracle=None,
+                  **solve_kw):
+    """``loglik_grad`` with the solves done by the compiled C / OpenMP oracle (one task per
+    (chain, series) trajectory with its parameter tangents): the CPU baseline of bench.py's NUTS
+    leg and the checker for chain counts the numpy form is too slow for.  Same restated
+    algorithm (``c_oracle.py``); out [CH, 1+P+S] float64, status [CH, M]."""
+    from .c_oracle import COracle
+
+    states, params, consts_n, odes, reactions = model
+    S, P = len(states), len(params)
+    orc = oracle or COracle(states, params, consts_n, odes, reactions, sens_theta=True, dtype=dtype)
+    y0s = np.asarray(y0s, dtype=dtype); ts = np.asarray(ts, dtype=dtype)
+    data = np.asarray(data, dtype=np.float64); consts = np.asarray(consts, dtype=dtype)
+    theta = np.asarray(theta, dtype=dtype)
+    M, T = ts.shape
+    CH = theta.shape[0]
+    if mask is None:
+        mask = np.isfinite(data)
+    r = orc.solve(np.tile(y0s, (CH, 1)), np.repeat(theta, M, axis=0), np.tile(consts, (CH, 1)),
+                  np.tile(ts, (CH, 1)), n_threads=n_threads, **solve_kw)
+    ys = r.ys.reshape(CH, M, T, -1)
+    loc = ys[..., :S].astype(np.float64)
+    tang = ys[..., S:].astype(np.float64).reshape(CH, M, T, P, S)
+    sg = np.asarray(sigma, dtype=np.float64)
+    s = np.abs(sg)[:, None, None, :]
+    with np.errstate(all="ignore"):
+        lp, dl_dloc, dl_ds = logpdf_terms(np.where(mask, data, 0.0)[None], loc, s, likelihood)
+        out = np.zeros((CH, 1 + P + S))
+        out[:, 0] = np.where(mask[None], lp, 0.0).sum(axis=(1, 2, 3))
+        w = np.where(mask[None], dl_dloc, 0.0)
+        out[:, 1:1 + P] = np.einsum("cmts,cmtps->cp", w, tang)
+        out[:, 1 + P:] = np.where(mask[None], dl_ds, 0.0).sum(axis=(1, 2)) * np.sign(sg)
+    return out, r.status.reshape(CH, M), r
+
+
 def surrogate_loglik_grad(model, t, y, theta, consts, inits, data, jac2, sigma, *, n_time,
                           mask=None, extra2=None, likelihood="softlaplace"):
     """Surrogate (rate-matching) mode of the same numpyro model.  PARITY ORACLE (test infra).

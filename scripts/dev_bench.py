@@ -14,6 +14,7 @@ ap.add_argument("--dtype", nargs="+", default=["float32", "float64"])
 ap.add_argument("--kernel", type=int, nargs="+", default=[1, 2])
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--rtol", type=float, default=1e-6)
+ap.add_argument("--neural", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 field = cg.generate_field(cases.field_spec(cases.michaelis_menten()))
@@ -41,7 +42,7 @@ for dtype in a.dtype:
                                   fails=int((o.status != 0).sum().item()))), flush=True)
 
 # ---- config 5: neural vector field
-if "--neural" in sys.argv or True:
+if "--neural" in sys.argv:
     import catalax_b200 as ctx
     from catalax_b200.neural import NeuralODE
     for x64 in (False,):

@@ -4,16 +4,9 @@ from __future__ import annotations
 import numpy as np
 import sympy as sp
 
-from catalax_b200.tools import codegen as cg
-
-
-def michaelis_menten():
-    """README model in ODE form (reference README.md:99-116)."""
-    S, E, P, Km, kc = sp.symbols("S E P K_m k_cat")
-    r = kc * E * S / (Km + S)
-    states, params, consts = ["E", "P", "S"], ["K_m", "k_cat"], []
-    odes = {"E": sp.Integer(0), "P": r, "S": -r}
-    return states, params, consts, odes, []
+from catalax_b200.tools import codegen as cg  # noqa: F401
+from catalax_b200.workloads import (field_spec, mass_action_inputs, mass_action_network,  # noqa: F401
+                                    michaelis_menten, mm_inputs)
 
 
 def menten_fixture():
@@ -33,48 +26,6 @@ def nonautonomous():
         "d": k3 * (a_init - d) + sp.tanh(c),
     }
     return ["a", "b", "c", "d"], ["k1", "k2", "k3"], ["q"], odes, []
-
-
-def mass_action_network(n_states=32):
-    """ring of first-order steps + second-order couplings."""
-    S = n_states
-    states = [f"x{i:02d}" for i in range(S)]
-    params = [f"k{j:02d}" for j in range(2 * S)]
-    reactions = []
-    for i in range(S):
-        xi = sp.Symbol(states[i])
-        reactions.append((f"r{i:02d}", [(1.0, states[i])], [(1.0, states[(i + 1) % S])],
-                          sp.Symbol(params[i]) * xi))
-    for i in range(S):
-        xi, xj = sp.Symbol(states[i]), sp.Symbol(states[(i + 5) % S])
-        reactions.append((f"r{S + i:02d}", [(1.0, states[i]), (1.0, states[(i + 5) % S])],
-                          [(1.0, states[(i + 11) % S])], sp.Symbol(params[S + i]) * xi * xj))
-    return states, params, [], {}, reactions
-
-
-def field_spec(model):
-    states, params, consts, odes, reactions = model
-    return cg.FieldSpec(list(states), list(params), list(consts), dict(odes), list(reactions))
-
-
-def mm_inputs(B, seed=0, dtype=np.float64, km_range=(0.5, 50.0)):
-    """BASELINE config 2 inputs (states ordered [E, P, S]): S0~U(50,300), E0~U(5,20), P0=0,
-    k_cat~LogU(0.02,0.5), K_m~LogU(0.5,50).
-
-    SURVEY §8d proposed K_m~LogU(0.01,1); with that range 3.6% of the rows become stiff after
-    substrate depletion (decay rate k_cat*E0/K_m up to 1000 per time unit) and exhaust
-    max_steps=4096, which the reference's default throw=True turns into an exception.  The
-    benchmark range keeps every row solvable; ``km_range=(0.01, 1.0)`` is kept as the
-    failure-semantics test case.
-    """
-    rng = np.random.default_rng(seed)
-    S0 = rng.uniform(50, 300, B)
-    E0 = rng.uniform(5, 20, B)
-    y0 = np.stack([E0, np.zeros(B), S0], axis=1).astype(dtype)
-    Km = np.exp(rng.uniform(np.log(km_range[0]), np.log(km_range[1]), B))
-    kc = np.exp(rng.uniform(np.log(0.02), np.log(0.5), B))
-    theta = np.stack([Km, kc], axis=1).astype(dtype)
-    return y0, theta, np.zeros((B, 0), dtype=dtype)
 
 
 def mm_closed_form(t, s0, V, K):

@@ -105,6 +105,54 @@ def test_mm_batch_per_row_theta(dtype, T, kernel):
         assert abs(steps_gpu - steps_ref) / steps_ref < 0.02
 
 
+@pytest.mark.parametrize("kernel,T,dtype", [(5, 384, np.float64), (0, 768, np.float64),
+                                            (5, 1000, np.float32), (0, 320, np.float32)])
+def test_warp_specialised_kernel_against_the_c_oracle(kernel, T, dtype):
+    """The headline kernel (ctx_solve_v2: producer warps step, consumer warps save) compared with
+    the oracle DIRECTLY -- explicitly (kernel 5) and as what ``kernel = 0`` selects for long shared
+    grids (f32 >= 320 points, f64 >= 768, >= 65 536 rows) -- on BASELINE config 2's distributions
+    at a size that engages every part of it (slot ring, guided queue, 8-point groups in f32).
+    x64: 1e-6 relative at every save point and identical accepted / rejected counts; f32: the
+    stated statistical bound against an x64 truth, next to the f32 oracle."""
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+    from oracle.c_oracle import COracle
+
+    B = 65536 + 1237      # ragged tail
+    model = cases.michaelis_menten()
+    y0, theta, consts = cases.mm_inputs(B, seed=11, dtype=dtype)
+    ts = np.linspace(0, 100, T).astype(dtype)
+    orc = COracle(*model[:4], model[4], dtype=dtype)
+    ref = orc.solve(y0, theta, consts, ts, rtol=1e-6, atol=1e-6, dt0=0.1, max_steps=4096)
+    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), np.dtype(dtype).name)
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    out = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), in_axes=(0, 0, 0, None), rtol=1e-6,
+                  atol=1e-6, dt0=0.1, max_steps=4096, kernel=kernel)
+    torch.cuda.synchronize()
+    assert engine.last_solve_kernel() == "ctx_solve_v2"
+    ys = out.ys.cpu().numpy()
+    assert (out.status.cpu().numpy() == 0).all() and (ref.status == 0).all()
+    if dtype == np.float64:
+        np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
+        np.testing.assert_array_equal(out.n_rejected.cpu().numpy(), ref.n_rejected)
+        _assert_close_f64(ys, ref.ys)
+    else:
+        sub = slice(0, 8192)
+        truth = COracle(*model[:4], model[4], dtype=np.float64).solve(
+            y0[sub].astype(np.float64), theta[sub].astype(np.float64), consts[sub].astype(np.float64),
+            ts.astype(np.float64), rtol=1e-10, atol=1e-10, dt0=0.1, max_steps=100000).ys
+        scale = 1e-6 + 1e-6 * np.abs(truth)
+        e_gpu = np.abs(ys[sub].astype(np.float64) - truth) / scale
+        e_ref = np.abs(ref.ys[sub].astype(np.float64) - truth) / scale
+        assert e_gpu.max() <= 200.0, e_gpu.max()
+        assert e_gpu.mean() <= 1.25 * e_ref.mean() + 0.05
+        assert np.percentile(e_gpu, 99.9) <= 1.5 * np.percentile(e_ref, 99.9) + 1.0
+        steps_gpu = int((out.n_accepted + out.n_rejected).sum().item())
+        steps_ref = int((ref.n_accepted.astype(np.int64) + ref.n_rejected).sum())
+        assert abs(steps_gpu - steps_ref) / steps_ref < 0.02
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("solver,dt0", [("tsit5", 0.1), ("dopri5", 0.1), ("euler", 0.01), ("heun", 0.02)])
 def test_nonautonomous_all_solvers_f64(solver, dt0, kernel):
