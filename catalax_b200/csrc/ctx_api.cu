@@ -130,6 +130,9 @@ struct SolveArgs {
   int q_div;
   int ts_smem;
   real rtol, atol, dt0;
+  const real* ll_data;     // CTX_LLSAVE builds (ctx_pointwise_loglik)
+  const real* ll_sigma;
+  int ll_likelihood;
 };
 
 template <typename real>
@@ -258,7 +261,7 @@ size_t theta_smem(const ctx_model* m) {
   return m->theta_ptr ? (size_t)m->p_pad * (m->desc.dtype == CTX_F64 ? 8 : 4) : 0;
 }
 
-int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0) {
+int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0, int ll = 0) {
   if (!v.cubin.empty()) return CTX_OK;
   std::string src;
   src += m->desc.dtype == CTX_F64 ? "typedef double real;\n#define R(x) x\n"
@@ -286,6 +289,8 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0)
       // 128 registers for the 3-state model: still 4 CTAs/SM.
       opts.push_back("-DCTX_GP=8");
     }
+    // the dense-output pass writes point-wise log-likelihoods instead of states (ctx_pointwise_loglik)
+    if (ll) opts.push_back("-DCTX_LLSAVE=1");
     mb = std::max<size_t>(1, std::min<size_t>(4, mb));
     if (m->theta_ptr) mb = 1;
     const char* ex = getenv("CTX_B200_NVRTC_FLAGS");
@@ -365,13 +370,13 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0)
 }
 
 int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_t* out,
-               int wide = 0) {
+               int wide = 0, int ll = 0) {
   if (solver < 0 || solver > 3) return fail(CTX_E_INVALID, "unknown solver id");
   if (tan && m->desc.n_dirs <= 0)
     return fail(CTX_E_INVALID, "model was generated without sensitivity directions");
   std::lock_guard<std::mutex> lk(m->mu);
-  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0)];
-  int rc = compile_variant(m, solver, tan, v, wide);
+  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0) + (ll ? 16 : 0)];
+  int rc = compile_variant(m, solver, tan, v, wide, ll);
   if (rc) return rc;
   int dev = 0;
   CTX_CUDA(cudaGetDevice(&dev));
@@ -391,9 +396,9 @@ int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_
 }
 
 // sizeof(ctx_warp_smem) of the loaded ctx_solve_v1 module (call after get_kernel)
-int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out, int wide = 0) {
+int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out, int wide = 0, int ll = 0) {
   std::lock_guard<std::mutex> lk(m->mu);
-  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0)];
+  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0) + (ll ? 16 : 0)];
   if (v.v1_warp_smem < 0) {
     void* dptr = nullptr;
     size_t nbytes = 0;
@@ -426,7 +431,8 @@ template <typename real>
 int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0,
                  const void* theta, const void* consts, const void* ts, void* ys, void* sens,
                  int32_t* status, int32_t* nacc, int32_t* nrej, void* ws, size_t ws_bytes,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const void* ll_data = nullptr, const void* ll_sigma = nullptr,
+                 int ll_likelihood = 0) {
   const ctx_model_desc& d = m->desc;
   if (cfg->batch <= 0) return CTX_OK;
   if (cfg->n_times <= 0) return fail(CTX_E_INVALID, "n_times must be >= 1");
@@ -465,10 +471,21 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.rtol = (real)cfg->rtol;
   a.atol = (real)cfg->atol;
   a.dt0 = (real)cfg->dt0;
+  a.ll_data = (const real*)ll_data;
+  a.ll_sigma = (const real*)ll_sigma;
+  a.ll_likelihood = ll_likelihood;
+  const int ll = ll_data ? 1 : 0;
 
   int kernel = cfg->kernel;
   bool auto_v2 = false;
   const int warps = v1_warps(m->desc, cfg->solver, tan, theta_smem(m));
+  if (ll) {
+    // the fused log-likelihood epilogue lives in the persistent kernel's cooperative save pass
+    if (tan || m->theta_ptr || warps <= 0 || (kernel != 0 && kernel != 2))
+      return fail(CTX_E_INVALID, "point-wise log-likelihood: symbolic models whose state fits the "
+                                 "persistent kernel (kernel 0 or 2), no tangents");
+    kernel = 2;
+  }
   if (kernel == 0) {
     // The persistent kernel wins while a trajectory's state fits registers (measured: S=3 f32
     // 1.6x at T=16, 3.3x at T=1000); with S*(1+D) = 32 it spills and the static kernel is 3x
@@ -560,14 +577,14 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     int wide = (!tan && d.dtype == CTX_F32 && !m->theta_ptr && d.n_states <= 4 &&
                 cfg->n_times >= 768) ? 1 : 0;
     if (const char* ev = getenv("CTX_B200_WIDE_SAVE")) wide = atoi(ev) ? (tan ? 0 : 1) : 0;
-    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k, wide);
+    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k, wide, ll);
     if (rc) return rc;
     const unsigned block = 32u * warps;
     int dev = 0, sms = 0, per_sm = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t per_warp = 0;
-    rc = v1_exact_warp_smem(m, cfg->solver, tan, &per_warp, wide);
+    rc = v1_exact_warp_smem(m, cfg->solver, tan, &per_warp, wide, ll);
     if (rc) return rc;
     size_t smem = theta_smem(m) + (size_t)warps * per_warp;
     if (m->theta_ptr && a.stride_theta != 0)
@@ -595,7 +612,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
                               stream));
     g_launches++;
-    g_last_kernel = "ctx_solve_v1";
+    g_last_kernel = ll ? "ctx_solve_v1 (log-likelihood save)" : "ctx_solve_v1";
   } else if (kernel == 3) {
     // K3: tcgen05 MLP tiles (ctx_mlp_tc.cuh); theta = [aux | UMMA weight pack]
     if (m->mlp_tc_smem <= 0 || m->desc.dtype != CTX_F32 || tan || cfg->solver > CTX_DOPRI5)
@@ -988,6 +1005,22 @@ int ctx_solve_sens(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
   if (!sens) return fail(CTX_E_INVALID, "sens output is null");
   return dispatch_solve(m, cfg, 1, y0, theta, consts, ts, ys, sens, status, nacc, nrej, ws,
                         ws_bytes, stream);
+}
+
+int ctx_pointwise_loglik(ctx_model* m, const ctx_solve_cfg* cfg, int32_t likelihood, const void* y0,
+                         const void* theta, const void* consts, const void* ts, const void* data,
+                         const void* sigma, void* ll, int32_t* status, int32_t* nacc, int32_t* nrej,
+                         void* ws, size_t ws_bytes, void* stream) {
+  if (!m || !cfg || !data || !sigma || !ll) return fail(CTX_E_INVALID, "null argument");
+  if (likelihood != CTX_LIK_NORMAL && likelihood != CTX_LIK_SOFTLAPLACE)
+    return fail(CTX_E_INVALID, "unknown likelihood id");
+  if (ctx_device_count() <= 0)
+    return fail(CTX_E_NOGPU, "no CUDA device visible: catalax_b200 has no CPU fallback");
+  if (m->desc.dtype == CTX_F64)
+    return launch_solve<double>(m, cfg, 0, y0, theta, consts, ts, ll, nullptr, status, nacc, nrej, ws,
+                                ws_bytes, (cudaStream_t)stream, data, sigma, likelihood);
+  return launch_solve<float>(m, cfg, 0, y0, theta, consts, ts, ll, nullptr, status, nacc, nrej, ws,
+                             ws_bytes, (cudaStream_t)stream, data, sigma, likelihood);
 }
 
 size_t ctx_loglik_workspace_bytes(const ctx_model* m, const ctx_loglik_cfg* cfg) {

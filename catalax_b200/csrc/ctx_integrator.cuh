@@ -70,6 +70,11 @@ struct ctx_solve_args {
   int ts_smem;     // 1: the shared time grid (stride_ts == 0) is staged in shared memory
   real rtol, atol, dt0;   // dt0 <= 0: every trajectory takes ts[1] - ts[0] of ITS time row, the
                           // reference's default `dt0 or ts[1] - ts[0]` under vmap (neuralode.py:44-47)
+  // CTX_LLSAVE builds (ctx_pointwise_loglik): ys receives log p(data | loc = y(t), |sigma|) instead
+  // of the states -- loo.py:180-193 `likelihood(loc, scale).log_prob(data_safe)` per draw
+  const real* ll_data;    // [M,T,S] observations (0 where masked: data_safe), row = the series
+  const real* ll_sigma;   // [D,S]   noise scale of the draw (row = b / inner)
+  int ll_likelihood;      // 0 Normal | 1 SoftLaplace
 };
 // first step size of a trajectory whose requested times are `row` (T of them)
 #define CTX_ROW_DT0(row, T) (((a.dt0 > R(0.0)) || (T) < 2) ? a.dt0 : ((row)[1] - (row)[0]))
@@ -573,6 +578,20 @@ __device__ __forceinline__ void ctx_dense_coefs_packed(const real dt, const real
   }
 }
 
+#ifndef CTX_LLSAVE
+#define CTX_LLSAVE 0
+#endif
+#if CTX_LLSAVE
+// numpyro's Normal / SoftLaplace log_prob (mcmc.py:59, 486-491) of x given loc and 1/|s|, log|s|
+__device__ __forceinline__ real ctx_point_logp(const int likelihood, const real x, const real loc,
+                                               const real inv_s, const real log_s) {
+  const real z = (x - loc) * inv_s;
+  if (likelihood == 0) return R(-0.5) * z * z - log_s - R(0.9189385332046727418);
+  const real az = fabs(z);
+  return R(-0.4515827052894548647) - log_s - (az + log1p(exp(R(-2.0) * az)));
+}
+#endif
+
 #ifndef CTX_NO_V1
 // Input queue of a persistent warp.  A finished lane must not wait ~1 us for the y0 / parameter
 // rows of its next trajectory to arrive from HBM (the whole warp would wait with it, once per
@@ -992,7 +1011,11 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #endif
         u.r.row_lo = (unsigned)rowp;
         u.r.row_hi = (unsigned)(rowp >> 32);
+#if CTX_LLSAVE
+        u.r.ri = (int)b;      // the evaluating lane needs both rows: series = b % inner, draw = b / inner
+#else
         u.r.ri = ri_row;
+#endif
         uint4* dstq = reinterpret_cast<uint4*>(&w.rec[s]);
 #pragma unroll
         for (int k = 0; k < CTX_REC_Q; ++k) dstq[k] = u.q[k];
@@ -1080,7 +1103,12 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #endif
               }
             } else {
-              const real* r_ts = ts_base + (size_t)rr.r.ri * a.stride_ts;
+#if CTX_LLSAVE
+              const int ri_t = a.inner > 0 ? rr.r.ri % a.inner : rr.r.ri;
+#else
+              const int ri_t = rr.r.ri;
+#endif
+              const real* r_ts = ts_base + (size_t)ri_t * a.stride_ts;
 #pragma unroll
               for (int u = 0; u < CTX_GP; ++u) tq[u] = (p0 + u < rr.r.i1) ? r_ts[p0 + u] : rr.r.v[0];
             }
@@ -1099,6 +1127,28 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
                 }
               }
             }
+#if CTX_LLSAVE
+            {   // states -> point-wise log-likelihood of the observations at these times
+              const int ro_l = a.inner > 0 ? rr.r.ri / a.inner : rr.r.ri;
+              const int ri_l = a.inner > 0 ? rr.r.ri - ro_l * a.inner : rr.r.ri;
+              real inv_s[CTX_S], log_s[CTX_S];
+#pragma unroll
+              for (int i = 0; i < CTX_S; ++i) {
+                const real sa_ = fabs(a.ll_sigma[(size_t)ro_l * CTX_S + i]);
+                inv_s[i] = R(1.0) / sa_;
+                log_s[i] = log(sa_);
+              }
+              const real* drow = a.ll_data + ((size_t)ri_l * T + p0) * CTX_S;
+#pragma unroll
+              for (int u = 0; u < CTX_GP; ++u)
+                if (p0 + u < T) {
+#pragma unroll
+                  for (int i = 0; i < CTX_S; ++i)
+                    o[u * CTX_S + i] = ctx_point_logp(a.ll_likelihood, drow[u * CTX_S + i],
+                                                      o[u * CTX_S + i], inv_s[i], log_s[i]);
+                }
+            }
+#endif
             if (p0 < rr.r.i0) {   // points of this group that earlier steps evaluated
               union { uint4 q[CTX_PEND_Q]; real v[CTX_GP * CTX_S]; } pd;
 #pragma unroll
@@ -1407,7 +1457,7 @@ ctx_solve_v1(const ctx_solve_args a) {
 // bytes of dynamic shared memory one warp of ctx_solve_v1 needs (read by the host at load time)
 extern "C" __device__ const unsigned ctx_v1_warp_smem_bytes = sizeof(ctx_warp_smem);
 
-#if !CTX_TAN && !CTX_THETA_PTR && CTX_QUEUE && (CTX_SOLVER == 0 || CTX_SOLVER == 1)
+#if !CTX_TAN && !CTX_THETA_PTR && CTX_QUEUE && (CTX_SOLVER == 0 || CTX_SOLVER == 1) && !CTX_LLSAVE
 #define CTX_HAVE_V2 1
 #include "ctx_solve_v2.cuh"
 #endif

@@ -51,7 +51,14 @@
 #ifndef V2_CPP
 #define V2_CPP 1          // consumers per producer: 1 (whole warp of trajectories) | 2 (half-warps)
 #endif
+#ifndef V2_PPC
+#define V2_PPC 1          // producers served by ONE consumer (> 1: short grids, where stepping dominates;
+#endif                    // needs V2_CPP == 1): the consumer polls its producers' rings round-robin
+#if V2_PPC > 1
+#define V2_NC ((V2_NP + V2_PPC - 1) / V2_PPC)
+#else
 #define V2_NC (V2_NP * V2_CPP)
+#endif
 #define V2_HL (32 / V2_CPP)   // producer lanes served by one consumer
 #ifndef V2_SLOTS
 #define V2_SLOTS 4
@@ -84,6 +91,8 @@ struct alignas(16) v2_prod_smem {
   v2_slot slot[V2_SLOTS];
   uint4 pend[32][CTX_PEND_Q];            // per producer lane: the group its trajectory has not completed
   unsigned long long full[V2_SLOTS], empty[V2_SLOTS];   // mbarriers
+  unsigned cons_count;                   // slots consumed so far (touched by the consumer only)
+  unsigned cons_done;
 };
 
 __device__ __forceinline__ void v2_mbar_init(const unsigned addr, const int count) {
@@ -105,6 +114,14 @@ __device__ __forceinline__ void v2_mbar_wait(const unsigned addr, const unsigned
 #endif
     }
   } while (!ok);
+}
+
+// non-blocking test of a phase (a consumer that serves several producers must not sleep on one)
+__device__ __forceinline__ bool v2_mbar_test(const unsigned addr, const unsigned parity) {
+  unsigned ok = 0;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok != 0;
 }
 
 // ------------------------------------------------------------------------------- producer
@@ -346,16 +363,13 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
 }
 
 // ------------------------------------------------------------------------------- consumer
-__device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_smem& w, const int half,
-                                            const unsigned ts_sa) {
+// evaluate and store everything slot `sl` of producer `w` holds; returns the slot's `done` flag
+__device__ __forceinline__ int v2_consume_slot(const ctx_solve_args& a, v2_prod_smem& w, const int half,
+                                               const unsigned ts_sa, const int sl) {
   const int lane = threadIdx.x & 31;
   const unsigned le_mask = CTX_FULL >> (31 - lane);
   const int T = a.T;
-  unsigned cons = 0;
-  while (true) {
-    const int sl = (int)(cons % V2_SLOTS);
-    const unsigned use = cons / V2_SLOTS;
-    v2_mbar_wait((unsigned)__cvta_generic_to_shared(&w.full[sl]), use & 1u);
+  {
     v2_slot& S = w.slot[sl];
     const int done = S.done;
     const int nseg = S.nseg[half];
@@ -518,8 +532,56 @@ __device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_sme
     }
     __syncwarp();
     if (lane == 0) v2_mbar_arrive((unsigned)__cvta_generic_to_shared(&w.empty[sl]));
+    return done;
+  }
+}
+
+// one consumer per producer (or per half of its lanes): blocks on that producer's ring
+__device__ __forceinline__ void v2_consumer(const ctx_solve_args& a, v2_prod_smem& w, const int half,
+                                            const unsigned ts_sa) {
+  unsigned cons = 0;
+  while (true) {
+    const int sl = (int)(cons % V2_SLOTS);
+    const unsigned use = cons / V2_SLOTS;
+    v2_mbar_wait((unsigned)__cvta_generic_to_shared(&w.full[sl]), use & 1u);
+    const int done = v2_consume_slot(a, w, half, ts_sa, sl);
     ++cons;
     if (done) break;
+  }
+}
+
+// one consumer for `n` producers P[0..n): polls their rings round-robin and takes whichever slot
+// is ready (short output grids: a step covers few requested times, so one saving warp keeps up
+// with several stepping warps and the SM holds more of those)
+__device__ __forceinline__ void v2_consumer_multi(const ctx_solve_args& a, v2_prod_smem* P, const int n,
+                                                  const unsigned ts_sa) {
+  int n_done = 0;
+  unsigned idle = 0;
+  while (n_done < n) {
+    bool any = false;
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      v2_prod_smem& w = P[j];
+      if (w.cons_done) continue;
+      const unsigned cons = w.cons_count;
+      const int sl = (int)(cons % V2_SLOTS);
+      const unsigned use = cons / V2_SLOTS;
+      if (!v2_mbar_test((unsigned)__cvta_generic_to_shared(&w.full[sl]), use & 1u)) continue;
+      any = true;
+      const int done = v2_consume_slot(a, w, 0, ts_sa, sl);
+      if ((threadIdx.x & 31) == 0) {
+        w.cons_count = cons + 1u;
+        if (done) w.cons_done = 1u;
+      }
+      __syncwarp();
+      if (done) ++n_done;
+    }
+    if (!any) {
+      if (++idle > (1u << 26)) __trap();    // a lost hand-off must not hang the GPU
+      __nanosleep(64);
+    } else {
+      idle = 0;
+    }
   }
 }
 
@@ -539,6 +601,8 @@ ctx_solve_v2(const ctx_solve_args a) {
       v2_mbar_init((unsigned)__cvta_generic_to_shared(&P[threadIdx.x].full[s]), 1);
       v2_mbar_init((unsigned)__cvta_generic_to_shared(&P[threadIdx.x].empty[s]), V2_CPP);
     }
+    P[threadIdx.x].cons_count = 0u;
+    P[threadIdx.x].cons_done = 0u;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
@@ -551,7 +615,12 @@ ctx_solve_v2(const ctx_solve_args a) {
 #if V2_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_CREG));
 #endif
+#if V2_PPC > 1
+    const int first = (warp - V2_NP) * V2_PPC;
+    v2_consumer_multi(a, P + first, min(V2_PPC, V2_NP - first), ts_sa);
+#else
     v2_consumer(a, P[(warp - V2_NP) / V2_CPP], (warp - V2_NP) % V2_CPP, ts_sa);
+#endif
   }
 }
 

@@ -113,6 +113,8 @@ def lib() -> C.CDLL:
     L.ctx_solve_sens.restype = C.c_int
     L.ctx_solve_sens.argtypes = [vp, C.POINTER(ctx_solve_cfg), vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  vp, C.c_size_t, vp]
+    L.ctx_pointwise_loglik.restype = C.c_int
+    L.ctx_pointwise_loglik.argtypes = [vp, C.POINTER(ctx_solve_cfg), C.c_int32] + [vp] * 11 + [C.c_size_t, vp]
     L.ctx_loglik_workspace_bytes.restype = C.c_size_t
     L.ctx_loglik_workspace_bytes.argtypes = [vp, C.POINTER(ctx_loglik_cfg)]
     L.ctx_loglik_grad.restype = C.c_int
@@ -313,6 +315,56 @@ class CompiledModel:
                 _check(lib().ctx_solve(self._h, C.byref(cfg), p(y0), p(theta), p(consts), p(ts), p(ys),
                                        p(status), p(nacc), p(nrej), p(ws), wsb, C.c_void_p(stream)))
         return SolveOutput(ys, status, nacc, nrej, sens)
+
+    def pointwise_loglik(self, y0, theta, consts, ts, data, sigma, *, likelihood="normal",
+                         solver="tsit5", in_axes=(0, 0, 0, 0), rtol=1e-5, atol=1e-5, dt0=0.1,
+                         max_steps=4096, inner=0, out=None):
+        """Fused solve + point-wise log-likelihood (ctx_pointwise_loglik): like ``solve`` but the
+        dense-output pass writes ``log p(data | loc = y(t), |sigma|)`` [B,T,S] instead of the
+        states.  Two-level batch (``inner=M``): theta [D,P] and sigma [D,S] per draw, y0 / consts /
+        ts / data [M,...] per series -> [D*M, T, S] (loo.py:180-193)."""
+        import torch
+
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = y0.device
+        if dev.type != "cuda":
+            raise EngineError("pointwise_loglik() needs CUDA tensors: catalax_b200 has no CPU fallback")
+        S, P, Cn = self.field.S, self.field.P, self.field.C
+        f = lambda x: x.to(device=dev, dtype=tdt).contiguous()
+        y0, theta, consts, ts, data, sigma = map(f, (y0, theta, consts, ts, data, sigma))
+        T = ts.shape[-1]
+        if inner:
+            M = int(inner)
+            D = theta.shape[0]
+            B = D * M
+            if (y0.shape != (M, S) or consts.shape != (M, Cn) or ts.shape != (M, T)
+                    or data.shape != (M, T, S) or sigma.shape != (D, S) or theta.shape != (D, P)):
+                raise ValueError("pointwise_loglik: two-level batch wants y0 [M,S], consts [M,C], "
+                                 "ts [M,T], data [M,T,S], theta [D,P], sigma [D,S]")
+            in_axes = (0, 0, 0, 0)
+        else:
+            B = y0.shape[0]
+            if data.shape != (B, T, S) or sigma.shape != (B, S):
+                raise ValueError("pointwise_loglik: data must be [B,T,S] and sigma [B,S]")
+        if not bool(torch.isfinite(data).all()):
+            raise ValueError("data must be finite (use 0 at masked points and mask the result)")
+        cfg = self.make_cfg(solver=solver, in_axes=in_axes, batch=B, n_times=T, max_steps=max_steps,
+                            rtol=rtol, atol=atol, dt0=dt0, kernel=0, inner=inner)
+        if out is not None and (tuple(out.shape) != (B, T, S) or out.dtype != tdt or out.device != dev
+                                or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous {tdt} tensor of shape {(B, T, S)} on {dev}")
+        with torch.cuda.device(dev):
+            ll = out if out is not None else torch.empty((B, T, S), dtype=tdt, device=dev)
+            cnt = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(3)]
+            wsb = int(lib().ctx_workspace_bytes(self._h, C.byref(cfg)))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            p = lambda t: C.c_void_p(t.data_ptr()) if t.numel() else C.c_void_p(0)
+            _check(lib().ctx_pointwise_loglik(self._h, C.byref(cfg), LIKELIHOOD_IDS[likelihood], p(y0),
+                                              p(theta), p(consts), p(ts), p(data), p(sigma), p(ll),
+                                              p(cnt[0]), p(cnt[1]), p(cnt[2]), p(ws), wsb,
+                                              C.c_void_p(stream)))
+        return SolveOutput(ll, cnt[0], cnt[1], cnt[2])
 
     def solve_host(self, y0, theta, consts, ts, *, solver="tsit5", in_axes=(0, None, 0, None),
                    rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096, kernel=0, out=None):

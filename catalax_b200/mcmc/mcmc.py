@@ -279,4 +279,24 @@ class BayesianModel:
             g_sigma += self.error_model.grad(sigma, hint.expand_as(sigma))
         return logp, g_theta, g_sigma
 
-    __call__ = log_density
+    def __call__(self, *args, **kw):
+        """Two call forms.  ``bm(theta, sigma)`` = ``log_density``.  ``bm(y0s, constants, times,
+        mask, data)`` -- the reference's model signature (mcmc.py:405: numpyro calls the model with
+        the data arguments to trace its log-joint) -- binds those arrays in place of the ones
+        extracted at construction and returns the log-density callable ``(theta, sigma) -> (logp,
+        dlogp/dtheta, dlogp/dsigma)`` over them."""
+        if len(args) + len(kw) == 5:
+            names = ("y0s", "constants", "times", "mask", "data")
+            vals = dict(zip(names, args))
+            vals.update(kw)
+            y0s, constants, times, mask, data = (np.asarray(vals[n]) for n in names)
+            data = np.where(mask.astype(bool), data, np.nan)     # the kernel's mask is isfinite(data)
+            lo, hi = self._series.start, self._series.stop
+            self._arrays = tuple(np.asarray(a, dtype=self.dtype)[lo:hi]
+                                 for a in (data, times, y0s, constants.reshape(y0s.shape[0], -1)))
+            self.mask = np.isfinite(self._arrays[0])
+            self._dev_arrays = None
+            if self._compiled is not None:
+                self._compiled = None
+            return self.log_density
+        return self.log_density(*args, **kw)

@@ -2,19 +2,21 @@
 
 Mirror of ``catalax/mcmc/predictive.py:109-155`` (``_integrate_ensemble``:
 ``jax.vmap(per_draw)(thetas)`` over ``sim_func(y0s, theta, constants, times)`` ->
-``[n_draws, n_meas, n_steps, n_obs]``) and of the mechanistic point-wise log-likelihood that
-LOO uses (``catalax/mcmc/loo.py:131-200``).  Both are the same CUDA kernel as ``Model.simulate``
-with a two-level batch (``ctx_solve_cfg.inner``): parameters are indexed by draw, initial values
-/ constants / times by series, so nothing is tiled or copied on the host.
+``[n_draws, n_meas, n_steps, n_obs]``), ``:158-175`` (``_aleatoric_variance``), ``:212-249``
+(``compute_ensemble``) and of the mechanistic point-wise log-likelihood that LOO uses
+(``catalax/mcmc/loo.py:131-200``, see ``loo.py`` here).  All are the same CUDA kernel as
+``Model.simulate`` with a two-level batch (``ctx_solve_cfg.inner``): parameters are indexed by
+draw, initial values / constants / times by series, so nothing is tiled or copied on the host;
+the log-likelihood form never materialises the ``[D,M,T,S]`` trajectories (ctx_pointwise_loglik).
 """
 from __future__ import annotations
 
-import math
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 
 from ..config import default_dtype
-from ..solvers import solver_name
+from ..solvers import Tsit5, solver_name
 from ..tools import codegen as cg
 
 
@@ -24,6 +26,35 @@ def ensemble_times(times: np.ndarray, n_steps: int) -> np.ndarray:
     t0, t1 = times.min(axis=-1), times.max(axis=-1)
     frac = np.linspace(0.0, 1.0, n_steps)
     return (t0[:, None] + (t1 - t0)[:, None] * frac[None, :]).astype(times.dtype)
+
+
+def stack_thetas(posterior: Dict[str, np.ndarray], param_names) -> Tuple[np.ndarray, Tuple[int, int]]:
+    """Parameter draws ``(n_chain, n_draw, ...)`` -> ``(n_chain*n_draw, n_params)`` in prior order
+    (loo.py:92-99)."""
+    cols = [np.asarray(posterior[name]) for name in param_names]
+    n_chain, n_draw = cols[0].shape[:2]
+    flat = [c.reshape(n_chain * n_draw, *c.shape[2:]) for c in cols]
+    return np.stack(flat, axis=-1), (n_chain, n_draw)
+
+
+def sigma_y_draws(posterior, n_chain: int, n_draw: int, n_obs: int) -> np.ndarray:
+    """Flattened per-observable ``sigma_y`` draws ``(n_chain*n_draw, n_obs)``; a shared scalar is
+    broadcast, a missing site gives ones (loo.py:102-117)."""
+    if "sigma_y" in posterior:
+        flat = np.asarray(posterior["sigma_y"]).reshape(n_chain * n_draw, -1)
+        return np.broadcast_to(flat, (n_chain * n_draw, n_obs)).copy()
+    return np.ones((n_chain * n_draw, n_obs))
+
+
+def subsample(posterior, max_draws: Optional[int]):
+    """Evenly subsample the draw axis (axis 1) of a grouped-by-chain sample dict (loo.py:120-128)."""
+    if max_draws is None:
+        return posterior
+    n_draw = next(iter(posterior.values())).shape[1]
+    if n_draw <= max_draws:
+        return posterior
+    idx = np.linspace(0, n_draw - 1, max_draws).astype(int)
+    return {k: np.asarray(v)[:, idx] for k, v in posterior.items()}
 
 
 class EnsembleIntegrator:
@@ -42,14 +73,17 @@ class EnsembleIntegrator:
         self.compiled = engine.CompiledModel(self.field, np.dtype(self.dtype).name)
         self.observables = list(range(self.field.S))
 
-    def integrate(self, y0s, thetas, constants, times, device=None):
-        """y0s [M,S], thetas [D,P], constants [M,C], times [M,T] -> torch CUDA [D,M,T,S]."""
+    def _tensors(self, *arrays, device=None):
         import torch
 
         dev = device or torch.device("cuda", torch.cuda.current_device())
         tt = lambda a: (a if isinstance(a, torch.Tensor) else
                         torch.as_tensor(np.asarray(a, dtype=self.dtype))).to(dev)
-        y0s, thetas, constants, times = tt(y0s), tt(thetas), tt(constants), tt(times)
+        return [tt(a) for a in arrays]
+
+    def integrate(self, y0s, thetas, constants, times, device=None):
+        """y0s [M,S], thetas [D,P], constants [M,C], times [M,T] -> torch CUDA [D,M,T,S]."""
+        y0s, thetas, constants, times = self._tensors(y0s, thetas, constants, times, device=device)
         M, T = times.shape
         D = thetas.shape[0]
         cfg = self.config
@@ -61,20 +95,59 @@ class EnsembleIntegrator:
         return out.ys.reshape(D, M, T, self.field.S)
 
     def pointwise_log_likelihood(self, y0s, thetas, sigmas, constants, times, data,
-                                 likelihood="normal"):
-        """log p(data[m,t,o] | draw d) for every draw and observation -> torch [D,M,T,S]
-        (NaN where the observation is missing).  The input of LOO's PSIS (loo.py:131-200)."""
-        import torch
+                                 likelihood="normal", device=None):
+        """log p(data[m,t,o] | draw d) for every draw and observation -> torch [D,M,T,S]: the input
+        of LOO's PSIS (loo.py:131-200).  One fused launch (ctx_pointwise_loglik): the dense-output
+        pass of the solve evaluates the likelihood of the observation at each requested time, the
+        ``[D,M,T,S]`` trajectories are never written.  ``data`` must be finite (``data_safe``:
+        0 where masked, loo.py:158); failed solves give -inf / NaN like the reference's inf states."""
+        y0s, thetas, sigmas, constants, times, data = self._tensors(
+            y0s, thetas, sigmas, constants, times, data, device=device)
+        M, T = times.shape
+        D = thetas.shape[0]
+        cfg = self.config
+        out = self.compiled.pointwise_loglik(
+            y0s, thetas, constants.reshape(M, self.field.C), times, data, sigmas,
+            likelihood=likelihood, solver=solver_name(cfg.solver), rtol=cfg.rtol, atol=cfg.atol,
+            dt0=cfg.dt0, max_steps=cfg.max_steps, inner=M)
+        self.last = out
+        return out.ys.reshape(D, M, T, self.field.S)
 
-        ys = self.integrate(y0s, thetas, constants, times)
-        dev = ys.device
-        data_t = torch.as_tensor(np.asarray(data, dtype=self.dtype), device=dev)
-        s = torch.as_tensor(np.asarray(sigmas, dtype=self.dtype), device=dev).abs()[:, None, None, :]
-        z = (data_t[None] - ys) / s
-        if likelihood == "normal":
-            lp = -0.5 * z * z - torch.log(s) - 0.5 * math.log(2 * math.pi)
-        elif likelihood == "softlaplace":
-            lp = math.log(2 / math.pi) - torch.log(s) - torch.logaddexp(z, -z)
-        else:
-            raise NotImplementedError(likelihood)
-        return lp
+
+def integrate_ensemble(results, dataset, posterior, *, n_steps: int):
+    """``_integrate_ensemble`` (predictive.py:109-155): Tsit5 solve of ``results.model`` once per
+    posterior draw on the dense per-series grid.  Returns ``(times [M,n_steps],
+    yhat_ens [n_draws, M, n_steps, n_obs])`` (numpy)."""
+    from ..model.simconfig import SimulationConfig
+    from .mcmc import extract_dataset_components
+
+    bm = results.bayesian_model
+    config = SimulationConfig(t1=1, t0=0, dt0=bm.config.dt0, solver=Tsit5, throw=False)
+    _, meas_times, y0s, constants = extract_dataset_components(dataset, results.model)
+    times = ensemble_times(meas_times, n_steps)
+    thetas, _ = stack_thetas(posterior, [name for name, _ in bm.priors])
+    integ = EnsembleIntegrator(results.model, config)
+    ys = integ.integrate(y0s, thetas, constants, times)
+    obs = results.model.get_observable_state_order(as_indices=True)
+    return times, ys[..., obs].cpu().numpy()
+
+
+def aleatoric_variance(posterior, yhat_shape) -> np.ndarray:
+    """Per-draw concentration-space aleatoric variance broadcast to ``yhat_shape``
+    (predictive.py:158-175): ``sigma_y**2``; a shared scalar is broadcast across observables."""
+    n_draws = yhat_shape[0]
+    sigma_y = np.asarray(posterior["sigma_y"]).reshape(n_draws, -1)
+    return np.broadcast_to((sigma_y ** 2)[:, None, None, :], yhat_shape).copy()
+
+
+def compute_ensemble(results, dataset, *, n_steps: int = 100, max_draws: Optional[int] = None,
+                     yerrs=None):
+    """``compute_ensemble`` (predictive.py:212-249): push the posterior through the model.
+    Returns ``(times [M,n_steps], yhat_ens, var_ens)``, the ensembles ``[n_draws, M, n_steps, n_obs]``."""
+    posterior = subsample(results.get_samples(group_by_chain=True), max_draws)
+    times, yhat_ens = integrate_ensemble(results, dataset, posterior, n_steps=n_steps)
+    if yerrs is not None:
+        var_ens = np.broadcast_to(np.asarray(yerrs, dtype=np.float64) ** 2, yhat_ens.shape).copy()
+    else:
+        var_ens = aleatoric_variance(posterior, yhat_ens.shape)
+    return times, yhat_ens, var_ens

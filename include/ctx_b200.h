@@ -143,6 +143,20 @@ int ctx_loglik_grad(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, co
                     const void* sigma, void* out, void* partial, int32_t* status, void* workspace,
                     size_t ws_bytes, void* stream);
 
+/* ---- fused point-wise log-likelihood of posterior draws ------------------------------------------
+ * Replaces `jax.vmap(per_draw)(thetas, sigma_y)` of catalax/mcmc/loo.py:180-193
+ * (`states = sim_func(y0s, theta, constants, times); likelihood(states[..., observables],
+ * scale).log_prob(data_safe)`): the solve of ctx_solve -- normally the two-level batch
+ * cfg->inner = M, theta [D,P] per draw, y0 / consts / ts per series -- whose dense-output pass
+ * writes  ll[d, m, t, o] = log p(data[m,t,o] | loc = y_o(t), scale = |sigma[d,o]|)  instead of the
+ * states: the [D,M,T,S] trajectory block never exists.  data [M,T,S] must be finite (0 where
+ * masked: `data_safe`; the caller applies the mask to ll), sigma [D,S]; without inner, data / sigma
+ * rows follow the trajectory index.  Same workspace and status outputs as ctx_solve. */
+int ctx_pointwise_loglik(ctx_model* m, const ctx_solve_cfg* cfg, int32_t likelihood, const void* y0,
+                         const void* theta, const void* consts, const void* ts, const void* data,
+                         const void* sigma, void* ll, int32_t* status, int32_t* n_accepted,
+                         int32_t* n_rejected, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- K4: right-hand side only ---------------------------------------------------------------
  * Replaces vmap(stack)(t, y, (theta, consts)) -- Model._setup_rate_function (model.py:1027-1051),
  * NeuralBase.rates (neuralbase.py:319-327), surrogate rate matching (mcmc.py:830-833).

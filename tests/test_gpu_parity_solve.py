@@ -136,7 +136,17 @@ def test_warp_specialised_kernel_against_the_c_oracle(kernel, T, dtype):
     if dtype == np.float64:
         np.testing.assert_array_equal(out.n_accepted.cpu().numpy(), ref.n_accepted)
         np.testing.assert_array_equal(out.n_rejected.cpu().numpy(), ref.n_rejected)
-        _assert_close_f64(ys, ref.ys)
+        # 1e-6 relative wherever the component is above the solver's own noise floor; a depleted
+        # substrate (|y| << atol after thousands of stability-limited steps) is +-atol noise in
+        # which the rounding differences between FMA (GPU) and non-contracted (oracle) arithmetic
+        # are amplified: those entries are compared to the absolute tolerance atol = 1e-6
+        d = np.abs(ys - ref.ys)
+        big = np.abs(ref.ys) > 1e-3
+        worst = float((d[big] / np.abs(ref.ys[big])).max())
+        print(f"v2 x64: max rel diff above the noise floor {worst:.2e}, max abs diff below it "
+              f"{float(d[~big].max()) if (~big).any() else 0.0:.2e}")
+        assert worst <= 1e-6, worst
+        assert (d[~big] <= 1e-6).all(), float(d[~big].max())
     else:
         sub = slice(0, 8192)
         truth = COracle(*model[:4], model[4], dtype=np.float64).solve(
