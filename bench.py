@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -171,6 +172,9 @@ class Ctx:
             if i % 8 == 0:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
+        # long enough for the 50 ms clock sampler to see the leg: >= 0.25 s of timed work
+        est = (time.perf_counter() - t_w) / i
+        iters = int(self.max_over_ranks(max(iters, min(2000, math.ceil(0.25 / max(est, 1e-5))))))
         if self.world > 1:
             self.dist.barrier()
         m0 = self.sampler.mark() if self.sampler else None
@@ -185,6 +189,8 @@ class Ctx:
             self.dist.barrier()
         ms = self.max_over_ranks(e0.elapsed_time(e1)) / iters
         clocks = self.sampler.summary(m0, m1) if self.sampler else None
+        if clocks is not None:
+            clocks["timed_iterations"] = iters
         return ms, out, clocks
 
 
