@@ -54,7 +54,12 @@
 #ifndef V2_PPC
 #define V2_PPC 1          // producers served by ONE consumer (> 1: short grids, where stepping dominates;
 #endif                    // needs V2_CPP == 1): the consumer polls its producers' rings round-robin
-#if V2_PPC > 1
+#ifndef V2_DYN
+#define V2_DYN 0          // > 0: V2_DYN consumer warps that take slots from ANY producer of the CTA
+#endif                    // (try-lock per producer keeps a producer's slots in order): absorbs bursts
+#if V2_DYN > 0
+#define V2_NC V2_DYN
+#elif V2_PPC > 1
 #define V2_NC ((V2_NP + V2_PPC - 1) / V2_PPC)
 #else
 #define V2_NC (V2_NP * V2_CPP)
@@ -93,6 +98,8 @@ struct alignas(16) v2_prod_smem {
   unsigned long long full[V2_SLOTS], empty[V2_SLOTS];   // mbarriers
   unsigned cons_count;                   // slots consumed so far (touched by the consumer only)
   unsigned cons_done;
+  unsigned lock;                         // V2_DYN: 1 while a consumer works on this producer's ring
+  unsigned pad_;
 };
 
 __device__ __forceinline__ void v2_mbar_init(const unsigned addr, const int count) {
@@ -585,6 +592,59 @@ __device__ __forceinline__ void v2_consumer_multi(const ctx_solve_args& a, v2_pr
   }
 }
 
+// Any consumer serves any producer: consumer `c` walks the CTA's producers starting at its own
+// index, takes the producer's ring with a try-lock (a producer's slots must be consumed in order by
+// ONE warp at a time: its trajectories' pending groups live in its shared-memory block), consumes
+// ONE ready slot and moves on.  A burst of save work from one producer is spread over all consumers
+// and the producer / consumer counts need not match.
+__device__ __forceinline__ void v2_consumer_dyn(const ctx_solve_args& a, v2_prod_smem* P, const int c,
+                                                const unsigned ts_sa) {
+  const int lane = threadIdx.x & 31;
+  unsigned idle = 0;
+  while (true) {
+    bool any = false, all_done = true;
+#pragma unroll 1
+    for (int jj = 0; jj < V2_NP; ++jj) {
+      int j = c + jj;
+      if (j >= V2_NP) j -= V2_NP;
+      v2_prod_smem& w = P[j];
+      if (*reinterpret_cast<volatile unsigned*>(&w.cons_done)) continue;
+      all_done = false;
+      // cheap look before the lock: is the next slot of this ring ready at all?
+      const unsigned peek = *reinterpret_cast<volatile unsigned*>(&w.cons_count);
+      if (!v2_mbar_test((unsigned)__cvta_generic_to_shared(&w.full[peek % V2_SLOTS]), (peek / V2_SLOTS) & 1u))
+        continue;
+      unsigned got = 0;
+      if (lane == 0) got = atomicCAS(&w.lock, 0u, 1u) == 0u ? 1u : 0u;
+      got = __shfl_sync(CTX_FULL, got, 0);
+      if (!got) continue;
+      __threadfence_block();     // acquire: see the previous holder's pending groups and counters
+      const unsigned cons = *reinterpret_cast<volatile unsigned*>(&w.cons_count);
+      const int sl = (int)(cons % V2_SLOTS);
+      const bool ready = !*reinterpret_cast<volatile unsigned*>(&w.cons_done) &&
+                         v2_mbar_test((unsigned)__cvta_generic_to_shared(&w.full[sl]), (cons / V2_SLOTS) & 1u);
+      if (ready) {
+        any = true;
+        const int done = v2_consume_slot(a, w, 0, ts_sa, sl);
+        if (lane == 0) {
+          w.cons_count = cons + 1u;
+          if (done) w.cons_done = 1u;
+        }
+      }
+      __syncwarp();
+      __threadfence_block();     // release
+      if (lane == 0) atomicExch(&w.lock, 0u);
+    }
+    if (all_done) break;
+    if (!any) {
+      if (++idle > (1u << 26)) __trap();    // a lost hand-off must not hang the GPU
+      __nanosleep(32);
+    } else {
+      idle = 0;
+    }
+  }
+}
+
 extern "C" __global__ void __launch_bounds__((V2_NP + V2_NC) * 32, V2_MIN_BLOCKS)
 ctx_solve_v2(const ctx_solve_args a) {
   // dynamic smem: [shared time grid, padded to a multiple of CTX_GP reals][V2_NP * v2_prod_smem]
@@ -603,6 +663,7 @@ ctx_solve_v2(const ctx_solve_args a) {
     }
     P[threadIdx.x].cons_count = 0u;
     P[threadIdx.x].cons_done = 0u;
+    P[threadIdx.x].lock = 0u;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
@@ -615,7 +676,9 @@ ctx_solve_v2(const ctx_solve_args a) {
 #if V2_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_CREG));
 #endif
-#if V2_PPC > 1
+#if V2_DYN > 0
+    v2_consumer_dyn(a, P, (warp - V2_NP) % V2_NP, ts_sa);
+#elif V2_PPC > 1
     const int first = (warp - V2_NP) * V2_PPC;
     v2_consumer_multi(a, P + first, min(V2_PPC, V2_NP - first), ts_sa);
 #else

@@ -96,6 +96,79 @@ def _transform_of(prior) -> _Transform:
     return _Transform()
 
 
+def hmc_sample(logp_and_grad, u, lp, g, *, num_warmup, num_samples, thinning=1, max_steps=31,
+               target_accept=0.8, generator=None, verbose=False):
+    """Batched HMC over ``CH`` chains in unconstrained space.  ``logp_and_grad(u [CH,dim]) ->
+    (logp [CH], grad [CH,dim])`` is evaluated for ALL chains at once (one fused kernel launch per
+    leapfrog step on the GPU).  Per-chain step size by dual averaging (Hoffman & Gelman 2014,
+    restarted after every mass-matrix update), diagonal mass matrix from the warm-up draws (three
+    windows, Stan's shrinkage), 1..max_steps leapfrog steps per iteration (jittered, shared by the
+    chains so that they stay in lock step).  Returns (list of kept states [CH,dim], stats)."""
+    import torch
+
+    CH, dim = u.shape
+    dev, tdt = u.device, u.dtype
+    gen = generator
+    rand = lambda *shape: torch.rand(shape, generator=gen, device=dev, dtype=tdt)
+    randn = lambda *shape: torch.randn(shape, generator=gen, device=dev, dtype=tdt)
+    inv_mass = torch.ones((CH, dim), dtype=tdt, device=dev)
+    eps = torch.full((CH,), 0.1, dtype=tdt, device=dev)
+    mu_da = torch.log(10 * eps)
+    h_bar = torch.zeros_like(eps); log_eps_bar = torch.log(eps)
+    gamma, t0_da, kappa, m_da = 0.05, 10.0, 0.75, 0
+    keep, accs, n_div, warm_buf = [], [], 0, []
+    windows = sorted({int(num_warmup * f) for f in (0.3, 0.55, 0.8)} - {0})
+    for it in range(num_warmup + num_samples):
+        L = int(torch.randint(1, max_steps + 1, (1,), generator=gen, device=dev).item())
+        r = randn(CH, dim) / torch.sqrt(inv_mass)
+        h0 = -lp + 0.5 * (r * r * inv_mass).sum(1)
+        un, rn, lpn, gn = u, r, lp, g
+        e = eps[:, None]
+        for _ in range(L):
+            rn = rn + 0.5 * e * gn
+            un = un + e * inv_mass * rn
+            lpn, gn = logp_and_grad(un)
+            rn = rn + 0.5 * e * gn
+        h1 = -lpn + 0.5 * (rn * rn * inv_mass).sum(1)
+        dH = h0 - h1
+        dH = torch.where(torch.isfinite(dH), dH, torch.full_like(dH, -math.inf))
+        acc_p = torch.exp(dH.clamp(max=0.0))
+        take = rand(CH) < acc_p
+        u = torch.where(take[:, None], un, u)
+        lp = torch.where(take, lpn, lp)
+        g = torch.where(take[:, None], gn, g)
+        if it < num_warmup:
+            m_da += 1
+            h_bar = (1 - 1 / (m_da + t0_da)) * h_bar + (target_accept - acc_p) / (m_da + t0_da)
+            log_eps = mu_da - math.sqrt(m_da) / gamma * h_bar
+            eta = m_da ** (-kappa)
+            log_eps_bar = eta * log_eps + (1 - eta) * log_eps_bar
+            eps = torch.exp(log_eps)
+            warm_buf.append(u.clone())
+            if (it + 1) in windows and len(warm_buf) >= 20:
+                w = torch.stack(warm_buf[len(warm_buf) // 2:], 0)            # [n, CH, dim]
+                n_w = w.shape[0]
+                inv_mass = (n_w / (n_w + 5.0)) * w.var(0, unbiased=True) + 1e-3 * (5.0 / (n_w + 5.0))
+                warm_buf = []
+                # restart the step-size search around the averaged value
+                eps = torch.exp(log_eps_bar)
+                mu_da = torch.log(10 * eps); h_bar = torch.zeros_like(eps); m_da = 0
+            if it == num_warmup - 1:
+                eps = torch.exp(log_eps_bar)
+        else:
+            accs.append(float(acc_p.mean().item()))
+            n_div += int((dH < -1000).sum().item())
+            if (it - num_warmup) % thinning == 0:
+                keep.append(u.clone())
+        if verbose and (it + 1) % max(1, (num_warmup + num_samples) // 10) == 0:
+            print(f"sample: {it + 1}/{num_warmup + num_samples}  step size {eps.mean().item():.3g}  "
+                  f"acc. prob {acc_p.mean().item():.2f}", flush=True)
+    stats = {"step_size": eps.cpu().numpy(), "mean_accept_prob": float(np.mean(accs)) if accs else None,
+             "num_divergences": n_div, "inverse_mass": inv_mass.cpu().numpy(),
+             "sampler": "batched HMC (dual averaging, diagonal mass); not numpyro NUTS"}
+    return keep, stats
+
+
 class HMC:
     """Same constructor as the reference's ``HMC`` (mcmc.py:116-168)."""
 
@@ -185,70 +258,16 @@ class HMC:
         if bool((~torch.isfinite(lp)).any()):
             raise RuntimeError("could not find an initial point with a finite log-density")
 
-        n_warm, n_samp, thin = int(cfg.num_warmup), int(cfg.num_samples), max(1, int(cfg.thinning))
-        l_max = min(2 ** int(cfg.max_tree_depth) - 1, 31)
-        inv_mass = torch.ones((CH, dim), dtype=tdt, device=dev)
-        # dual averaging (Hoffman & Gelman 2014), one step size per chain
-        eps = torch.full((CH,), 0.1, dtype=tdt, device=dev)
-        mu_da = torch.log(10 * eps)
-        h_bar = torch.zeros_like(eps); log_eps_bar = torch.zeros_like(eps)
-        gamma, t0_da, kappa = 0.05, 10.0, 0.75
-        keep, accs, n_div = [], [], 0
-        warm_buf = []
-        windows = sorted({int(n_warm * f) for f in (0.3, 0.55, 0.8)} - {0})
-        for it in range(n_warm + n_samp):
-            L = int(torch.randint(1, l_max + 1, (1,), generator=gen, device=dev).item())
-            r = torch.randn((CH, dim), generator=gen, device=dev, dtype=tdt) / torch.sqrt(inv_mass)
-            h0 = -lp + 0.5 * (r * r * inv_mass).sum(1)
-            un, rn, lpn, gn = u, r, lp, g
-            e = eps[:, None]
-            for _ in range(L):
-                rn = rn + 0.5 * e * gn
-                un = un + e * inv_mass * rn
-                lpn, gn = logp_and_grad(un)
-                rn = rn + 0.5 * e * gn
-            h1 = -lpn + 0.5 * (rn * rn * inv_mass).sum(1)
-            dH = h0 - h1
-            dH = torch.where(torch.isfinite(dH), dH, torch.full_like(dH, -math.inf))
-            acc_p = torch.exp(dH.clamp(max=0.0))
-            take = torch.rand((CH,), generator=gen, device=dev, dtype=tdt) < acc_p
-            if it >= n_warm:
-                n_div += int((dH < -1000).sum().item())
-            u = torch.where(take[:, None], un, u)
-            lp = torch.where(take, lpn, lp)
-            g = torch.where(take[:, None], gn, g)
-            if it < n_warm:
-                m = it + 1
-                h_bar = (1 - 1 / (m + t0_da)) * h_bar + (cfg.target_accept_prob - acc_p) / (m + t0_da)
-                log_eps = mu_da - math.sqrt(m) / gamma * h_bar
-                eta = m ** (-kappa)
-                log_eps_bar = eta * log_eps + (1 - eta) * log_eps_bar
-                eps = torch.exp(log_eps)
-                warm_buf.append(u.clone())
-                if (it + 1) in windows and len(warm_buf) >= 20:
-                    w = torch.stack(warm_buf[len(warm_buf) // 2:], 0)            # [n, CH, dim]
-                    var = w.var(0, unbiased=True)
-                    n_w = w.shape[0]
-                    inv_mass = (n_w / (n_w + 5.0)) * var + 1e-3 * (5.0 / (n_w + 5.0))   # Stan's shrinkage
-                    warm_buf = []
-                    # restart the step-size search around the current value
-                    mu_da = torch.log(10 * eps); h_bar.zero_(); log_eps_bar.zero_()
-                if it == n_warm - 1:
-                    eps = torch.exp(log_eps_bar)
-            else:
-                accs.append(acc_p.mean().item())
-                if (it - n_warm) % thin == 0:
-                    keep.append(constrain(u)[0].cpu().numpy())
-            if cfg.verbose and (it + 1) % max(1, (n_warm + n_samp) // 10) == 0:
-                print(f"sample: {it + 1}/{n_warm + n_samp}  step size {eps.mean().item():.3g}  "
-                      f"acc. prob {acc_p.mean().item():.2f}", flush=True)
+        keep_u, stats = hmc_sample(logp_and_grad, u, lp, g, num_warmup=int(cfg.num_warmup),
+                                   num_samples=int(cfg.num_samples), thinning=max(1, int(cfg.thinning)),
+                                   max_steps=min(2 ** int(cfg.max_tree_depth) - 1, 31),
+                                   target_accept=float(cfg.target_accept_prob), generator=gen,
+                                   verbose=bool(cfg.verbose))
+        keep = [constrain(uu)[0].cpu().numpy() for uu in keep_u]
         draws = np.stack(keep, 1) if keep else np.zeros((CH, 0, dim))     # [CH, n_draw, dim]
         samples = {name: draws[:, :, j] for j, (name, _) in enumerate(bm.priors)}
         if sampled:
             samples["sigma_y"] = draws[:, :, P:]
-        stats = {"step_size": eps.cpu().numpy(), "mean_accept_prob": float(np.mean(accs)) if accs else None,
-                 "num_divergences": n_div, "inverse_mass": inv_mass.cpu().numpy(),
-                 "sampler": "batched HMC (dual averaging, diagonal mass); not numpyro NUTS"}
         return HMCResults(samples, bm, model, stats)
 
 

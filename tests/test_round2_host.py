@@ -201,3 +201,28 @@ def test_workloads_are_shared_with_the_tests():
     src = open(__import__("pathlib").Path(__file__).parents[1] / "bench.py").read()
     imports = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.ImportFrom)]
     assert not any((n.module or "").startswith("tests") for n in imports), "bench.py must not import tests/"
+
+
+def test_batched_hmc_adapts_step_size_and_mass_on_a_badly_scaled_gaussian():
+    """The sampler behind ``HMC.run`` on a density with a known answer (CPU, no engine): scales
+    spanning 3000x must be recovered, with the acceptance rate near its target."""
+    import torch
+
+    from catalax_b200.mcmc.sampler import hmc_sample
+
+    scales = torch.tensor([1.0, 0.01, 30.0], dtype=torch.float64)
+    mean = torch.tensor([2.0, -1.0, 50.0], dtype=torch.float64)
+
+    def lpg(u):
+        z = (u - mean) / scales
+        return -0.5 * (z * z).sum(1), -z / scales
+
+    gen = torch.Generator().manual_seed(1)
+    u = torch.rand((32, 3), generator=gen, dtype=torch.float64) * 4 - 2
+    lp, g = lpg(u)
+    keep, st = hmc_sample(lpg, u, lp, g, num_warmup=300, num_samples=300, max_steps=15, generator=gen)
+    x = torch.stack(keep, 1).reshape(-1, 3)
+    assert 0.6 < st["mean_accept_prob"] <= 1.0 and st["num_divergences"] == 0
+    assert torch.allclose(x.mean(0), mean, atol=0.0, rtol=0.0) or \
+        (((x.mean(0) - mean) / scales).abs() < 0.1).all()
+    assert ((x.std(0) / scales - 1).abs() < 0.1).all()
