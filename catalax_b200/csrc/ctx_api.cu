@@ -797,12 +797,14 @@ int adj_plan(ctx_model* m, const ctx_adjoint_cfg* cfg, AdjPlan& p) {
     return fail(CTX_E_INVALID, "model has no weight-gradient kernels (plain NeuralODE fields only)");
   if (cfg->batch <= 0 || cfg->n_times <= 0 || cfg->cap <= 0)
     return fail(CTX_E_INVALID, "adjoint: batch, n_times and cap must be positive");
+  if (cfg->solver != CTX_TSIT5 && cfg->solver != CTX_DOPRI5)
+    return fail(CTX_E_INVALID, "adjoint: Tsit5 or Dopri5");
   cudaKernel_t k;
-  int rc = get_kernel(m, CTX_TSIT5, 0, "ctx_mlp_adj_forward", &k);
+  int rc = get_kernel(m, cfg->solver, 0, "ctx_mlp_adj_forward", &k);
   if (rc) return rc;
   {
     std::lock_guard<std::mutex> lk(m->mu);
-    Variant& v = m->variants[CTX_TSIT5 * 2 + 0];
+    Variant& v = m->variants[cfg->solver * 2 + 0];
     void* dptr = nullptr;
     size_t nbytes = 0;
     unsigned info[5] = {0, 0, 0, 0, 0};
@@ -859,7 +861,7 @@ int launch_adjoint(ctx_model* m, const ctx_adjoint_cfg* cfg, bool backward, cons
   a.stride_ts = cfg->ts_per_row ? cfg->n_times : 0;
   a.rtol = (real)cfg->rtol; a.atol = (real)cfg->atol; a.dt0 = (real)cfg->dt0;
   cudaKernel_t k;
-  rc = get_kernel(m, CTX_TSIT5, 0, backward ? "ctx_mlp_adj_backward" : "ctx_mlp_adj_forward", &k);
+  rc = get_kernel(m, cfg->solver, 0, backward ? "ctx_mlp_adj_backward" : "ctx_mlp_adj_forward", &k);
   if (rc) return rc;
   const size_t smem = backward ? p.smem_bwd : p.smem_fwd;
   if (smem > 227 * 1024) return fail(CTX_E_INVALID, "adjoint: the network does not fit shared memory");
@@ -872,7 +874,7 @@ int launch_adjoint(ctx_model* m, const ctx_adjoint_cfg* cfg, bool backward, cons
   g_launches++;
   if (backward) {
     cudaKernel_t kr;
-    rc = get_kernel(m, CTX_TSIT5, 0, "ctx_mlp_adj_reduce", &kr);
+    rc = get_kernel(m, cfg->solver, 0, "ctx_mlp_adj_reduce", &kr);
     if (rc) return rc;
     const real* part = a.partial;
     real* g = (real*)grad_theta;

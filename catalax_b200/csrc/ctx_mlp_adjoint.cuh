@@ -28,7 +28,7 @@
 // (adj_soff: Wt block, then bias block), ADJ_SPACK, ADJ_WMAX, ADJ_ACT / ADJ_FACT, ADJ_P.
 #pragma once
 
-#if CTX_SOLVER == 0   // Tsit5 only (the reference's default for every neural model)
+#if CTX_SOLVER == 0 || CTX_SOLVER == 1   // Tsit5 (the reference's default) and Dopri5 (trainer.py:128-132)
 
 #ifndef ADJ_KIND
 #define ADJ_KIND 0                           // 0 NeuralODE | 1 RateFlowODE
@@ -266,6 +266,26 @@ __device__ __forceinline__ void adj_mlp_vjp(const real* pack, real* gp, const re
   __syncwarp();
 }
 
+// Interpolation weights of the solver's dense output written as y + dt * sum_i b_i(theta) f_i.
+#if CTX_SOLVER == 1
+// Dopri5: diffrax evaluates Shampine's quartic through (y0, y1, ymid, f0, f1) (ctx_dense); with
+// y1 = y0 + dt sum A7i f_i, ymid = y0 + dt sum M_i f_i, f0 = dt f_1, f1 = dt f_7 its y0 terms cancel
+// and b_i(theta) = theta (d_i1 + theta (c_i + theta (b_i + theta a_i))),
+//   a_i = 2 (d_i7 - d_i1) - 8 A7i + 16 M_i,  b_i = 5 d_i1 - 3 d_i7 + 14 A7i - 32 M_i,
+//   c_i = d_i7 - 4 d_i1 - 5 A7i + 16 M_i                       (b_i(1) = A7i: the step itself).
+__device__ __forceinline__ void adj_tsit5_weights(const real th, real* b) {
+  const real A7[7] = {A71, A72, A73, A74, A75, A76, R(0.0)};
+  const real M[7] = {M1, M2, M3, M4, M5, M6, M7};
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const real d1 = i == 0 ? R(1.0) : R(0.0), d7 = i == 6 ? R(1.0) : R(0.0);
+    const real qa = R(2.0) * (d7 - d1) - R(8.0) * A7[i] + R(16.0) * M[i];
+    const real qb = R(5.0) * d1 - R(3.0) * d7 + R(14.0) * A7[i] - R(32.0) * M[i];
+    const real qc = d7 - R(4.0) * d1 - R(5.0) * A7[i] + R(16.0) * M[i];
+    b[i] = th * (d1 + th * (qc + th * (qb + th * qa)));
+  }
+}
+#else
 // Tsit5 interpolation weights b_i(theta), i = 1..7 (same factored forms as ctx_dense)
 __device__ __forceinline__ void adj_tsit5_weights(const real th, real* b) {
   const real t2 = th * th;
@@ -278,6 +298,7 @@ __device__ __forceinline__ void adj_tsit5_weights(const real th, real* b) {
   b[5] = R(-34.87065786149660974) * (th - R(1.2)) * (th - R(0.666666666666666667)) * t2;
   b[6] = R(2.5) * (th - R(1.0)) * (th - R(0.6)) * t2;
 }
+#endif
 
 __device__ const real adj_A[7][6] = {
     {R(0.0), R(0.0), R(0.0), R(0.0), R(0.0), R(0.0)},
@@ -587,4 +608,4 @@ extern "C" __device__ const unsigned ctx_adj_info[5] = {
     (unsigned)ADJ_SPACK, (unsigned)(ADJ_NACT * ADJ_WMAX), (unsigned)ADJ_WARPS, (unsigned)ADJ_P,
     (unsigned)ADJ_WMAX};
 
-#endif  // CTX_SOLVER == 0
+#endif  // CTX_SOLVER == 0 || CTX_SOLVER == 1

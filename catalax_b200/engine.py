@@ -45,7 +45,8 @@ class ctx_solve_cfg(C.Structure):
 class ctx_adjoint_cfg(C.Structure):
     _fields_ = [("batch", C.c_int64), ("n_times", C.c_int32), ("max_steps", C.c_int32),
                 ("cap", C.c_int32), ("ts_per_row", C.c_int32), ("rtol", C.c_double),
-                ("atol", C.c_double), ("dt0", C.c_double)]
+                ("atol", C.c_double), ("dt0", C.c_double), ("solver", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class ctx_xla_solve_desc(C.Structure):
@@ -606,7 +607,7 @@ class CompiledModel:
 
     # ------------------------------------------------------------------ NeuralODE training
     def adjoint_forward(self, y0, theta, ts, *, rtol=1e-3, atol=1e-6, dt0=0.1, max_steps=4096,
-                        cap=512):
+                        cap=512, solver="tsit5"):
         """Forward solve that records every accepted step (ctx_mlp_adjoint_forward).
         y0 [B,S], theta [P] (flat layout), ts [B,T] or [T].  Returns a context dict holding ys
         [B,T,S], status / step counts and the workspace `adjoint_backward` needs."""
@@ -624,6 +625,7 @@ class CompiledModel:
         cfg.batch, cfg.n_times, cfg.max_steps, cfg.cap = B, T, int(max_steps), int(cap)
         cfg.ts_per_row = 1 if ts.dim() == 2 else 0
         cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
+        cfg.solver = SOLVER_IDS[solver]
         p = lambda t: C.c_void_p(t.data_ptr()) if (t is not None and t.numel()) else C.c_void_p(0)
         with torch.cuda.device(dev):
             wsb = int(lib().ctx_mlp_adjoint_workspace_bytes(self._h, C.byref(cfg)))

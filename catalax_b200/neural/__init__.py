@@ -1,3 +1,5 @@
 from .neuralbase import NeuralBase, NeuralODE, RateFlowODE, RBFLayer, UniversalODE
+from .trainer import AdaBelief, Adam, Modes, Penalties, Step, Strategy, train_neural_ode
 
-__all__ = ["NeuralBase", "NeuralODE", "RateFlowODE", "UniversalODE", "RBFLayer"]
+__all__ = ["NeuralBase", "NeuralODE", "RateFlowODE", "UniversalODE", "RBFLayer", "Strategy", "Step",
+           "Modes", "Penalties", "AdaBelief", "Adam", "train_neural_ode"]

@@ -396,7 +396,7 @@ class NeuralBase:
 
     # ---- training: value and gradient of the loss (trainer.py:268-306)
     def value_and_grad(self, ts, y0, data, *, loss="l2", mask=None, rtol=None, atol=None, dt0=None,
-                       want_y0: bool = False, cap: int = 512):
+                       want_y0: bool = False, cap: int = 512, solver=None):
         """Loss of ``vmap(self)(ts, y0)`` against ``data`` and its gradient w.r.t. every weight.
 
         ts [B,T] (or [T]), y0 [B,S], data [B,T,S]; ``mask`` [T] weights the time points (temporal
@@ -412,8 +412,9 @@ class NeuralBase:
         if not model.field.source.count("#define CTX_MLP_ADJ 1"):
             raise NotImplementedError("weight gradients: neural fields of <= 8 states whose network "
                                       "fits shared memory")
-        if solver_name(self.solver) != "tsit5":
-            raise NotImplementedError("weight gradients are implemented for Tsit5")
+        sname = solver_name(solver or self.solver)
+        if sname not in ("tsit5", "dopri5"):
+            raise NotImplementedError("weight gradients are implemented for Tsit5 and Dopri5")
         dev = y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda else \
             torch.device("cuda", torch.cuda.current_device())
         tt = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=dtype))).to(dev)
@@ -423,7 +424,7 @@ class NeuralBase:
         ctx = model.adjoint_forward(y0_t, torch.as_tensor(theta, device=dev), ts_t,
                                     rtol=1e-3 if rtol is None else rtol,
                                     atol=1e-6 if atol is None else atol, dt0=dt0,
-                                    max_steps=self._max_steps(), cap=cap)
+                                    max_steps=self._max_steps(), cap=cap, solver=sname)
         self.last = ctx
         bad = int((ctx["status"] != 0).sum().item())
         if bad:
@@ -487,9 +488,16 @@ class NeuralBase:
                     self.spec, self.weights, self.biases, self.max_time, np.dtype(key),
                     **self._pack_extra()))
 
-    def train(self, ts, y0, data, *, steps: int = 100, lr: float = 1e-3, loss="l2", **kw):
-        """Minimal Adam loop over ``value_and_grad`` (the role of trainer.py:173-253's optax loop;
-        strategies, penalties and batching are left to the caller).  Returns the loss history."""
+    def train(self, ts, y0=None, data=None, *, steps: int = 100, lr: float = 1e-3, loss="l2", **kw):
+        """Two call forms.  ``train(dataset, strategy, ...)`` is the reference's
+        ``NeuralBase.train`` (neuralbase.py:185-250): the curriculum of ``neural/trainer.py``.
+        ``train(ts, y0, data, steps=, lr=)`` is a plain Adam loop over ``value_and_grad`` on arrays
+        and returns the loss history."""
+        if hasattr(ts, "measurements"):
+            from .trainer import train_neural_ode
+
+            strategy = y0 if y0 is not None else kw.pop("strategy")
+            return train_neural_ode(self, ts, strategy, **kw)
         m = [[np.zeros_like(w) for w in self.weights], [None if b is None else np.zeros_like(b) for b in self.biases]]
         v = [[np.zeros_like(w) for w in self.weights], [None if b is None else np.zeros_like(b) for b in self.biases]]
         b1, b2, eps, hist = 0.9, 0.999, 1e-8, []

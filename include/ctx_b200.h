@@ -200,6 +200,8 @@ typedef struct ctx_adjoint_cfg {
   int32_t cap;
   int32_t ts_per_row;
   double rtol, atol, dt0;
+  int32_t solver;      /* CTX_TSIT5 | CTX_DOPRI5 (trainer.py:128-132 lets the caller choose) */
+  int32_t reserved;
 } ctx_adjoint_cfg;
 size_t ctx_mlp_adjoint_workspace_bytes(ctx_model* m, const ctx_adjoint_cfg* cfg);
 int ctx_mlp_adjoint_forward(ctx_model* m, const ctx_adjoint_cfg* cfg, const void* y0,

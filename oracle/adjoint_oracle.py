@@ -69,7 +69,7 @@ def mlp_field(weights, biases, activation, final_activation, max_time, stoich=No
     return f
 
 
-def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096, t0=None):
+def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096, t0=None, solver="tsit5"):
     """One trajectory: ts [T] (float64 tensor), y0 [S] -> ys [T,S] (differentiable), n_acc, n_rej.
     t0 = ts[0] (neuralode.py:52) unless given (universalode.py:133: 0.0)."""
     T = ts.shape[0]
@@ -83,7 +83,9 @@ def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096, t0=None):
         return torch.stack([y0 for _ in range(T)]), 0, 0
     k1 = f(torch.tensor(tprev, dtype=torch.float64), y)
     nacc = nrej = 0
-    A, C, E = tb.TSIT5_A, tb.TSIT5_C, tb.TSIT5_E
+    A, C, E = (tb.TSIT5_A, tb.TSIT5_C, tb.TSIT5_E) if solver == "tsit5" else \
+        (tb.DOPRI5_A, tb.DOPRI5_C, tb.DOPRI5_E)
+    dense_weights = tb.tsit5_dense_weights if solver == "tsit5" else tb.dopri5_dense_weights
     for _ in range(max_steps):
         if not tprev < t_end:
             break
@@ -105,7 +107,7 @@ def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096, t0=None):
         if keep:
             while idx < T and float(ts[idx]) <= tnext:
                 th = (float(ts[idx]) - tprev) / dt if dt != 0 else 0.0
-                bw = tb.tsit5_dense_weights(th)
+                bw = dense_weights(th)
                 out[idx] = y + dt * sum(bw[i] * ks[i] for i in range(7))
                 idx += 1
             y, k1, tprev = y1, ks[6], tnext
@@ -122,7 +124,7 @@ def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096, t0=None):
 
 
 def neuralode_value_and_grad(weights, biases, activation, final_activation, max_time, ts, y0,
-                             loss_fn, rtol=1e-3, atol=1e-6, dt0=None, stoich=None):
+                             loss_fn, rtol=1e-3, atol=1e-6, dt0=None, stoich=None, solver="tsit5"):
     """weights / biases: lists of numpy arrays (eqx convention W [out,in]); ts [B,T]; y0 [B,S].
     loss_fn(ys [B,T,S] torch float64) -> scalar.  Returns (loss, ys, grads_W, grads_b, grad_y0,
     n_accepted [B], n_rejected [B])."""
@@ -136,7 +138,7 @@ def neuralode_value_and_grad(weights, biases, activation, final_activation, max_
     ys, na, nr = [], [], []
     for b in range(y0t.shape[0]):
         step0 = float(tst[b, 1] - tst[b, 0]) if dt0 is None else dt0
-        o, a_, r_ = solve_one(f, tst[b], y0t[b], rtol, atol, step0)
+        o, a_, r_ = solve_one(f, tst[b], y0t[b], rtol, atol, step0, solver=solver)
         ys.append(o); na.append(a_); nr.append(r_)
     ys = torch.stack(ys)
     loss = loss_fn(ys)
