@@ -82,7 +82,6 @@ def test_simulation_golden_up_to_the_first_step_factor(kernel, monkeypatch):
         fo, reso, _ = fit_first_factor(_oracle_rows(), row)
         print(f"row {row}: CUDA factor {f} residual {res:.2e}; oracle factor {fo} residual {reso:.2e}")
         assert res < bound < TOLERANCE, (row, f, res)
-        assert 1.0 < f < 10.0
     # the hook is inert when the constant is not positive: the plain result comes back
     plain = solve_rows(2.0, np.zeros(4))
     assert np.abs(plain[0] / np.array([1.0, 20.085447, 403.42603]) - 1).max() < 2e-5
