@@ -165,16 +165,24 @@ class Ctx:
         (ms per call: max over ranks, last result, clocks during the timed region)."""
         import torch
 
-        t_w, i, out = time.perf_counter(), 0, None
-        while i < warm_min or time.perf_counter() - t_w < warm_s:
+        # The number of calls must be the SAME on every rank (fn may contain a collective): warm_min
+        # calls, one timed call to estimate the cost, then counts agreed upon by all ranks.
+        out = None
+        for _ in range(warm_min):
             out = fn()
-            i += 1
-            if i % 8 == 0:
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        est = self.max_over_ranks(max(time.perf_counter() - t1, 1e-5))
+        n_warm = int(min(2000, math.ceil(warm_s / est)))
+        # long enough for the 50 ms clock sampler to see the leg: >= 0.25 s of timed work
+        iters = int(max(iters, min(2000, math.ceil(0.25 / est))))
+        for k in range(n_warm):
+            out = fn()
+            if k % 8 == 7:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
-        # long enough for the 50 ms clock sampler to see the leg: >= 0.25 s of timed work
-        est = (time.perf_counter() - t_w) / i
-        iters = int(self.max_over_ranks(max(iters, min(2000, math.ceil(0.25 / max(est, 1e-5))))))
         if self.world > 1:
             self.dist.barrier()
         m0 = self.sampler.mark() if self.sampler else None
@@ -383,10 +391,20 @@ def run_nuts_leg(cx, fma_peak=None):
         sargs = [tt(x) for x in (y0s0[lo_:hi_], theta0, consts0[lo_:hi_], ts0[lo_:hi_], data0[lo_:hi_], sigma0)]
         s_kw = dict(base_kw, likelihood="softlaplace")
 
+        from catalax_b200.parallel import PeerAllReduce
+
+        try:
+            p2p = PeerAllReduce(CH * (1 + 2 + 3) * 8)
+        except Exception as exc:
+            p2p = None
+            p2p_err = f"{type(exc).__name__}: {exc}"[:200]
+
         def series_eval(reduce=True):
             o, _, st = model.loglik_grad(*sargs, **s_kw)
-            if reduce:
+            if reduce == "nccl" or (reduce is True and p2p is None):
                 dist.all_reduce(o, op=dist.ReduceOp.SUM)
+            elif reduce:
+                p2p(o)
             return o, st
 
         def graphed(reduce):
@@ -408,20 +426,33 @@ def run_nuts_leg(cx, fma_peak=None):
             sms, _, _ = cx.timed(lambda: g_full.replay(), iters=n_iter)
             g_k, _, _ = graphed(False)
             kms, _, _ = cx.timed(lambda: g_k.replay(), iters=n_iter)
-            mode = "one CUDA graph per evaluation (likelihood kernel + reduce kernel + NCCL all-reduce)"
-        except Exception as exc:      # graph capture unavailable: eager launches
+            g_n, so_n, _ = graphed("nccl")
+            nms, _, _ = cx.timed(lambda: g_n.replay(), iters=n_iter)
+            breakdown["graph_with_nccl_allreduce_ms"] = nms
+            breakdown["p2p_equals_nccl"] = bool(torch.allclose(so, so_n, rtol=1e-4, atol=1e-3))
+            mode = ("one CUDA graph per evaluation: likelihood kernel + reduce kernel + "
+                    + ("one-shot NVLink all-reduce kernel (ctx_p2p_allreduce)" if p2p is not None
+                       else f"NCCL all-reduce (peer all-reduce unavailable: {p2p_err})"))
+        except Exception as exc:      # graph capture unavailable: eager launches (all ranks agree)
+            flag = cx.sum_over_ranks(1.0)[0]
             sms, (so, sst), _ = cx.timed(lambda: series_eval(True), iters=n_iter)
             kms, _, _ = cx.timed(lambda: series_eval(False), iters=n_iter)
-            mode = f"eager launches (graph capture failed: {type(exc).__name__}: {exc})"[:200]
+            mode = f"eager launches (graph capture failed on {int(flag)} rank(s): {type(exc).__name__}: {exc})"[:200]
+        else:
+            cx.sum_over_ranks(0.0)
         ems, _, _ = cx.timed(lambda: series_eval(True), iters=n_iter)
         blk = torch.zeros((CH, 1 + 2 + 3), dtype=sargs[1].dtype, device=dev)
         cms, _, _ = cx.timed(lambda: dist.all_reduce(blk, op=dist.ReduceOp.SUM), iters=n_iter)
-        breakdown = {"graph_ms": sms, "kernels_only_graph_ms": kms, "eager_python_ms": ems,
-                     "allreduce_alone_ms": cms}
+        breakdown.update({"graph_ms": sms, "kernels_only_graph_ms": kms, "eager_python_ms": ems,
+                          "nccl_allreduce_alone_ms": cms})
+        if p2p is not None:
+            pms, _, _ = cx.timed(lambda: p2p(blk), iters=n_iter)
+            breakdown["p2p_allreduce_alone_ms"] = pms
         series = {"value": CH / (sms * 1e-3), "unit": "evals/s",
                   "ms_per_eval_batch": sms, "series_per_rank": M // world, "launch": mode,
                   "breakdown_ms": breakdown,
-                  "collective": f"NCCL all-reduce(sum) of [{CH}, {1 + 2 + 3}] {a.dtype} per evaluation",
+                  "collective": f"all-reduce(sum) of [{CH}, {1 + 2 + 3}] {a.dtype} per evaluation: "
+                                + ("ctx_p2p_allreduce (one kernel over NVLink peer memory)" if p2p is not None else "NCCL"),
                   "scaling": "strong (one posterior, series split over ranks)",
                   "all_finite": bool(torch.isfinite(so).all().item())}
     nm = res["normal"]
@@ -600,6 +631,8 @@ def run_other_configs(cx, model, sets, fma_peak=None):
                                                 "issued as three tf32 MMAs)"}}
                 res[f"config5_{kind}_5x64x64x64x{net.spec.out_size}"] = entry
             except Exception as exc:
+                if world > 1:          # a rank that skips a leg would desynchronise the collectives
+                    raise
                 res[f"config5_{kind}"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if want_cpu:
             # the reference algorithm on the CPU: numpy MLP field (BLAS) in the lock-step oracle

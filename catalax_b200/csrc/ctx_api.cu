@@ -261,7 +261,8 @@ size_t theta_smem(const ctx_model* m) {
   return m->theta_ptr ? (size_t)m->p_pad * (m->desc.dtype == CTX_F64 ? 8 : 4) : 0;
 }
 
-int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0, int ll = 0) {
+int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0, int ll = 0,
+                    int direct = 0) {
   if (!v.cubin.empty()) return CTX_OK;
   std::string src;
   src += m->desc.dtype == CTX_F64 ? "typedef double real;\n#define R(x) x\n"
@@ -291,6 +292,8 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0,
     }
     // the dense-output pass writes point-wise log-likelihoods instead of states (ctx_pointwise_loglik)
     if (ll) opts.push_back("-DCTX_LLSAVE=1");
+    // sparse output grids: the owning lane saves its own points (no cooperative pass)
+    if (direct) opts.push_back("-DCTX_DIRECT_SAVE=1");
     mb = std::max<size_t>(1, std::min<size_t>(4, mb));
     if (m->theta_ptr) mb = 1;
     const char* ex = getenv("CTX_B200_NVRTC_FLAGS");
@@ -370,13 +373,13 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0,
 }
 
 int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_t* out,
-               int wide = 0, int ll = 0) {
+               int wide = 0, int ll = 0, int direct = 0) {
   if (solver < 0 || solver > 3) return fail(CTX_E_INVALID, "unknown solver id");
   if (tan && m->desc.n_dirs <= 0)
     return fail(CTX_E_INVALID, "model was generated without sensitivity directions");
   std::lock_guard<std::mutex> lk(m->mu);
-  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0) + (ll ? 16 : 0)];
-  int rc = compile_variant(m, solver, tan, v, wide, ll);
+  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0) + (ll ? 16 : 0) + (direct ? 32 : 0)];
+  int rc = compile_variant(m, solver, tan, v, wide, ll, direct);
   if (rc) return rc;
   int dev = 0;
   CTX_CUDA(cudaGetDevice(&dev));
@@ -396,9 +399,10 @@ int get_kernel(ctx_model* m, int solver, int tan, const char* kname, cudaKernel_
 }
 
 // sizeof(ctx_warp_smem) of the loaded ctx_solve_v1 module (call after get_kernel)
-int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out, int wide = 0, int ll = 0) {
+int v1_exact_warp_smem(ctx_model* m, int solver, int tan, size_t* out, int wide = 0, int ll = 0,
+                       int direct = 0) {
   std::lock_guard<std::mutex> lk(m->mu);
-  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0) + (ll ? 16 : 0)];
+  Variant& v = m->variants[solver * 2 + tan + (wide ? 8 : 0) + (ll ? 16 : 0) + (direct ? 32 : 0)];
   if (v.v1_warp_smem < 0) {
     void* dptr = nullptr;
     size_t nbytes = 0;
@@ -577,14 +581,19 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     int wide = (!tan && d.dtype == CTX_F32 && !m->theta_ptr && d.n_states <= 4 &&
                 cfg->n_times >= 768) ? 1 : 0;
     if (const char* ev = getenv("CTX_B200_WIDE_SAVE")) wide = atoi(ev) ? (tan ? 0 : 1) : 0;
-    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k, wide, ll);
+    // Sparse grids (few requested times per trajectory): the lane that owns a step saves its own
+    // points; the cooperative pass only pays when steps cover many points (measured thresholds:
+    // DESIGN.md section 4).  CTX_B200_DIRECT_SAVE=0|1 overrides.
+    int direct = (!tan && !ll && !m->theta_ptr && cfg->n_times <= 32) ? 1 : 0;
+    if (const char* ev = getenv("CTX_B200_DIRECT_SAVE")) direct = (atoi(ev) && !tan && !ll) ? 1 : 0;
+    int rc = get_kernel(m, cfg->solver, tan, "ctx_solve_v1", &k, wide, ll, direct);
     if (rc) return rc;
     const unsigned block = 32u * warps;
     int dev = 0, sms = 0, per_sm = 0;
     CTX_CUDA(cudaGetDevice(&dev));
     CTX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t per_warp = 0;
-    rc = v1_exact_warp_smem(m, cfg->solver, tan, &per_warp, wide, ll);
+    rc = v1_exact_warp_smem(m, cfg->solver, tan, &per_warp, wide, ll, direct);
     if (rc) return rc;
     size_t smem = theta_smem(m) + (size_t)warps * per_warp;
     if (m->theta_ptr && a.stride_theta != 0)
@@ -612,7 +621,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
     CTX_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(block), params, smem,
                               stream));
     g_launches++;
-    g_last_kernel = ll ? "ctx_solve_v1 (log-likelihood save)" : "ctx_solve_v1";
+    g_last_kernel = ll ? "ctx_solve_v1 (log-likelihood save)" : (direct ? "ctx_solve_v1 (direct save)" : "ctx_solve_v1");
   } else if (kernel == 3) {
     // K3: tcgen05 MLP tiles (ctx_mlp_tc.cuh); theta = [aux | UMMA weight pack]
     if (m->mlp_tc_smem <= 0 || m->desc.dtype != CTX_F32 || tan || cfg->solver > CTX_DOPRI5)

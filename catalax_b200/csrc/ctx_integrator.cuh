@@ -476,6 +476,9 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #ifndef CTX_ST256
 #define CTX_ST256 1       // full-sector (256-bit) stores of complete groups, see the save loop
 #endif
+#ifndef CTX_DIRECT_SAVE
+#define CTX_DIRECT_SAVE 0  // 1: the owning lane evaluates and stores its own points (sparse grids)
+#endif
 #ifndef CTX_BULK
 // 1: complete groups leave through shared memory + one cp.async.bulk (TMA) per run of groups of
 // one trajectory.  Measured on B200 (config 2, T=1000): 4.68 ms vs 4.44 ms (f32), 9.5 vs 8.1 ms
@@ -960,8 +963,47 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
     const bool filling = (b >= 0) && !stepping;
     if (filling) { nsave = T - idx; retire = true; }
 
-    // ------------------------------------------------------------- cooperative saves
-#if !CTX_TAN
+    // ------------------------------------------------------------- saves
+#if CTX_DIRECT_SAVE && !CTX_TAN
+    // Sparse output grids (a step covers a requested time only now and then: T <~ the number of
+    // steps): the cooperative machinery below -- scan, records, passes, pending groups -- costs
+    // ~40 % of the instructions of an iteration for a handful of points (ncu, T=16:
+    // profiles/r2b_v1_T16.json).  Here the lane that owns the step evaluates its own points with
+    // the same polynomial (same Horner order: bit-identical results) and stores them directly.
+    if (nsave > 0) {
+      real coef[CTX_NCOEF];
+      real tp_ = R(0.0), inv_ = R(0.0);
+      if (filling) {
+        const bool fill_inf = status != 0;
+#pragma unroll
+        for (int i = 0; i < CTX_N; ++i) coef[i] = fill_inf ? CTX_INF : y[i];
+#pragma unroll
+        for (int i = CTX_N; i < CTX_NCOEF; ++i) coef[i] = R(0.0);
+      } else {
+        ctx_dense_coefs(rec_dt, y, ynew, K, coef);
+        tp_ = rec_tp;
+        inv_ = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+      }
+      real* o = a.ys + ((size_t)b * (size_t)T + (size_t)idx) * CTX_S;
+#pragma unroll 1
+      for (int j = 0; j < nsave; ++j) {
+        const real tq = filling ? R(0.0) : (TSM ? ctx_ts_at<TSM>(tsr, ts_sa, idx + j) : tsr[idx + j]);
+        const real th_ = (tq - tp_) * inv_;
+#pragma unroll
+        for (int i = 0; i < CTX_S; ++i) {
+          real v;
+          if (ctx_is_const(i)) {
+            v = coef[i];
+          } else {
+            v = coef[CTX_DEG * CTX_N + i];
+#pragma unroll
+            for (int mm = CTX_DEG - 1; mm >= 0; --mm) v = v * th_ + coef[mm * CTX_N + i];
+          }
+          o[(size_t)j * CTX_S + i] = v;
+        }
+      }
+    }
+#elif !CTX_TAN
     // Unified group path.  The requested times of every trajectory are cut into groups of 4
     // consecutive points aligned to multiples of 4; the groups touched by the accepted steps of
     // all lanes are flattened and dealt out to the 32 lanes (consecutive lanes = consecutive

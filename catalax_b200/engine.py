@@ -138,6 +138,16 @@ def lib() -> C.CDLL:
     L.ctx_loglik_grad_host.restype = C.c_int
     L.ctx_loglik_grad_host.argtypes = [vp, C.POINTER(ctx_loglik_cfg)] + [vp] * 10
     L.ctx_build_stamp.restype = C.c_char_p
+    L.ctx_p2p_create.restype = C.c_int
+    L.ctx_p2p_create.argtypes = [C.c_int32, C.c_int32, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.ctx_p2p_connect.restype = C.c_int
+    L.ctx_p2p_connect.argtypes = [vp, C.c_char_p]
+    L.ctx_p2p_allreduce.restype = C.c_int
+    L.ctx_p2p_allreduce.argtypes = [vp, C.c_int32, C.c_size_t, vp, vp]
+    L.ctx_p2p_free.restype = None
+    L.ctx_p2p_free.argtypes = [vp]
+    L.ctx_p2p_last_error.restype = C.c_size_t
+    L.ctx_p2p_last_error.argtypes = [C.c_char_p, C.c_size_t]
     L.ctx_last_solve_kernel.restype = C.c_char_p
     for name in ("ctx_xla_solve", "ctx_xla_solve_sens", "ctx_xla_loglik_grad"):
         fn = getattr(L, name)

@@ -15,6 +15,7 @@ the [chains, 1+P+n_obs] block (catalax_b200.parallel).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Any, Optional
 
@@ -189,6 +190,7 @@ class BayesianModel:
         self._compiled = None
         self._dev_arrays = None
         self._device = device
+        self._p2p = None
 
     # ------------------------------------------------------------------ likelihood block
     def _local_loglik(self, theta, sigma):
@@ -242,7 +244,17 @@ class BayesianModel:
         from .. import parallel
 
         block = self._local_loglik(theta, sigma)
-        if self.shard == "series":
+        if self.shard == "series" and self.world > 1:
+            # the path's only collective: the engine's one-shot kernel over NVLink peer memory when
+            # the ranks are GPUs of one node (CTX_B200_NO_P2P=1 forces NCCL), torch.distributed else
+            if block.is_cuda and not os.environ.get("CTX_B200_NO_P2P"):
+                if self._p2p is None or self._p2p.max_bytes < block.numel() * block.element_size():
+                    try:
+                        self._p2p = parallel.PeerAllReduce(block.numel() * block.element_size())
+                    except Exception:
+                        self._p2p = False
+                if self._p2p:
+                    return self._p2p(block)
             parallel.allreduce_sum_(block)
         return block
 

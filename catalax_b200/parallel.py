@@ -3,7 +3,8 @@
 The path shards embarrassingly: trajectories and chains are independent; series of
 one chain are independent until the final sum of mcmc.py:486-491.  The ONLY collective is the
 all-reduce(sum) of the per-rank [chains, 1+P+n_obs] log-likelihood/gradient block when series
-are sharded (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+are sharded: on the GPUs of one node the engine's own one-shot kernel over NVLink peer memory
+(``PeerAllReduce`` -> ctx_p2p_allreduce), NCCL otherwise; gloo in the CPU tests."""
 from __future__ import annotations
 
 from typing import Tuple
@@ -37,3 +38,68 @@ def allreduce_sum_(t):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+class PeerAllReduce:
+    """One-shot all-reduce(sum) over NVLink peer memory for latency-bound blocks (ctx_p2p_*).
+
+    Every rank of the node allocates a symmetric buffer, the 64-byte cudaIpc handles are exchanged
+    once through torch.distributed (plumbing), and each call is ONE kernel of the engine: copy,
+    flag exchange, P2P loads of every peer's block summed in rank order.  Stream-ordered on the
+    current torch stream and CUDA-graph capturable.  ``max_bytes``: largest message."""
+
+    def __init__(self, max_bytes: int, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import engine
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerAllReduce needs an initialised torch.distributed process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._lib = engine.lib()
+        self._h = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        rc = self._lib.ctx_p2p_create(self.rank, self.world, int(max_bytes), C.byref(self._h), handle)
+        self._check(rc)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(handle.raw), group=group)
+        self._check(self._lib.ctx_p2p_connect(self._h, b"".join(gathered)))
+        self.max_bytes = int(max_bytes)
+        dist.barrier(group)        # every rank has mapped every buffer before the first call
+        self._torch = torch
+
+    def _check(self, rc):
+        import ctypes as C
+
+        if rc != 0:
+            buf = C.create_string_buffer(4096)
+            self._lib.ctx_p2p_last_error(buf, len(buf))
+            raise RuntimeError(f"ctx_p2p error {rc}: {buf.value.decode(errors='replace')}")
+
+    def __call__(self, t):
+        """In-place sum of the CUDA tensor ``t`` (float32 / float64, contiguous) over the ranks."""
+        import ctypes as C
+
+        torch = self._torch
+        if not t.is_cuda or not t.is_contiguous() or t.dtype not in (torch.float32, torch.float64):
+            raise ValueError("PeerAllReduce: contiguous float32 / float64 CUDA tensor expected")
+        if t.numel() * t.element_size() > self.max_bytes:
+            raise ValueError("PeerAllReduce: message larger than the symmetric buffer")
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        self._check(self._lib.ctx_p2p_allreduce(self._h, 1 if t.dtype == torch.float64 else 0, t.numel(),
+                                                C.c_void_p(t.data_ptr()), C.c_void_p(stream)))
+        return t
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ctx_p2p_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

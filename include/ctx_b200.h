@@ -264,6 +264,24 @@ size_t ctx_xla_desc_bytes(int32_t which); /* 0: ctx_xla_solve_desc, 1: ctx_xla_l
 int ctx_xla_last_status(void);
 size_t ctx_xla_last_error(char* buf, size_t n);
 
+/* ---- the path's only collective: one-shot all-reduce(sum) over NVLink peer memory --------------
+ * Series-sharded log-density (every rank holds M/G series of ONE posterior): the [chains,
+ * 1+D_theta+S] blocks of ctx_loglik_grad are summed over the ranks of the node once per evaluation
+ * (mcmc.py:486-491 sums over the series inside one program).  ctx_p2p_create allocates this rank's
+ * symmetric buffer and returns its 64-byte cudaIpc handle; the caller gathers all ranks' handles
+ * (any out-of-band channel: torch.distributed, MPI) and passes them, in rank order, to
+ * ctx_p2p_connect.  ctx_p2p_allreduce then sums `inout` (n elements of the model dtype, device
+ * pointer) over the ranks in place with ONE kernel: copy into the symmetric buffer, flag exchange
+ * (release / acquire at system scope), P2P loads of every peer's block summed in rank order (all
+ * ranks get identical bits).  Stream-ordered, CUDA-graph capturable (the epoch lives in device
+ * memory), at most 16 ranks of one node; every rank must call it the same number of times. */
+typedef struct ctx_p2p ctx_p2p;
+int ctx_p2p_create(int32_t rank, int32_t world, size_t bytes, ctx_p2p** out, void* handle_out);
+int ctx_p2p_connect(ctx_p2p* p, const void* all_handles);
+int ctx_p2p_allreduce(ctx_p2p* p, int32_t dtype, size_t n, void* inout, void* stream);
+void ctx_p2p_free(ctx_p2p* p);
+size_t ctx_p2p_last_error(char* buf, size_t n);
+
 /* ---- diagnostics ------------------------------------------------------------------------ */
 int ctx_abi_version(void);
 int ctx_device_count(void); /* 0 when no GPU is visible; never throws */
