@@ -283,6 +283,7 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0,
     // tighter caps spill.  Budget ~96 registers + 10 per 32-bit word of trajectory state.
     const size_t words = (size_t)m->desc.n_states * (1 + (tan ? m->desc.n_dirs : 0)) *
                          (m->desc.dtype == CTX_F64 ? 2 : 1);
+    const char* extra_probe = getenv("CTX_B200_NVRTC_FLAGS");
     size_t mb = 512 / (96 + 10 * words);
     if (wide) {
       // 8 requested times per lane and pass instead of 4 (CTX_GP=8): long output grids in f32
@@ -296,6 +297,13 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0,
     if (direct) opts.push_back("-DCTX_DIRECT_SAVE=1");
     mb = std::max<size_t>(1, std::min<size_t>(4, mb));
     if (m->theta_ptr) mb = 1;
+    if (tan && !m->theta_ptr) {
+      // log-likelihood kernels: a tighter cap than the solve kernel of the same build (measured on
+      // config 4: f32 4 CTAs/SM +14 %, f64 3 CTAs/SM +4 %, 5 / 4 lose; see ctx_integrator.cuh)
+      size_t llmb = std::max<size_t>(1, std::min<size_t>(4, 640 / (64 + 8 * words)));
+      if (!(extra_probe && strstr(extra_probe, "-DCTX_LL_MIN_BLOCKS=")))
+        opts.push_back("-DCTX_LL_MIN_BLOCKS=" + std::to_string(std::max(llmb, mb)));
+    }
     const char* ex = getenv("CTX_B200_NVRTC_FLAGS");
     if (!(ex && strstr(ex, "-DCTX_MIN_BLOCKS=")))   // developer override for A/B runs
       opts.push_back("-DCTX_MIN_BLOCKS=" + std::to_string(mb));

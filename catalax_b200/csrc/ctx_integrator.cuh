@@ -1550,7 +1550,15 @@ __device__ __forceinline__ real ctx_log1p_exp_neg2a(const real a) {  // log(1 + 
   return log1p(exp(R(-2.0) * a));
 }
 
-extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
+// Register cap of the log-likelihood kernels.  Uncapped they take 164 (f32) registers = 12 warps
+// per SM; capped to 4 CTAs/SM (128 registers, a few spilled words) the f32 kernel of config 4 runs
+// 1.92 -> 1.69 ms, f64 at 3 CTAs/SM 6.43 -> 6.20 ms, same bits (measured on B200, round 2); 5 CTAs/SM
+// loses (2.12 ms).  The host passes the cap per model (ctx_api.cu compile_variant).
+#ifndef CTX_LL_MIN_BLOCKS
+#define CTX_LL_MIN_BLOCKS CTX_MIN_BLOCKS
+#endif
+
+extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_LL_MIN_BLOCKS)
 ctx_loglik_v1(const ctx_loglik_args a) {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -1740,7 +1748,7 @@ struct ctx_ll_warp_smem {
   int owner[32];             // publishing lane
 };
 
-extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_LL_MIN_BLOCKS)
 ctx_loglik_v2(const ctx_loglik_args a) {
   extern __shared__ __align__(16) unsigned char ctx_dyn_smem[];
   ctx_ll_warp_smem& w = reinterpret_cast<ctx_ll_warp_smem*>(ctx_dyn_smem)[threadIdx.x >> 5];

@@ -264,3 +264,49 @@ def test_warp_specialised_kernel_is_bit_identical_to_the_persistent_kernel(S, so
         np.testing.assert_array_equal(a_, b_)
     if S == 3:
         assert (outs[0][1] != 0).any()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("T,shared_ts,solver", [(16, True, "tsit5"), (7, False, "dopri5"), (32, True, "euler"),
+                                                (1, True, "tsit5")])
+def test_direct_save_variant_is_bit_identical(T, shared_ts, solver, dtype, monkeypatch):
+    """Sparse grids (T <= 32) take the variant of ctx_solve_v1 whose lanes evaluate and store their
+    own requested times (no cooperative pass): the same polynomial in the same Horner order, so the
+    same bits as the cooperative path -- incl. failed rows (inf fill), t0 == t1 (constant fill),
+    constant states and per-row grids."""
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+
+    B = 4099
+    model = cases.michaelis_menten()
+    y0, theta, consts = cases.mm_inputs(B, seed=9, dtype=dtype)
+    theta[:5, 0] = 1e-3                       # stiff rows -> max_steps -> inf fill
+    rng = np.random.default_rng(2)
+    if shared_ts:
+        ts = np.linspace(0, 100, T).astype(dtype) if T > 1 else np.array([0.0], dtype=dtype)
+    else:
+        ts = np.sort(rng.uniform(0, 100, (B, T)), axis=1).astype(dtype)
+        ts[:, 0] = 0.0
+        ts[3] = 0.0                            # t0 == t1: every requested time is t0
+    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), np.dtype(dtype).name)
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CTX_B200_DIRECT_SAVE", flag)
+        o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), solver=solver,
+                    in_axes=(0, 0, 0, None if shared_ts else 0), rtol=1e-6, atol=1e-6,
+                    dt0=0.05 if solver == "euler" else 0.1, max_steps=4096, kernel=2)
+        torch.cuda.synchronize()
+        assert engine.last_solve_kernel() == ("ctx_solve_v1 (direct save)" if flag == "1" else "ctx_solve_v1")
+        res[flag] = (o.ys.cpu().numpy(), o.status.cpu().numpy(), o.n_accepted.cpu().numpy())
+    np.testing.assert_array_equal(res["0"][0], res["1"][0])
+    np.testing.assert_array_equal(res["0"][1], res["1"][1])
+    np.testing.assert_array_equal(res["0"][2], res["1"][2])
+    if solver != "euler" and T > 1:
+        assert (res["1"][1][:5] == 1).all() and np.isinf(res["1"][0][:5, -1, 1:]).all()
+    monkeypatch.delenv("CTX_B200_DIRECT_SAVE")
+    # the automatic choice for T <= 32 is the direct variant
+    m.solve(tt(y0), tt(theta), tt(consts), tt(ts), solver=solver, in_axes=(0, 0, 0, None if shared_ts else 0),
+            dt0=0.05 if solver == "euler" else 0.1)
+    assert engine.last_solve_kernel() == "ctx_solve_v1 (direct save)"
