@@ -99,19 +99,27 @@ class EnsembleIntegrator:
         """log p(data[m,t,o] | draw d) for every draw and observation -> torch [D,M,T,S]: the input
         of LOO's PSIS (loo.py:131-200).  One fused launch (ctx_pointwise_loglik): the dense-output
         pass of the solve evaluates the likelihood of the observation at each requested time, the
-        ``[D,M,T,S]`` trajectories are never written.  ``data`` must be finite (``data_safe``:
-        0 where masked, loo.py:158); failed solves give -inf / NaN like the reference's inf states."""
+        ``[D,M,T,S]`` trajectories are never written.  Missing observations (NaN in ``data``) are
+        scored on 0 inside the kernel (``data_safe``, loo.py:158) and come back as NaN; failed solves
+        give -inf / NaN like the reference's inf states."""
+        import torch
+
         y0s, thetas, sigmas, constants, times, data = self._tensors(
             y0s, thetas, sigmas, constants, times, data, device=device)
         M, T = times.shape
         D = thetas.shape[0]
         cfg = self.config
+        missing = ~torch.isfinite(data)                       # mcmc.py:566: the mask is isfinite(data)
+        data_safe = torch.where(missing, torch.zeros_like(data), data)
         out = self.compiled.pointwise_loglik(
-            y0s, thetas, constants.reshape(M, self.field.C), times, data, sigmas,
+            y0s, thetas, constants.reshape(M, self.field.C), times, data_safe, sigmas,
             likelihood=likelihood, solver=solver_name(cfg.solver), rtol=cfg.rtol, atol=cfg.atol,
             dt0=cfg.dt0, max_steps=cfg.max_steps, inner=M)
         self.last = out
-        return out.ys.reshape(D, M, T, self.field.S)
+        ll = out.ys.reshape(D, M, T, self.field.S)
+        if bool(missing.any()):
+            ll = torch.where(missing[None].expand_as(ll), torch.full_like(ll, float("nan")), ll)
+        return ll
 
 
 def integrate_ensemble(results, dataset, posterior, *, n_steps: int):

@@ -296,15 +296,18 @@ def test_direct_save_variant_is_bit_identical(T, shared_ts, solver, dtype, monke
         monkeypatch.setenv("CTX_B200_DIRECT_SAVE", flag)
         o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), solver=solver,
                     in_axes=(0, 0, 0, None if shared_ts else 0), rtol=1e-6, atol=1e-6,
-                    dt0=0.05 if solver == "euler" else 0.1, max_steps=4096, kernel=2)
+                    dt0=0.05 if solver == "euler" else 0.1, max_steps=60 if solver != "euler" else 4096,
+                    kernel=2)
         torch.cuda.synchronize()
         assert engine.last_solve_kernel() == ("ctx_solve_v1 (direct save)" if flag == "1" else "ctx_solve_v1")
         res[flag] = (o.ys.cpu().numpy(), o.status.cpu().numpy(), o.n_accepted.cpu().numpy())
     np.testing.assert_array_equal(res["0"][0], res["1"][0])
     np.testing.assert_array_equal(res["0"][1], res["1"][1])
     np.testing.assert_array_equal(res["0"][2], res["1"][2])
-    if solver != "euler" and T > 1:
-        assert (res["1"][1][:5] == 1).all() and np.isinf(res["1"][0][:5, -1, 1:]).all()
+    if solver != "euler" and T > 1:      # max_steps = 60: many rows fail -> inf fill in both variants
+        failed = res["1"][1] == 1
+        assert 10 < failed.sum() < B and np.isinf(res["1"][0][failed][:, -1, 1:]).all()
+        assert np.isfinite(res["1"][0][~failed]).all()
     monkeypatch.delenv("CTX_B200_DIRECT_SAVE")
     # the automatic choice for T <= 32 is the direct variant
     m.solve(tt(y0), tt(theta), tt(consts), tt(ts), solver=solver, in_axes=(0, 0, 0, None if shared_ts else 0),
