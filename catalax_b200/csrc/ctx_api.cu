@@ -133,6 +133,7 @@ struct SolveArgs {
   const real* ll_data;     // CTX_LLSAVE builds (ctx_pointwise_loglik)
   const real* ll_sigma;
   int ll_likelihood;
+  const int* order;        // scheduling hint (cfg->order)
 };
 
 template <typename real>
@@ -173,7 +174,7 @@ size_t v1_warp_smem(const ctx_model_desc& d, int solver, int tan, bool theta_ptr
   const size_t N = S * (1 + (tan ? d.n_dirs : 0));
   const size_t deg = solver <= 1 ? 4 : 1;
   const size_t qw = S + (theta_ptr ? 0 : (size_t)d.n_params) + (size_t)d.n_consts + 2;
-  const size_t q_in = 2 * qw * 32 * w;
+  const size_t q_in = 2 * qw * 32 * w + 2 * 32 * 4;   // operands + trajectory indices
   if (!tan) {   // ctx_rec records (16-byte aligned) + one pending group per lane
     const size_t rec = (((2 + (deg + 1) * N) * w + 7 * 4) + 15) / 16 * 16;
     return q_in + 32 * rec + 32 * 8 * S * w + 64;   // (pending groups of up to 8 points)
@@ -486,6 +487,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.ll_data = (const real*)ll_data;
   a.ll_sigma = (const real*)ll_sigma;
   a.ll_likelihood = ll_likelihood;
+  a.order = (const int*)cfg->order;
   const int ll = ll_data ? 1 : 0;
 
   int kernel = cfg->kernel;
@@ -704,6 +706,7 @@ struct LoglikArgs {
   long long n_traj;
   int M, T, likelihood, max_steps;
   real rtol, atol, dt0;
+  const int* order;
 };
 
 template <typename real>
@@ -730,6 +733,7 @@ int launch_loglik(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, cons
   a.n_traj = n_traj; a.M = cfg->n_series; a.T = cfg->n_times; a.likelihood = cfg->likelihood;
   a.max_steps = cfg->max_steps;
   a.rtol = (real)cfg->rtol; a.atol = (real)cfg->atol; a.dt0 = (real)cfg->dt0;
+  a.order = (const int*)cfg->order;
   // kernel (cfg->kernel): 0 = automatic, 1 = per-lane likelihood terms (ctx_loglik_v1),
   // 2 = warp-cooperative likelihood terms (ctx_loglik_v2, the default)
   const int which = cfg->kernel == 1 ? 1 : 2;
@@ -1254,6 +1258,7 @@ int ctx_solve_host(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const
   auto al = [](size_t n) { return (n + 255) / 256 * 256; };
   ctx_solve_cfg ccfg = *cfg;
   ccfg.batch = (int64_t)R;
+  ccfg.order = nullptr;          // (a DEVICE pointer indexing the whole batch: not applicable to chunks)
   // per buffer: inputs of one chunk, its outputs, counters, workspace
   const size_t n_y0 = al(rows(0, R) * S * w), n_th = al(rows(1, R) * d.n_params * w),
                n_c = al(rows(2, R) * d.n_consts * w), n_ts = al(rows(3, R) * T * w),
@@ -1329,6 +1334,9 @@ int ctx_loglik_grad_host(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0
                n_sg = al(CH * S * w), n_out = al(CH * KR * w), n_part = al(CH * M * KP * w),
                n_st = al(CH * M * 4), n_ws = al(ctx_loglik_workspace_bytes(m, cfg));
   const size_t total = n_y0 + n_th + n_c + n_ts + n_d + n_m + n_sg + n_out + n_part + n_st + n_ws;
+  ctx_loglik_cfg lcfg = *cfg;
+  lcfg.order = nullptr;
+  cfg = &lcfg;
   std::lock_guard<std::mutex> lk(m->host_mu);
   int rc = host_stage(m, total);
   if (rc) return rc;

@@ -75,6 +75,10 @@ struct ctx_solve_args {
   const real* ll_data;    // [M,T,S] observations (0 where masked: data_safe), row = the series
   const real* ll_sigma;   // [D,S]   noise scale of the draw (row = b / inner)
   int ll_likelihood;      // 0 Normal | 1 SoftLaplace
+  // Scheduling hint of the persistent kernels: queue position u is trajectory order[u] (a
+  // permutation of [0, B), usually "most expensive first" from the step counts of a previous solve
+  // of similar inputs).  Results do not depend on it; null = index order.
+  const int* order;
 };
 // first step size of a trajectory whose requested times are `row` (T of them)
 #define CTX_ROW_DT0(row, T) (((a.dt0 > R(0.0)) || (T) < 2) ? a.dt0 : ((row)[1] - (row)[0]))
@@ -642,6 +646,7 @@ union ctx_rec_u {
 
 struct ctx_warp_smem {
   real q_in[2][CTX_QW][32];      // input queue: two buffers, one column per entry
+  int q_idx[2][32];              // ... and the trajectory index of each entry (order hint applied)
 #if !CTX_TAN
   ctx_rec rec[32];               // one record per publishing lane of this iteration
   uint4 pend[32][CTX_PEND_Q];    // per lane: the group of 4 points its trajectory has not completed
@@ -702,11 +707,14 @@ __device__ __forceinline__ int ctx_upper_bound(const real* ts, const unsigned sa
 
 // issue the operand copies of the batch [base, base + q_batch) into queue buffer `buf`
 __device__ __forceinline__ void ctx_queue_fetch_q(const ctx_solve_args& a, real (*q_in)[CTX_QW][32],
-                                                  const int buf, const unsigned long long base,
-                                                  const int count, const int lane) {
+                                                  int (*q_idx)[32], const int buf,
+                                                  const unsigned long long base, const int count,
+                                                  const int lane) {
   const unsigned long long u = base + (unsigned long long)lane;
   if (lane < count && u < (unsigned long long)a.B) {
-    CTX_ROWS((long long)u, ro, ri);
+    const long long bq = a.order ? (long long)a.order[u] : (long long)u;
+    q_idx[buf][lane] = (int)bq;
+    CTX_ROWS(bq, ro, ri);
     (void)ro;
     int k = 0;
 #pragma unroll
@@ -727,7 +735,7 @@ __device__ __forceinline__ void ctx_queue_fetch_q(const ctx_solve_args& a, real 
 __device__ __forceinline__ void ctx_queue_fetch(const ctx_solve_args& a, ctx_warp_smem& w,
                                                 const int buf, const unsigned long long base,
                                                 const int count, const int lane) {
-  ctx_queue_fetch_q(a, w.q_in, buf, base, count, lane);
+  ctx_queue_fetch_q(a, w.q_in, w.q_idx, buf, base, count, lane);
 }
 
 // TSM: the time grid is shared by all trajectories and staged in shared memory (ts_sm).
@@ -817,7 +825,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       const int rank = __popc(need & lt_mask);
       if (b < 0 && rank < take) {
         const int e = q_pos + rank;
-        b = (long long)qb_cur + e;
+        b = (long long)w.q_idx[q_cur][e];
         CTX_ROWS(b, ro, ri);
         (void)ro;
         ts_row = TSM ? 0 : ri * (long long)a.stride_ts;
@@ -876,7 +884,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       if (b < 0) {
         const unsigned long long nb = base + __popc(need & lt_mask);
         if (nb < (unsigned long long)a.B) {
-          b = (long long)nb;
+          b = a.order ? (long long)a.order[nb] : (long long)nb;
           CTX_ROWS(b, ro, ri);
           (void)ro;
           ts_row = TSM ? 0 : ri * (long long)a.stride_ts;
@@ -1544,6 +1552,7 @@ struct ctx_loglik_args {
   long long n_traj;     // CH*M
   int M, T, likelihood, max_steps;
   real rtol, atol, dt0;
+  const int* order;     // scheduling hint: position u of the work queue is trajectory order[u]; null = u
 };
 
 __device__ __forceinline__ real ctx_log1p_exp_neg2a(const real a) {  // log(1 + exp(-2a)), a >= 0
@@ -1585,7 +1594,7 @@ ctx_loglik_v1(const ctx_loglik_args a) {
       if (u < 0) {
         const unsigned long long nu = base + __popc(need & lt_mask);
         if (nu < (unsigned long long)a.n_traj) {
-          u = (long long)nu;
+          u = a.order ? (long long)a.order[nu] : (long long)nu;
           const long long ch = u / a.M;
           m = (int)(u - ch * a.M);
 #pragma unroll
@@ -1777,7 +1786,7 @@ ctx_loglik_v2(const ctx_loglik_args a) {
       if (u < 0) {
         const unsigned long long nu = base + __popc(need & lt_mask);
         if (nu < (unsigned long long)a.n_traj) {
-          u = (long long)nu;
+          u = a.order ? (long long)a.order[nu] : (long long)nu;
           const long long ch = u / a.M;
           m = (int)(u - ch * a.M);
 #pragma unroll

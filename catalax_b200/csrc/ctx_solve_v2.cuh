@@ -93,6 +93,7 @@ struct alignas(16) v2_slot {
 
 struct alignas(16) v2_prod_smem {
   real q_in[2][CTX_QW][32];              // input queue of the producer
+  int q_idx[2][32];                      // trajectory index of each queue entry (order hint applied)
   v2_slot slot[V2_SLOTS];
   uint4 pend[32][CTX_PEND_Q];            // per producer lane: the group its trajectory has not completed
   unsigned long long full[V2_SLOTS], empty[V2_SLOTS];   // mbarriers
@@ -164,8 +165,8 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
     if (lane == 0) qb_cur = atomicAdd(a.work_counter, (unsigned long long)(2 * qn_cur));
     qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
     qb_nxt = qb_cur + qn_cur;
-    ctx_queue_fetch_q(a, w.q_in, 0, qb_cur, qn_cur, lane);
-    ctx_queue_fetch_q(a, w.q_in, 1, qb_nxt, qn_nxt, lane);
+    ctx_queue_fetch_q(a, w.q_in, w.q_idx, 0, qb_cur, qn_cur, lane);
+    ctx_queue_fetch_q(a, w.q_in, w.q_idx, 1, qb_nxt, qn_nxt, lane);
     qn_pend = V2_CLAIM(qb_nxt + qn_nxt);
     if (lane == 0) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);
     CTX_CP_WAIT(1);
@@ -182,7 +183,7 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
       const int rank = __popc(need & lt_mask);
       if (b < 0 && rank < take) {
         const int e = q_pos + rank;
-        b = (long long)qb_cur + e;
+        b = (long long)w.q_idx[q_cur][e];
         CTX_ROWS(b, ro, ri);
         (void)ro;
         ri_row = (int)ri;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
         CTX_CP_WAIT(0);
         __syncwarp();
         const unsigned long long nbase = __shfl_sync(CTX_FULL, qb_pend, 0);
-        ctx_queue_fetch_q(a, w.q_in, q_cur, nbase, qn_pend, lane);
+        ctx_queue_fetch_q(a, w.q_in, w.q_idx, q_cur, nbase, qn_pend, lane);
         qb_cur = qb_nxt; qn_cur = qn_nxt;
         qb_nxt = nbase; qn_nxt = qn_pend;
         qn_pend = V2_CLAIM(nbase + qn_nxt);

@@ -39,7 +39,8 @@ class ctx_solve_cfg(C.Structure):
     _fields_ = [("solver", C.c_int32), ("in_axes", C.c_int32 * 4), ("batch", C.c_int64),
                 ("n_times", C.c_int32), ("max_steps", C.c_int32), ("rtol", C.c_double),
                 ("atol", C.c_double), ("dt0", C.c_double), ("kernel", C.c_int32),
-                ("t0_from_ts", C.c_int32), ("inner", C.c_int32), ("reserved", C.c_int32)]
+                ("t0_from_ts", C.c_int32), ("inner", C.c_int32), ("reserved", C.c_int32),
+                ("order", C.c_void_p)]
 
 
 class ctx_adjoint_cfg(C.Structure):
@@ -59,7 +60,7 @@ class ctx_loglik_cfg(C.Structure):
     _fields_ = [("solver", C.c_int32), ("likelihood", C.c_int32), ("n_chains", C.c_int64),
                 ("n_series", C.c_int32), ("n_times", C.c_int32), ("max_steps", C.c_int32),
                 ("kernel", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
-                ("dt0", C.c_double)]
+                ("dt0", C.c_double), ("order", C.c_void_p)]
 
 
 class ctx_xla_loglik_desc(C.Structure):
@@ -68,7 +69,7 @@ class ctx_xla_loglik_desc(C.Structure):
                 ("ws_bytes", C.c_uint64), ("cfg", ctx_loglik_cfg)]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def lib() -> C.CDLL:
@@ -203,6 +204,15 @@ def last_solve_kernel() -> str:
     return lib().ctx_last_solve_kernel().decode()
 
 
+def cost_order(n_accepted, n_rejected):
+    """Rows in descending order of the step attempts they needed (int32 permutation): the
+    scheduling hint ``order=`` of the next solve of similar inputs."""
+    import torch
+
+    cost = n_accepted.to(torch.int64) + n_rejected.to(torch.int64)
+    return torch.argsort(cost, descending=True, stable=True).to(torch.int32).contiguous()
+
+
 @dataclass
 class SolveOutput:
     ys: "object"            # torch.Tensor [B,T,S]
@@ -210,6 +220,9 @@ class SolveOutput:
     n_accepted: "object"
     n_rejected: "object"
     sens: Optional["object"] = None  # [B,T,S,D]
+
+    def cost_order(self):
+        return cost_order(self.n_accepted, self.n_rejected)
 
 
 class CompiledModel:
@@ -258,8 +271,13 @@ class CompiledModel:
 
     def solve(self, y0, theta, consts, ts, *, solver="tsit5", in_axes=(0, None, 0, None),
               rtol=1e-5, atol=1e-5, dt0=0.1, max_steps=4096, tangents=False, kernel=0,
-              out=None, t0_from_ts=False, inner=0):
+              out=None, t0_from_ts=False, inner=0, order=None):
         """Device-resident solve.  All inputs are torch CUDA tensors of this model's dtype.
+
+        order: optional scheduling hint -- an int32 CUDA tensor holding a permutation of the rows,
+        e.g. ``previous_output.cost_order()`` ("most expensive first" from the step counts of a
+        previous solve of similar inputs).  The persistent kernels hand out rows in that order;
+        results do not depend on it.
 
         inner=M > 0: two-level batch -- theta is [D,P] (one row per posterior draw), y0 / consts /
         ts have M rows (one per series) and ys is [D*M, T, S] (predictive.py:150-154)."""
@@ -307,6 +325,11 @@ class CompiledModel:
                     or not out.is_contiguous()):
                 raise ValueError(f"out must be a contiguous {tdt} tensor of shape {(B, T, S)} on {dev}, "
                                  f"got {tuple(out.shape)} {out.dtype} on {out.device}")
+        if order is not None:
+            if (order.dtype != torch.int32 or order.device != dev or tuple(order.shape) != (B,)
+                    or not order.is_contiguous()):
+                raise ValueError(f"order must be a contiguous int32 tensor of shape ({B},) on {dev}")
+            cfg.order = order.data_ptr()
         with torch.cuda.device(dev):
             ys = out if out is not None else torch.empty((B, T, S), dtype=tdt, device=dev)
             status = torch.empty(B, dtype=torch.int32, device=dev)
@@ -522,8 +545,10 @@ class CompiledModel:
 
     def loglik_grad(self, y0s, theta, consts, ts, data, sigma, *, mask=None,
                     likelihood="softlaplace", solver="tsit5", rtol=1e-5, atol=1e-5, dt0=0.1,
-                    max_steps=4096, kernel=0):
+                    max_steps=4096, kernel=0, order=None):
         """Fused log-likelihood + gradient for CH chains over M series (ctx_loglik_grad).
+        order: optional int32 permutation of the CH*M trajectories (scheduling hint, e.g.
+        ``engine.cost_order(*model.last_loglik_counts)`` of the previous evaluation).
         kernel: 0 automatic | 1 per-lane likelihood terms | 2 warp-cooperative likelihood terms.
 
         y0s [M,S], theta [CH,P], consts [M,C], ts [M,T], data [M,T,S], sigma [CH,S],
@@ -553,6 +578,11 @@ class CompiledModel:
         cfg.n_chains, cfg.n_series, cfg.n_times, cfg.max_steps = CH, M, T, int(max_steps)
         cfg.rtol, cfg.atol, cfg.dt0 = float(rtol), float(atol), float(dt0)
         cfg.kernel = int(kernel)
+        if order is not None:
+            if (order.dtype != torch.int32 or order.device != dev or tuple(order.shape) != (CH * M,)
+                    or not order.is_contiguous()):
+                raise ValueError(f"order must be a contiguous int32 tensor of shape ({CH * M},) on {dev}")
+            cfg.order = order.data_ptr()
         kp = 1 + P + S + (D - P)
         with torch.cuda.device(dev):
             out = torch.empty((CH, 1 + P + S), dtype=tdt, device=dev)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CTX_ABI_VERSION 3
+#define CTX_ABI_VERSION 4
 
 enum { CTX_F32 = 0, CTX_F64 = 1 };
 /* solver ids: simconfig.py:16 (`solver: Any = Tsit5`), simulation.py:23-26 (non-adaptive list) */
@@ -78,6 +78,13 @@ typedef struct ctx_solve_cfg {
                           vmap(per_draw)(thetas) over sim_func(y0s, theta, constants, times)
                           (predictive.py:150-154, loo.py:180-193); ys is [D, M, T, S] */
   int32_t reserved;
+  const void* order;   /* optional DEVICE pointer to an int32 permutation of [0, batch): the persistent
+                          kernels hand out rows in this order.  A scheduling hint only -- results do
+                          not depend on it -- meant for "most expensive first" from the step counts of
+                          a previous solve of similar inputs (a sampler's previous evaluation): one
+                          launch is bound by the critical path of its longest trajectories, which then
+                          start first.  MUST be a permutation (a missing row is never solved).
+                          NULL = index order.  Ignored by the static kernels and the host-buffer calls. */
 } ctx_solve_cfg;
 
 /* ---- model lifetime -------------------------------------------------------------------
@@ -136,6 +143,8 @@ typedef struct ctx_loglik_cfg {
   int32_t max_steps;
   int32_t kernel;     /* 0 = automatic (cooperative), 1 = per-lane likelihood terms, 2 = cooperative */
   double rtol, atol, dt0;
+  const void* order;  /* optional DEVICE int32 permutation of [0, n_chains * n_series): scheduling hint
+                         as in ctx_solve_cfg (trajectory u = chain * n_series + series) */
 } ctx_loglik_cfg;
 size_t ctx_loglik_workspace_bytes(const ctx_model* m, const ctx_loglik_cfg* cfg);
 int ctx_loglik_grad(ctx_model* m, const ctx_loglik_cfg* cfg, const void* y0s, const void* theta,

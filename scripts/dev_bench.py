@@ -15,6 +15,7 @@ ap.add_argument("--kernel", type=int, nargs="+", default=[1, 2])
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--rtol", type=float, default=1e-6)
 ap.add_argument("--neural", action="store_true")
+ap.add_argument("--hint", action="store_true", help="cost-ordered schedule from a previous solve")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 field = cg.generate_field(cases.field_spec(cases.michaelis_menten()))
@@ -27,10 +28,14 @@ for dtype in a.dtype:
         out_buf = torch.empty((a.B, T, 3), dtype=y0.dtype, device=dev)
         for kernel in a.kernel:
             times = []
+            order = None
+            if a.hint:
+                order = m.solve(y0, th, c, ts, in_axes=(0, 0, 0, None), rtol=a.rtol, atol=a.rtol, kernel=kernel, out=out_buf).cost_order()
+                ref_bits = out_buf.clone() if a.B * T <= (1 << 28) else None
             for it in range(a.iters + 1):
                 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
                 e0.record()
-                o = m.solve(y0, th, c, ts, in_axes=(0, 0, 0, None), rtol=a.rtol, atol=a.rtol, kernel=kernel, out=out_buf)
+                o = m.solve(y0, th, c, ts, in_axes=(0, 0, 0, None), rtol=a.rtol, atol=a.rtol, kernel=kernel, out=out_buf, order=order)
                 e1.record(); torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1))
             steps = int((o.n_accepted.sum() + o.n_rejected.sum()).item())
@@ -39,7 +44,8 @@ for dtype in a.dtype:
             print(json.dumps(dict(dtype=dtype, T=T, kernel=kernel, ms=round(ms, 3), first_ms=round(times[0], 1),
                                   steps=steps, steps_per_traj=round(steps / a.B, 1), rej_frac=round(float(o.n_rejected.sum().item()) / steps, 3),
                                   gsteps_s=round(steps / ms / 1e6, 2), out_GBs=round(byt / ms / 1e6, 1),
-                                  fails=int((o.status != 0).sum().item()))), flush=True)
+                                  fails=int((o.status != 0).sum().item()), hint=bool(a.hint),
+                                  same_bits=(bool(torch.equal(ref_bits, out_buf)) if (a.hint and ref_bits is not None) else None))), flush=True)
 
 # ---- config 5: neural vector field
 if "--neural" in sys.argv:

@@ -27,6 +27,16 @@ for _ in range(30):
     out, _, st = model.loglik_grad(*args, **kw)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 30
+order = engine.cost_order(*model.last_loglik_counts)
+ref = out.clone()
+for _ in range(5):
+    out, _, st = model.loglik_grad(*args, order=order, **kw)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(30):
+    out, _, st = model.loglik_grad(*args, order=order, **kw)
+e1.record(); torch.cuda.synchronize()
+print(json.dumps({"hinted_ms": round(e0.elapsed_time(e1) / 30, 4), "same_bits": bool(torch.equal(ref, out))}))
 print(json.dumps({"dtype": dtype, "chains": CH, "likelihood": lik, "ms": round(ms, 4),
                   "evals_per_s": round(CH / ms * 1e3), "finite": bool(torch.isfinite(out).all()),
                   "checksum": float(out[:, 0].double().sum())}))

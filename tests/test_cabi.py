@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in _declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     lib.ctx_abi_version.restype = ctypes.c_int
-    assert lib.ctx_abi_version() == 3
+    assert lib.ctx_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -16,7 +16,7 @@ GOLD = __import__("pathlib").Path(__file__).parent / "golden" / "reference_fixtu
 
 def test_xla_descriptors_match_the_library_layout():
     L = engine.lib()
-    assert L.ctx_abi_version() == engine.ABI_VERSION == 3
+    assert L.ctx_abi_version() == engine.ABI_VERSION == 4
     assert C.sizeof(engine.ctx_xla_solve_desc) == L.ctx_xla_desc_bytes(0)
     assert C.sizeof(engine.ctx_xla_loglik_desc) == L.ctx_xla_desc_bytes(1)
     assert L.ctx_xla_desc_bytes(7) == 0
