@@ -709,8 +709,8 @@ __device__ __forceinline__ int ctx_upper_bound(const real* ts, const unsigned sa
 __device__ __forceinline__ void ctx_queue_fetch_q(const ctx_solve_args& a, real (*q_in)[CTX_QW][32],
                                                   int (*q_idx)[32], const int buf,
                                                   const unsigned long long base, const int count,
-                                                  const int lane) {
-  const unsigned long long u = base + (unsigned long long)lane;
+                                                  const int lane, const unsigned long long stride = 1ull) {
+  const unsigned long long u = base + (unsigned long long)lane * stride;
   if (lane < count && u < (unsigned long long)a.B) {
     const long long bq = a.order ? (long long)a.order[u] : (long long)u;
     q_idx[buf][lane] = (int)bq;
@@ -734,8 +734,9 @@ __device__ __forceinline__ void ctx_queue_fetch_q(const ctx_solve_args& a, real 
 
 __device__ __forceinline__ void ctx_queue_fetch(const ctx_solve_args& a, ctx_warp_smem& w,
                                                 const int buf, const unsigned long long base,
-                                                const int count, const int lane) {
-  ctx_queue_fetch_q(a, w.q_in, w.q_idx, buf, base, count, lane);
+                                                const int count, const int lane,
+                                                const unsigned long long stride = 1ull) {
+  ctx_queue_fetch_q(a, w.q_in, w.q_idx, buf, base, count, lane, stride);
 }
 
 // TSM: the time grid is shared by all trajectories and staged in shared memory (ts_sm).
@@ -803,14 +804,32 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
   int qn_cur = CTX_CLAIM(0ull), qn_nxt = qn_cur, qn_pend = qn_cur;
   int q_cur = 0, q_pos = 0;
   bool q_empty = false;
+  // With an order hint (most expensive rows first) the first two buffers of every warp are dealt
+  // out STRIDED over the front of the queue -- warp g takes positions g, g + W, g + 2W, ... (W =
+  // warps of the grid) -- so that the 32 W heaviest rows start at once, one per lane, instead of
+  // the very heaviest all landing in the lanes of the first few warps; everything behind the
+  // first 64 W positions is claimed from the shared counter in order, as without a hint.
+  unsigned q_off = 0u;
+  int qv_cur = 0, qv_nxt = 0;      // valid entries of the two buffers
   {
-    if (lane == 0) qb_cur = atomicAdd(a.work_counter, (unsigned long long)(2 * qn_cur));
-    qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
-    qb_nxt = qb_cur + qn_cur;
-    ctx_queue_fetch(a, w, 0, qb_cur, qn_cur, lane);
-    ctx_queue_fetch(a, w, 1, qb_nxt, qn_nxt, lane);
-    qn_pend = CTX_CLAIM(qb_nxt + qn_nxt);
-    if (lane == 0) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);  // read one buffer later
+    if (a.order) {
+      const unsigned Wq = gridDim.x * CTX_WARPS;
+      q_off = 64u * Wq;
+      qn_cur = qn_nxt = 32;
+      qb_cur = (unsigned long long)blockIdx.x * CTX_WARPS + (threadIdx.x >> 5);
+      qb_nxt = qb_cur + (unsigned long long)(32u * Wq);
+    } else {
+      if (lane == 0) qb_cur = atomicAdd(a.work_counter, (unsigned long long)(2 * qn_cur));
+      qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
+      qb_nxt = qb_cur + qn_cur;
+    }
+    const unsigned long long qs0 = a.order ? (unsigned long long)(q_off / 64u) : 1ull;
+    ctx_queue_fetch(a, w, 0, qb_cur, qn_cur, lane, qs0);
+    ctx_queue_fetch(a, w, 1, qb_nxt, qn_nxt, lane, qs0);
+    qv_cur = qb_cur < Bq ? (int)min((unsigned long long)qn_cur, (Bq - qb_cur + qs0 - 1ull) / qs0) : 0;
+    qv_nxt = qb_nxt < Bq ? (int)min((unsigned long long)qn_nxt, (Bq - qb_nxt + qs0 - 1ull) / qs0) : 0;
+    qn_pend = CTX_CLAIM(a.order ? (unsigned long long)q_off : qb_nxt + qn_nxt);
+    if (lane == 0) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend) + q_off;  // read one buffer later
     CTX_CP_WAIT(1);
     __syncwarp();
     q_empty = qb_cur >= Bq;
@@ -820,7 +839,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
     // ------------------------------------------------------------- refill free lanes
     const unsigned need = __ballot_sync(CTX_FULL, b < 0);
     if (need && !q_empty) {
-      const int nval = (int)min((unsigned long long)qn_cur, Bq - qb_cur);   // entries of this buffer
+      const int nval = qv_cur;   // valid entries of this buffer
       const int take = min(__popc(need), nval - q_pos);
       const int rank = __popc(need & lt_mask);
       if (b < 0 && rank < take) {
@@ -863,10 +882,11 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
         __syncwarp();
         const unsigned long long nbase = __shfl_sync(CTX_FULL, qb_pend, 0);
         ctx_queue_fetch(a, w, q_cur, nbase, qn_pend, lane);
-        qb_cur = qb_nxt; qn_cur = qn_nxt;
+        qb_cur = qb_nxt; qn_cur = qn_nxt; qv_cur = qv_nxt;
         qb_nxt = nbase; qn_nxt = qn_pend;
+        qv_nxt = nbase < Bq ? (int)min((unsigned long long)qn_pend, Bq - nbase) : 0;
         qn_pend = CTX_CLAIM(nbase + qn_nxt);
-        if (lane == 0 && nbase < Bq) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);
+        if (lane == 0 && nbase < Bq) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend) + q_off;
         q_cur ^= 1; q_pos = 0;
         q_empty = qb_cur >= Bq;
       }

@@ -161,14 +161,29 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
   int qn_cur = V2_CLAIM(0ull), qn_nxt = qn_cur, qn_pend = qn_cur;
   int q_cur = 0, q_pos = 0;
   bool q_empty = false;
+  // order hint: strided first two buffers (see ctx_solve_v1): the 32 W heaviest rows start at
+  // once, one per producer lane
+  unsigned q_off = 0u;
+  int qv_cur = 0, qv_nxt = 0;      // valid entries of the two buffers
   {
-    if (lane == 0) qb_cur = atomicAdd(a.work_counter, (unsigned long long)(2 * qn_cur));
-    qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
-    qb_nxt = qb_cur + qn_cur;
-    ctx_queue_fetch_q(a, w.q_in, w.q_idx, 0, qb_cur, qn_cur, lane);
-    ctx_queue_fetch_q(a, w.q_in, w.q_idx, 1, qb_nxt, qn_nxt, lane);
-    qn_pend = V2_CLAIM(qb_nxt + qn_nxt);
-    if (lane == 0) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);
+    if (a.order) {
+      const unsigned Wq = gridDim.x * V2_NP;
+      q_off = 64u * Wq;
+      qn_cur = qn_nxt = 32;
+      qb_cur = (unsigned long long)blockIdx.x * V2_NP + (threadIdx.x >> 5);
+      qb_nxt = qb_cur + (unsigned long long)(32u * Wq);
+    } else {
+      if (lane == 0) qb_cur = atomicAdd(a.work_counter, (unsigned long long)(2 * qn_cur));
+      qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
+      qb_nxt = qb_cur + qn_cur;
+    }
+    const unsigned long long qs0 = a.order ? (unsigned long long)(q_off / 64u) : 1ull;
+    ctx_queue_fetch_q(a, w.q_in, w.q_idx, 0, qb_cur, qn_cur, lane, qs0);
+    ctx_queue_fetch_q(a, w.q_in, w.q_idx, 1, qb_nxt, qn_nxt, lane, qs0);
+    qv_cur = qb_cur < Bq ? (int)min((unsigned long long)qn_cur, (Bq - qb_cur + qs0 - 1ull) / qs0) : 0;
+    qv_nxt = qb_nxt < Bq ? (int)min((unsigned long long)qn_nxt, (Bq - qb_nxt + qs0 - 1ull) / qs0) : 0;
+    qn_pend = V2_CLAIM(a.order ? (unsigned long long)q_off : qb_nxt + qn_nxt);
+    if (lane == 0) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend) + q_off;
     CTX_CP_WAIT(1);
     __syncwarp();
     q_empty = qb_cur >= Bq;
@@ -178,7 +193,7 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
     // ------------------------------------------------------------- refill free lanes
     const unsigned need = __ballot_sync(CTX_FULL, b < 0);
     if (need && !q_empty) {
-      const int nval = (int)min((unsigned long long)qn_cur, Bq - qb_cur);
+      const int nval = qv_cur;
       const int take = min(__popc(need), nval - q_pos);
       const int rank = __popc(need & lt_mask);
       if (b < 0 && rank < take) {
@@ -210,10 +225,11 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
         __syncwarp();
         const unsigned long long nbase = __shfl_sync(CTX_FULL, qb_pend, 0);
         ctx_queue_fetch_q(a, w.q_in, w.q_idx, q_cur, nbase, qn_pend, lane);
-        qb_cur = qb_nxt; qn_cur = qn_nxt;
+        qb_cur = qb_nxt; qn_cur = qn_nxt; qv_cur = qv_nxt;
         qb_nxt = nbase; qn_nxt = qn_pend;
+        qv_nxt = nbase < Bq ? (int)min((unsigned long long)qn_pend, Bq - nbase) : 0;
         qn_pend = V2_CLAIM(nbase + qn_nxt);
-        if (lane == 0 && nbase < Bq) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend);
+        if (lane == 0 && nbase < Bq) qb_pend = atomicAdd(a.work_counter, (unsigned long long)qn_pend) + q_off;
         q_cur ^= 1; q_pos = 0;
         q_empty = qb_cur >= Bq;
       }

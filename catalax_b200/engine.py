@@ -204,13 +204,27 @@ def last_solve_kernel() -> str:
     return lib().ctx_last_solve_kernel().decode()
 
 
-def cost_order(n_accepted, n_rejected):
-    """Rows in descending order of the step attempts they needed (int32 permutation): the
-    scheduling hint ``order=`` of the next solve of similar inputs."""
+def cost_order(n_accepted, n_rejected, heavy_fraction=None):
+    """Scheduling hint ``order=`` for the next solve of similar inputs, from the step attempts every
+    row needed in a previous one: the ``heavy_fraction`` most expensive rows first (descending
+    cost), every other row behind them IN INDEX ORDER.  One launch is bound by the critical path
+    of its longest trajectories, so only those need to start early; a full sort would also
+    concentrate the cheap rows (refill-bound) and scatter the memory accesses of the bulk
+    (measured: DESIGN.md section 4).  int32 permutation of the rows."""
     import torch
 
     cost = n_accepted.to(torch.int64) + n_rejected.to(torch.int64)
-    return torch.argsort(cost, descending=True, stable=True).to(torch.int32).contiguous()
+    B = cost.numel()
+    if heavy_fraction is None:
+        heavy_fraction = float(os.environ.get("CTX_B200_COST_ORDER_FRAC", "0.0625"))
+    k = int(min(B, max(1, round(B * heavy_fraction))))
+    if k >= B:
+        return torch.argsort(cost, descending=True, stable=True).to(torch.int32).contiguous()
+    top = torch.topk(cost, k, sorted=True).indices
+    keep = torch.ones(B, dtype=torch.bool, device=cost.device)
+    keep[top] = False
+    rest = torch.nonzero(keep).reshape(-1)
+    return torch.cat([top, rest]).to(torch.int32).contiguous()
 
 
 @dataclass

@@ -191,6 +191,8 @@ class BayesianModel:
         self._dev_arrays = None
         self._device = device
         self._p2p = None
+        self._order = None
+        self._evals = 0
 
     # ------------------------------------------------------------------ likelihood block
     def _local_loglik(self, theta, sigma):
@@ -211,10 +213,20 @@ class BayesianModel:
         if self.mode == "surrogate":
             return self._local_rate_loglik(theta, sigma)
         cfg = self.config
+        # A sampler evaluates the same posterior thousands of times with slowly moving parameters:
+        # the step counts of an earlier evaluation tell which (chain, series) trajectories are the
+        # expensive ones, and handing those out first shortens the critical path of the launch
+        # (scheduling hint only: results do not depend on it).  Refreshed every 16 evaluations.
+        n_traj = theta.shape[0] * y0s.shape[0]
+        order = self._order if (self._order is not None and self._order.numel() == n_traj
+                                and self._order.device == theta.device) else None
         out, self._partial, self._status = self._compiled.loglik_grad(
             y0s, theta, constants, times, data, sigma, mask=mask, likelihood=self.likelihood,
             solver=solver_name(cfg.solver), rtol=cfg.rtol, atol=cfg.atol, dt0=cfg.dt0,
-            max_steps=cfg.max_steps)
+            max_steps=cfg.max_steps, order=order)
+        if not os.environ.get("CTX_B200_NO_COST_ORDER") and (order is None or self._evals % 16 == 0):
+            self._order = self._engine.cost_order(*self._compiled.last_loglik_counts)
+        self._evals += 1
         return out
 
     def _local_rate_loglik(self, theta, sigma):

@@ -313,3 +313,47 @@ def test_direct_save_variant_is_bit_identical(T, shared_ts, solver, dtype, monke
     m.solve(tt(y0), tt(theta), tt(consts), tt(ts), solver=solver, in_axes=(0, 0, 0, None if shared_ts else 0),
             dt0=0.05 if solver == "euler" else 0.1)
     assert engine.last_solve_kernel() == "ctx_solve_v1 (direct save)"
+
+
+@pytest.mark.parametrize("kernel,T,B", [(2, 64, 5003), (2, 16, 5003), (5, 400, 70001)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_order_hint_changes_the_schedule_not_the_results(kernel, T, B, dtype):
+    """``order=`` hands the rows to the persistent warps in a caller-given order (cost-ordered from
+    a previous solve: the longest trajectories start first).  Any permutation must give the same
+    bits, step counts and status for every row -- through the cooperative, the direct-save and the
+    warp-specialised kernel."""
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+
+    model = cases.michaelis_menten()
+    y0, theta, consts = cases.mm_inputs(B, seed=21, dtype=dtype)
+    theta[:9, 0] = 1e-3
+    ts = np.linspace(0, 100, T).astype(dtype)
+    m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), np.dtype(dtype).name)
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    kw = dict(in_axes=(0, 0, 0, None), rtol=1e-6, atol=1e-6, max_steps=300, kernel=kernel)
+    base = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), **kw)
+    torch.cuda.synchronize()
+    order = base.cost_order()           # default: the heaviest 1/16 first, the rest in index order
+    assert order.dtype == torch.int32 and sorted(order.tolist()) == list(range(B))
+    steps = base.n_accepted + base.n_rejected
+    k = round(B * 0.0625)
+    head, rest = steps[order[:k].long()], order[k:]
+    assert bool((head[:-1] >= head[1:]).all()) and int(head.min()) >= int(steps[rest.long()].max())
+    assert bool((rest[1:] > rest[:-1]).all())
+    full = engine.cost_order(base.n_accepted, base.n_rejected, heavy_fraction=1.0)
+    cost = steps[full.long()]
+    assert bool((cost[:-1] >= cost[1:]).all()) and sorted(full.tolist()) == list(range(B))
+    rnd = torch.as_tensor(np.random.default_rng(0).permutation(B).astype(np.int32), device=dev)
+    for o in (order, full, rnd):
+        got = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), order=o, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(got.ys, base.ys) or bool(((got.ys == base.ys) | (got.ys.isnan() & base.ys.isnan())).all())
+        assert torch.equal(got.status, base.status) and torch.equal(got.n_accepted, base.n_accepted)
+        assert torch.equal(got.n_rejected, base.n_rejected)
+    assert int((base.status != 0).sum()) > 0          # failed rows (inf fill) are part of the comparison
+    with pytest.raises(ValueError, match="order must be"):
+        m.solve(tt(y0), tt(theta), tt(consts), tt(ts), order=order[:-1].contiguous(), **kw)
+    with pytest.raises(ValueError, match="order must be"):
+        m.solve(tt(y0), tt(theta), tt(consts), tt(ts), order=order.long(), **kw)

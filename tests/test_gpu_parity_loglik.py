@@ -275,3 +275,33 @@ def test_cooperative_loglik_is_reproducible_and_handles_long_segments():
     z1 = _gpu(model, y0s, theta, consts, ts0, data, sigma, "normal", np.float64, kernel=1)
     assert np.allclose(z2[0], z1[0], rtol=1e-12, atol=1e-12)
     assert (z2[2] == 0).all()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_order_hint_leaves_the_log_density_bits_unchanged(kernel, dtype):
+    """The scheduling hint of ctx_loglik_grad (trajectories handed out most-expensive-first, from
+    the step counts of the previous evaluation -- what a sampler has at every leapfrog step): any
+    permutation gives the same [CH, 1+P+S] block, partial rows and status, bit for bit."""
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+
+    CH, M = 150, 13
+    model, y0s, theta, consts, ts, data, sigma = _config4(CH, M, dtype=dtype)
+    field = cg.generate_field(cases.field_spec(model), sens_theta=True)
+    m = engine.CompiledModel(field, np.dtype(dtype).name)
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(np.asarray(a, dtype=dtype), device=dev)
+    args = [tt(x) for x in (y0s, theta, consts, ts, np.nan_to_num(data), sigma)]
+    mask = torch.as_tensor(np.isfinite(data), device=dev)
+    base = m.loglik_grad(*args, mask=mask, kernel=kernel)
+    order = engine.cost_order(*m.last_loglik_counts)
+    assert sorted(order.tolist()) == list(range(CH * M))
+    rnd = torch.as_tensor(np.random.default_rng(1).permutation(CH * M).astype(np.int32), device=dev)
+    for o in (order, rnd):
+        got = m.loglik_grad(*args, mask=mask, kernel=kernel, order=o)
+        torch.cuda.synchronize()
+        for a_, b_ in zip(got, base):
+            assert torch.equal(a_, b_)
+    with pytest.raises(ValueError, match="order must be"):
+        m.loglik_grad(*args, mask=mask, order=order[:5].contiguous())
