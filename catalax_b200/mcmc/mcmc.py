@@ -225,7 +225,9 @@ class BayesianModel:
             solver=solver_name(cfg.solver), rtol=cfg.rtol, atol=cfg.atol, dt0=cfg.dt0,
             max_steps=cfg.max_steps, order=order)
         if not os.environ.get("CTX_B200_NO_COST_ORDER") and (order is None or self._evals % 16 == 0):
-            self._order = self._engine.cost_order(*self._compiled.last_loglik_counts)
+            # (full sort: the likelihood kernel refills lanes straight from global memory, so it
+            #  also gains from the lanes of a warp retiring together; measured 1.69 -> 1.28 ms)
+            self._order = self._engine.cost_order(*self._compiled.last_loglik_counts, heavy_fraction=1.0)
         self._evals += 1
         return out
 

@@ -335,7 +335,8 @@ def test_order_hint_changes_the_schedule_not_the_results(kernel, T, B, dtype):
     kw = dict(in_axes=(0, 0, 0, None), rtol=1e-6, atol=1e-6, max_steps=300, kernel=kernel)
     base = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), **kw)
     torch.cuda.synchronize()
-    order = base.cost_order()           # default: the heaviest 1/16 first, the rest in index order
+    order = engine.cost_order(base.n_accepted, base.n_rejected, heavy_fraction=0.0625)
+    # (the default of SolveOutput.cost_order(): the heaviest 1/16 first, the rest in index order)
     assert order.dtype == torch.int32 and sorted(order.tolist()) == list(range(B))
     steps = base.n_accepted + base.n_rejected
     k = round(B * 0.0625)
