@@ -1768,6 +1768,15 @@ ctx_loglik_v1(const ctx_loglik_args a) {
 // tp, 1/dt, coefficients [power][component], then per observable 1/|sigma|, 1/sigma, log|sigma|
 // (the chain's scale enters every term only through these: computed once by the publisher)
 #define CTX_LL_RW (2 + CTX_NCOEF + 3 * CTX_S)
+// Input queue of the cooperative kernel (as in ctx_solve_v1): without it a lane that retires waits
+// ~1 us for the operands of its next trajectory (atomic claim, then dependent global loads) and
+// the whole warp waits with it -- at ~17 steps per trajectory that happens in nearly every
+// iteration.  Every warp claims 32 trajectories at a time and copies their operands with
+// cp.async into one of two shared-memory buffers while the other one is being consumed.
+#ifndef CTX_LL_QUEUE
+#define CTX_LL_QUEUE 1
+#endif
+#define CTX_LLQW (2 * CTX_S + CTX_P + CTX_C + 1)   // y0, theta, constants, sigma, ts[T-1]
 struct ctx_ll_warp_smem {
   real rec[CTX_LL_RW][32];   // one column per publishing lane of this iteration
   real acc[CTX_KP][32];      // accumulators of the trajectory each lane integrates
@@ -1775,7 +1784,37 @@ struct ctx_ll_warp_smem {
   int off[32];               // flat offset of the segment
   int cnt[32];               // requested times it covers
   int owner[32];             // publishing lane
+#if CTX_LL_QUEUE
+  real q_in[2][CTX_LLQW][32];   // input queue: operands of the next trajectories (two buffers)
+  int q_idx[2][32];             // their trajectory indices (order hint applied)
+#endif
 };
+
+#if CTX_LL_QUEUE
+// operands of the 32 queue positions [base, base + 32) -> buffer `buf` (cp.async, lane = entry)
+__device__ __forceinline__ void ctx_ll_queue_fetch(const ctx_loglik_args& a, ctx_ll_warp_smem& w,
+                                                   const int buf, const unsigned long long base,
+                                                   const int lane) {
+  const unsigned long long uq = base + (unsigned long long)lane;
+  if (uq < (unsigned long long)a.n_traj) {
+    const long long u = a.order ? (long long)a.order[uq] : (long long)uq;
+    w.q_idx[buf][lane] = (int)u;
+    const long long ch = u / a.M;
+    const long long m = u - ch * a.M;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.y0s + (size_t)m * CTX_S + i);
+#pragma unroll
+    for (int i = 0; i < CTX_P; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.theta + (size_t)ch * CTX_P + i);
+#pragma unroll
+    for (int i = 0; i < CTX_C; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.consts + (size_t)m * CTX_C + i);
+#pragma unroll
+    for (int i = 0; i < CTX_S; ++i) ctx_cp_async(&w.q_in[buf][k++][lane], a.sigma + (size_t)ch * CTX_S + i);
+    ctx_cp_async(&w.q_in[buf][k++][lane], a.ts + (size_t)m * a.T + (a.T - 1));
+  }
+  CTX_CP_COMMIT();
+}
+#endif
 
 extern "C" __global__ void __launch_bounds__(CTX_WARPS * 32, CTX_LL_MIN_BLOCKS)
 ctx_loglik_v2(const ctx_loglik_args a) {
@@ -1792,8 +1831,76 @@ ctx_loglik_v2(const ctx_loglik_args a) {
   real K[CTX_NST][CTX_N];
   real tprev = R(0.0), tnext = R(0.0), t_end = R(0.0);
   int idx = 0, nacc = 0, nrej = 0, status = 0, m = 0;
-  bool exhausted = false;
   const real* tsr = a.ts;
+#if CTX_LL_QUEUE
+  const unsigned long long NT = (unsigned long long)a.n_traj;
+  unsigned long long qb_cur = 0, qb_nxt = 0, qb_pend = 0;
+  int q_cur = 0, q_pos = 0;
+  bool q_empty = false;
+  {
+    if (lane == 0) qb_cur = atomicAdd(a.work_counter, 64ull);
+    qb_cur = __shfl_sync(CTX_FULL, qb_cur, 0);
+    qb_nxt = qb_cur + 32ull;
+    ctx_ll_queue_fetch(a, w, 0, qb_cur, lane);
+    ctx_ll_queue_fetch(a, w, 1, qb_nxt, lane);
+    if (lane == 0) qb_pend = atomicAdd(a.work_counter, 32ull);   // read one buffer later
+    CTX_CP_WAIT(1);
+    __syncwarp();
+    q_empty = qb_cur >= NT;
+  }
+
+  while (true) {
+    const unsigned need = __ballot_sync(CTX_FULL, u < 0);
+    if (need && !q_empty) {
+      const int nval = (int)min(32ull, NT - qb_cur);
+      const int take = min(__popc(need), nval - q_pos);
+      const int rank = __popc(need & lt_mask);
+      if (u < 0 && rank < take) {
+        const int e = q_pos + rank;
+        u = (long long)w.q_idx[q_cur][e];
+        const long long ch = u / a.M;
+        m = (int)(u - ch * a.M);
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < CTX_S; ++i) y0[i] = y[i] = w.q_in[q_cur][k++][e];
+#pragma unroll
+        for (int i = 0; i < CTX_P; ++i) th[i] = w.q_in[q_cur][k++][e];
+#pragma unroll
+        for (int i = 0; i < CTX_C; ++i) c[i] = w.q_in[q_cur][k++][e];
+#pragma unroll
+        for (int i = 0; i < CTX_S; ++i) sg[i] = w.q_in[q_cur][k++][e];
+        t_end = w.q_in[q_cur][k++][e];
+#pragma unroll
+        for (int i = CTX_S; i < CTX_N; ++i) y[i] = R(0.0);
+#pragma unroll
+        for (int i = 0; i < CTX_D_Y0; ++i) y[CTX_S + (CTX_D_THETA + i) * CTX_S + i] = R(1.0);
+#pragma unroll
+        for (int kk = 0; kk < CTX_KP; ++kk) w.acc[kk][lane] = R(0.0);
+        tsr = a.ts + (size_t)m * T;
+        tprev = R(0.0);
+        tnext = fmin(tprev + a.dt0, t_end);
+        idx = 0; nacc = 0; nrej = 0; status = 0;
+        ctx_field(tprev, y, th, c, y0, K[0]);
+      }
+      q_pos += take;
+      if (q_pos >= nval) {
+        CTX_CP_WAIT(0);
+        __syncwarp();
+        const unsigned long long nbase = __shfl_sync(CTX_FULL, qb_pend, 0);
+        ctx_ll_queue_fetch(a, w, q_cur, nbase, lane);
+        qb_cur = qb_nxt;
+        qb_nxt = nbase;
+        if (lane == 0 && nbase < NT) qb_pend = atomicAdd(a.work_counter, 32ull);
+        q_cur ^= 1; q_pos = 0;
+        q_empty = qb_cur >= NT;
+      }
+    }
+    if (__ballot_sync(CTX_FULL, u >= 0) == 0u) {
+      if (q_empty) break;
+      continue;
+    }
+#else
+  bool exhausted = false;
 
   while (true) {
     const unsigned need = __ballot_sync(CTX_FULL, u < 0);
@@ -1833,6 +1940,7 @@ ctx_loglik_v2(const ctx_loglik_args a) {
       }
     }
     if (__ballot_sync(CTX_FULL, u >= 0) == 0u) break;
+#endif   // CTX_LL_QUEUE
 
     // ------------------------------------------------------------- one step attempt
     bool keep = false, done = false;
