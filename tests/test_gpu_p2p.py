@@ -2,7 +2,7 @@
 peer memory (ctx_p2p_allreduce, csrc/ctx_p2p.cu) against NCCL -- correctness for both dtypes and
 several message sizes, bit-identical results on every rank, both buffer slots / the epoch protocol
 over 25 back-to-back calls, CUDA-graph replay.  Needs two GPUs on one node (skipped otherwise; the
-single-GPU box of the driver's `-m gpu` run skips it, `scripts/r2g.sh` / `r2h.sh` ran it at N = 2 / 8)."""
+single-GPU box of the driver's `-m gpu` run skips it, `scripts/runs/r2g.sh` / `r2h.sh` ran it at N = 2 / 8)."""
 import json
 import os
 import subprocess
