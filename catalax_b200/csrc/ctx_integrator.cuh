@@ -1768,13 +1768,15 @@ ctx_loglik_v1(const ctx_loglik_args a) {
 // tp, 1/dt, coefficients [power][component], then per observable 1/|sigma|, 1/sigma, log|sigma|
 // (the chain's scale enters every term only through these: computed once by the publisher)
 #define CTX_LL_RW (2 + CTX_NCOEF + 3 * CTX_S)
-// Input queue of the cooperative kernel (as in ctx_solve_v1): without it a lane that retires waits
-// ~1 us for the operands of its next trajectory (atomic claim, then dependent global loads) and
-// the whole warp waits with it -- at ~17 steps per trajectory that happens in nearly every
-// iteration.  Every warp claims 32 trajectories at a time and copies their operands with
-// cp.async into one of two shared-memory buffers while the other one is being consumed.
+// Optional input queue of the cooperative kernel (as in ctx_solve_v1: every warp claims 32
+// trajectories at a time and copies their operands with cp.async into one of two shared-memory
+// buffers).  Built and measured on B200 (config 4, round 2) -- and it LOSES: under the 128-register
+// cap its 64-bit bookkeeping spills (f32 24 B, f64 272 B of stack): f32 1.68 -> 1.89 ms, with the
+// order hint 1.28 -> 1.44 ms, f64 6.21 -> 8.55 ms.  The direct refill (atomic claim + operand loads
+// by the retiring lanes) stays the default; its stalls are what the order hint removes (lanes of a
+// warp retire together).
 #ifndef CTX_LL_QUEUE
-#define CTX_LL_QUEUE 1
+#define CTX_LL_QUEUE 0
 #endif
 #define CTX_LLQW (2 * CTX_S + CTX_P + CTX_C + 1)   // y0, theta, constants, sigma, ts[T-1]
 struct ctx_ll_warp_smem {
