@@ -63,21 +63,36 @@ class PeerAllReduce:
         self._h = C.c_void_p()
         handle = C.create_string_buffer(64)
         rc = self._lib.ctx_p2p_create(self.rank, self.world, int(max_bytes), C.byref(self._h), handle)
-        self._check(rc)
+        # every rank takes part in every exchange and all ranks fail TOGETHER: a rank that left
+        # early would leave the others waiting in a collective
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, bytes(handle.raw), group=group)
-        self._check(self._lib.ctx_p2p_connect(self._h, b"".join(gathered)))
+        dist.all_gather_object(gathered, (rc, self._error() if rc else "", bytes(handle.raw)), group=group)
+        bad = [(r, g[1]) for r, g in enumerate(gathered) if g[0] != 0]
+        if bad:
+            self.close()
+            raise RuntimeError(f"ctx_p2p_create failed on rank(s) {bad}")
+        rc = self._lib.ctx_p2p_connect(self._h, b"".join(g[2] for g in gathered))
+        oks = [None] * self.world
+        dist.all_gather_object(oks, (rc, self._error() if rc else ""), group=group)
+        bad = [(r, g[1]) for r, g in enumerate(oks) if g[0] != 0]
+        if bad:
+            self.close()
+            raise RuntimeError(f"ctx_p2p_connect failed on rank(s) {bad} (peer access over NVLink / "
+                               f"cudaIpc needs the ranks to be GPUs of one node)")
         self.max_bytes = int(max_bytes)
         dist.barrier(group)        # every rank has mapped every buffer before the first call
         self._torch = torch
 
-    def _check(self, rc):
+    def _error(self) -> str:
         import ctypes as C
 
+        buf = C.create_string_buffer(4096)
+        self._lib.ctx_p2p_last_error(buf, len(buf))
+        return buf.value.decode(errors="replace")
+
+    def _check(self, rc):
         if rc != 0:
-            buf = C.create_string_buffer(4096)
-            self._lib.ctx_p2p_last_error(buf, len(buf))
-            raise RuntimeError(f"ctx_p2p error {rc}: {buf.value.decode(errors='replace')}")
+            raise RuntimeError(f"ctx_p2p error {rc}: {self._error()}")
 
     def __call__(self, t):
         """In-place sum of the CUDA tensor ``t`` (float32 / float64, contiguous) over the ranks."""

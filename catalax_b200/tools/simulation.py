@@ -79,6 +79,8 @@ class SolveFunction:
                                        sens_y0=sensitivity_index == 0)
         self.model = engine.CompiledModel(self.field, self.dtype.name)
         self.last = None  # SolveOutput of the most recent call (status, step counts)
+        self._order = None  # cost order of an earlier call with the same batch size (scheduling hint)
+        self._calls = 0
 
     def __call__(self, y0, parameters, constants, time):
         import torch
@@ -102,9 +104,20 @@ class SolveFunction:
             if w == 0:
                 a = a.reshape((a.shape[0], 0) if ax == 0 else (0,))
             dev_args.append(a)
+        # Repeated solves of the same batch (an optimiser's objective, a sweep over parameters) have
+        # similar per-row costs: the step counts of an earlier call order the rows of this one,
+        # most expensive first (scheduling hint only -- results do not depend on it; refreshed
+        # every 8 calls; large batches only).
+        Bs = [a.shape[0] for a, ax in zip(dev_args, axes) if ax == 0]
+        B = Bs[0] if Bs else 1
+        order = self._order if (self._order is not None and self._order.numel() == B
+                                and self._order.device == dev) else None
         out = self.model.solve(*dev_args, solver=self.solver, in_axes=axes, rtol=self.rtol,
                                atol=self.atol, dt0=self.dt0, max_steps=self.max_steps,
-                               tangents=self.sensitivity_index is not None)
+                               tangents=self.sensitivity_index is not None, order=order)
+        self._calls += 1
+        if B >= 4096 and (order is None or self._calls % 8 == 0):
+            self._order = out.cost_order()
         self.last = out
         if self.throw:
             bad = int((out.status != 0).sum().item())
