@@ -26,6 +26,8 @@ extern const char ctx_integrator_src[];  // generated from ctx_integrator.cuh (e
 extern const char ctx_mlp_tc_src[];      // generated from ctx_mlp_tc.cuh
 extern const char ctx_mlp_adjoint_src[]; // generated from ctx_mlp_adjoint.cuh
 extern const char ctx_solve_v2_src[];    // generated from ctx_solve_v2.cuh
+extern "C" int ctx_sched_heavy_first(const int* nacc, const int* nrej, int cap, long long B, int* order,
+                                     int* scratch, void* stream);   // ctx_sched.cu
 
 namespace {
 
@@ -445,7 +447,9 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
                  const void* theta, const void* consts, const void* ts, void* ys, void* sens,
                  int32_t* status, int32_t* nacc, int32_t* nrej, void* ws, size_t ws_bytes,
                  cudaStream_t stream, const void* ll_data = nullptr, const void* ll_sigma = nullptr,
-                 int ll_likelihood = 0) {
+                 int ll_likelihood = 0, int probe_ts_stride = -1) {
+  // probe_ts_stride >= 0: this IS the scheduling probe (one requested time per row, taken from the
+  // caller's grid with this row stride); it must not start another one
   const ctx_model_desc& d = m->desc;
   if (cfg->batch <= 0) return CTX_OK;
   if (cfg->n_times <= 0) return fail(CTX_E_INVALID, "n_times must be >= 1");
@@ -475,6 +479,7 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
   a.stride_theta = cfg->in_axes[1] == 0 ? d.n_params : 0;
   a.stride_consts = cfg->in_axes[2] == 0 ? d.n_consts : 0;
   a.stride_ts = cfg->in_axes[3] == 0 ? cfg->n_times : 0;
+  if (probe_ts_stride >= 0) a.stride_ts = probe_ts_stride;
   a.t0_from_ts = cfg->t0_from_ts ? 1 : 0;
   a.inner = cfg->inner > 0 ? cfg->inner : 0;
   a.q_div = 1;
@@ -523,6 +528,44 @@ int launch_solve(ctx_model* m, const ctx_solve_cfg* cfg, int tan, const void* y0
       kernel = 5;
       auto_v2 = true;
     }
+  }
+  // ---- scheduling probe (ctx_sched.cu): no order hint from the caller, a large batch of a
+  // small-state model at a tight tolerance -> classify the rows with a capped, loose-tolerance
+  // solve of the same batch and hand the heavy ones out first.  The probe's outputs land in the
+  // caller's own output arrays (all of them are overwritten by the real launch, stream-ordered).
+  // cfg->reserved bit 0 or CTX_B200_NO_PROBE=1 disables it.  Measured: DESIGN.md section 4.
+  if ((kernel == 2 || kernel == 5) && probe_ts_stride < 0 && !tan && !ll && !m->theta_ptr && warps > 0 &&
+      a.order == nullptr && cfg->solver <= CTX_DOPRI5 && !cfg->t0_from_ts && !(cfg->reserved & 1) &&
+      cfg->batch >= (1ll << 18) && cfg->batch <= (1ll << 22) && cfg->rtol <= 1e-4 && cfg->rtol > 0 &&
+      cfg->dt0 > 0 &&
+      !getenv("CTX_B200_NO_PROBE")) {
+    // A/B knobs (development): CTX_B200_PROBE_CAP / CTX_B200_PROBE_RTOL
+    const char* e_cap = getenv("CTX_B200_PROBE_CAP");
+    const char* e_tol = getenv("CTX_B200_PROBE_RTOL");
+    const int cap = e_cap ? std::max(2, atoi(e_cap)) : 24;
+    const double probe_rtol = e_tol ? atof(e_tol) : 1e-2;
+    const double loosen = probe_rtol / cfg->rtol;
+    ctx_solve_cfg pc = *cfg;
+    pc.n_times = 1;
+    pc.max_steps = cap;
+    pc.rtol = probe_rtol;
+    pc.atol = cfg->atol * loosen;
+    pc.kernel = 2;
+    pc.order = nullptr;
+    const real* ts_probe = (const real*)ts + (cfg->n_times - 1);
+    int rc = launch_solve<real>(m, &pc, 0, y0, theta, consts, ts_probe, ys, nullptr, a.status,
+                                a.n_accepted, a.n_rejected, ws, ws_bytes, stream, nullptr, nullptr, 0,
+                                a.stride_ts);
+    if (rc) return rc;
+    char* q = (char*)ws + 256 + 3 * sizeof(int32_t) * (size_t)cfg->batch;
+    q = (char*)(((uintptr_t)q + 255) / 256 * 256);
+    int* order_ws = (int*)q;
+    int* scratch_ws = order_ws + cfg->batch;
+    cudaError_t e = (cudaError_t)ctx_sched_heavy_first(a.n_accepted, a.n_rejected, cap, cfg->batch, order_ws,
+                                                       scratch_ws, stream);
+    if (e != cudaSuccess) return fail(CTX_E_CUDA, std::string("ctx_sched_heavy_first: ") + cudaGetErrorString(e));
+    a.order = order_ws;
+    g_launches += 3;
   }
   cudaKernel_t k;
   void* params[] = {&a};
@@ -1012,7 +1055,10 @@ int ctx_model_cubin(ctx_model* m, int32_t solver, int32_t with_tangents, const v
 size_t ctx_workspace_bytes(const ctx_model* m, const ctx_solve_cfg* cfg) {
   (void)m;
   if (!cfg || cfg->batch <= 0) return 0;
-  return 256 + 3 * sizeof(int32_t) * (size_t)cfg->batch;
+  // [256 B: work counter][3 x int32[B]: dummies for NULL status / counts][probe: order int32[B] +
+  // (B / 1024 + 2) ints of scan scratch, 256-byte aligned]
+  const size_t B = (size_t)cfg->batch;
+  return 256 + 3 * sizeof(int32_t) * B + 256 + sizeof(int32_t) * B + sizeof(int32_t) * (B / 1024 + 2) + 256;
 }
 
 int ctx_solve(ctx_model* m, const ctx_solve_cfg* cfg, const void* y0, const void* theta,
