@@ -2,16 +2,18 @@
 //
 // One launch of the persistent solve kernels is bound by the critical path of its longest
 // trajectories: rows are handed out in queue order and a 600-step row that is
-// claimed when the queue runs dry finishes long after everything else.  When the caller gives no
-// order hint, ctx_solve first runs a cheap PROBE of the same batch -- the same integrator at a
-// loose tolerance, capped at a few step attempts, one requested time -- whose only product is a
-// per-row bit "this row is still running after `cap` attempts at 1e-2": the rows that are
-// stability-limited (stiff after depletion) rather than accuracy-limited, i.e. exactly the long
-// ones, whatever the tolerance of the real solve.  The kernels below turn that bit into the
-// `order` permutation of the real launch: heavy rows first (index order among themselves; the
-// strided queue start spreads them one per lane), every other row behind them in index order
-// (a STABLE partition, so the bulk keeps its memory locality).  Three tiny launches, no host
-// round trip; results of the solve do not depend on any of it.
+// claimed when the queue runs dry finishes long after everything else.  A caller that solves
+// similar batches repeatedly passes `order` (cost-ordered from the previous step counts).  For a
+// one-shot solve ctx_solve can (opt-in, ctx_solve_cfg.reserved bit 1) first run a PROBE of the same
+// batch -- the same integrator at 100 x rtol, capped at 32 step attempts, one requested time -- whose
+// only product is a per-row bit "still running at the cap".  The kernels below turn that bit into
+// the `order` permutation of the real launch: flagged rows first (index order among themselves;
+// the strided queue start spreads them one per lane), every other row behind them in index order
+// (a STABLE partition, so the bulk keeps its memory locality).  Three tiny launches, no host round
+// trip; results of the solve do not depend on any of it.
+// Measured (B200, config 2): NOT a win there -- the long rows of that workload are long only at
+// the tight tolerance, a probe cheap enough to pay (rtol 1e-2, 0.18 ms) flags none of them and
+// the launch stays at 3.53 ms + the probe; hence opt-in.
 #include "../../include/ctx_b200.h"
 
 #include <cuda_runtime_api.h>

@@ -288,10 +288,25 @@ class NeuralBase:
                    use_final_bias=use_final_bias, key=seed, **kwargs)
 
     def get_weights_and_biases(self):
-        return [a for pair in zip(self.weights, self.biases) for a in pair if a is not None]
+        """Every array leaf of the model (neuralbase.py:576-584 flattens the whole pytree): MLP
+        weights and biases, RBF centres, ``max_time`` once training made it an array, and the
+        class-specific leaves (stoichiometric matrix / mass constraint; mechanistic parameters,
+        residual scale, gate matrix)."""
+        out = [a for pair in zip(self.weights, self.biases) for a in pair if a is not None]
+        if getattr(self, "rbf_mu", None) is not None:
+            out += list(self.rbf_mu)
+        if getattr(self, "_max_time_is_leaf", False):
+            out.append(np.asarray(self.max_time, dtype=np.float64))
+        if self.kind == "rateflow":
+            out.append(self.stoich_matrix)
+            if self.mass_constraint is not None:
+                out.append(self.mass_constraint)
+        if self.kind == "universalode":
+            out += [self.parameters, self.alpha_residual, self.gate_matrix]
+        return out
 
     def n_parameters(self) -> int:
-        return int(sum(a.size for a in self.get_weights_and_biases()))
+        return int(sum(a.size for pair in zip(self.weights, self.biases) for a in pair if a is not None))
 
     # ------------------------------------------------------------------ forward
     def predict_arrays(self, ts, y0s, solver=None, rtol: Optional[float] = None,

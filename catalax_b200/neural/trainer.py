@@ -3,7 +3,7 @@
 Mirror of ``catalax/neural/strategy.py:16-190`` (``Modes``, ``Step``, ``Strategy.add_step``) and
 ``catalax/neural/trainer.py:28-253`` (``train_neural_ode``: per-strategy-step optimiser, truncated
 time length, shuffled mini-batches, temporal dropout mask, weight / bias scaling, max_time from the
-data) with ``catalax/neural/penalties`` reduced to the weight / gate / alpha regularisers.  Every
+data); the regularisers of ``catalax/neural/penalties`` live in ``penalties.py``.  Every
 optimisation step is ONE ``value_and_grad`` of the model = the adjoint kernel pair
 (ctx_mlp_adj_forward / backward, Tsit5 or Dopri5); the optimiser update (optax's AdaBelief, the
 reference default, or Adam) is element-wise host arithmetic on a few thousand parameters.
@@ -16,72 +16,13 @@ from typing import Callable, List, Optional
 
 import numpy as np
 
+from .penalties import Penalties, Penalty  # noqa: F401
+
 
 class Modes(Enum):
     BOTH = "both"
     VECTOR_FIELD = "vector_field"
     MLP = "mlp"
-
-
-@dataclass
-class Penalty:
-    name: str
-    target: str            # "weights" | "gate" | "alpha"
-    kind: str              # "l1" | "l2"
-    alpha: float
-
-
-class Penalties:
-    """Collection of regularisers added to the loss (penalties.py:31-130): ``alpha * sum(x**2)`` /
-    ``alpha * sum(|x|)`` over all weights and biases (weight.py:6-44), the gate matrix or the
-    residual scale of a UniversalODE (uode.py)."""
-
-    def __init__(self, penalties: Optional[List[Penalty]] = None):
-        self.penalties = list(penalties or [])
-
-    def add_penalty(self, name: str, target: str, kind: str, alpha: float) -> "Penalties":
-        self.penalties.append(Penalty(name, target, kind, float(alpha)))
-        return self
-
-    @classmethod
-    def for_neural_ode(cls, l2_alpha: Optional[float] = 1e-3, l1_alpha: Optional[float] = None):
-        p = cls()
-        if l2_alpha is not None:
-            p.add_penalty("l2", "weights", "l2", l2_alpha)
-        if l1_alpha is not None:
-            p.add_penalty("l1", "weights", "l1", l1_alpha)
-        return p
-
-    @classmethod
-    def for_universal_ode(cls, l2_gate_alpha: Optional[float] = 1e-3, l1_gate_alpha: Optional[float] = None,
-                          l2_residual_alpha: Optional[float] = 1e-3, l1_residual_alpha: Optional[float] = None,
-                          l2_mlp_alpha: Optional[float] = 1e-3, l1_mlp_alpha: Optional[float] = None):
-        p = cls.for_neural_ode(l2_mlp_alpha, l1_mlp_alpha)
-        for a, tgt, kind in ((l2_gate_alpha, "gate", "l2"), (l1_gate_alpha, "gate", "l1"),
-                             (l2_residual_alpha, "alpha", "l2"), (l1_residual_alpha, "alpha", "l1")):
-            if a is not None:
-                p.add_penalty(f"{kind}_{tgt}", tgt, kind, a)
-        return p
-
-    def value_and_grads(self, model):
-        """(penalty value, {target: gradient arrays}) for the model's current parameters."""
-        val = 0.0
-        leaves = {"weights": model.get_weights_and_biases()}
-        if hasattr(model, "gate_matrix"):
-            leaves["gate"] = [model.gate_matrix]
-            leaves["alpha"] = [np.logaddexp(model.alpha_residual, 0.0)]      # softplus(alpha): uode.py
-        grads = {k: [np.zeros_like(a) for a in v] for k, v in leaves.items()}
-        for pen in self.penalties:
-            if pen.target not in leaves:
-                continue
-            for a, g in zip(leaves[pen.target], grads[pen.target]):
-                if pen.kind == "l2":
-                    val += pen.alpha * float(np.sum(a * a)); g += 2.0 * pen.alpha * a
-                else:
-                    val += pen.alpha * float(np.sum(np.abs(a))); g += pen.alpha * np.sign(a)
-        if "alpha" in grads:     # chain rule through softplus
-            grads["alpha"][0] = grads["alpha"][0] / (1.0 + np.exp(-model.alpha_residual))
-        return val, grads
 
 
 @dataclass
@@ -209,6 +150,10 @@ def train_neural_ode(model, dataset, strategy: Strategy, optimizer: Callable = A
     model.biases = [None if b is None else (b * weight_scale if l < len(model.biases) - 1 else b)
                     for l, b in enumerate(model.biases)]
     model.max_time = float(times.max())
+    # trainer.py:85-89 replaces max_time by the ARRAY times.max(): from here on it is one of the
+    # leaves get_weights_and_biases() returns (so l1 / l2 regularisation count it).  The reference
+    # then also lets the optimiser move it (it sits inside `func`, strategy.py:62); here it stays fixed.
+    model._max_time_is_leaf = True
     model._compiled.clear()
     if solver is not None:
         model.solver = solver
@@ -237,12 +182,12 @@ def train_neural_ode(model, dataset, strategy: Strategy, optimizer: Callable = A
                     if gb is not None:
                         flat[f"b{l}"] = gb + pg["weights"][k]; k += 1
             if "stoich" in groups:
-                flat["stoich"] = g["stoich"]
+                flat["stoich"] = g["stoich"] + pg["stoich"][0]
             if "gate_matrix" in groups:
                 flat["gate"] = g["gate_matrix"] + pg["gate"][0]
                 flat["alpha"] = g["alpha_residual"] + pg["alpha"][0]
             if "parameters" in groups:
-                flat["parameters"] = g["parameters"]
+                flat["parameters"] = g["parameters"] + pg["parameters"][0]
             upd = opt.update(flat)
             L = len(model.weights)
             zeros_w = [np.zeros_like(w) for w in model.weights]

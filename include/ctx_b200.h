@@ -77,18 +77,18 @@ typedef struct ctx_solve_cfg {
                           b = d*M + m -- parameters are indexed by d, y0 / constants / time by m:
                           vmap(per_draw)(thetas) over sim_func(y0s, theta, constants, times)
                           (predictive.py:150-154, loo.py:180-193); ys is [D, M, T, S] */
-  int32_t reserved;    /* flags; bit 0: never run the scheduling probe (below) */
+  int32_t reserved;    /* flags; bit 1 (value 2): run the scheduling probe (below) when `order` is NULL */
   const void* order;   /* optional DEVICE pointer to an int32 permutation of [0, batch): the persistent
                           kernels hand out rows in this order.  A scheduling hint only -- results do
                           not depend on it -- meant for "most expensive first" from the step counts of
                           a previous solve of similar inputs (a sampler's previous evaluation): one
                           launch is bound by the critical path of its longest trajectories, which then
                           start first.  MUST be a permutation (a missing row is never solved).
-                          NULL = index order -- or, for batches of 2^18 .. 2^22 rows of a small-state
-                          model at rtol <= 1e-4, the order found by the library's own scheduling probe
-                          (a capped solve of the same batch at rtol 1e-2 that marks the stability-limited
-                          rows; ~3 % extra work, csrc/ctx_sched.cu).  Ignored by the static kernels and
-                          the host-buffer calls. */
+                          NULL = index order -- or, with flag bit 1 set, the order found by the
+                          library's scheduling probe (a solve of the same batch at 100 x rtol capped at
+                          32 step attempts; rows that hit the cap start first; csrc/ctx_sched.cu;
+                          opt-in: it pays only where looser tolerances keep the long rows long).
+                          Ignored by the static kernels and the host-buffer calls. */
 } ctx_solve_cfg;
 
 /* ---- model lifetime -------------------------------------------------------------------

@@ -16,7 +16,7 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--rtol", type=float, default=1e-6)
 ap.add_argument("--neural", action="store_true")
 ap.add_argument("--hint", action="store_true", help="cost-ordered schedule from a previous solve")
-ap.add_argument("--no-probe", action="store_true", help="switch the library's scheduling probe off")
+ap.add_argument("--probe", action="store_true", help="switch the library's scheduling probe on")
 ap.add_argument("--km", type=float, nargs=2, default=None, help="K_m range (default: the benchmark's 0.5 .. 50)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -37,7 +37,7 @@ for dtype in a.dtype:
             for it in range(a.iters + 1):
                 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
                 e0.record()
-                o = m.solve(y0, th, c, ts, in_axes=(0, 0, 0, None), rtol=a.rtol, atol=a.rtol, kernel=kernel, out=out_buf, order=order, probe=not a.no_probe)
+                o = m.solve(y0, th, c, ts, in_axes=(0, 0, 0, None), rtol=a.rtol, atol=a.rtol, kernel=kernel, out=out_buf, order=order, probe=a.probe)
                 e1.record(); torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1))
             steps = int((o.n_accepted.sum() + o.n_rejected.sum()).item())
@@ -46,7 +46,7 @@ for dtype in a.dtype:
             print(json.dumps(dict(dtype=dtype, T=T, kernel=kernel, ms=round(ms, 3), first_ms=round(times[0], 1),
                                   steps=steps, steps_per_traj=round(steps / a.B, 1), rej_frac=round(float(o.n_rejected.sum().item()) / steps, 3),
                                   gsteps_s=round(steps / ms / 1e6, 2), out_GBs=round(byt / ms / 1e6, 1),
-                                  fails=int((o.status != 0).sum().item()), hint=bool(a.hint), probe=not a.no_probe, km=a.km,
+                                  fails=int((o.status != 0).sum().item()), hint=bool(a.hint), probe=a.probe, km=a.km,
                                   same_bits=(bool(torch.equal(ref_bits, out_buf)) if (a.hint and ref_bits is not None) else None))), flush=True)
 
 # ---- config 5: neural vector field
