@@ -122,16 +122,18 @@ class EnsembleIntegrator:
         return ll
 
 
-def integrate_ensemble(results, dataset, posterior, *, n_steps: int):
+def integrate_ensemble(results, dataset, posterior, *, n_steps: int, arrays=None):
     """``_integrate_ensemble`` (predictive.py:109-155): Tsit5 solve of ``results.model`` once per
     posterior draw on the dense per-series grid.  Returns ``(times [M,n_steps],
-    yhat_ens [n_draws, M, n_steps, n_obs])`` (numpy)."""
+    yhat_ens [n_draws, M, n_steps, n_obs])`` (numpy).  ``arrays``: optional ``(data, times, y0s,
+    constants)`` instead of a Dataset."""
     from ..model.simconfig import SimulationConfig
     from .mcmc import extract_dataset_components
 
     bm = results.bayesian_model
     config = SimulationConfig(t1=1, t0=0, dt0=bm.config.dt0, solver=Tsit5, throw=False)
-    _, meas_times, y0s, constants = extract_dataset_components(dataset, results.model)
+    _, meas_times, y0s, constants = arrays if arrays is not None else \
+        extract_dataset_components(dataset, results.model)
     times = ensemble_times(meas_times, n_steps)
     thetas, _ = stack_thetas(posterior, [name for name, _ in bm.priors])
     integ = EnsembleIntegrator(results.model, config)

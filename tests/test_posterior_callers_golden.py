@@ -1,0 +1,43 @@
+"""Posterior re-integration callers against arrays produced by the reference's own
+functions (tests/golden/make_posterior_callers_golden.py executes loo.py:92-200, 306-437 and
+predictive.py:109-175 unmodified over numpy stand-ins).  CPU half: the host bookkeeping around the
+fused kernel; the GPU half is in tests/test_gpu_posterior_callers_golden.py."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+G = np.load(Path(__file__).parent / "golden" / "posterior_callers_reference_lines.npz")
+POSTERIOR = {"K_m": G["post_K_m"], "k_cat": G["post_k_cat"], "sigma_y": G["post_sigma_y"]}
+
+
+@pytest.mark.parametrize("lik", ["normal", "softlaplace"])
+@pytest.mark.parametrize("leave_out", ["point", "curve"])
+def test_leave_out_bookkeeping(lik, leave_out):
+    from catalax_b200.mcmc import loo
+
+    loglik, meta = loo.leave_out_groups(G[f"{lik}/full"], G["mask"], leave_out)
+    key = f"{lik}/{leave_out}/None"
+    np.testing.assert_array_equal(meta["kept_idx"], G[f"{key}/kept_idx"])
+    assert meta["n_dropped"] == int(G[f"{key}/n_dropped"])
+    np.testing.assert_allclose(loglik, G[f"{key}/loglik"], rtol=0, atol=0)
+    with pytest.raises(ValueError, match="leave_out"):
+        loo.leave_out_groups(G[f"{lik}/full"], G["mask"], "series")
+
+
+def test_draw_helpers():
+    from catalax_b200.mcmc import predictive as pr
+
+    sub = pr.subsample(POSTERIOR, 3)
+    np.testing.assert_array_equal(sub["K_m"], G["normal/point/3/post_K_m"])
+    assert pr.subsample(POSTERIOR, None) is POSTERIOR and pr.subsample(POSTERIOR, 100) is POSTERIOR
+    sub4 = pr.subsample(POSTERIOR, 4)
+    np.testing.assert_array_equal(sub4["K_m"], G["ens/sub_K_m"])
+    thetas, (n_chain, n_draw) = pr.stack_thetas(sub4, ["K_m", "k_cat"])
+    assert (n_chain, n_draw) == (3, 4) and thetas.shape == (12, 2)
+    np.testing.assert_array_equal(thetas[:, 0], sub4["K_m"].reshape(-1))
+    sig = pr.sigma_y_draws(sub4, 3, 4, 3)
+    np.testing.assert_array_equal(sig, sub4["sigma_y"].reshape(12, 3))
+    np.testing.assert_array_equal(pr.sigma_y_draws({}, 3, 4, 3), np.ones((12, 3)))
+    np.testing.assert_allclose(pr.ensemble_times(G["times"], 17), G["ens/times"], rtol=1e-15)
+    np.testing.assert_allclose(pr.aleatoric_variance(sub4, G["ens/yhat"].shape), G["ens/var"], rtol=1e-15)
