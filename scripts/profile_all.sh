@@ -17,4 +17,10 @@ ncu --set full --clock-control none --import-source on -k regex:ctx_loglik_v2 -s
 python scripts/dev_bench5.py 262144 3 > gpurun_out/${TAG}_mlp_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:ctx_solve_mlp_tc -s 1 -c 1 \
     -o gpurun_out/${TAG}_mlp_tc_full python scripts/dev_bench5.py 262144 3 > gpurun_out/${TAG}_mlp_ncu.log 2>&1
+python scripts/dev_bench3_stab.py > gpurun_out/${TAG}_cfg3_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:ctx_solve_w -s 3 -c 1 \
+    -o gpurun_out/${TAG}_solve_w_full python scripts/dev_bench3_stab.py > gpurun_out/${TAG}_cfg3_ncu.log 2>&1
+python scripts/dev_bench.py --T 16 --kernel 0 --dtype float32 > gpurun_out/${TAG}_t16_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:ctx_solve_v1 -s 2 -c 1 \
+    -o gpurun_out/${TAG}_v1_T16 python scripts/dev_bench.py --T 16 --kernel 0 --dtype float32 > gpurun_out/${TAG}_t16_ncu.log 2>&1
 tail -n 1 gpurun_out/${TAG}_plain.log | cut -c1-300; tail -n 1 gpurun_out/${TAG}_nuts_plain.log | cut -c1-200; tail -n 2 gpurun_out/${TAG}_mlp_plain.log | cut -c1-200

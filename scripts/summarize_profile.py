@@ -81,5 +81,6 @@ full("solve_full", "ctx_solve_v2" if tag >= "r1n" else "ctx_solve_v1",
      "bench.py f32 T=1000 B=2^20 (Michaelis-Menten, config 2)")
 full("loglik_full", "ctx_loglik_v2" if tag >= "r1i" else "ctx_loglik_v1", "config 4: 16384 chains x 64 series x 20 points, f32, SoftLaplace")
 full("mlp_tc_full", "ctx_solve_mlp_tc", "config 5 (B=262144): NeuralODE 5-64-64-64-4 tanh, f32, tcgen05")
+full("solve_w_full", "ctx_solve_w", "config 3: mass-action network 32 states / 64 reactions, 262144 rows, T=32, f32 (scripts/dev_bench3_stab.py)")
 full("v1_T16", "ctx_solve_v1", "config 2 in the integrator-bound regime: f32 T=16 B=2^20 (scripts/dev_bench.py --T 16 --kernel 2)")
 full("v2_T16", "ctx_solve_v2", "config 2 in the integrator-bound regime: f32 T=16 B=2^20, stepping-heavy layout")
