@@ -272,6 +272,12 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0,
                                   : "typedef float real;\n#define R(x) x##f\n";
   src += "__device__ __forceinline__ real ctx_sign(real x) { return x > R(0.0) ? R(1.0) : "
          "(x < R(0.0) ? R(-1.0) : x); }\n";
+  // divisions of the generated field (the code generator prints CTX_DIV(a, b)): IEEE, or for f32
+  // builds with CTX_FAST_DIV bit 1 the SFU form (see ctx_integrator.cuh)
+  src += m->desc.dtype == CTX_F64
+             ? "#define CTX_DIV(a, b) ((a) / (b))\n"
+             : "#if defined(CTX_FAST_DIV) && (CTX_FAST_DIV & 2)\n#define CTX_DIV(a, b) __fdividef((a), (b))\n"
+               "#else\n#define CTX_DIV(a, b) ((a) / (b))\n#endif\n";
   src += m->field_src;
   src += "\n#include \"ctx_integrator.cuh\"\n";
   std::vector<std::string> opts = {

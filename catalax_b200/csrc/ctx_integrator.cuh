@@ -23,9 +23,11 @@
 
 #if CTX_F64
 #define CTX_INF __longlong_as_double(0x7ff0000000000000LL)
+#define CTX_QNAN __longlong_as_double(0x7ff8000000000000LL)
 #define CTX_TOL_END 1e-10
 #else
 #define CTX_INF __int_as_float(0x7f800000)
+#define CTX_QNAN __int_as_float(0x7fc00000)
 #define CTX_TOL_END 1e-6f
 #endif
 #define CTX_ST_OK 0
@@ -81,6 +83,26 @@ struct ctx_solve_args {
   const int* order;
 };
 // first step size of a trajectory whose requested times are `row` (T of them)
+// Divisions of the step loop.  f32 builds may use the SFU form (MUFU.RCP + FMUL, 2 ulp) instead
+// of the IEEE sequence (RCP + 4 FFMA + FCHK + a slow-path CALL for zero / denormal / extreme
+// operands): CTX_FAST_DIV bit 0 = the integrator's own divisions (error norm, 1/scaled, 1/dt),
+// bit 1 = the divisions of the generated field (CTX_DIV in the generated source).  The host
+// chooses (ctx_api.cu: compile_variant); f64 always divides in IEEE.
+#ifndef CTX_FAST_DIV
+#define CTX_FAST_DIV 0
+#endif
+#if !CTX_F64 && (CTX_FAST_DIV & 1)
+#define CTX_IDIV(a, b) __fdividef((a), (b))
+#else
+#define CTX_IDIV(a, b) ((a) / (b))
+#endif
+#ifndef CTX_NORM_SKIP_CONST
+#define CTX_NORM_SKIP_CONST 1
+#endif
+#ifndef CTX_CONST_MASK
+#define CTX_CONST_MASK 0u     // bit i: the generated right-hand side of model state i is identically 0
+#endif
+__host__ __device__ constexpr bool ctx_rhs_is_zero(int i) { return i < 32 && ((CTX_CONST_MASK >> i) & 1u); }
 #define CTX_ROW_DT0(row, T) (((a.dt0 > R(0.0)) || (T) < 2) ? a.dt0 : ((row)[1] - (row)[0]))
 
 // operand rows of trajectory b: `ro` for the parameters, `ri` for y0 / constants / times
@@ -249,15 +271,28 @@ __device__ __forceinline__ real ctx_scaled_error(const real dt, const real* y, c
   real ssq = R(0.0);
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) {
+#if CTX_NORM_SKIP_CONST
+    // A state whose right-hand side is identically zero (CTX_CONST_MASK) has all-zero slopes:
+    // its error estimate is dt * 0 and its term (0 / sc)^2 is exactly 0 -- except where that
+    // quotient is NaN (sc zero or NaN, dt not finite), which is kept.  Skipping the division
+    // leaves every bit as it was and keeps a zero numerator away from the slow path of the IEEE
+    // division (FCHK -> CALL on every step attempt).
+    if (ctx_rhs_is_zero(i)) {
+      const real sc = atol + fabs(y[i]) * rtol;       // (ynew == y for such a state)
+      const real nan_or_zero = dt - dt;               // NaN when dt is inf / NaN
+      ssq += (sc == R(0.0) || sc != sc) ? CTX_QNAN : nan_or_zero;
+      continue;
+    }
+#endif
     real e = dt * (E1 * K[0][i] + E2 * K[1][i] + E3 * K[2][i] + E4 * K[3][i] + E5 * K[4][i] +
                    E6 * K[5][i] + E7 * K[6][i]);
     if (e != e) e = CTX_INF;
     const real y1 = has_nan ? y[i] : ynew[i];
     const real sc = atol + fmax(fabs(y[i]), fabs(y1)) * rtol;
-    const real r = e / sc;
+    const real r = CTX_IDIV(e, sc);
     ssq += r * r;
   }
-  return sqrt(ssq / (real)CTX_S);
+  return sqrt(CTX_IDIV(ssq, (real)CTX_S));
 }
 #endif
 
@@ -281,7 +316,7 @@ __device__ __forceinline__ void ctx_dense(const real tq, const real tp, const re
                                           const real (*K)[CTX_N], real* out) {
   const real den = tn - tp;
   const real dt = den;
-  const real th = (den == R(0.0)) ? R(0.0) : (tq - tp) / den;
+  const real th = (den == R(0.0)) ? R(0.0) : CTX_IDIV(tq - tp, den);
 #if CTX_SOLVER == 0
   const real t2 = th * th;
   const real b1 = R(-1.0530884977290216) * th * (th - R(1.3299890189751412)) *
@@ -386,7 +421,7 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
 #if CTX_ADAPTIVE
     const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
     keep = scaled < R(1.0);
-    const real inv = R(1.0) / scaled;
+    const real inv = CTX_IDIV(R(1.0), scaled);
     real factor = R(0.9) * ctx_pow02(inv);
     factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
     if (factor != factor) factor = inv;  // clip(NaN) stays NaN in the reference
@@ -953,7 +988,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
 #if CTX_ADAPTIVE
       const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
       keep = scaled < R(1.0);
-      const real inv = R(1.0) / scaled;
+      const real inv = CTX_IDIV(R(1.0), scaled);
       real factor = R(0.9) * ctx_pow02(inv);
       factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
       CTX_DBG_FACTOR(nacc + nrej, c, factor);
@@ -1010,7 +1045,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       } else {
         ctx_dense_coefs(rec_dt, y, ynew, K, coef);
         tp_ = rec_tp;
-        inv_ = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+        inv_ = (rec_dt == R(0.0)) ? R(0.0) : CTX_IDIV(R(1.0), rec_dt);
       }
       real* o = a.ys + ((size_t)b * (size_t)T + (size_t)idx) * CTX_S;
 #pragma unroll 1
@@ -1066,7 +1101,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
         } else {
           ctx_dense_coefs_packed(rec_dt, y, ynew, K, u.r.v + 2);
           u.r.v[0] = rec_tp;
-          u.r.v[1] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+          u.r.v[1] = (rec_dt == R(0.0)) ? R(0.0) : CTX_IDIV(R(1.0), rec_dt);
         }
         u.r.i0 = idx;
         u.r.i1 = idx + nsave;
@@ -1395,7 +1430,7 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
         } else {
           ctx_dense_coefs(rec_dt, y, ynew, K, coef);
           w.rec[0][s] = rec_tp;
-          w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+          w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : CTX_IDIV(R(1.0), rec_dt);
         }
 #pragma unroll
         for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
@@ -1652,7 +1687,7 @@ ctx_loglik_v1(const ctx_loglik_args a) {
 #if CTX_ADAPTIVE
         const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
         keep = scaled < R(1.0);
-        const real inv = R(1.0) / scaled;
+        const real inv = CTX_IDIV(R(1.0), scaled);
         real factor = R(0.9) * ctx_pow02(inv);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         dt_next = dt * factor;
@@ -1961,7 +1996,7 @@ ctx_loglik_v2(const ctx_loglik_args a) {
 #if CTX_ADAPTIVE
         const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
         keep = scaled < R(1.0);
-        const real inv = R(1.0) / scaled;
+        const real inv = CTX_IDIV(R(1.0), scaled);
         real factor = R(0.9) * ctx_pow02(inv);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         dt_next = dt * factor;
@@ -2008,7 +2043,7 @@ ctx_loglik_v2(const ctx_loglik_args a) {
         real coef[CTX_NCOEF];
         ctx_dense_coefs(rec_dt, y, ynew, K, coef);
         w.rec[0][s] = rec_tp;
-        w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+        w.rec[1][s] = (rec_dt == R(0.0)) ? R(0.0) : CTX_IDIV(R(1.0), rec_dt);
 #pragma unroll
         for (int i = 0; i < CTX_NCOEF; ++i) w.rec[2 + i][s] = coef[i];
 #pragma unroll
@@ -2469,7 +2504,7 @@ ctx_solve_w(const ctx_solve_args a) {
         ssq = __shfl_sync(CTX_FULL, ssq, 0);
         const real scaled = sqrt(ssq / (real)CTX_S);
         keep = scaled < R(1.0);
-        const real inv = R(1.0) / scaled;
+        const real inv = CTX_IDIV(R(1.0), scaled);
         real factor = R(0.9) * ctx_pow02(inv);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         if (factor != factor) factor = inv;

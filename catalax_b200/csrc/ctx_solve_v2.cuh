@@ -252,7 +252,7 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
 #if CTX_ADAPTIVE
       const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
       keep = scaled < R(1.0);
-      const real inv = R(1.0) / scaled;
+      const real inv = CTX_IDIV(R(1.0), scaled);
       real factor = R(0.9) * ctx_pow02(inv);
       factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
       dt_next = dt * factor;
@@ -316,7 +316,7 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
         } else {
           ctx_dense_coefs_packed(rec_dt, y, ynew, K, u.r.v + 2);
           u.r.v[0] = rec_tp;
-          u.r.v[1] = (rec_dt == R(0.0)) ? R(0.0) : R(1.0) / rec_dt;
+          u.r.v[1] = (rec_dt == R(0.0)) ? R(0.0) : CTX_IDIV(R(1.0), rec_dt);
         }
         u.r.i0 = idx;
         u.r.i1 = idx + nsave;

@@ -113,8 +113,7 @@ class _Printer:
                     num.append(self._paren(f, mul=True))
             s = " * ".join(num) if num else _lit(1.0)
             if den:
-                d = " * ".join(den)
-                s = f"{s} / {d}" if _is_atom(d) else f"{s} / ({d})"
+                s = f"CTX_DIV({s}, {' * '.join(den)})"
             return f"{sign}({s})" if sign else s
         if isinstance(e, sp.Pow):
             b, x = e.base, e.exp
@@ -127,12 +126,12 @@ class _Printer:
                     bs = f"({bs})"
                 if 1 <= abs(n) <= 4:
                     prod = " * ".join([bs] * abs(n))
-                    return prod if n > 0 else f"{_lit(1.0)} / ({prod})"
+                    return prod if n > 0 else f"CTX_DIV({_lit(1.0)}, {prod})"
                 return f"pow({self.p(b)}, {_lit(n)})"
             if x == sp.Rational(1, 2):
                 return f"sqrt({self.p(b)})"
             if x == sp.Rational(-1, 2):
-                return f"{_lit(1.0)} / sqrt({self.p(b)})"
+                return f"CTX_DIV({_lit(1.0)}, sqrt({self.p(b)}))"
             return f"pow({self.p(b)}, {self.p(x)})"
         if isinstance(e, sp.sign):
             a = self.p(e.args[0])

@@ -41,12 +41,16 @@ for dtype in a.dtype:
                 e1.record(); torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1))
             steps = int((o.n_accepted.sum() + o.n_rejected.sum()).item())
+            per_row = (o.n_accepted + o.n_rejected).float()
+            tail = dict(max=int(per_row.max().item()), p999=int(torch.quantile(per_row[:1 << 20], 0.999).item()),
+                        over300=int((per_row > 300).sum().item()),
+                        checksum=float(torch.nan_to_num(out_buf[:, -1, :].double(), posinf=0.0).sum().item()))
             ms = min(times[1:])
             byt = a.B * T * 3 * y0.element_size()
             print(json.dumps(dict(dtype=dtype, T=T, kernel=kernel, ms=round(ms, 3), first_ms=round(times[0], 1),
                                   steps=steps, steps_per_traj=round(steps / a.B, 1), rej_frac=round(float(o.n_rejected.sum().item()) / steps, 3),
                                   gsteps_s=round(steps / ms / 1e6, 2), out_GBs=round(byt / ms / 1e6, 1),
-                                  fails=int((o.status != 0).sum().item()), hint=bool(a.hint), probe=a.probe, km=a.km,
+                                  fails=int((o.status != 0).sum().item()), tail=tail, hint=bool(a.hint), probe=a.probe, km=a.km,
                                   same_bits=(bool(torch.equal(ref_bits, out_buf)) if (a.hint and ref_bits is not None) else None))), flush=True)
 
 # ---- config 5: neural vector field

@@ -14,6 +14,7 @@ _TEMPLATE = r"""
 #include <cmath>
 typedef double real;
 #define R(x) x
+#define CTX_DIV(a, b) ((a) / (b))
 #define __device__
 #define __forceinline__ inline
 using std::fmax; using std::fmin; using std::fabs;

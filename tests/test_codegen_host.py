@@ -185,7 +185,7 @@ def test_generated_mechanistic_vjp_matches_finite_differences():
     net = UniversalODE(2, 16, 1, model, max_time=1.0, key=0)
     lines = cm._adjoint_mech_source(net.spec, cm.layout_of(net.spec), cm.adjoint_dims(net.spec))
     body = "\n".join(l for l in lines if not l.startswith("#define"))
-    src = ("#include <cmath>\ntypedef double real;\n#define R(x) x\n#define __device__\n"
+    src = ("#include <cmath>\ntypedef double real;\n#define R(x) x\n#define CTX_DIV(a, b) ((a) / (b))\n#define __device__\n"
            "#define __forceinline__ inline\nusing std::exp; using std::log; using std::sqrt;\n" + body +
            "\nextern \"C\" void f(double t, const double* y, const double* th, const double* y0, double* m)"
            " { adj_mech(t, y, th, y0, m); }\n"
