@@ -83,11 +83,13 @@ struct ctx_solve_args {
   const int* order;
 };
 // first step size of a trajectory whose requested times are `row` (T of them)
-// Divisions of the step loop.  f32 builds may use the SFU form (MUFU.RCP + FMUL, 2 ulp) instead
-// of the IEEE sequence (RCP + 4 FFMA + FCHK + a slow-path CALL for zero / denormal / extreme
-// operands): CTX_FAST_DIV bit 0 = the integrator's own divisions (error norm, 1/scaled, 1/dt),
-// bit 1 = the divisions of the generated field (CTX_DIV in the generated source).  The host
-// chooses (ctx_api.cu: compile_variant); f64 always divides in IEEE.
+// Divisions of the step loop are IEEE (what the reference's XLA path computes).  A/B switch for
+// f32 builds: the SFU form (MUFU.RCP + FMUL, 2 ulp) instead of the IEEE sequence (RCP + 4 FFMA +
+// FCHK + a slow-path CALL for zero / denormal / extreme operands): CTX_FAST_DIV bit 0 = the
+// integrator's own divisions (error norm, 1/scaled, 1/dt), bit 1 = the divisions of the generated
+// field (CTX_DIV in the generated source).  Measured on config 2 (B200, f32): T=16 1.34 -> 1.15 ms,
+// T=1000 3.44 -> 3.30 ms, K2 1.57 -> 1.44 ms -- not taken: it changes f32 bits for 4 % of the
+// headline.  f64 always divides in IEEE.
 #ifndef CTX_FAST_DIV
 #define CTX_FAST_DIV 0
 #endif
@@ -725,7 +727,10 @@ __device__ __forceinline__ int ctx_upper_bound(const real* ts, const unsigned sa
   const real t_lo = ctx_ts_at<SM>(ts, sa, lo);
   if (t_lo > t) return lo;
   // invariant from here: ts[lo] <= t < ts[hi]
-  int g = lo + 1 + (int)((t - t_lo) / (t_end - t_lo) * (real)(hi - lo));
+  // (a position GUESS, verified by the probes below: the SFU division in f32 is enough for both
+  //  dtypes and cannot change the result)
+  const float frac = fminf(fmaxf(__fdividef((float)(t - t_lo), (float)(t_end - t_lo)), 0.0f), 1.0f);
+  int g = lo + 1 + (int)(frac * (float)(hi - lo));
   g = min(max(g, lo + 1), hi);
 #pragma unroll 1
   for (int probe = 0; probe < 3 && hi - lo > 1; ++probe) {
