@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -284,6 +285,7 @@ int compile_variant(ctx_model* m, int solver, int tan, Variant& v, int wide = 0,
       "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
       std::string("-DCTX_F64=") + (m->desc.dtype == CTX_F64 ? "1" : "0"),
       "-DCTX_SOLVER=" + std::to_string(solver), "-DCTX_TAN=" + std::to_string(tan),
+      "-DCTX_LOG2S=" + std::to_string(std::log2((double)std::max(1, m->desc.n_states))) + "f",
       "-DCTX_WARPS=" + std::to_string(std::max(1, v1_warps(m->desc, solver, tan, theta_smem(m))))};
   if (v1_warps(m->desc, solver, tan, theta_smem(m)) <= 0) opts.push_back("-DCTX_NO_V1=1");
   {

@@ -105,6 +105,15 @@ struct ctx_solve_args {
 #define CTX_CONST_MASK 0u     // bit i: the generated right-hand side of model state i is identically 0
 #endif
 __host__ __device__ constexpr bool ctx_rhs_is_zero(int i) { return i < 32 && ((CTX_CONST_MASK >> i) & 1u); }
+// component i of the (augmented) state: model states first, then the tangents direction-major
+// (comp = S * (1 + d) + state).  The tangent of a state with an identically-zero right-hand side
+// has an identically-zero right-hand side too (its Jacobian row and parameter derivatives vanish).
+#ifndef CTX_STAGE_SKIP_CONST
+#define CTX_STAGE_SKIP_CONST 1
+#endif
+__host__ __device__ constexpr bool ctx_comp_is_const(int i) {
+  return CTX_STAGE_SKIP_CONST && ctx_rhs_is_zero(i % CTX_S);
+}
 #define CTX_ROW_DT0(row, T) (((a.dt0 > R(0.0)) || (T) < 2) ? a.dt0 : ((row)[1] - (row)[0]))
 
 // operand rows of trajectory b: `ro` for the parameters, `ri` for y0 / constants / times
@@ -211,30 +220,35 @@ __device__ __forceinline__ void ctx_rk_stages(const real tp, const real dt, cons
                                               real (*K)[CTX_N], const real* th, const real* c,
                                               const real* y0, real* ynew) {
 #if CTX_SOLVER == 0 || CTX_SOLVER == 1
+  // (components with an identically-zero right-hand side keep their value: y + dt * 0)
   real yt[CTX_N];
 #pragma unroll
-  for (int i = 0; i < CTX_N; ++i) yt[i] = y[i] + dt * (A21 * K[0][i]);
+  for (int i = 0; i < CTX_N; ++i) yt[i] = ctx_comp_is_const(i) ? y[i] : y[i] + dt * (A21 * K[0][i]);
   ctx_field(tp + C2 * dt, yt, th, c, y0, K[1]);
 #pragma unroll
-  for (int i = 0; i < CTX_N; ++i) yt[i] = y[i] + dt * (A31 * K[0][i] + A32 * K[1][i]);
+  for (int i = 0; i < CTX_N; ++i)
+    yt[i] = ctx_comp_is_const(i) ? y[i] : y[i] + dt * (A31 * K[0][i] + A32 * K[1][i]);
   ctx_field(tp + C3 * dt, yt, th, c, y0, K[2]);
 #pragma unroll
   for (int i = 0; i < CTX_N; ++i)
-    yt[i] = y[i] + dt * (A41 * K[0][i] + A42 * K[1][i] + A43 * K[2][i]);
+    yt[i] = ctx_comp_is_const(i) ? y[i] : y[i] + dt * (A41 * K[0][i] + A42 * K[1][i] + A43 * K[2][i]);
   ctx_field(tp + C4 * dt, yt, th, c, y0, K[3]);
 #pragma unroll
   for (int i = 0; i < CTX_N; ++i)
-    yt[i] = y[i] + dt * (A51 * K[0][i] + A52 * K[1][i] + A53 * K[2][i] + A54 * K[3][i]);
+    yt[i] = ctx_comp_is_const(i) ? y[i]
+                                 : y[i] + dt * (A51 * K[0][i] + A52 * K[1][i] + A53 * K[2][i] + A54 * K[3][i]);
   ctx_field(tp + C5 * dt, yt, th, c, y0, K[4]);
 #pragma unroll
   for (int i = 0; i < CTX_N; ++i)
-    yt[i] = y[i] + dt * (A61 * K[0][i] + A62 * K[1][i] + A63 * K[2][i] + A64 * K[3][i] +
-                         A65 * K[4][i]);
+    yt[i] = ctx_comp_is_const(i) ? y[i]
+                                 : y[i] + dt * (A61 * K[0][i] + A62 * K[1][i] + A63 * K[2][i] +
+                                                A64 * K[3][i] + A65 * K[4][i]);
   ctx_field(tp + dt, yt, th, c, y0, K[5]);
 #pragma unroll
   for (int i = 0; i < CTX_N; ++i)
-    ynew[i] = y[i] + dt * (A71 * K[0][i] + A72 * K[1][i] + A73 * K[2][i] + A74 * K[3][i] +
-                           A75 * K[4][i] + A76 * K[5][i]);
+    ynew[i] = ctx_comp_is_const(i) ? y[i]
+                                   : y[i] + dt * (A71 * K[0][i] + A72 * K[1][i] + A73 * K[2][i] +
+                                                  A74 * K[3][i] + A75 * K[4][i] + A76 * K[5][i]);
   ctx_field(tp + dt, ynew, th, c, y0, K[6]);
 #elif CTX_SOLVER == 2
 #pragma unroll
@@ -264,9 +278,9 @@ __device__ __forceinline__ real ctx_pow02(const real x) {
 
 // scaled error norm of PIDController: rms(y_err / (atol + rtol*max(|y0|,|y1|))) over the S
 // model states only (tangents never enter the norm: the factor is under stop_gradient).
-__device__ __forceinline__ real ctx_scaled_error(const real dt, const real* y, const real* ynew,
-                                                 const real (*K)[CTX_N], const real rtol,
-                                                 const real atol) {
+__device__ __forceinline__ real ctx_error_ssq(const real dt, const real* y, const real* ynew,
+                                              const real (*K)[CTX_N], const real rtol,
+                                              const real atol) {
   bool has_nan = false;
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) has_nan |= (ynew[i] != ynew[i]);
@@ -294,7 +308,38 @@ __device__ __forceinline__ real ctx_scaled_error(const real dt, const real* y, c
     const real r = CTX_IDIV(e, sc);
     ssq += r * r;
   }
-  return sqrt(CTX_IDIV(ssq, (real)CTX_S));
+  return ssq;
+}
+__device__ __forceinline__ real ctx_scaled_error(const real dt, const real* y, const real* ynew,
+                                                 const real (*K)[CTX_N], const real rtol,
+                                                 const real atol) {
+  return sqrt(CTX_IDIV(ctx_error_ssq(dt, y, ynew, K, rtol, atol), (real)CTX_S));
+}
+
+// Accept / reject decision and raw step-size factor 0.9 * scaled^(-1/5) of one step attempt;
+// `bad`: the error norm is NaN.  f64 (and CTX_FUSED_FACTOR=0): scaled = sqrt(ssq / S), keep =
+// scaled < 1, factor through 1 / scaled and pow, as the reference writes it.  f32: the SAME
+// decisions without the division, the square root and the reciprocal -- sqrt and the division by
+// S are monotone with sqrt(1) = 1 and S / S = 1, so `scaled < 1` holds exactly when `ssq < S`; and
+// the factor, which the SFU pow already computes only to f32 rounding level, is evaluated as
+// 0.9 * 2^(-0.1 * (log2(ssq) - log2(S))).  0 -> inf, inf -> 0, NaN -> NaN as before.
+#ifndef CTX_FUSED_FACTOR
+#define CTX_FUSED_FACTOR 1
+#endif
+__device__ __forceinline__ real ctx_error_control(const real dt, const real* y, const real* ynew,
+                                                  const real (*K)[CTX_N], const real rtol,
+                                                  const real atol, bool& keep, bool& bad) {
+  const real ssq = ctx_error_ssq(dt, y, ynew, K, rtol, atol);
+#if !CTX_F64 && CTX_FUSED_FACTOR
+  keep = ssq < (real)CTX_S;
+  bad = ssq != ssq;
+  return R(0.9) * exp2f(fmaf(-0.1f, __log2f(ssq), 0.1f * CTX_LOG2S));
+#else
+  const real scaled = sqrt(CTX_IDIV(ssq, (real)CTX_S));
+  keep = scaled < R(1.0);
+  bad = scaled != scaled;
+  return R(0.9) * ctx_pow02(CTX_IDIV(R(1.0), scaled));
+#endif
 }
 #endif
 
@@ -421,12 +466,10 @@ extern "C" __global__ void __launch_bounds__(128) ctx_solve_v0(const ctx_solve_a
     bool keep = true;
     real dt_next = dt0_r;
 #if CTX_ADAPTIVE
-    const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
-    keep = scaled < R(1.0);
-    const real inv = CTX_IDIV(R(1.0), scaled);
-    real factor = R(0.9) * ctx_pow02(inv);
+    bool bad_norm = false;
+    real factor = ctx_error_control(dt, y, ynew, K, a.rtol, a.atol, keep, bad_norm);
     factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
-    if (factor != factor) factor = inv;  // clip(NaN) stays NaN in the reference
+    if (bad_norm) factor = CTX_QNAN;  // clip(NaN) stays NaN in the reference
     CTX_DBG_FACTOR(n, c, factor);
     dt_next = dt * factor;
 #endif
@@ -991,14 +1034,12 @@ __device__ __forceinline__ void ctx_solve_v1_body(const ctx_solve_args& a) {
       bool keep = true;
       real dt_next = dt0_l;
 #if CTX_ADAPTIVE
-      const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
-      keep = scaled < R(1.0);
-      const real inv = CTX_IDIV(R(1.0), scaled);
-      real factor = R(0.9) * ctx_pow02(inv);
+      bool bad_norm = false;
+      real factor = ctx_error_control(dt, y, ynew, K, a.rtol, a.atol, keep, bad_norm);
       factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
       CTX_DBG_FACTOR(nacc + nrej, c, factor);
       dt_next = dt * factor;
-      if (scaled != scaled) dt_next = scaled;  // NaN error norm poisons the step size
+      if (bad_norm) dt_next = CTX_QNAN;  // NaN error norm poisons the step size
 #endif
       rec_tp = tprev; rec_dt = dt;
       real tp_new = tprev;
@@ -1690,13 +1731,11 @@ ctx_loglik_v1(const ctx_loglik_args a) {
         ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
         real dt_next = a.dt0;
 #if CTX_ADAPTIVE
-        const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
-        keep = scaled < R(1.0);
-        const real inv = CTX_IDIV(R(1.0), scaled);
-        real factor = R(0.9) * ctx_pow02(inv);
+        bool bad_norm = false;
+        real factor = ctx_error_control(dt, y, ynew, K, a.rtol, a.atol, keep, bad_norm);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         dt_next = dt * factor;
-        if (scaled != scaled) dt_next = scaled;
+        if (bad_norm) dt_next = CTX_QNAN;
 #endif
         real tp_new = keep ? tnext : tprev;
         if (keep) ++nacc; else ++nrej;
@@ -1999,13 +2038,11 @@ ctx_loglik_v2(const ctx_loglik_args a) {
         ctx_rk_stages(tprev, dt, y, K, th, c, y0, ynew);
         real dt_next = a.dt0;
 #if CTX_ADAPTIVE
-        const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
-        keep = scaled < R(1.0);
-        const real inv = CTX_IDIV(R(1.0), scaled);
-        real factor = R(0.9) * ctx_pow02(inv);
+        bool bad_norm = false;
+        real factor = ctx_error_control(dt, y, ynew, K, a.rtol, a.atol, keep, bad_norm);
         factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
         dt_next = dt * factor;
-        if (scaled != scaled) dt_next = scaled;
+        if (bad_norm) dt_next = CTX_QNAN;
 #endif
         real tp_new = keep ? tnext : tprev;
         if (keep) ++nacc; else ++nrej;

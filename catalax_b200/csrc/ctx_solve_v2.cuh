@@ -250,13 +250,11 @@ __device__ __forceinline__ void v2_producer(const ctx_solve_args& a, v2_prod_sme
       bool keep = true;
       real dt_next = a.dt0;
 #if CTX_ADAPTIVE
-      const real scaled = ctx_scaled_error(dt, y, ynew, K, a.rtol, a.atol);
-      keep = scaled < R(1.0);
-      const real inv = CTX_IDIV(R(1.0), scaled);
-      real factor = R(0.9) * ctx_pow02(inv);
+      bool bad_norm = false;
+      real factor = ctx_error_control(dt, y, ynew, K, a.rtol, a.atol, keep, bad_norm);
       factor = fmin(fmax(factor, keep ? R(1.0) : R(0.2)), R(10.0));
       dt_next = dt * factor;
-      if (scaled != scaled) dt_next = scaled;
+      if (bad_norm) dt_next = CTX_QNAN;
 #endif
       rec_tp = tprev; rec_dt = dt;
       real tp_new = tprev;
