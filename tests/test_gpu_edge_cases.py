@@ -358,3 +358,40 @@ def test_order_hint_changes_the_schedule_not_the_results(kernel, T, B, dtype):
         m.solve(tt(y0), tt(theta), tt(consts), tt(ts), order=order[:-1].contiguous(), **kw)
     with pytest.raises(ValueError, match="order must be"):
         m.solve(tt(y0), tt(theta), tt(consts), tt(ts), order=order.long(), **kw)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel,T", [(1, 40), (2, 16), (2, 100), (5, 400)])
+def test_zero_rhs_states_skip_the_error_norm_and_stage_sums_bit_identically(kernel, T, dtype, monkeypatch):
+    """States whose generated right-hand side is identically zero (CTX_CONST_MASK: the enzyme of
+    Michaelis-Menten) are left out of the error norm's division and of the stage sums.  That must
+    not change one bit, one step count or one status -- including the cases where the skipped
+    quotient would have been NaN: a constant state that is 0 with atol = 0 (0 / 0), NaN, or inf."""
+    from catalax_b200 import engine
+    from catalax_b200.tools import codegen as cg
+
+    model = cases.michaelis_menten()
+    B = 20011
+    y0, theta, consts = cases.mm_inputs(B, seed=13, dtype=dtype)
+    y0[:5, 0] = 0.0              # E = 0: no reaction; with atol = 0 the reference's norm is 0 / 0 = NaN
+    y0[5:8, 0] = np.nan
+    y0[8:11, 0] = np.inf
+    ts = np.linspace(0, 100, T).astype(dtype)
+    dev = torch.device("cuda:0")
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    for atol in (1e-6, 0.0):
+        res = []
+        for flags in ("", "-DCTX_NORM_SKIP_CONST=0 -DCTX_STAGE_SKIP_CONST=0"):
+            monkeypatch.setenv("CTX_B200_NVRTC_FLAGS", flags)
+            m = engine.CompiledModel(cg.generate_field(cases.field_spec(model)), np.dtype(dtype).name)
+            o = m.solve(tt(y0), tt(theta), tt(consts), tt(ts), in_axes=(0, 0, 0, None), rtol=1e-6,
+                        atol=atol, max_steps=400, kernel=kernel)
+            torch.cuda.synchronize()
+            res.append(o)
+        a, b = res
+        assert torch.equal(a.status, b.status)
+        assert torch.equal(a.n_accepted, b.n_accepted) and torch.equal(a.n_rejected, b.n_rejected)
+        same = (a.ys == b.ys) | (a.ys.isnan() & b.ys.isnan())
+        assert bool(same.all()), int((~same).sum())
+        assert int((a.status[:11] != 0).sum()) >= 6         # the NaN / inf rows fail in both builds
+        assert int((a.status[11:] == 0).sum()) > 0.9 * (B - 11)
