@@ -63,6 +63,77 @@ def mechanistic_loglik(results, dataset, posterior: Dict[str, np.ndarray], *,
     return ll, mask, info
 
 
+def _log_prob(likelihood: str, x, loc, scale):
+    """numpyro's Normal / SoftLaplace log-density (the two likelihoods of the reference)."""
+    z = (x - loc) / scale
+    if likelihood == "normal":
+        return -0.5 * z * z - np.log(scale) - 0.5 * np.log(2 * np.pi)
+    if likelihood == "softlaplace":
+        return np.log(2 / np.pi) - np.log(scale) - np.logaddexp(z, -z)
+    raise ValueError(f"unknown likelihood {likelihood!r}")
+
+
+def surrogate_loglik(results, dataset, posterior: Dict[str, np.ndarray], *, sigma_source: str = "reuse",
+                     yerrs=None, integration: str = "euler", arrays=None, draw_chunk: int = 256):
+    """loo.py:203-303 for a surrogate-mode (rate-matching) fit: the mechanistic rates of every
+    posterior draw at the measured states (ONE ``ctx_rates`` launch per chunk of draws: draws x
+    points with per-point parameters), forward-Euler integrated along the measurement times
+    (``predictive.euler_integrate_rates``) and scored against the measured concentrations.
+    ``arrays``: optional ``(full_data [M,T,S], times [M,T], y0s (unused), constants [M,C])``.
+    Returns ``(loglik [n_chain, n_draw, M, T, n_obs], mask, info)``."""
+    import torch
+
+    from .. import engine
+    from ..config import default_dtype
+    from ..tools import codegen as cg
+    from .predictive import euler_integrate_rates
+
+    bm, model = results.bayesian_model, results.model
+    if arrays is not None:
+        full_data, full_times, _, constants = arrays
+    else:
+        full_data, full_times, _, constants = extract_dataset_components(dataset, model)
+    full_data, full_times = np.asarray(full_data, dtype=np.float64), np.asarray(full_times, dtype=np.float64)
+    M, T, S = full_data.shape
+    mask = np.isfinite(full_data)
+    data_safe = np.where(mask, full_data, 0.0)
+    y0_full = full_data[:, 0, :]
+    dt = np.diff(full_times, axis=-1)
+    thetas, (n_chain, n_draw) = stack_thetas(posterior, [name for name, _ in bm.priors])
+    if sigma_source == "reuse":
+        scale = sigma_y_draws(posterior, n_chain, n_draw, S)[:, None, None, :]
+    elif sigma_source == "yerrs":
+        if yerrs is None:       # loo.py:316-325: the stored error of a surrogate fit is rate-shaped
+            raise ValueError("`yerrs` was not provided: pass concentration-space `yerrs` explicitly")
+        scale = np.broadcast_to(np.asarray(yerrs, dtype=np.float64), (M, T, S))[None]
+    else:
+        raise ValueError(f"unknown sigma_source {sigma_source!r}")
+    dtype = default_dtype()
+    compiled = engine.CompiledModel(
+        cg.generate_field(model._replace_assignments().sim_input.field_spec()), np.dtype(dtype).name)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=dtype), device=dev)
+    N = M * T
+    pts, t_flat = tt(full_data.reshape(N, S)), tt(full_times.reshape(N))
+    c_flat = tt(np.repeat(np.asarray(constants, dtype=np.float64).reshape(M, -1), T, axis=0))
+    inits = tt(np.repeat(y0_full, T, axis=0))              # "{state}_init" = first measured state
+    D = thetas.shape[0]
+    rates = np.empty((D, M, T, S))
+    for lo in range(0, D, draw_chunk):
+        th = tt(thetas[lo:lo + draw_chunk])
+        d = th.shape[0]
+        r = compiled.rates(t_flat.repeat(d), pts.repeat(d, 1), th.repeat_interleave(N, dim=0),
+                           c_flat.repeat(d, 1), y0=inits.repeat(d, 1))
+        rates[lo:lo + d] = r.reshape(d, M, T, S).cpu().numpy()
+    yhat, _ = euler_integrate_rates(rates, y0_full, dt, np.zeros((M, T, S)), integration=integration,
+                                    data_safe=data_safe)
+    with np.errstate(all="ignore"):
+        ll = _log_prob(bm.likelihood, data_safe[None], yhat, scale)
+    ll = ll.reshape(n_chain, n_draw, M, T, S)
+    info = {"data": full_data, "times": full_times, "species": list(model.get_state_order())}
+    return ll, mask, info
+
+
 def leave_out_groups(ll: np.ndarray, mask: np.ndarray, leave_out: str = "point"):
     """loo.py:395-426: turn ``ll [n_chain, n_draw, M, T, n_obs]`` into the held-out units arviz
     scores.  ``"point"``: one column per OBSERVED (series, time, observable) entry; ``"curve"``: one
@@ -89,24 +160,29 @@ def leave_out_groups(ll: np.ndarray, mask: np.ndarray, leave_out: str = "point")
 
 
 def reconstruct_log_likelihood(results, dataset, *, yerrs=None, sigma_source: str = "reuse",
-                               leave_out: str = "point", max_draws: Optional[int] = None,
+                               leave_out: str = "point", integration: str = "euler",
+                               max_draws: Optional[int] = None,
                                config: Optional[SimulationConfig] = None, arrays=None):
-    """loo.py:331-437 for mechanistic fits: per-observation, per-draw concentration-space
-    log-likelihoods ready for ``arviz.loo``.  Returns ``(loglik [chains, draws, n_kept], posterior,
-    meta)``.  (A surrogate-mode fit is scored by Euler-integrating its sampled rates in the
-    reference, :203-303 -- host arithmetic on the K4 rate kernel's output, not built here.)"""
+    """loo.py:331-437: per-observation, per-draw concentration-space log-likelihoods ready for
+    ``arviz.loo``, for mechanistic fits (one fused solve + likelihood launch) and surrogate-mode
+    fits (rates at the measured states, Euler-integrated: ``integration`` = ``"euler"`` |
+    ``"euler_onestep"``).  Returns ``(loglik [chains, draws, n_kept], posterior, meta)``."""
     from .predictive import subsample
 
     bm = results.bayesian_model
-    if getattr(bm, "mode", "integrated") not in ("integrated", "mechanistic"):
-        raise NotImplementedError("reconstruct_log_likelihood: surrogate-mode fits are not supported")
     posterior = subsample(results.mcmc.get_samples(group_by_chain=True), max_draws)
-    ll, mask, info = mechanistic_loglik(results, dataset, posterior, sigma_source=sigma_source,
-                                        yerrs=yerrs, config=config, arrays=arrays)
+    surrogate = getattr(bm, "mode", "integrated") == "surrogate"
+    if surrogate:
+        ll, mask, info = surrogate_loglik(results, dataset, posterior, sigma_source=sigma_source,
+                                          yerrs=yerrs, integration=integration, arrays=arrays)
+    else:
+        ll, mask, info = mechanistic_loglik(results, dataset, posterior, sigma_source=sigma_source,
+                                            yerrs=yerrs, config=config, arrays=arrays)
     loglik, meta = leave_out_groups(ll, mask, leave_out)
     names = [name for name, _ in bm.priors]
     posterior_np = {n: np.asarray(posterior[n]) for n in names if n in posterior}
-    meta.update(sigma_source=sigma_source, mode="MECHANISTIC", integration="euler", info=info)
+    meta.update(sigma_source=sigma_source, mode="SURROGATE" if surrogate else "MECHANISTIC",
+                integration=integration, info=info)
     return loglik, posterior_np, meta
 
 

@@ -142,6 +142,27 @@ def integrate_ensemble(results, dataset, posterior, *, n_steps: int, arrays=None
     return times, ys[..., obs].cpu().numpy()
 
 
+def euler_integrate_rates(rates, y0_obs, dt, rate_var, *, integration: str = "euler", data_safe=None):
+    """predictive.py:54-106: forward-Euler integration of observable rates into concentrations
+    (shared by the surrogate-mode LOO and the predictive bands).  ``rates`` / ``rate_var``
+    ``[..., M, T, n_obs]`` (any leading draw axes), ``y0_obs [M, n_obs]``, ``dt [M, T-1]``;
+    ``"euler"`` integrates from the measured initial state, ``"euler_onestep"`` predicts every point
+    from the previous MEASURED state (``data_safe``).  Returns ``(yhat, var_y)``."""
+    rates, rate_var = np.asarray(rates), np.asarray(rate_var)
+    lead = rates.shape[:-3]
+    y0b = np.broadcast_to(np.asarray(y0_obs)[:, None, :], lead + (rates.shape[-3], 1, rates.shape[-1]))
+    step = rates[..., :-1, :] * np.asarray(dt)[..., None]
+    var_inc = (np.asarray(dt)[..., None] ** 2) * rate_var[..., :-1, :]
+    zeros = np.zeros(lead + (rates.shape[-3], 1, rates.shape[-1]))
+    if integration == "euler_onestep":
+        yhat = np.concatenate([y0b, np.asarray(data_safe)[..., :-1, :] + step], axis=-2)
+        var_y = np.concatenate([zeros, np.broadcast_to(var_inc, step.shape)], axis=-2)
+    else:
+        yhat = np.concatenate([y0b, y0b + np.cumsum(step, axis=-2)], axis=-2)
+        var_y = np.concatenate([zeros, np.cumsum(np.broadcast_to(var_inc, step.shape), axis=-2)], axis=-2)
+    return yhat, var_y
+
+
 def aleatoric_variance(posterior, yhat_shape) -> np.ndarray:
     """Per-draw concentration-space aleatoric variance broadcast to ``yhat_shape``
     (predictive.py:158-175): ``sigma_y**2``; a shared scalar is broadcast across observables."""

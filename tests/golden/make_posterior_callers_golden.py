@@ -4,8 +4,9 @@ reference's own functions (run in the build container, where /root/reference exi
 Executed UNMODIFIED, extracted with ``ast`` from catalax/mcmc/loo.py and catalax/mcmc/predictive.py:
 
   loo.py         _stack_thetas :92, _sigma_y_draws :103, _subsample :120, _mechanistic_loglik :131,
-                 _resolve_yerrs :306, reconstruct_log_likelihood :331 (point / curve leave-out)
-  predictive.py  _integrate_ensemble :109, _aleatoric_variance :158
+                 _surrogate_loglik :203, _resolve_yerrs :306, reconstruct_log_likelihood :331 (point /
+                 curve leave-out, both fit modes)
+  predictive.py  euler_integrate_rates :54, _integrate_ensemble :109, _aleatoric_variance :158
 
 over stand-ins: ``jax.numpy`` -> numpy, ``jax.vmap(f)`` -> a Python loop over the leading axis,
 ``catalax.mcmc.mcmc._prepare_mcmc_data`` -> a record holding the arrays and the parity oracle's solve
@@ -127,6 +128,56 @@ def main():
         full, mask, info = ns["_mechanistic_loglik"](results, None, posterior, sigma_source="reuse",
                                                      yerrs=None, config=None)
         out[f"{tag}/full"], out["mask"] = full, mask
+    # ---- surrogate-mode fit: loo.py:203-303 (_surrogate_loglik) + predictive.py:54-106
+    # (euler_integrate_rates): the sampled mechanistic rates at the measured states, forward-Euler
+    # integrated along the measurement times and scored against the measured concentrations
+    full = np.nan_to_num(clean) * np.exp(rng.normal(0, 0.02, clean.shape))
+    full[2, 4, 1] = np.nan                              # a missing concentration
+    exec(compile(definitions(REF / "predictive.py", "euler_integrate_rates"), str(REF / "predictive.py"), "exec"), ns_p)
+    fake_pred = types.ModuleType("catalax.mcmc.predictive")
+    fake_pred.euler_integrate_rates = ns_p["euler_integrate_rates"]
+    sys.modules["catalax.mcmc.predictive"] = fake_pred
+    for n in ("cumsum", "concatenate"):
+        setattr(jnp, n, getattr(np, n))
+    exec(compile(definitions(REF / "loo.py", "_surrogate_loglik"), str(REF / "loo.py"), "exec"), ns)
+
+    er = dict(rates=rng.normal(size=(M, T, S)), y0_obs=rng.normal(size=(M, S)), dt=rng.uniform(0.1, 1.0, (M, T - 1)),
+              rate_var=rng.uniform(0, 1, (M, T, S)), data_safe=rng.normal(size=(M, T, S)))
+    for k, v in er.items():
+        out[f"euler/{k}"] = v
+    for mode in ("euler", "euler_onestep"):
+        yh, vy = ns_p["euler_integrate_rates"](er["rates"], er["y0_obs"], er["dt"], er["rate_var"],
+                                               integration=mode, data_safe=er["data_safe"])
+        out[f"euler/{mode}/yhat"], out[f"euler/{mode}/var_y"] = yh, vy
+
+    def rate_sim_func(points, theta_, constants_, times_):
+        n = points.shape[0]
+        ini = np.repeat(points.reshape(-1, T, S)[:, 0, :], T, axis=0)
+        return rhs(times_, points, np.broadcast_to(np.asarray(theta_, dtype=float), (n, P)), constants_, ini)
+
+    dataset = types.SimpleNamespace(to_jax_arrays=lambda order: (full, times, None),
+                                    to_y0_matrix=lambda state_order: consts)
+    out["surr/full_data"] = full
+    for lik in ("Normal", "SoftLaplace"):
+        bm = types.SimpleNamespace(observables=np.arange(S), likelihood=getattr(lj.dist, lik),
+                                   priors=[("K_m", None), ("k_cat", None)], sim_func=rate_sim_func,
+                                   yerrs=np.broadcast_to(0.8, (M * T, S)), mode=Modes.SURROGATE, dt0=0.1,
+                                   solver="tsit5")
+        smodel = types.SimpleNamespace(get_state_order=lambda modeled=False: list(mm[0]),
+                                       get_constants_order=lambda: [],
+                                       get_observable_state_order=lambda: list(mm[0]))
+        sresults = types.SimpleNamespace(
+            bayesian_model=bm, model=smodel,
+            mcmc=types.SimpleNamespace(get_samples=lambda group_by_chain=True: posterior))
+        for integration in ("euler", "euler_onestep"):
+            ll, post_np, meta = ns["reconstruct_log_likelihood"](sresults, dataset, integration=integration,
+                                                                 max_draws=4)
+            out[f"surr/{lik.lower()}/{integration}/loglik"] = ll
+            out[f"surr/{lik.lower()}/{integration}/kept_idx"] = meta["kept_idx"]
+        ll, _, _ = ns["reconstruct_log_likelihood"](sresults, dataset, sigma_source="yerrs", yerrs=1.3,
+                                                    leave_out="curve", max_draws=4)
+        out[f"surr/{lik.lower()}/yerrs_curve/loglik"] = ll
+
     # ---- predictive: dense per-series grids, ensemble, aleatoric variance
     sub = ns["_subsample"](posterior, 4)
     t_dense, yhat = ns_p["_integrate_ensemble"](results, None, sub, n_steps=17)

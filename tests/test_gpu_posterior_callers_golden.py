@@ -72,3 +72,34 @@ def test_integrate_ensemble_equals_the_reference_function():
         assert np.abs(yhat - want).max() <= 1e-9 * np.abs(want).max()
     finally:
         ctx.enable_x64(False)
+
+
+@pytest.mark.parametrize("lik", ["normal", "softlaplace"])
+def test_surrogate_mode_reconstruction_equals_the_reference_functions(lik):
+    """loo.py:203-303: rates of every draw at the measured states (ctx_rates), Euler-integrated and
+    scored -- against the reference's `_surrogate_loglik` + `euler_integrate_rates` executed over
+    the oracle's rate function."""
+    import catalax_b200 as ctx
+    from catalax_b200.mcmc import loo
+
+    ctx.enable_x64(True)
+    try:
+        res = _results(lik)
+        res.bayesian_model.mode = "surrogate"
+        M = G["y0s"].shape[0]
+        arrays = (G["surr/full_data"], G["times"], None, np.zeros((M, 0)))
+        for integration in ("euler", "euler_onestep"):
+            ll, _, meta = loo.reconstruct_log_likelihood(res, None, integration=integration, max_draws=4,
+                                                         arrays=arrays)
+            want = G[f"surr/{lik}/{integration}/loglik"]
+            np.testing.assert_array_equal(meta["kept_idx"], G[f"surr/{lik}/{integration}/kept_idx"])
+            assert meta["mode"] == "SURROGATE" and ll.shape == want.shape
+            assert np.abs(ll - want).max() <= 1e-9 * np.abs(want).max()
+        ll, _, _ = loo.reconstruct_log_likelihood(res, None, sigma_source="yerrs", yerrs=1.3, leave_out="curve",
+                                                  max_draws=4, arrays=arrays)
+        want = G[f"surr/{lik}/yerrs_curve/loglik"]
+        assert np.abs(ll - want).max() <= 1e-9 * np.abs(want).max()
+        with pytest.raises(ValueError, match="yerrs"):
+            loo.reconstruct_log_likelihood(res, None, sigma_source="yerrs", arrays=arrays)
+    finally:
+        ctx.enable_x64(False)

@@ -41,3 +41,18 @@ def test_draw_helpers():
     np.testing.assert_array_equal(pr.sigma_y_draws({}, 3, 4, 3), np.ones((12, 3)))
     np.testing.assert_allclose(pr.ensemble_times(G["times"], 17), G["ens/times"], rtol=1e-15)
     np.testing.assert_allclose(pr.aleatoric_variance(sub4, G["ens/yhat"].shape), G["ens/var"], rtol=1e-15)
+
+
+@pytest.mark.parametrize("mode", ["euler", "euler_onestep"])
+def test_euler_integrate_rates(mode):
+    """predictive.py:54-106, single draw and with a leading draw axis."""
+    from catalax_b200.mcmc.predictive import euler_integrate_rates
+
+    kw = dict(integration=mode, data_safe=G["euler/data_safe"])
+    yhat, var_y = euler_integrate_rates(G["euler/rates"], G["euler/y0_obs"], G["euler/dt"], G["euler/rate_var"], **kw)
+    np.testing.assert_allclose(yhat, G[f"euler/{mode}/yhat"], rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(var_y, G[f"euler/{mode}/var_y"], rtol=1e-14, atol=1e-14)
+    stacked = np.stack([G["euler/rates"], 2.0 * G["euler/rates"]])
+    yhat2, _ = euler_integrate_rates(stacked, G["euler/y0_obs"], G["euler/dt"], G["euler/rate_var"], **kw)
+    np.testing.assert_allclose(yhat2[0], yhat, rtol=1e-14, atol=1e-14)
+    assert yhat2.shape == (2,) + yhat.shape
