@@ -182,3 +182,58 @@ def compute_ensemble(results, dataset, *, n_steps: int = 100, max_draws: Optiona
     else:
         var_ens = aleatoric_variance(posterior, yhat_ens.shape)
     return times, yhat_ens, var_ens
+
+
+#: HDI band identifier -> percentile of the predictive distribution (predictive.py:43-51)
+PERCENTILE = {"lower": 2.5, "upper": 97.5, "lower_50": 25.0, "upper_50": 75.0}
+
+
+def band_values(yhat_ens, var_ens, *, hdi: Optional[str] = None, include_noise: bool = True) -> np.ndarray:
+    """predictive.py:252-293 without the Dataset wrapping: the posterior-median trajectory
+    (``hdi=None``) or the percentile band ``[M, n_steps, n_obs]`` of the ensemble.  With
+    ``include_noise`` the aleatoric component is sampled per draw and pooled in -- the noise is
+    ``jax.random.normal(PRNGKey(0), shape)`` in the reference, reproduced here by the Threefry
+    restatement of ``dataset/jaxrandom.py`` so that the same ensemble gives the same band."""
+    yhat_ens = np.asarray(yhat_ens)
+    if hdi is None:
+        return np.nanmedian(yhat_ens, axis=0)
+    if hdi not in PERCENTILE:
+        raise KeyError(hdi)
+    pooled = yhat_ens
+    if include_noise:
+        from ..dataset.jaxrandom import normal
+
+        noise = normal(0, yhat_ens.size, np.float64 if default_dtype() == np.float64 else np.float32)
+        pooled = yhat_ens + np.sqrt(np.asarray(var_ens)) * noise.reshape(yhat_ens.shape)
+    return np.nanpercentile(pooled, PERCENTILE[hdi], axis=0)
+
+
+def ensemble_to_dataset(reference, results, times, values):
+    """predictive.py:177-209: wrap ``values [M, n_time, n_obs]`` on ``times [M, n_time]`` into a
+    Dataset whose measurement ids and initial conditions are copied from ``reference``."""
+    from ..dataset import Dataset, Measurement
+
+    obs = list(results.model.get_observable_state_order())
+    times, values = np.asarray(times), np.asarray(values)
+    out = Dataset(states=reference.states, id=reference.id, name=reference.name)
+    for i, ref in enumerate(reference.measurements):
+        out.add_measurement(Measurement(id=ref.id, initial_conditions=dict(ref.initial_conditions),
+                                        time=times[i],
+                                        data={s: values[i, :, k] for k, s in enumerate(obs)}))
+    return out
+
+
+def band_from_ensemble(results, reference, times, yhat_ens, var_ens, *, hdi: Optional[str] = None,
+                       include_noise: bool = True):
+    """predictive.py:252-293."""
+    return ensemble_to_dataset(reference, results, times,
+                               band_values(yhat_ens, var_ens, hdi=hdi, include_noise=include_noise))
+
+
+def posterior_predictive(results, dataset, *, hdi: Optional[str] = None, n_steps: int = 100,
+                         max_draws: Optional[int] = None, include_noise: bool = True, yerrs=None):
+    """predictive.py:296-331: ``compute_ensemble`` + ``band_from_ensemble`` in one call."""
+    times, yhat_ens, var_ens = compute_ensemble(results, dataset, n_steps=n_steps, max_draws=max_draws,
+                                                yerrs=yerrs)
+    return band_from_ensemble(results, dataset, times, yhat_ens, var_ens, hdi=hdi,
+                              include_noise=include_noise)

@@ -184,6 +184,25 @@ def main():
     out["ens/times"], out["ens/yhat"] = t_dense, yhat
     out["ens/var"] = ns_p["_aleatoric_variance"](results, sub, yhat.shape)
     out["ens/sub_K_m"] = sub["K_m"]
+    # ---- bands: predictive.py:252-293 (band_from_ensemble) with its _PERCENTILE table; the Dataset
+    # wrapping is replaced by a pass-through, jax.random.normal(PRNGKey(0), shape) by the Threefry
+    # restatement of catalax_b200/dataset/jaxrandom.py (pinned on jax's known answers separately)
+    from catalax_b200.dataset.jaxrandom import normal as threefry_normal
+
+    ptext = (REF / "predictive.py").read_text()
+    for node in ast.parse(ptext).body:
+        if isinstance(node, ast.AnnAssign) and getattr(node.target, "id", "") == "_PERCENTILE":
+            ns_p["_PERCENTILE"] = ast.literal_eval(node.value)
+    ns_p["_ensemble_to_dataset"] = lambda reference, results_, times_, values: np.asarray(values)
+    ns_p["jax"] = types.SimpleNamespace(
+        vmap=vmap, numpy=jnp,
+        random=types.SimpleNamespace(PRNGKey=lambda seed: seed,
+                                     normal=lambda key, shape: threefry_normal(key, int(np.prod(shape)), np.float32).reshape(shape)))
+    exec(compile(definitions(REF / "predictive.py", "band_from_ensemble"), str(REF / "predictive.py"), "exec"), ns_p)
+    for hdi in (None, "lower", "upper", "lower_50", "upper_50"):
+        for noise in (True, False):
+            out[f"band/{hdi}/{noise}"] = ns_p["band_from_ensemble"](results, None, t_dense, yhat, out["ens/var"],
+                                                                   hdi=hdi, include_noise=noise)
     np.savez_compressed(OUT, **out)
     for k in sorted(out):
         print(k, out[k].shape)

@@ -56,3 +56,16 @@ def test_euler_integrate_rates(mode):
     yhat2, _ = euler_integrate_rates(stacked, G["euler/y0_obs"], G["euler/dt"], G["euler/rate_var"], **kw)
     np.testing.assert_allclose(yhat2[0], yhat, rtol=1e-14, atol=1e-14)
     assert yhat2.shape == (2,) + yhat.shape
+
+
+@pytest.mark.parametrize("hdi", [None, "lower", "upper", "lower_50", "upper_50"])
+@pytest.mark.parametrize("noise", [True, False])
+def test_band_values(hdi, noise):
+    """predictive.py:252-293: posterior-median trajectory and percentile bands, with the aleatoric
+    noise of PRNGKey(0) pooled in."""
+    from catalax_b200.mcmc.predictive import band_values
+
+    got = band_values(G["ens/yhat"], G["ens/var"], hdi=hdi, include_noise=noise)
+    np.testing.assert_allclose(got, G[f"band/{hdi}/{noise}"], rtol=1e-6, atol=1e-6)
+    with pytest.raises(KeyError):
+        band_values(G["ens/yhat"], G["ens/var"], hdi="median")
