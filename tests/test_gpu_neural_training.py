@@ -264,3 +264,47 @@ def test_strategy_curriculum_trains_a_neural_ode_on_the_reference_dataset():
     # an untrained field leaves the substrate where it started (mae ~ the consumed amount)
     assert after < 0.35 * before, (before, after)
     assert len(net.history) == 400 and np.isfinite(net.history).all()
+
+
+def test_rateflow_and_universal_ode_train_with_their_penalty_presets():
+    """``Penalties.for_rateflow`` / ``for_universal_ode`` inside the curriculum: the stoichiometric
+    matrix, the gate matrix and the residual scale get the kernel's data gradient PLUS the host
+    autograd gradient of the penalties, and the penalised loss goes down."""
+    import catalax_b200 as ctx
+    from catalax_b200.neural import Modes, Penalties, RateFlowODE, Strategy, UniversalODE
+
+    ctx.enable_x64(False)
+    rng = np.random.default_rng(5)
+    M, T = 24, 12
+    times = np.tile(np.linspace(0, 5, T), (M, 1))
+    a0, b0 = rng.uniform(0.5, 2.0, M), rng.uniform(0.0, 0.5, M)
+    k = 0.6
+    a = a0[:, None] * np.exp(-k * times)
+    b = b0[:, None] + a0[:, None] * (1 - np.exp(-k * times))
+    data = np.stack([a, b], axis=-1)
+
+    model = ctx.Model(name="decay")
+    model.add_state(a="A", b="B")
+    model.add_ode("a", "-k1 * a")
+    model.add_ode("b", "k1 * a")
+    model.parameters["k1"].value = 0.3
+    ds = ctx.Dataset.from_jax_arrays(["a", "b"], data, times, data[:, 0, :])
+
+    rf = RateFlowODE.from_model(model, width_size=8, depth=1, reaction_size=2, seed=2)
+    s0 = rf.stoich_matrix.copy()
+    pen = Penalties.for_rateflow(alpha=1e-3, conservation_alpha=1e-3)
+    strat = Strategy(penalties=pen, batch_size=8).add_step(lr=5e-3, steps=40, length=1.0)
+    rf.train(ds, strat, weight_scale=1e-1, seed=1, print_every=1000)
+    assert np.isfinite(rf.history).all() and len(rf.history) == 40
+    assert np.abs(rf.stoich_matrix - s0).max() > 1e-4          # learn_stoich: the matrix moved
+    assert np.mean(rf.history[-5:]) < np.mean(rf.history[:5])
+
+    uo = UniversalODE.from_model(model, width_size=8, depth=1, seed=3)
+    g0, a_res0, p0 = uo.gate_matrix.copy(), uo.alpha_residual.copy(), uo.parameters.copy()
+    strat = Strategy(penalties=Penalties.for_universal_ode(), batch_size=8)
+    strat.add_step(lr=5e-3, steps=30, length=1.0, train=Modes.BOTH)
+    uo.train(ds, strat, weight_scale=1e-1, seed=1, print_every=1000)
+    assert np.isfinite(uo.history).all()
+    assert np.abs(uo.gate_matrix - g0).max() > 0 and np.abs(uo.alpha_residual - a_res0).max() > 0
+    assert np.abs(uo.parameters - p0).max() > 0                # Modes.BOTH also fits the mechanistic k1
+    assert np.mean(uo.history[-5:]) < np.mean(uo.history[:5])
