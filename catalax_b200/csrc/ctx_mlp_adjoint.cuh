@@ -159,10 +159,12 @@ __device__ __forceinline__ void adj_mlp_forward(const real* pack, real* acts, co
 // Vector-Jacobian product of one MLP evaluation: fbar[S] (replicated) = cotangent of dy.
 // Accumulates the weight / bias gradient into the warp's private pack `gp`; returns the cotangent
 // of the input state in ybar[S] (replicated).  dl: [2][ADJ_WMAX] scratch in shared memory.
+// g_invt accumulates the cotangent of 1 / max_time: the network's last input is t / max_time, and
+// the reference's trainer turns max_time into a trainable array leaf (trainer.py:85-89).
 __device__ __forceinline__ void adj_mlp_vjp(const real* pack, real* gp, const real* acts,
                                             real* dl, const real* fbar_in, real* ybar, const int lane,
-                                            const real t, const real* yinit) {
-  (void)t; (void)yinit;
+                                            const real t, const real* yinit, real& g_invt) {
+  (void)yinit;
 #if ADJ_KIND == 2
   // gate / alpha / mechanistic part (replicated in all lanes; lane 0 accumulates the gradients):
   //   f = mech + a * g * o,  g = sigmoid(10 G y):  obar = fbar a g  (-> through the MLP below),
@@ -259,6 +261,7 @@ __device__ __forceinline__ void adj_mlp_vjp(const real* pack, real* gp, const re
   }
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) ybar[i] = cur[i];
+  g_invt += cur[CTX_S] * t;        // input CTX_S is t * (1 / max_time)
 #if ADJ_KIND == 2
 #pragma unroll
   for (int i = 0; i < CTX_S; ++i) ybar[i] += yex[i];
@@ -478,6 +481,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
   real* acts = gp + ADJ_SPACK;                        // [7][ADJ_NACT][ADJ_WMAX]
   real* dl = acts + 7 * ADJ_NACT * ADJ_WMAX;          // [2][ADJ_WMAX]
   adj_stage_weights(a.theta, pack);
+  real g_invt = R(0.0);      // d loss / d (1 / max_time) over this warp's trajectories (replicated)
   for (int e = lane; e < ADJ_SPACK; e += 32) gp[e] = R(0.0);
   __syncthreads();
   const real inv_max_t = a.theta[ADJ_INVT];
@@ -532,7 +536,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
       }
       // stage 7: f_7 = MLP(t + dt, y1), y1 = y + dt sum_j A7j f_j
       real Yb[CTX_S];
-      adj_mlp_vjp(pack, gp, acts + 6 * (ADJ_NACT * ADJ_WMAX), dl, fb[6], Yb, lane, t + dt, yinit);
+      adj_mlp_vjp(pack, gp, acts + 6 * (ADJ_NACT * ADJ_WMAX), dl, fb[6], Yb, lane, t + dt, yinit, g_invt);
 #pragma unroll
       for (int i = 0; i < CTX_S; ++i) {
         const real tot = lam[i] + Yb[i];
@@ -544,7 +548,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
 #pragma unroll
       for (int k = 5; k >= 1; --k) {
         adj_mlp_vjp(pack, gp, acts + k * (ADJ_NACT * ADJ_WMAX), dl, fb[k], Yb, lane,
-                    t + adj_C[k] * dt, yinit);
+                    t + adj_C[k] * dt, yinit, g_invt);
 #pragma unroll
         for (int i = 0; i < CTX_S; ++i) {
           yb[i] += Yb[i];
@@ -557,7 +561,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
 #pragma unroll
         for (int i = 0; i < CTX_S; ++i) carry[i] = fb[0][i];
       } else {
-        adj_mlp_vjp(pack, gp, acts, dl, fb[0], Yb, lane, t, yinit);
+        adj_mlp_vjp(pack, gp, acts, dl, fb[0], Yb, lane, t, yinit, g_invt);
 #pragma unroll
         for (int i = 0; i < CTX_S; ++i) yb[i] += Yb[i];
       }
@@ -576,6 +580,7 @@ ctx_mlp_adj_backward(const ctx_adj_args a) {
   real* prow = a.partial + ((size_t)blockIdx.x * ADJ_WARPS + wid) * ADJ_P;
   for (int e = lane; e < ADJ_P; e += 32) prow[e] = R(0.0);
   __syncwarp();
+  if (lane == 0) prow[ADJ_INVT] = g_invt;
   for (int l = 0; l < ADJ_L; ++l) {
     const int ni = adj_nin[l], no = adj_nout[l];
     for (int e = lane; e < ni * no; e += 32) {

@@ -467,7 +467,9 @@ class NeuralBase:
             ip = lay.in_pad[l]
             gW.append(g[lay.w_off[l]: lay.w_off[l] + n_out * ip].reshape(n_out, ip)[:, :n_in].copy())
             gb.append(None if self.biases[l] is None else g[lay.b_off[l]: lay.b_off[l] + n_out].copy())
-        grads = {"weights": gW, "biases": gb}
+        grads = {"weights": gW, "biases": gb,
+                 # the kernel differentiates w.r.t. 1 / max_time (the value its parameter pack carries)
+                 "max_time": float(-g[lay.inv_max_time] / (self.max_time * self.max_time))}
         if self.kind == "rateflow":
             S, R_ = self.data_size, self.spec.out_size
             grads["stoich"] = g[lay.stoich: lay.stoich + S * R_].reshape(S, R_).copy()
@@ -481,8 +483,12 @@ class NeuralBase:
             grads["y0"] = gy0
         return float(value.item()), grads
 
-    def apply_updates(self, dW, db, dstoich=None, dgate=None, dalpha=None, dparameters=None):
+    def apply_updates(self, dW, db, dstoich=None, dgate=None, dalpha=None, dparameters=None,
+                      dmax_time=None):
         """weights += dW, biases += db (and the class-specific leaves); the packs are rebuilt."""
+        if dmax_time is not None:
+            self.max_time = float(self.max_time + dmax_time)
+            self._compiled.pop("tc", None)
         if dstoich is not None:
             self.stoich_matrix = self.stoich_matrix + np.asarray(dstoich, dtype=np.float64)
         if dgate is not None:

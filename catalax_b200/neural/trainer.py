@@ -124,7 +124,9 @@ def _trainable(model, mode: Modes):
     """Which gradient groups a step updates (strategy.py:31-116)."""
     groups = set()
     if mode in (Modes.MLP, Modes.BOTH):
-        groups |= {"weights", "biases"}
+        # everything inside `func` (strategy.py:62): the layers and -- an array leaf since
+        # trainer.py:85-89 -- max_time
+        groups |= {"weights", "biases", "max_time"}
     if model.kind == "rateflow" and getattr(model, "learn_stoich", False):
         groups.add("stoich")
     if model.kind == "universalode":
@@ -151,8 +153,8 @@ def train_neural_ode(model, dataset, strategy: Strategy, optimizer: Callable = A
                     for l, b in enumerate(model.biases)]
     model.max_time = float(times.max())
     # trainer.py:85-89 replaces max_time by the ARRAY times.max(): from here on it is one of the
-    # leaves get_weights_and_biases() returns (so l1 / l2 regularisation count it).  The reference
-    # then also lets the optimiser move it (it sits inside `func`, strategy.py:62); here it stays fixed.
+    # leaves get_weights_and_biases() returns (so l1 / l2 regularisation count it) and, sitting
+    # inside `func` (strategy.py:62), one of the parameters the optimiser moves.
     model._max_time_is_leaf = True
     model._compiled.clear()
     if solver is not None:
@@ -181,6 +183,8 @@ def train_neural_ode(model, dataset, strategy: Strategy, optimizer: Callable = A
                     flat[f"W{l}"] = gw + pg["weights"][k]; k += 1
                     if gb is not None:
                         flat[f"b{l}"] = gb + pg["weights"][k]; k += 1
+            if "max_time" in groups:
+                flat["max_time"] = np.asarray(g["max_time"] + float(pg["max_time"][0]))
             if "stoich" in groups:
                 flat["stoich"] = g["stoich"] + pg["stoich"][0]
             if "gate_matrix" in groups:
@@ -195,7 +199,8 @@ def train_neural_ode(model, dataset, strategy: Strategy, optimizer: Callable = A
             model.apply_updates([upd.get(f"W{l}", zeros_w[l]) for l in range(L)],
                                 [None if model.biases[l] is None else upd.get(f"b{l}", zeros_b[l]) for l in range(L)],
                                 dstoich=upd.get("stoich"), dgate=upd.get("gate"), dalpha=upd.get("alpha"),
-                                dparameters=upd.get("parameters"))
+                                dparameters=upd.get("parameters"),
+                                dmax_time=None if "max_time" not in upd else float(upd["max_time"]))
             history.append(val + pval)
             if (step % print_every) == 0 or step == st.steps - 1:
                 pred = model.predict_arrays(_t, y0s)

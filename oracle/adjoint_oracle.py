@@ -124,7 +124,8 @@ def solve_one(f, ts, y0, rtol, atol, dt0, max_steps=4096, t0=None, solver="tsit5
 
 
 def neuralode_value_and_grad(weights, biases, activation, final_activation, max_time, ts, y0,
-                             loss_fn, rtol=1e-3, atol=1e-6, dt0=None, stoich=None, solver="tsit5"):
+                             loss_fn, rtol=1e-3, atol=1e-6, dt0=None, stoich=None, solver="tsit5",
+                             want_max_time=False):
     """weights / biases: lists of numpy arrays (eqx convention W [out,in]); ts [B,T]; y0 [B,S].
     loss_fn(ys [B,T,S] torch float64) -> scalar.  Returns (loss, ys, grads_W, grads_b, grad_y0,
     n_accepted [B], n_rejected [B])."""
@@ -134,7 +135,10 @@ def neuralode_value_and_grad(weights, biases, activation, final_activation, max_
     y0t = torch.tensor(np.asarray(y0, dtype=np.float64), requires_grad=True)
     tst = torch.tensor(np.asarray(ts, dtype=np.float64))
     St = None if stoich is None else torch.tensor(np.asarray(stoich, dtype=np.float64), requires_grad=True)
-    f = mlp_field(Ws, bs, activation, final_activation, float(max_time), St)
+    # (the reference's trainer makes max_time an array leaf of `func`, trainer.py:85-89: with
+    #  want_max_time its gradient is appended to the returned tuple)
+    mt = torch.tensor(float(max_time), dtype=torch.float64, requires_grad=True)
+    f = mlp_field(Ws, bs, activation, final_activation, mt if want_max_time else float(max_time), St)
     ys, na, nr = [], [], []
     for b in range(y0t.shape[0]):
         step0 = float(tst[b, 1] - tst[b, 0]) if dt0 is None else dt0
@@ -143,16 +147,21 @@ def neuralode_value_and_grad(weights, biases, activation, final_activation, max_
     ys = torch.stack(ys)
     loss = loss_fn(ys)
     nb = sum(b is not None for b in bs)
-    params = Ws + [b for b in bs if b is not None] + [y0t] + ([St] if St is not None else [])
+    params = Ws + [b for b in bs if b is not None] + [y0t] + ([St] if St is not None else []) \
+        + ([mt] if want_max_time else [])
     grads = torch.autograd.grad(loss, params, allow_unused=True)
+    extra = ()
+    if want_max_time:
+        extra = (0.0 if grads[-1] is None else float(grads[-1]),)
+        grads = grads[:-1]
     gW = [g.numpy() for g in grads[:len(Ws)]]
     gb_iter = iter(grads[len(Ws):len(Ws) + nb])
     gb = [None if b is None else next(gb_iter).numpy() for b in bs]
     gy0 = grads[len(Ws) + nb].numpy()
     if St is not None:
         return (float(loss.detach()), ys.detach().numpy(), gW, gb, gy0, np.array(na), np.array(nr),
-                grads[-1].numpy())
-    return float(loss.detach()), ys.detach().numpy(), gW, gb, gy0, np.array(na), np.array(nr)
+                grads[-1].numpy()) + extra
+    return (float(loss.detach()), ys.detach().numpy(), gW, gb, gy0, np.array(na), np.array(nr)) + extra
 
 
 def uode_value_and_grad(weights, biases, activation, final_activation, max_time, ts, y0, loss_fn,

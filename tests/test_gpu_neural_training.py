@@ -257,7 +257,9 @@ def test_strategy_curriculum_trains_a_neural_ode_on_the_reference_dataset():
     strategy.add_step(lr=1e-2, steps=250, length=1.0, train=Modes.MLP)
     before = float(np.mean(np.abs(net.predict_arrays(ds.to_jax_arrays(["s1"])[1], g["data"][sub, :1]) - g["data"][sub, :, None])))
     trained = net.train(ds, strategy, weight_scale=1e-2, seed=3, temporal_dropout_p=0.1, print_every=100)
-    assert trained is net and abs(net.max_time - 100.0) < 1e-3
+    # max_time starts at times.max() = 100 and is then TRAINED like the reference's array leaf
+    # (trainer.py:85-89, strategy.py:62)
+    assert trained is net and 50.0 < net.max_time < 200.0 and abs(net.max_time - 100.0) > 1e-6
     pred = net.predict_arrays(np.tile(g["times"], (40, 1)), g["data"][sub, :1])
     after = float(np.mean(np.abs(pred - g["data"][sub, :, None])))
     print(f"mae before {before:.2f} -> after {after:.2f}")
@@ -308,3 +310,54 @@ def test_rateflow_and_universal_ode_train_with_their_penalty_presets():
     assert np.abs(uo.gate_matrix - g0).max() > 0 and np.abs(uo.alpha_residual - a_res0).max() > 0
     assert np.abs(uo.parameters - p0).max() > 0                # Modes.BOTH also fits the mechanistic k1
     assert np.mean(uo.history[-5:]) < np.mean(uo.history[:5])
+
+
+@pytest.mark.parametrize("kind", ["neuralode", "rateflow"])
+def test_max_time_gradient_matches_autograd(kind):
+    """The reference's trainer replaces ``func.max_time`` by the array ``times.max()``
+    (trainer.py:85-89), which makes it a trainable leaf of the MLP (strategy.py:62).  Its gradient
+    comes out of the backward kernel (cotangent of the network's time input) and equals autograd
+    through the discrete scheme; the curriculum then moves it like every other leaf."""
+    import catalax_b200 as ctx
+    from catalax_b200.neural import RateFlowODE
+    from oracle import adjoint_oracle as ao
+
+    ctx.enable_x64(True)
+    try:
+        net, ts, y0, data = _problem(3, 16, 2, "tanh", 6, 9, seed=11)
+        stoich = None
+        if kind == "rateflow":
+            net = RateFlowODE(3, 4, 16, 2, ["a", "b", "c"], activation="celu", max_time=float(ts.max()), key=4)
+            net.stoich_matrix = net.stoich_matrix * 0.05      # mild dynamics (see the RateFlow test above)
+            stoich = net.stoich_matrix
+        val, g = net.value_and_grad(ts, y0, data, rtol=1e-7, atol=1e-9)
+        d = torch.tensor(data)
+        loss_fn = lambda ys: (0.5 * (ys - d) ** 2).mean()
+        ref = ao.neuralode_value_and_grad(net.weights, net.biases, net.spec.activation,
+                                          net.spec.final_activation, net.max_time, ts, y0, loss_fn,
+                                          rtol=1e-7, atol=1e-9, stoich=stoich, want_max_time=True)
+        # (relu kinks: an accept / reject decision within rounding of the threshold may differ
+        #  between the two implementations and moves that trajectory by O(rtol))
+        rna, rnr = ref[5], ref[6]
+        same_path = np.array_equal(net.last["n_accepted"].cpu().numpy(), rna) and \
+            np.array_equal(net.last["n_rejected"].cpu().numpy(), rnr)
+        tol = 1e-9 if same_path else 2e-6
+        assert abs(val - ref[0]) <= 10 * tol * abs(ref[0])
+        want = ref[-1]
+        assert want != 0.0 and abs(g["max_time"] - want) <= 100 * tol * abs(want), (g["max_time"], want)
+        # ... and a finite difference of the loss in max_time
+        h = 1e-5 * net.max_time
+        keep = net.max_time
+        vals = []
+        for mt in (keep + h, keep - h):
+            net.max_time = mt
+            net._compiled.clear()
+            vals.append(net.value_and_grad(ts, y0, data, rtol=1e-7, atol=1e-9)[0])
+        net.max_time = keep
+        net._compiled.clear()
+        fd = (vals[0] - vals[1]) / (2 * h)
+        # (the finite difference also sees the step sequence move with max_time; the gradient is
+        #  the derivative on the frozen sequence: agreement to the solver's own accuracy)
+        assert abs(fd - want) <= (1e-4 if kind == "neuralode" else 1e-2) * abs(want), (fd, want)
+    finally:
+        ctx.enable_x64(False)
