@@ -39,6 +39,26 @@ class RBFLayer:
         self.gamma = float(gamma)
 
 
+def masked_loss(pred, target, loss="l2", mask=None):
+    """The training loss of ``grad_loss`` (trainer.py:270-311) without the penalties, on torch
+    tensors: per-point loss ``[B,T,S]`` weighted by the temporal-dropout mask ``[T]`` and normalised
+    by the KEPT points, ``sum(mask * per_point) / (sum(mask) * B * S)``.  ``loss``: "l2"
+    (``optax.l2_loss`` = 0.5 (p - y)^2), "l1", or a callable ``(pred, target) -> per-point loss``."""
+    import torch
+
+    if callable(loss):
+        per_point = loss(pred, target)
+    elif loss == "l2":
+        per_point = 0.5 * (pred - target) ** 2
+    elif loss == "l1":
+        per_point = (pred - target).abs()
+    else:
+        raise ValueError(f"unknown loss {loss!r}")
+    B, T, S = pred.shape
+    m = torch.ones(T, dtype=pred.dtype, device=pred.device) if mask is None else mask.to(pred.dtype)
+    return (per_point * m[None, :, None]).sum() / (m.sum() * B * S)
+
+
 class NeuralBase:
     kind = "neuralode"
     default_activation = "tanh"      # neuralbase.py:79 (jax.nn.tanh)
@@ -446,17 +466,7 @@ class NeuralBase:
             raise RuntimeError(f"{bad} trajectories failed in the training solve "
                                f"(status {int(ctx['status'].max().item())}; 3 = more than cap={cap} steps)")
         pred = ctx["ys"].detach().clone().requires_grad_(True)
-        if callable(loss):
-            per_point = loss(pred, data_t.to(pred.dtype))
-        elif loss == "l2":
-            per_point = 0.5 * (pred - data_t.to(pred.dtype)) ** 2
-        elif loss == "l1":
-            per_point = (pred - data_t.to(pred.dtype)).abs()
-        else:
-            raise ValueError(f"unknown loss {loss!r}")
-        B, T, S = pred.shape
-        m = torch.ones(T, dtype=pred.dtype, device=dev) if mask is None else tt(mask).to(pred.dtype)
-        value = (per_point * m[None, :, None]).sum() / (m.sum() * B * S)
+        value = masked_loss(pred, data_t.to(pred.dtype), loss, None if mask is None else tt(mask))
         (gys,) = torch.autograd.grad(value, pred)
         g = model.adjoint_backward(ctx, gys, want_y0=want_y0)
         g, gy0 = g if want_y0 else (g, None)

@@ -147,6 +147,38 @@ def main():
         out[f"no/preset_{name}/value"] = np.array(float(pen(no)))
         out[f"no/preset_{name}/grad_w0"] = fd_grad(
             lambda m: pen(m), types.SimpleNamespace(w=weights[0], get_weights_and_biases=lambda: weights), "w")
+    # ---- the training loss: trainer.py:257-311 (_prepare_step_and_loss -> grad_loss) executed
+    # unmodified; eqx.filter_value_and_grad / filter_jit -> pass-through decorators, eqx.combine ->
+    # the differentiable part, jax.vmap(model, in_axes=(0, 0)) -> a loop, optax.l2_loss -> its
+    # documented formula 0.5 (p - y)^2, the penalties -> the reference's own for_neural_ode preset
+    import ast
+    ttext = Path("/root/reference/catalax/neural/trainer.py").read_text()
+    tlines = ttext.splitlines()
+    fn = next(n for n in ast.parse(ttext).body if isinstance(n, ast.FunctionDef) and n.name == "_prepare_step_and_loss")
+    eqx = types.SimpleNamespace(filter_value_and_grad=lambda f: f, filter_jit=lambda f: f,
+                                combine=lambda diff, static: diff, filter=None, is_inexact_array=None,
+                                apply_updates=None)
+    jax_t = types.SimpleNamespace(vmap=lambda f, in_axes=None: (lambda a, b: np.stack([f(x, y) for x, y in zip(a, b)])),
+                                  Array=np.ndarray)
+    ns_t = {"eqx": eqx, "jax": jax_t, "Tuple": tuple, "Callable": object, "Penalties": ref.Penalties}
+    exec(compile("from __future__ import annotations\n" + "\n".join(tlines[fn.lineno - 1: fn.end_lineno]),
+                 "trainer.py", "exec"), ns_t)
+    for loss_name, loss_fun in (("l2", lambda p_, y_: 0.5 * (p_ - y_) ** 2), ("l1", lambda p_, y_: np.abs(p_ - y_))):
+        _, grad_loss = ns_t["_prepare_step_and_loss"](loss_fun)
+        Bq, Tq, Sq = 5, 7, 3
+        pred = rng.normal(size=(Bq, Tq, Sq)); target = rng.normal(size=(Bq, Tq, Sq))
+        mask = np.concatenate([np.ones(1), (rng.uniform(size=Tq - 1) < 0.6).astype(float)])
+        model_t = types.SimpleNamespace(get_weights_and_biases=lambda: weights)
+        call = lambda t_, y0_: pred[int(y0_[0])]
+        ti, y0i = np.zeros((Bq, Tq)), np.arange(Bq, dtype=float)[:, None]
+        class Diff:
+            def __call__(self, t_, y0_): return call(t_, y0_)
+            def get_weights_and_biases(self): return weights
+        pen = ref.Penalties.for_neural_ode(l2_alpha=1e-3)
+        total = grad_loss(Diff(), None, ti, target, y0i, pen, mask)
+        out[f"loss/{loss_name}/pred"], out[f"loss/{loss_name}/target"], out[f"loss/{loss_name}/mask"] = pred, target, mask
+        out[f"loss/{loss_name}/total"] = np.array(float(total))
+        out[f"loss/{loss_name}/penalty"] = np.array(float(pen(Diff())))
     np.savez_compressed(OUT, **out)
     for k in sorted(out):
         if k.endswith("value") or k.endswith("names"):

@@ -113,3 +113,21 @@ def test_custom_penalty_and_all_array_leaves():
     val, grads = first.value_and_grads(net)
     assert val == pytest.approx(2.0 * net.weights[0].sum())
     assert np.allclose(grads["weights"][0], 2.0) and all(np.all(g == 0) for g in grads["weights"][1:])
+
+
+@pytest.mark.parametrize("loss", ["l2", "l1"])
+def test_masked_training_loss_matches_the_reference_grad_loss(loss):
+    """trainer.py:270-311 (`grad_loss`, executed unmodified by the golden maker): per-point loss,
+    temporal-dropout mask, normalisation by the kept points, plus the penalties."""
+    from catalax_b200.neural.neuralbase import masked_loss
+    from catalax_b200.neural.penalties import Penalties
+
+    pred, target, mask = (torch.as_tensor(G[f"loss/{loss}/{k}"]) for k in ("pred", "target", "mask"))
+    data_term = float(masked_loss(pred, target, loss, mask))
+    node = types.SimpleNamespace(kind="neuralode", **_mlp())
+    penalty = Penalties.for_neural_ode(l2_alpha=1e-3)(node)
+    np.testing.assert_allclose(penalty, G[f"loss/{loss}/penalty"], rtol=1e-12)
+    np.testing.assert_allclose(data_term + penalty, G[f"loss/{loss}/total"], rtol=1e-12)
+    # a callable loss and no mask
+    custom = float(masked_loss(pred, target, lambda p, y: (p - y) ** 2))
+    np.testing.assert_allclose(custom, float(((pred - target) ** 2).mean()), rtol=1e-12)
