@@ -125,10 +125,43 @@ def _mod(name, **attrs):
     return m
 
 
+class _At:
+    """``x.at[idx].add(v)`` / ``.set(v)`` of jax arrays: functional scatter updates."""
+
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __getitem__(self, idx):
+        arr = self.arr
+
+        class _Upd:
+            def add(self, v):
+                out = arr.copy()
+                np.add.at(out, idx, v)
+                return out
+
+            def set(self, v):
+                out = arr.copy()
+                out[idx] = v
+                return out
+
+        return _Upd()
+
+
+class JArray(np.ndarray):
+    """numpy array with jax's ``.at`` property (what ``jnp.zeros`` hands out below)."""
+
+    @property
+    def at(self):
+        return _At(self)
+
+
 class _NumpyStub(_Stub):
-    """jax.numpy -> numpy: every function numpy has, by name."""
+    """jax.numpy -> numpy: every function numpy has, by name (``zeros`` returns a JArray)."""
 
     def __getattr__(self, name):
+        if name == "zeros":
+            return lambda *a, **k: np.zeros(*a, **k).view(JArray)
         if hasattr(np, name):
             return getattr(np, name)
         return super().__getattr__(name)
@@ -137,8 +170,38 @@ class _NumpyStub(_Stub):
 jnp = _NumpyStub("jax.numpy")
 jnp.__path__ = []
 sys.modules["jax.numpy"] = jnp
-_mod("jax", numpy=jnp, Array=np.ndarray, config=MagicMock())
-_mod("equinox", Module=Module, field=lambda *a, **k: None)
+def tree_map(f, tree, *rest, is_leaf=None):
+    """jax.tree_util.tree_map for the trees the reference builds (single leaves, lists, dicts)."""
+    if is_leaf is not None and is_leaf(tree):
+        return f(tree)
+    if isinstance(tree, (list, tuple)):
+        return type(tree)(tree_map(f, x, is_leaf=is_leaf) for x in tree)
+    if isinstance(tree, dict):
+        return {k: tree_map(f, v, is_leaf=is_leaf) for k, v in tree.items()}
+    return f(tree)
+
+
+import scipy.special as _sps  # noqa: E402
+
+_mod("jax.tree_util", tree_map=tree_map)
+_mod("jax.scipy", special=_sps)
+_mod("jax.scipy.special", **{k: getattr(_sps, k) for k in ("erf", "erfc", "gammaln") if hasattr(_sps, k)})
+_mod("jax", numpy=jnp, Array=np.ndarray, config=MagicMock(), tree_util=sys.modules["jax.tree_util"],
+     scipy=sys.modules["jax.scipy"])
+def tree_at(where, pytree, replace):
+    """equinox.tree_at for the two shapes the reference uses: ``where`` selects ONE attribute of
+    the module (``lambda tree: tree.modules``); a shallow copy with that attribute replaced."""
+    import copy as _copy
+
+    target = where(pytree)
+    names = [k for k, v in vars(pytree).items() if v is target]
+    assert len(names) == 1, names
+    out = _copy.copy(pytree)
+    object.__setattr__(out, names[0], replace)
+    return out
+
+
+_mod("equinox", Module=Module, field=lambda *a, **k: None, tree_at=tree_at)
 _mod("dotted_dict", DottedDict=DottedDict)
 _mod("bigtree")
 _mod("bigtree.node")
