@@ -271,6 +271,26 @@ def dataset_records():
         rec["padded_BAC"] = {"data": _tolist(data), "time": _tolist(time), "y0": _tolist(y0)}
         _, _, y0d = padded.to_jax_arrays(["A", "B"])
         rec["inits_dicts"] = [dict(d) for d in y0d]
+    # augment (dataset.py:1201-1250, measurement.py:759-817) with jax.random -> the Threefry
+    # restatement of catalax_b200/dataset/jaxrandom.py (pinned on jax's known answers separately)
+    sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
+    from catalax_b200.dataset.jaxrandom import normal as threefry_normal
+
+    jrandom = sys.modules.get("jax.random") or _mod("jax.random")
+    jrandom.PRNGKey = lambda seed: int(seed)
+    jrandom.normal = lambda key, shape=(), dtype=np.float32: threefry_normal(key, int(np.prod(shape)), dtype).reshape(shape)
+    sys.modules["jax"].random = jrandom
+    f32 = Dataset(id="d", name="n", states=["A", "B"])
+    for mid, scale in (("a1", 1.0), ("a2", 3.0)):
+        f32.add_measurement(Measurement(id=mid, initial_conditions={"A": 1.0, "B": 2.0}, time=np.linspace(0, 1, 7),
+                                        data={"A": (scale * np.linspace(1, 2, 7)).astype(np.float32),
+                                              "B": (scale * np.linspace(3, 5, 7)).astype(np.float32)}))
+    for tag, kw in (("mult_append", dict(n_augmentations=2, sigma=0.05, seed=0, append=True, multiplicative=True)),
+                    ("add_only", dict(n_augmentations=1, sigma=0.3, seed=7, append=False, multiplicative=False))):
+        aug = f32.augment(**kw)
+        rec[f"augment_{tag}"] = {"n": len(aug.measurements),
+                                 "data": [[[float(v) for v in np.asarray(m.data[s], dtype=np.float64)] for s in ("A", "B")]
+                                          for m in aug.measurements]}
     rec["y0_matrix_ABC"] = _tolist(ds.to_y0_matrix(state_order=["A", "B", "C"]))
     rec["y0_matrix_CA"] = _tolist(ds.to_y0_matrix(state_order=["C", "A"]))
     return rec

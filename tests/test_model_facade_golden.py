@@ -130,3 +130,26 @@ def test_dataset_arrays_match_the_reference_classes():
         assert [dict(d) for d in y0d] == want["inits_dicts"]
     np.testing.assert_allclose(np.asarray(ds.to_y0_matrix(state_order=["A", "B", "C"])), _nan(want["y0_matrix_ABC"]), rtol=1e-6)
     np.testing.assert_allclose(np.asarray(ds.to_y0_matrix(state_order=["C", "A"])), _nan(want["y0_matrix_CA"]), rtol=1e-6)
+
+
+def test_augment_matches_the_reference_classes():
+    """dataset.py:1201-1250 / measurement.py:759-817: augmentation i uses seed + i for every
+    measurement, multiplicative noise is ``x * (1 + sigma * n)``, ``append`` keeps the originals in
+    front -- with the Threefry normal of PRNGKey(seed) (f32)."""
+    import numpy as np
+
+    import catalax_b200 as ctx
+
+    ctx.enable_x64(False)
+    ds = ctx.Dataset(id="d", name="n", states=["A", "B"])
+    for mid, scale in (("a1", 1.0), ("a2", 3.0)):
+        ds.add_measurement(ctx.Measurement(id=mid, initial_conditions={"A": 1.0, "B": 2.0}, time=np.linspace(0, 1, 7),
+                                           data={"A": (scale * np.linspace(1, 2, 7)).astype(np.float32),
+                                                 "B": (scale * np.linspace(3, 5, 7)).astype(np.float32)}))
+    for tag, kw in (("mult_append", dict(n_augmentations=2, sigma=0.05, seed=0, append=True, multiplicative=True)),
+                    ("add_only", dict(n_augmentations=1, sigma=0.3, seed=7, append=False, multiplicative=False))):
+        want = G["__dataset__"][f"augment_{tag}"]
+        aug = ds.augment(**kw)
+        assert len(aug.measurements) == want["n"]
+        got = np.array([[np.asarray(m.data[s], dtype=np.float64) for s in ("A", "B")] for m in aug.measurements])
+        np.testing.assert_allclose(got, np.array(want["data"]), rtol=2e-7, atol=0)
