@@ -165,6 +165,26 @@ def main():
     t_arr, ys = run("parameters", config=SimulationConfig(t1=30, nsteps=5), parameters=np.array([1.0, 60.0, 0.9]),
                     return_array=True)
     out["parameters/ys"] = np.asarray(ys)
+    # 4. Model.predict (model.py:569-603): config from the data set's own time spans
+    #    (Dataset.to_config: per-measurement t0 / t1 arrays -> a 2-D linspace grid), and use_times
+    Measurement = sys.modules["catalax.dataset.measurement"].Measurement
+    pds = Dataset.from_model(m)
+    for i, (s0, e0, inh, t) in enumerate(((100.0, 10.0, 0.0, np.linspace(0, 40, 6)),
+                                          (200.0, 5.0, 1.5, np.linspace(5, 90, 6)))):
+        pds.add_measurement(Measurement(id=f"p{i}", initial_conditions={"S": s0, "E": e0, "P": 0.0, "I": inh}, time=t,
+                                        data={"S": np.zeros(6), "P": np.zeros(6), "E": np.zeros(6)}))
+    out["predict/times_in"] = np.stack([np.asarray(meas.time) for meas in pds.measurements])
+    for tag, kw in (("predict", dict(n_steps=7)), ("predict_use_times", dict(use_times=True))):
+        CALLS.clear()
+        res = m.predict(pds, **kw)
+        out[f"{tag}/n_calls"] = np.array(len(CALLS))
+        for k in ("y0", "parameters", "constants", "inits", "ts"):
+            out[f"{tag}/{k}"] = np.stack([c[k] for c in CALLS])
+        out[f"{tag}/scalars"] = np.array(json.dumps([{k: c[k] for k in ("solver", "t0", "t1", "dt0", "rtol", "atol",
+                                                                       "max_steps", "throw")} for c in CALLS]))
+        out[f"{tag}/data"] = np.stack([np.stack([meas.data[s] for s in m.get_state_order()], axis=-1)
+                                       for meas in res.measurements])
+        out[f"{tag}/time"] = np.stack([np.asarray(meas.time) for meas in res.measurements])
     out["model"] = np.array(json.dumps({"state_order": m.get_state_order(), "parameter_order": m.get_parameter_order(),
                                         "constants_order": m.get_constants_order()}))
     np.savez_compressed(OUT, **out)

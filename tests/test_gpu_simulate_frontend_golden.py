@@ -104,5 +104,21 @@ def test_simulate_matches_the_reference_front_end(recorded):
                            return_array=True)
         _check_operands(recorded[-1], "parameters")
         np.testing.assert_allclose(np.asarray(ys), G["parameters/ys"], rtol=1e-9, atol=1e-11)
+
+        # 4. Model.predict: the grid comes from the data set's own time spans (per-measurement t0 / t1
+        #    -> a 2-D linspace), or the measured times themselves (use_times); the solve still starts
+        #    at t = 0 (simulation.py:262) even where a series' first time is 5
+        pds = ctx.Dataset.from_model(m)
+        for i, (s0, e0, inh, t) in enumerate(((100.0, 10.0, 0.0, np.linspace(0, 40, 6)),
+                                              (200.0, 5.0, 1.5, np.linspace(5, 90, 6)))):
+            pds.add_measurement(ctx.Measurement(id=f"p{i}", initial_conditions={"S": s0, "E": e0, "P": 0.0, "I": inh},
+                                                time=t, data={"S": np.zeros(6), "P": np.zeros(6), "E": np.zeros(6)}))
+        for tag, kw in (("predict", dict(n_steps=7)), ("predict_use_times", dict(use_times=True))):
+            res = m.predict(pds, **kw)
+            assert recorded[-1]["kw"]["in_axes"] == (0, None, 0, 0)
+            _check_operands(recorded[-1], tag)
+            data = np.stack([np.stack([meas.data[s] for s in m.get_state_order()], axis=-1) for meas in res.measurements])
+            np.testing.assert_allclose(data, G[f"{tag}/data"], rtol=1e-9, atol=1e-11)
+            np.testing.assert_allclose(np.stack([meas.time for meas in res.measurements]), G[f"{tag}/time"], rtol=1e-14)
     finally:
         ctx.enable_x64(False)
