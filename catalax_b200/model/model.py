@@ -348,6 +348,71 @@ class Model:
                                parameters=self.get_parameter_order(),
                                constants=self.get_constants_order())
 
+    # ------------------------------------------------------------------ rate function (K4)
+    def _setup_rate_function(self, in_axes=None):
+        """model.py:1027-1051: the vector field as a callable ``f(t, y, (parameters, constants[,
+        inits]))`` -- the reference returns its stack (or ``jit(vmap(stack))``); here one ``ctx_rates``
+        launch evaluates the generated field, natively batched: ``t`` scalar | [N], ``y`` [S] | [N,S],
+        ``parameters`` [P] | [N,P], ``constants`` [C] | [N,C], ``inits`` [S] | [N,S] -> [S] | [N,S].
+        ``in_axes`` is accepted for signature compatibility (the callable broadcasts by shape)."""
+        assert in_axes is None or len(in_axes) == 4, \
+            "Got invalid dimension for 'in_axes' - Needs to have four ints/Nones"
+        from .. import engine
+        from ..tools import codegen as cg
+
+        dtype = default_dtype()
+        field = cg.generate_field(self._replace_assignments().sim_input.field_spec())
+        compiled = engine.CompiledModel(field, np.dtype(dtype).name)
+
+        def rate_fun(t, y, args):
+            import torch
+
+            parameters, constants, *rest = args
+            inits = rest[0] if rest else None
+            on_device = isinstance(y, torch.Tensor) and y.is_cuda
+            dev = y.device if on_device else torch.device("cuda", torch.cuda.current_device())
+            tt = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=dtype))).to(dev)
+            y_t = tt(y)
+            single = y_t.dim() == 1
+            if single:
+                y_t = y_t[None]
+            if field.C == 0:
+                c_t = torch.empty((0,), dtype=y_t.dtype, device=dev)
+            else:
+                c_t = tt(constants).reshape(-1, field.C) if np.ndim(constants) > 1 else tt(constants).reshape(field.C)
+            out = compiled.rates(tt(t), y_t, tt(parameters), c_t, y0=None if inits is None else tt(inits))
+            out = out[0] if single else out
+            return out if on_device else out.cpu().numpy()
+
+        return rate_fun
+
+    def rates(self, t, y, constants=None):
+        """model.py:605-629: the model's rates at N points, ``t`` [N], ``y`` [N,S], ``constants``
+        [N,C] | None -> [N,S], with the model's current parameter values.  (The reference's body
+        hands these arguments to its SOLVE function; this does what its docstring says.)"""
+        y = np.asarray(y)
+        y = y.reshape(-1, 1) if y.ndim == 1 else y
+        t = np.asarray(t)
+        assert t.shape[0] == y.shape[0], "Time and state must have the same number of rows"
+        C = len(self.get_constants_order())
+        if constants is None:
+            constants = np.zeros((y.shape[0], 0))
+        constants = np.asarray(constants)
+        constants = constants.reshape(-1, 1) if constants.ndim == 1 else constants
+        assert constants.shape[0] == y.shape[0] or C == 0, \
+            "Constants must have the same number of rows as time and state"
+        f = self._setup_rate_function()
+        return f(t, y, (self._get_parameters(), constants.reshape(y.shape[0], C)))
+
+    def predict_rates(self, dataset: Dataset):
+        """model.py:631-645: rates at every measured point of a Dataset, [M*T, S]; the constants of
+        a measurement apply to all of its time points."""
+        data, times, _ = dataset.to_jax_arrays(self.get_state_order())
+        data, times = np.asarray(data), np.asarray(times)
+        constants = np.asarray(dataset.to_y0_matrix(state_order=self.get_constants_order()))
+        M, T, S = data.shape
+        return self.rates(times.ravel(), data.reshape(M * T, S), np.repeat(constants.reshape(M, -1), T, axis=0))
+
     def simulate(self, dataset: Dataset, config: SimulationConfig, saveat=None, parameters=None,
                  in_axes: InAxes = InAxes.Y0, return_array: bool = False, use_hdi=None,
                  hdi_prob: float = 0.95):
