@@ -19,7 +19,7 @@ on ``results.bayesian_model.log_density``.
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 

@@ -19,7 +19,6 @@ from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
-import sympy as sp
 from sympy import Expr, Symbol, sympify
 
 from ..config import default_dtype

@@ -28,7 +28,6 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 import sympy as sp
-from sympy.printing.precedence import precedence
 
 T_SYM = sp.Symbol("t")
 
